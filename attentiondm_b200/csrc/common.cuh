@@ -1,0 +1,82 @@
+// Shared helpers for the attndm_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/attndm_b200.h"
+
+namespace attndm {
+
+void set_error(const char* fmt, ...);
+
+#define ATTNDM_CHECK_ARG(cond, ...)            \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::attndm::set_error(__VA_ARGS__);        \
+      return ATTNDM_ERR_ARG;                   \
+    }                                          \
+  } while (0)
+
+#define ATTNDM_CUDA_LAUNCH_CHECK(name)                                              \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      ::attndm::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));  \
+      return ATTNDM_ERR_CUDA;                                                       \
+    }                                                                               \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+constexpr int kNumSMs = 148;       // B200
+constexpr int kGnGroups = 32;      // every GroupNorm in the reference uses 32 groups
+
+// ---- exact (non-contracted) fp32 arithmetic of the reference quantizer -----
+// utils/quant_util.py:273-279: mul, sub, round-half-even, clamp, add, divide,
+// each a separately rounded fp32 op.  The _rn intrinsics are never fused.
+__device__ __forceinline__ float quant_code(float v, float s, float zp, float lo, float hi) {
+  float q = rintf(__fsub_rn(__fmul_rn(s, v), zp));
+  return fminf(fmaxf(q, lo), hi);
+}
+__device__ __forceinline__ float dequant(float code, float s, float zp) {
+  return __fdiv_rn(__fadd_rn(code, zp), s);
+}
+
+__device__ __forceinline__ float silu_f(float v) {
+  // x * sigmoid(x) == x / (1 + exp(-x)); accurate expf (no fast-math)
+  return __fdiv_rn(v, __fadd_rn(1.0f, expf(-v)));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit global accesses (activations are touched once per kernel)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+}  // namespace attndm

@@ -1,0 +1,74 @@
+// Parameter block and epilogue arithmetic shared by the two int8 convolution
+// kernels (conv_simt.cu, conv_tc.cu), so that both produce bit-identical output.
+#pragma once
+#include "common.cuh"
+
+namespace attndm {
+
+struct ConvI8Params {
+  const int8_t* codes;     // [rows][Cp]
+  const int32_t* rowsum;   // [rows]
+  int B, H, W, C, Cp;
+  int Hp, Wp;              // row geometry: H+2, W+2 for taps == 9 (halo rows), H, W for taps == 1
+  long long rows;
+  const int8_t* qw;        // [O][taps*Cp]
+  const int32_t* wsum;     // [O]
+  const int32_t* w_zp;     // [O]
+  int O, taps;
+  const float* mult;       // [O]
+  const int32_t* act_zp;   // [1]
+  const float* bias;       // [O] or NULL
+  const float* residual;   // [B*H*W][O] or NULL
+  const float* temb;       // [B][O] or NULL
+  float* out;              // [B*H*W][O]
+};
+
+// code-row index -> output pixel.  For 3x3 the GEMM row r is the halo-layout row of
+// the window's top-left corner, so output pixel (h, w) = (hp, wp) and it is valid for
+// hp < H, wp < W.
+__device__ __forceinline__ bool conv_row_to_pixel(const ConvI8Params& p, long long row, long long& pix, int& b) {
+  if (row >= p.rows) return false;
+  if (p.taps == 1) {
+    pix = row;
+    b = (int)(row / ((long long)p.H * p.W));
+    return true;
+  }
+  const long long per = (long long)p.Hp * p.Wp;
+  b = (int)(row / per);
+  const int rem = (int)(row - (long long)b * per);
+  const int hp = rem / p.Wp, wp = rem - hp * p.Wp;
+  if (hp >= p.H || wp >= p.W) return false;
+  pix = ((long long)b * p.H + hp) * p.W + wp;
+  return true;
+}
+
+// sum of the per-pixel code sums over the receptive field of GEMM row `row`
+__device__ __forceinline__ long long conv_window_rowsum(const ConvI8Params& p, long long row) {
+  if (p.taps == 1) return p.rowsum[row];
+  long long s = 0;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) s += p.rowsum[row + (long long)kh * p.Wp + kw];
+  return s;
+}
+
+// I = acc + zp*wsum[o] + w_zp[o]*(CS + zp*K)  (exact, 64-bit), then * mult[o] + bias[o]
+__device__ __forceinline__ float conv_i8_finish(const ConvI8Params& p, int acc, int zp, long long cs_plus_zpk, int o) {
+  long long I = (long long)acc + (long long)zp * p.wsum[o] + (long long)p.w_zp[o] * cs_plus_zpk;
+  float v = __fmul_rn((float)I, p.mult[o]);
+  if (p.bias) v = __fadd_rn(v, p.bias[o]);
+  return v;
+}
+
+__device__ __forceinline__ float conv_epilogue_add(const float* residual, const float* temb, float v,
+                                                   long long pix, int b, int o, int O) {
+  if (residual) v = __fadd_rn(v, residual[pix * O + o]);     // ResidualBlock: x + h
+  if (temb) v = __fadd_rn(v, temb[(long long)b * O + o]);    // block: x + time_mlp(t_emb)
+  return v;
+}
+
+int launch_qconv_i8_simt(const ConvI8Params& p, cudaStream_t st);
+int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st);
+
+}  // namespace attndm

@@ -1,0 +1,301 @@
+// int8 implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared -> tcgen05.mma kind::i8
+//   -> s32 accumulators in TMEM -> tcgen05.ld -> fused epilogue -> NHWC fp32.
+// Reference op: QConv2d.forward -> F.conv2d, utils/quant_util.py:383-385.
+//
+// GEMM view.  Codes live in HBM as rows of Cp bytes.  For a 3x3/pad-1 conv the
+// rows are the halo layout [B][H+2][W+2] (ring = code of 0.0), so tap (kh, kw) is
+// the SAME matrix shifted by kh*(W+2)+kw rows: the A tile of every k-block is one
+// plain 2-D TMA box {128 channels, 128 rows} at row m0 + shift, no im2col, no
+// border logic; rows past the end / channels past Cp are zero-filled by TMA.
+// Weights are [O][taps*Cp] (K-major), tile {128, BN}.  One CTA computes a
+// 128-row x BN-output tile: M = 128 (TMEM lanes), N = BN <= 256 (TMEM columns).
+//
+// Warp roles (192 threads): warp 0 = TMEM allocator + TMA producer (one lane),
+// warp 1 = barrier init + MMA issuer (one lane), warps 2..5 = epilogue (TMEM lane
+// quarter = warp_idx % 4).  Two CTAs fit per SM (<= 112 KB smem, <= 256 TMEM
+// columns each) so one CTA's epilogue overlaps the other's main loop.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace attndm {
+
+constexpr int TC_BM = 128;        // rows per tile  (UMMA M)
+constexpr int TC_BK = 128;        // bytes of K per stage (one SWIZZLE_128B row)
+constexpr int TC_UMMA_K = 32;     // K per tcgen05.mma for 8-bit operands
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_BUDGET = 110 * 1024;   // per CTA, so that two CTAs share an SM
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a lost arrival traps (fails the launch) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = clock64();
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && clock64() - t0 > 4000000000LL) __trap();
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address >> 4
+  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                           // layout type SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- kernel -------------------------------------------------------------------
+struct TcGeom {
+  int BN;            // outputs per tile (multiple of 16, <= 256)
+  int stages;
+  int stage_bytes;   // 16384 + BN*128
+  int ncb;           // channel blocks of 128 per tap
+  int tmem_cols;     // power of two >= max(32, BN)
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+qconv_i8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const ConvI8Params p, const TcGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024-B alignment
+  const long long m0 = (long long)blockIdx.x * TC_BM;
+  const int n0 = blockIdx.y * g.BN;
+  const int num_kb = p.taps * g.ncb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
+        const long long shift = p.taps == 9 ? (long long)(tap / 3) * p.Wp + (tap % 3) : 0;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+        const uint32_t a_dst = tiles + (uint32_t)s * g.stage_bytes;
+        const uint32_t b_dst = a_dst + TC_BM * TC_BK;
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        mbar_expect_tx(bar, (uint32_t)g.stage_bytes);
+        tma_load_2d(a_dst, &tmA, bar, cb * TC_BK, (int)(m0 + shift));
+        tma_load_2d(b_dst, &tmB, bar, tap * p.Cp + cb * TC_BK, n0);
+        if (++s == g.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      // instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = BN
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int cb = kb % g.ncb;
+        int ksteps = (p.Cp - cb * TC_BK + TC_UMMA_K - 1) / TC_UMMA_K;   // skip all-zero K tails
+        if (ksteps > TC_BK / TC_UMMA_K) ksteps = TC_BK / TC_UMMA_K;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tcgen05_fence_after();
+        const uint32_t a_addr = tiles + (uint32_t)s * g.stage_bytes;
+        const uint32_t b_addr = a_addr + TC_BM * TC_BK;
+        for (int k = 0; k < ksteps; ++k) {
+          umma_i8(tmem_base, umma_desc_sw128(a_addr + k * TC_UMMA_K), umma_desc_sw128(b_addr + k * TC_UMMA_K), idesc,
+                  (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        tcgen05_commit(smem_u32(&empty_bar[s]));     // frees the smem slot when these MMAs retire
+        if (++s == g.stages) { s = 0; ph ^= 1; }
+      }
+      tcgen05_commit(smem_u32(&tmem_full_bar));      // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> fused scale/bias/residual/temb -> NHWC fp32 =====
+    const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
+    const long long row = m0 + quarter * 32 + lane;
+    long long pix = 0;
+    int b = 0;
+    const bool valid = conv_row_to_pixel(p, row, pix, b);
+    const int zp = *p.act_zp;
+    long long cs = 0;
+    if (valid) cs = conv_window_rowsum(p, row) + (long long)zp * ((long long)p.taps * p.C);
+    mbar_wait(smem_u32(&tmem_full_bar), 0);
+    tcgen05_fence_after();
+    const bool vec_ok = (p.O & 3) == 0;
+    for (int c0 = 0; c0 < g.BN; c0 += 16) {
+      uint32_t v[16];
+      __syncwarp();                                   // tcgen05.ld is .sync.aligned: whole warp, converged
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      const int o0 = n0 + c0;
+      if (valid && o0 < p.O) {
+        float* orow = p.out + pix * p.O;
+        if (vec_ok && o0 + 16 <= p.O) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 r;
+            r.x = conv_epilogue_add(p.residual, p.temb, conv_i8_finish(p, (int)v[j + 0], zp, cs, o0 + j + 0), pix, b, o0 + j + 0, p.O);
+            r.y = conv_epilogue_add(p.residual, p.temb, conv_i8_finish(p, (int)v[j + 1], zp, cs, o0 + j + 1), pix, b, o0 + j + 1, p.O);
+            r.z = conv_epilogue_add(p.residual, p.temb, conv_i8_finish(p, (int)v[j + 2], zp, cs, o0 + j + 2), pix, b, o0 + j + 2, p.O);
+            r.w = conv_epilogue_add(p.residual, p.temb, conv_i8_finish(p, (int)v[j + 3], zp, cs, o0 + j + 3), pix, b, o0 + j + 3, p.O);
+            *reinterpret_cast<float4*>(orow + o0 + j) = r;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int o = o0 + j;
+            if (o < p.O) orow[o] = conv_epilogue_add(p.residual, p.temb, conv_i8_finish(p, (int)v[j], zp, cs, o), pix, b, o, p.O);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    // resolved through the runtime so the library has no link-time libcuda dependency
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+static int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                       uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("qconv_i8_tc: cuTensorMapEncodeTiled not available"); return ATTNDM_ERR_CUDA; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner};          // bytes between rows (uint8 elements)
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("qconv_i8_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return ATTNDM_ERR_CUDA; }
+  return ATTNDM_OK;
+}
+
+int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st) {
+  ATTNDM_CHECK_ARG(((uintptr_t)p.codes & 15) == 0 && ((uintptr_t)p.qw & 15) == 0, "qconv_i8_tc: operands must be 16-byte aligned");
+  ATTNDM_CHECK_ARG(p.rows + 2LL * p.Wp + 2 + TC_BM < 0x7fffffffLL, "qconv_i8_tc: too many rows for 32-bit TMA coordinates");
+  TcGeom g;
+  g.BN = p.O <= 256 ? round_up(p.O, 16) : 256;
+  g.stage_bytes = TC_BM * TC_BK + g.BN * TC_BK;
+  g.stages = TC_SMEM_BUDGET / g.stage_bytes;
+  if (g.stages > TC_MAX_STAGES) g.stages = TC_MAX_STAGES;
+  if (g.stages < 2) g.stages = 2;
+  g.ncb = cdiv(p.Cp, TC_BK);
+  g.tmem_cols = 32;
+  while (g.tmem_cols < g.BN) g.tmem_cols <<= 1;
+  CUtensorMap tmA, tmB;
+  int rc = make_map_2d(&tmA, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, TC_BM);
+  if (rc) return rc;
+  rc = make_map_2d(&tmB, p.qw, (uint64_t)p.taps * p.Cp, (uint64_t)p.O, TC_BK, (uint32_t)g.BN);
+  if (rc) return rc;
+  const int smem = g.stages * g.stage_bytes + 1024;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(qconv_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  if (attr_err != cudaSuccess) { set_error("qconv_i8_tc: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
+  dim3 grid(cdiv(p.rows, TC_BM), cdiv(p.O, g.BN));
+  qconv_i8_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p, g);
+  ATTNDM_CUDA_LAUNCH_CHECK("qconv_i8_tc");
+  return ATTNDM_OK;
+}
+
+}  // namespace attndm

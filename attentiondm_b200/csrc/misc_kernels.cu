@@ -1,0 +1,257 @@
+// Attention core, UNet glue and the sampler update.
+#include "common.cuh"
+
+namespace attndm {
+
+// ---------------------------------------------------------------------------
+// attention: one warp per (sample, head, query row)
+// models/self_attention.py:141-144; utils/attention_quant_utils.py:65-107
+// ---------------------------------------------------------------------------
+struct AttnParams {
+  const float* q;
+  const float* k;
+  const float* v;
+  float* out;
+  int B, N, d, dv, heads;
+  float scale, softmax_scale;
+  attndm_attn_quant qk_q, p_q;
+};
+
+__device__ __forceinline__ float attn_fake_quant(float x, float s, float zp, float qmax) {
+  // clamp(round(x / scale) + zero_point, 0, qmax); (x_q - zero_point) * scale
+  float q = __fadd_rn(rintf(__fdiv_rn(x, s)), zp);
+  q = fminf(fmaxf(q, 0.f), qmax);
+  return __fmul_rn(__fsub_rn(q, zp), s);
+}
+
+__global__ void __launch_bounds__(128) attention_kernel(AttnParams p) {
+  extern __shared__ float sm[];                       // [4 warps][N]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* sc = sm + (long long)w * p.N;
+  const long long gw = (long long)blockIdx.x * 4 + w;
+  const long long total = (long long)p.B * p.heads * p.N;
+  if (gw >= total) return;
+  const int i = (int)(gw % p.N);
+  const int head = (int)((gw / p.N) % p.heads);
+  const int b = (int)(gw / ((long long)p.N * p.heads));
+  const int dq = p.d / p.heads, dvh = p.dv / p.heads;
+  const float* qrow = p.q + ((long long)b * p.N + i) * p.d + head * dq;      // q: head-major channels
+  const float* kb = p.k + (long long)b * p.N * p.d;                          // k: channel = e*heads + head
+  float mx = -INFINITY;
+  for (int j = lane; j < p.N; j += 32) {
+    const float* krow = kb + (long long)j * p.d;
+    float acc = 0.f;
+    for (int e = 0; e < dq; ++e) acc = fmaf(qrow[e], krow[e * p.heads + head], acc);
+    float s = __fmul_rn(acc, p.scale);
+    if (p.qk_q.bits > 0) s = attn_fake_quant(s, p.qk_q.scale, p.qk_q.zero_point, (float)((1 << p.qk_q.bits) - 1));
+    s = __fmul_rn(s, p.softmax_scale);
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < p.N; j += 32) {
+    float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  for (int j = lane; j < p.N; j += 32) {
+    float pr = __fdiv_rn(sc[j], sum);
+    if (p.p_q.bits > 0) pr = attn_fake_quant(pr, p.p_q.scale, p.p_q.zero_point, (float)((1 << p.p_q.bits) - 1));
+    sc[j] = pr;
+  }
+  __syncwarp();
+  const float* vb = p.v + (long long)b * p.N * p.dv + head * dvh;
+  float* orow = p.out + ((long long)b * p.N + i) * p.dv + head * dvh;
+  for (int c = lane; c < dvh; c += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < p.N; ++j) acc = fmaf(sc[j], vb[(long long)j * p.dv + c], acc);
+    orow[c] = acc;
+  }
+}
+
+__global__ void scale_add_kernel(const float* __restrict__ a, const float* __restrict__ x, const float* __restrict__ gamma,
+                                 float* __restrict__ out, long long n) {
+  const float g = *gamma;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(__fmul_rn(g, a[i]), x[i]);
+}
+
+// ---------------------------------------------------------------------------
+// UNet glue (NHWC)
+// ---------------------------------------------------------------------------
+__global__ void maxpool2_kernel(const float* __restrict__ x, int B, int H, int W, int C, float* __restrict__ y) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long n = (long long)B * Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int wo = (int)(t % Wo);
+    t /= Wo;
+    int ho = (int)(t % Ho);
+    int b = (int)(t / Ho);
+    const float* p00 = x + (((long long)b * H + 2 * ho) * W + 2 * wo) * C + c;
+    float m = fmaxf(fmaxf(p00[0], p00[C]), fmaxf(p00[(long long)W * C], p00[(long long)W * C + C]));
+    y[i] = m;
+  }
+}
+
+__global__ void upsample_concat_kernel(const float* __restrict__ x, int B, int H, int W, int Cx,
+                                       const float* __restrict__ skip, int Hs, int Ws, int Cs,
+                                       float* __restrict__ out) {
+  const int Ct = Cx + Cs;
+  const long long n = (long long)B * Hs * Ws * Ct;
+  // nearest x2 (src = dst/2) followed, when sizes differ, by nearest resize 2H x 2W -> Hs x Ws
+  // (src = min(floor(dst * in/out), in-1) in fp32, as ATen's nearest kernel computes it)
+  const bool same = (2 * H == Hs) && (2 * W == Ws);
+  const float sh = (float)(2 * H) / (float)Hs, sw = (float)(2 * W) / (float)Ws;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Ct);
+    long long t = i / Ct;
+    int ws = (int)(t % Ws);
+    t /= Ws;
+    int hs = (int)(t % Hs);
+    int b = (int)(t / Hs);
+    float v;
+    if (c < Cx) {
+      int uh = hs, uw = ws;
+      if (!same) {
+        uh = min((int)floorf(__fmul_rn((float)hs, sh)), 2 * H - 1);
+        uw = min((int)floorf(__fmul_rn((float)ws, sw)), 2 * W - 1);
+      }
+      v = x[(((long long)b * H + (uh >> 1)) * W + (uw >> 1)) * Cx + c];
+    } else {
+      v = skip[(((long long)b * Hs + hs) * Ws + ws) * Cs + (c - Cx)];
+    }
+    out[i] = v;
+  }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, float* __restrict__ emb) {
+  const int half = dim / 2;
+  const float coef = -(float)(log(10000.0) / (double)(half - 1));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
+    int b = i / half, e = i - b * half;
+    float f = expf(__fmul_rn((float)e, coef));
+    float a = __fmul_rn(t[b], f);
+    emb[(long long)b * dim + e] = sinf(a);
+    emb[(long long)b * dim + half + e] = cosf(a);
+    if ((dim & 1) && e == 0) emb[(long long)b * dim + dim - 1] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// sampler
+// ---------------------------------------------------------------------------
+__global__ void ddim_step_kernel(const float* __restrict__ xt, const float* __restrict__ eps,
+                                 const float* __restrict__ coef, const float* __restrict__ noise,
+                                 float* __restrict__ x_next, float* __restrict__ x0_out, long long n) {
+  const float s1mat = coef[0], sat = coef[1], satn = coef[2], c1 = coef[3], c2 = coef[4];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = xt[i], e = eps[i];
+    // x0_t = (xt - et * (1 - at).sqrt()) / at.sqrt()
+    const float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(e, s1mat)), sat);
+    // xt_next = at_next.sqrt() * x0_t + c1 * randn + c2 * et
+    float r = __fmul_rn(satn, x0);
+    if (noise) r = __fadd_rn(r, __fmul_rn(c1, noise[i]));
+    r = __fadd_rn(r, __fmul_rn(c2, e));
+    x_next[i] = r;
+    if (x0_out) x0_out[i] = x0;
+  }
+}
+
+__global__ void stage_copy_kernel(const float* __restrict__ table, long long n, const int* __restrict__ step,
+                                  float* __restrict__ dst) {
+  const float* src = table + (long long)(*step) * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+__global__ void stage_advance_kernel(int* step, int T) {
+  int s = *step + 1;
+  *step = s >= T ? 0 : s;
+}
+
+static inline int ew_blocks(long long n) {
+  long long b = (n + 255) / 256;
+  long long cap = (long long)kNumSMs * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace attndm
+
+using namespace attndm;
+
+extern "C" {
+
+int attndm_attention(const float* q, const float* k, const float* v, float* out, int B, int N, int d, int dv,
+                     float scale, int heads, float softmax_scale, attndm_attn_quant qk_q, attndm_attn_quant p_q,
+                     void* stream) {
+  ATTNDM_CHECK_ARG(q && k && v && out && B > 0 && N > 0 && d > 0 && dv > 0, "attention: bad args");
+  ATTNDM_CHECK_ARG(heads >= 1 && d % heads == 0 && dv % heads == 0, "attention: heads must divide d and dv");
+  ATTNDM_CHECK_ARG(N <= 8192, "attention: N <= 8192 (per-warp score row lives in shared memory)");
+  ATTNDM_CHECK_ARG(qk_q.bits >= 0 && qk_q.bits <= 8 && p_q.bits >= 0 && p_q.bits <= 8, "attention: bad quant bits");
+  AttnParams p;
+  p.q = q; p.k = k; p.v = v; p.out = out; p.B = B; p.N = N; p.d = d; p.dv = dv; p.heads = heads;
+  p.scale = scale; p.softmax_scale = softmax_scale; p.qk_q = qk_q; p.p_q = p_q;
+  long long total = (long long)B * heads * N;
+  size_t smem = 4 * (size_t)N * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("attention: smem attr: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
+  }
+  attention_kernel<<<cdiv(total, 4), 128, smem, (cudaStream_t)stream>>>(p);
+  ATTNDM_CUDA_LAUNCH_CHECK("attention");
+  return ATTNDM_OK;
+}
+
+int attndm_scale_add(const float* a, const float* x, const float* gamma, float* out, long long n, void* stream) {
+  ATTNDM_CHECK_ARG(a && x && gamma && out && n > 0, "scale_add: bad args");
+  scale_add_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, x, gamma, out, n);
+  ATTNDM_CUDA_LAUNCH_CHECK("scale_add");
+  return ATTNDM_OK;
+}
+
+int attndm_maxpool2(const float* x, int B, int H, int W, int C, float* y, void* stream) {
+  ATTNDM_CHECK_ARG(x && y && B > 0 && H >= 2 && W >= 2 && C > 0, "maxpool2: bad args");
+  long long n = (long long)B * (H / 2) * (W / 2) * C;
+  maxpool2_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, y);
+  ATTNDM_CUDA_LAUNCH_CHECK("maxpool2");
+  return ATTNDM_OK;
+}
+
+int attndm_upsample_concat(const float* x, int B, int H, int W, int Cx, const float* skip, int Hs, int Ws, int Cs,
+                           float* out, void* stream) {
+  ATTNDM_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0 && Cx > 0 && Hs > 0 && Ws > 0 && Cs >= 0, "upsample_concat: bad args");
+  ATTNDM_CHECK_ARG(Cs == 0 || skip, "upsample_concat: skip is NULL");
+  long long n = (long long)B * Hs * Ws * (Cx + Cs);
+  upsample_concat_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, Cx, skip, Hs, Ws, Cs, out);
+  ATTNDM_CUDA_LAUNCH_CHECK("upsample_concat");
+  return ATTNDM_OK;
+}
+
+int attndm_timestep_embedding(const float* t, int B, int dim, float* emb, void* stream) {
+  ATTNDM_CHECK_ARG(t && emb && B > 0 && dim >= 4, "timestep_embedding: bad args");
+  timestep_embedding_kernel<<<cdiv((long long)B * (dim / 2), 256), 256, 0, (cudaStream_t)stream>>>(t, B, dim, emb);
+  ATTNDM_CUDA_LAUNCH_CHECK("timestep_embedding");
+  return ATTNDM_OK;
+}
+
+int attndm_ddim_step(const float* xt, const float* eps, const float* coef, const float* noise, float* x_next,
+                     float* x0_out, long long n, void* stream) {
+  ATTNDM_CHECK_ARG(xt && eps && coef && x_next && n > 0, "ddim_step: bad args");
+  ddim_step_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(xt, eps, coef, noise, x_next, x0_out, n);
+  ATTNDM_CUDA_LAUNCH_CHECK("ddim_step");
+  return ATTNDM_OK;
+}
+
+int attndm_stage_tables(const float* table, long long n, int T, int* step, int advance, float* dst, void* stream) {
+  ATTNDM_CHECK_ARG(table && step && dst && n > 0 && T > 0, "stage_tables: bad args");
+  stage_copy_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(table, n, step, dst);
+  if (advance) stage_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, T);
+  ATTNDM_CUDA_LAUNCH_CHECK("stage_tables");
+  return ATTNDM_OK;
+}
+
+}  // extern "C"

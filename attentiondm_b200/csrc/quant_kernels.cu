@@ -1,0 +1,752 @@
+// HBM-bound quantizer / collector kernels.
+//   act_quant      : utils/quant_util.py:260-282 (+ fused GroupNorm/SiLU producer)
+//   gn_stats       : GroupNorm(32) statistics, double accumulation
+//   minmax_c       : utils/quant_util.py:187-191
+//   group_ranges   : utils/quant_util.py:193-205, 403-437
+//   calib_mix      : utils/quant_util.py:207-224, 54-66
+//   kth_value      : utils/quant_util.py:440-450
+// Mapping used by the row kernels: one warp owns one NHWC pixel row at a time and
+// its lanes walk the row in float4 steps (fully coalesced 512 B per request), so
+// the per-pixel code sum is a warp shuffle reduction and never an atomic.  Warps
+// own contiguous row ranges so per-sample state (GroupNorm mean/rstd, held one
+// group per lane) is refreshed only when the sample index changes.
+#include "common.cuh"
+
+namespace attndm {
+
+// ---------------------------------------------------------------------------
+// act_quant
+// ---------------------------------------------------------------------------
+struct ActQuantParams {
+  const float* x;
+  int B, H, W, C, Cp;
+  const float* scale;
+  const float* zp;
+  float qlo, qhi;
+  const double* gn_stats;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int8_t* codes;
+  int32_t* rowsum;
+  int halo;
+  float* y;
+  long long rows;          // rows of the code layout (halo or plain)
+  long long rows_per_warp;
+};
+
+template <int PRE>
+__device__ __forceinline__ float pre_op(float v, float a, float b) {
+  if (PRE == ATTNDM_PRE_GN_SILU) return silu_f(fmaf(v, a, b));
+  if (PRE == ATTNDM_PRE_SILU) return silu_f(v);
+  return v;
+}
+
+__device__ __forceinline__ void gn_refresh(const double* stats, int b, int lane, double inv_n,
+                                           float eps, float& mean, float& rstd) {
+  // lane g owns group g
+  double s = stats[((long long)b * kGnGroups + lane) * 2 + 0];
+  double ss = stats[((long long)b * kGnGroups + lane) * 2 + 1];
+  double m = s * inv_n;
+  double var = ss * inv_n - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+template <int PRE, bool QUANT, bool VEC>
+__global__ void __launch_bounds__(256) act_quant_kernel(ActQuantParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  long long r0 = warp * p.rows_per_warp;
+  long long r1 = r0 + p.rows_per_warp;
+  if (r1 > p.rows) r1 = p.rows;
+  const int Hp = p.halo ? p.H + 2 : p.H, Wp = p.halo ? p.W + 2 : p.W;
+  const int cpg = p.C / kGnGroups;
+  const double inv_n = (PRE == ATTNDM_PRE_GN_SILU) ? 1.0 / ((double)p.H * p.W * cpg) : 0.0;
+  int cur_b = -1;
+  float mean = 0.f, rstd = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    int b = (int)(r / ((long long)Hp * Wp));
+    int rem = (int)(r - (long long)b * Hp * Wp);
+    int hp = rem / Wp, wp = rem - hp * Wp;
+    bool interior = true;
+    int h = hp, w = wp;
+    if (p.halo) {
+      interior = (hp >= 1 && hp <= p.H && wp >= 1 && wp <= p.W);
+      h = hp - 1;
+      w = wp - 1;
+    }
+    const long long pix = ((long long)b * p.H + h) * p.W + w;
+    if (PRE == ATTNDM_PRE_GN_SILU && interior && b != cur_b) {
+      gn_refresh(p.gn_stats, b, lane, inv_n, p.eps, mean, rstd);
+      cur_b = b;
+    }
+    int acc = 0;
+    if (VEC) {
+      const int Q = p.C >> 2;
+      // uniform trip count: the GroupNorm shuffles below need every lane present
+      for (int q0 = 0; q0 < Q; q0 += 32) {
+        const bool act = (q0 + lane) < Q;
+        const int c = act ? ((q0 + lane) << 2) : 0;
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (QUANT) {
+          s4 = *reinterpret_cast<const float4*>(p.scale + c);
+          z4 = *reinterpret_cast<const float4*>(p.zp + c);
+        }
+        float4 cd;
+        if (interior) {
+          float4 v = ldg_stream(reinterpret_cast<const float4*>(p.x + pix * p.C + c));
+          float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+          if (PRE == ATTNDM_PRE_GN_SILU) {
+            // group of each of the 4 channels (cpg may be < 4 for tiny models)
+            float4 g4 = *reinterpret_cast<const float4*>(p.gamma + c);
+            float4 b4 = *reinterpret_cast<const float4*>(p.beta + c);
+            int g0 = c / cpg, g1 = (c + 1) / cpg, g2 = (c + 2) / cpg, g3 = (c + 3) / cpg;
+            float m0 = __shfl_sync(0xffffffffu, mean, g0), r0_ = __shfl_sync(0xffffffffu, rstd, g0);
+            float m1 = m0, r1_ = r0_, m2 = m0, r2_ = r0_, m3 = m0, r3_ = r0_;
+            if (cpg < 4) {   // warp-uniform branch (cpg is a kernel-wide constant)
+              m1 = __shfl_sync(0xffffffffu, mean, g1); r1_ = __shfl_sync(0xffffffffu, rstd, g1);
+              m2 = __shfl_sync(0xffffffffu, mean, g2); r2_ = __shfl_sync(0xffffffffu, rstd, g2);
+              m3 = __shfl_sync(0xffffffffu, mean, g3); r3_ = __shfl_sync(0xffffffffu, rstd, g3);
+            }
+            ga.x = r0_ * g4.x; gb.x = fmaf(-m0, ga.x, b4.x);
+            ga.y = r1_ * g4.y; gb.y = fmaf(-m1, ga.y, b4.y);
+            ga.z = r2_ * g4.z; gb.z = fmaf(-m2, ga.z, b4.z);
+            ga.w = r3_ * g4.w; gb.w = fmaf(-m3, ga.w, b4.w);
+          }
+          v.x = pre_op<PRE>(v.x, ga.x, gb.x);
+          v.y = pre_op<PRE>(v.y, ga.y, gb.y);
+          v.z = pre_op<PRE>(v.z, ga.z, gb.z);
+          v.w = pre_op<PRE>(v.w, ga.w, gb.w);
+          if (QUANT) {
+            cd.x = quant_code(v.x, s4.x, z4.x, p.qlo, p.qhi);
+            cd.y = quant_code(v.y, s4.y, z4.y, p.qlo, p.qhi);
+            cd.z = quant_code(v.z, s4.z, z4.z, p.qlo, p.qhi);
+            cd.w = quant_code(v.w, s4.w, z4.w, p.qlo, p.qhi);
+            if (p.y && act) {
+              float4 o;
+              o.x = dequant(cd.x, s4.x, z4.x);
+              o.y = dequant(cd.y, s4.y, z4.y);
+              o.z = dequant(cd.z, s4.z, z4.z);
+              o.w = dequant(cd.w, s4.w, z4.w);
+              *reinterpret_cast<float4*>(p.y + pix * p.C + c) = o;
+            }
+          } else {
+            if (p.y && act) *reinterpret_cast<float4*>(p.y + pix * p.C + c) = v;
+            cd = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+          // halo ring: the code of 0.0, i.e. -zero_point (asserted in range by the host)
+          cd.x = fminf(fmaxf(-z4.x, p.qlo), p.qhi);
+          cd.y = fminf(fmaxf(-z4.y, p.qlo), p.qhi);
+          cd.z = fminf(fmaxf(-z4.z, p.qlo), p.qhi);
+          cd.w = fminf(fmaxf(-z4.w, p.qlo), p.qhi);
+        }
+        if (QUANT && p.codes && act) {
+          int ix = (int)cd.x, iy = (int)cd.y, iz = (int)cd.z, iw = (int)cd.w;
+          acc += ix + iy + iz + iw;
+          char4 c4 = make_char4((signed char)ix, (signed char)iy, (signed char)iz, (signed char)iw);
+          *reinterpret_cast<char4*>(p.codes + r * p.Cp + c) = c4;
+        }
+      }
+    } else {
+      for (int c = lane; c < p.Cp; c += 32) {
+        float cd = 0.f;
+        if (c < p.C) {
+          float s = QUANT ? p.scale[c] : 1.f, z = QUANT ? p.zp[c] : 0.f;
+          if (interior) {
+            float v = p.x[pix * p.C + c];
+            // C % 4 != 0 only occurs for the image latent, which has no GroupNorm (host-checked)
+            v = pre_op<PRE == ATTNDM_PRE_GN_SILU ? ATTNDM_PRE_NONE : PRE>(v, 0.f, 0.f);
+            if (QUANT) {
+              cd = quant_code(v, s, z, p.qlo, p.qhi);
+              if (p.y) p.y[pix * p.C + c] = dequant(cd, s, z);
+            } else if (p.y) {
+              p.y[pix * p.C + c] = v;
+            }
+          } else {
+            cd = fminf(fmaxf(-z, p.qlo), p.qhi);
+          }
+        }
+        if (QUANT && p.codes) {
+          acc += (int)cd;
+          p.codes[r * p.Cp + c] = (int8_t)(int)cd;
+        }
+      }
+    }
+    if (QUANT && p.rowsum) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) p.rowsum[r] = acc;
+    }
+  }
+}
+
+template <int PRE, bool QUANT>
+static void launch_act_quant(const ActQuantParams& p, int blocks, cudaStream_t st) {
+  // the GN shuffle in the scalar path needs all lanes converged per channel step;
+  // it is only used for C % 4 != 0 (the 3-channel latent), which never has a GN.
+  if ((p.C & 3) == 0)
+    act_quant_kernel<PRE, QUANT, true><<<blocks, 256, 0, st>>>(p);
+  else
+    act_quant_kernel<PRE, QUANT, false><<<blocks, 256, 0, st>>>(p);
+}
+
+static int act_quant_impl(const float* x, int B, int H, int W, int C, const float* scale,
+                          const float* zp, int a_bit, int pre, const double* gn_stats,
+                          const float* gamma, const float* beta, float eps, int8_t* codes,
+                          int32_t* rowsum, int rows_layout, float* y, bool quant,
+                          cudaStream_t st) {
+  ATTNDM_CHECK_ARG(x && B > 0 && H > 0 && W > 0 && C > 0, "act_quant: bad shape");
+  ATTNDM_CHECK_ARG(!quant || (scale && zp && a_bit >= 2 && a_bit <= 8), "act_quant: bad quant params");
+  ATTNDM_CHECK_ARG(pre != ATTNDM_PRE_GN_SILU || (gn_stats && gamma && beta && C % kGnGroups == 0 && C % 4 == 0),
+                   "act_quant: GroupNorm pre-op needs stats/gamma/beta and C %% 32 == 0");
+  ATTNDM_CHECK_ARG(rows_layout == ATTNDM_ROWS_PLAIN || rows_layout == ATTNDM_ROWS_HALO, "act_quant: bad layout");
+  ActQuantParams p;
+  p.x = x; p.B = B; p.H = H; p.W = W; p.C = C; p.Cp = round_up(C, 16);
+  p.scale = scale; p.zp = zp;
+  p.qlo = quant ? -(float)(1 << (a_bit - 1)) : 0.f;
+  p.qhi = quant ? (float)((1 << (a_bit - 1)) - 1) : 0.f;
+  p.gn_stats = gn_stats; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.codes = codes; p.rowsum = rowsum; p.halo = (rows_layout == ATTNDM_ROWS_HALO && codes) ? 1 : 0;
+  p.y = y;
+  p.rows = p.halo ? (long long)B * (H + 2) * (W + 2) : (long long)B * H * W;
+  // ~8 warps per block; aim at <= 16 resident blocks per SM worth of warps, rows contiguous per warp
+  long long max_warps = (long long)kNumSMs * 8 * 8;
+  long long warps = p.rows < max_warps ? p.rows : max_warps;
+  p.rows_per_warp = (p.rows + warps - 1) / warps;
+  warps = (p.rows + p.rows_per_warp - 1) / p.rows_per_warp;
+  int blocks = cdiv(warps, 8);
+  if (!quant) {
+    if (pre == ATTNDM_PRE_GN_SILU) launch_act_quant<ATTNDM_PRE_GN_SILU, false>(p, blocks, st);
+    else if (pre == ATTNDM_PRE_SILU) launch_act_quant<ATTNDM_PRE_SILU, false>(p, blocks, st);
+    else launch_act_quant<ATTNDM_PRE_NONE, false>(p, blocks, st);
+  } else {
+    if (pre == ATTNDM_PRE_GN_SILU) launch_act_quant<ATTNDM_PRE_GN_SILU, true>(p, blocks, st);
+    else if (pre == ATTNDM_PRE_SILU) launch_act_quant<ATTNDM_PRE_SILU, true>(p, blocks, st);
+    else launch_act_quant<ATTNDM_PRE_NONE, true>(p, blocks, st);
+  }
+  ATTNDM_CUDA_LAUNCH_CHECK("act_quant");
+  return ATTNDM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// GroupNorm statistics
+// ---------------------------------------------------------------------------
+// block = (C/4 channel quads) x P pixel lanes, fixed quad per thread; grid = (splits, B)
+__global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int P, int rows_per_block,
+                                double* __restrict__ stats) {
+  __shared__ double s_sum[kGnGroups], s_sq[kGnGroups];
+  const int b = blockIdx.y;
+  const int Q = C >> 2;
+  const int cpg = C / kGnGroups;
+  if (threadIdx.x < kGnGroups) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+  __syncthreads();
+  const int q = threadIdx.x % Q, pl = threadIdx.x / Q;
+  int r0 = blockIdx.x * rows_per_block, r1 = min(HW, r0 + rows_per_block);
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+  if (pl < P) {
+    const float* base = x + ((long long)b * HW) * C + (q << 2);
+    for (int r = r0 + pl; r < r1; r += P) {
+      float4 v = ldg_stream(reinterpret_cast<const float4*>(base + (long long)r * C));
+      a0 += v.x; q0 += (double)v.x * v.x;
+      a1 += v.y; q1 += (double)v.y * v.y;
+      a2 += v.z; q2 += (double)v.z * v.z;
+      a3 += v.w; q3 += (double)v.w * v.w;
+    }
+    const int c = q << 2;
+    if (cpg >= 4) {
+      int g = c / cpg;
+      atomicAdd(&s_sum[g], (a0 + a1) + (a2 + a3));
+      atomicAdd(&s_sq[g], (q0 + q1) + (q2 + q3));
+    } else {
+      atomicAdd(&s_sum[c / cpg], a0); atomicAdd(&s_sq[c / cpg], q0);
+      atomicAdd(&s_sum[(c + 1) / cpg], a1); atomicAdd(&s_sq[(c + 1) / cpg], q1);
+      atomicAdd(&s_sum[(c + 2) / cpg], a2); atomicAdd(&s_sq[(c + 2) / cpg], q2);
+      atomicAdd(&s_sum[(c + 3) / cpg], a3); atomicAdd(&s_sq[(c + 3) / cpg], q3);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kGnGroups) {
+    atomicAdd(&stats[((long long)b * kGnGroups + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
+    atomicAdd(&stats[((long long)b * kGnGroups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-channel min / max
+// ---------------------------------------------------------------------------
+constexpr int kMinMaxBlocks = 2 * kNumSMs;
+
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// pass 1: block partials -> workspace[blk][2][C]
+__global__ void minmax_partial_kernel(const float* __restrict__ x, long long rows, int C, int P,
+                                      long long rows_per_block, float* __restrict__ ws) {
+  extern __shared__ float sm[];   // [2][C]
+  float* smin = sm;
+  float* smax = sm + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { smin[c] = INFINITY; smax[c] = -INFINITY; }
+  __syncthreads();
+  long long r0 = blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  if ((C & 3) == 0) {
+    const int Q = C >> 2;
+    const int q = threadIdx.x % Q, pl = threadIdx.x / Q;
+    if (pl < P && r0 + pl < r1) {
+      float4 mn = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+      float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      for (long long r = r0 + pl; r < r1; r += P) {
+        float4 v = ldg_stream(reinterpret_cast<const float4*>(x + r * C + (q << 2)));
+        mn.x = fminf(mn.x, v.x); mx.x = fmaxf(mx.x, v.x);
+        mn.y = fminf(mn.y, v.y); mx.y = fmaxf(mx.y, v.y);
+        mn.z = fminf(mn.z, v.z); mx.z = fmaxf(mx.z, v.z);
+        mn.w = fminf(mn.w, v.w); mx.w = fmaxf(mx.w, v.w);
+      }
+      const int c = q << 2;
+      atomic_min_f(&smin[c], mn.x); atomic_max_f(&smax[c], mx.x);
+      atomic_min_f(&smin[c + 1], mn.y); atomic_max_f(&smax[c + 1], mx.y);
+      atomic_min_f(&smin[c + 2], mn.z); atomic_max_f(&smax[c + 2], mx.z);
+      atomic_min_f(&smin[c + 3], mn.w); atomic_max_f(&smax[c + 3], mx.w);
+    }
+  } else {
+    const int c = threadIdx.x % C, pl = threadIdx.x / C;
+    if (pl < P && r0 + pl < r1) {
+      float mn = INFINITY, mx = -INFINITY;
+      for (long long r = r0 + pl; r < r1; r += P) {
+        float v = x[r * C + c];
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+      }
+      atomic_min_f(&smin[c], mn); atomic_max_f(&smax[c], mx);
+    }
+  }
+  __syncthreads();
+  float* o = ws + (long long)blockIdx.x * 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { o[c] = smin[c]; o[C + c] = smax[c]; }
+}
+
+__global__ void minmax_final_kernel(const float* __restrict__ ws, int nblk, int C,
+                                    float* __restrict__ min_c, float* __restrict__ max_c) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int b = 0; b < nblk; ++b) {
+    mn = fminf(mn, ws[(long long)b * 2 * C + c]);
+    mx = fmaxf(mx, ws[(long long)b * 2 * C + C + c]);
+  }
+  min_c[c] = mn;
+  max_c[c] = mx;
+}
+
+// ---------------------------------------------------------------------------
+// group ranges (floor + GroupWise_Quantizaion x2), one block
+// ---------------------------------------------------------------------------
+__device__ float block_reduce(float v, bool is_max, float* red) {
+  v = is_max ? warp_max(v) : warp_min(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  int nw = blockDim.x >> 5;
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : (is_max ? -INFINITY : INFINITY);
+  if (w == 0) {
+    r = is_max ? warp_max(r) : warp_min(r);
+    if (lane == 0) red[0] = r;
+  }
+  __syncthreads();
+  r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// one GroupWise pass on vec[C] (already floored, in smem); writes vals[G], xq[C]
+__device__ void group_wise_device(const float* vec, int C, int G, bool mode_max, float* edges,
+                                  float* vals, int* mark, float* red, float* xq_out) {
+  float lmx = -INFINITY, lmn = INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { lmx = fmaxf(lmx, vec[c]); lmn = fminf(lmn, vec[c]); }
+  float rmax = block_reduce(lmx, true, red);
+  float rmin = block_reduce(lmn, false, red);
+  float div = __fsub_rn(rmax, rmin);
+  if (threadIdx.x == 0) {
+    edges[0] = rmin;
+    for (int m = 0; m < G; ++m)
+      edges[m + 1] = __fadd_rn(rmin, __fdiv_rn(__fmul_rn(div, (float)(m + 1)), (float)G));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = vec[c];
+    int mk = 0;
+    for (int m = 0; m < G; ++m)
+      if (v >= edges[m] && v <= edges[m + 1]) mk = m + 1;   // later bins win ties
+    mark[c] = mk;
+  }
+  __syncthreads();
+  for (int m = 0; m < G; ++m) {
+    float l = mode_max ? -INFINITY : INFINITY;
+    int cnt = 0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      if (mark[c] == m + 1) { l = mode_max ? fmaxf(l, vec[c]) : fminf(l, vec[c]); cnt = 1; }
+    float r = block_reduce(l, mode_max, red);
+    int any = __syncthreads_or(cnt);
+    if (threadIdx.x == 0) vals[m] = any ? r : edges[m + 1];   // empty bin -> its upper edge
+    __syncthreads();
+  }
+  if (xq_out)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) xq_out[c] = mark[c] ? vals[mark[c] - 1] : 0.f;
+  __syncthreads();
+}
+
+__global__ void group_ranges_kernel(const float* __restrict__ min_c, const float* __restrict__ max_c, int C,
+                                    int G, float init_min, float init_max, float* __restrict__ gr,
+                                    float* __restrict__ xq_min, float* __restrict__ xq_max) {
+  extern __shared__ float sm[];
+  float* vec = sm;                    // [C]
+  int* mark = reinterpret_cast<int*>(sm + C);   // [C]
+  __shared__ float edges[65], vals[64], red[32];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = min_c[c];
+    vec[c] = (v > init_min) ? init_min : v;       // utils/quant_util.py:193-194
+  }
+  __syncthreads();
+  group_wise_device(vec, C, G, false, edges, vals, mark, red, xq_min);
+  if (threadIdx.x < G) gr[threadIdx.x * 2 + 0] = vals[threadIdx.x];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = max_c[c];
+    vec[c] = (v < init_max) ? init_max : v;       // utils/quant_util.py:195-196
+  }
+  __syncthreads();
+  group_wise_device(vec, C, G, true, edges, vals, mark, red, xq_max);
+  if (threadIdx.x < G) gr[threadIdx.x * 2 + 1] = vals[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------
+// calibration mix
+// ---------------------------------------------------------------------------
+constexpr int kMaxGroups = 16;
+
+__global__ void __launch_bounds__(256) calib_mix_kernel(const float* __restrict__ x, long long rows, int C, int G,
+                                                        const float* __restrict__ gr, const float* __restrict__ sw,
+                                                        int a_bit, float* __restrict__ y, double* lp_sum, float lp_p,
+                                                        long long rows_per_warp) {
+  __shared__ float s_s[kMaxGroups], s_z[kMaxGroups];
+  __shared__ double s_lp[8];
+  if (threadIdx.x < G) {
+    float lo = gr[threadIdx.x * 2], hi = gr[threadIdx.x * 2 + 1];
+    float n = (float)((1 << a_bit) - 1);
+    float s = __fdiv_rn(n, __fsub_rn(hi, lo));                       // quant_utils.py:119-123
+    s_s[threadIdx.x] = s;
+    s_z[threadIdx.x] = __fadd_rn(rintf(__fmul_rn(s, lo)), (float)(1 << (a_bit - 1)));
+  }
+  __syncthreads();
+  const float qlo = -(float)(1 << (a_bit - 1)), qhi = (float)((1 << (a_bit - 1)) - 1);
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  long long r0 = warp * rows_per_warp, r1 = r0 + rows_per_warp;
+  if (r1 > rows) r1 = rows;
+  double lp = 0.0;
+  const bool vec = (C & 3) == 0;
+  for (long long r = r0; r < r1; ++r) {
+    if (vec) {
+      for (int q = lane; q < (C >> 2); q += 32) {
+        const int c = q << 2;
+        float4 v = ldg_stream(reinterpret_cast<const float4*>(x + r * C + c));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < G; ++g) {
+          float4 w4 = *reinterpret_cast<const float4*>(sw + (long long)g * C + c);
+          float s = s_s[g], z = s_z[g];
+          float t0 = __fmul_rn(dequant(quant_code(v.x, s, z, qlo, qhi), s, z), w4.x);
+          float t1 = __fmul_rn(dequant(quant_code(v.y, s, z, qlo, qhi), s, z), w4.y);
+          float t2 = __fmul_rn(dequant(quant_code(v.z, s, z, qlo, qhi), s, z), w4.z);
+          float t3 = __fmul_rn(dequant(quant_code(v.w, s, z, qlo, qhi), s, z), w4.w);
+          if (g == 0) { acc.x = t0; acc.y = t1; acc.z = t2; acc.w = t3; }
+          else {
+            acc.x = __fadd_rn(acc.x, t0); acc.y = __fadd_rn(acc.y, t1);
+            acc.z = __fadd_rn(acc.z, t2); acc.w = __fadd_rn(acc.w, t3);
+          }
+        }
+        *reinterpret_cast<float4*>(y + r * C + c) = acc;
+        if (lp_sum) {
+          lp += pow((double)fabsf(acc.x - v.x), (double)lp_p) + pow((double)fabsf(acc.y - v.y), (double)lp_p) +
+                pow((double)fabsf(acc.z - v.z), (double)lp_p) + pow((double)fabsf(acc.w - v.w), (double)lp_p);
+        }
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        float v = x[r * C + c];
+        float acc = 0.f;
+        for (int g = 0; g < G; ++g) {
+          float s = s_s[g], z = s_z[g];
+          float t = __fmul_rn(dequant(quant_code(v, s, z, qlo, qhi), s, z), sw[(long long)g * C + c]);
+          acc = (g == 0) ? t : __fadd_rn(acc, t);
+        }
+        y[r * C + c] = acc;
+        if (lp_sum) lp += pow((double)fabsf(acc - v), (double)lp_p);
+      }
+    }
+  }
+  if (lp_sum) {
+    lp = warp_sum_d(lp);
+    if (lane == 0) s_lp[threadIdx.x >> 5] = lp;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_lp[i];
+      atomicAdd(lp_sum, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k-th smallest (radix select, 4 x 8 bits)
+// workspace: hist[4][256] | state: {prefix, k_lo, k_hi(unused), pad...}
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_key(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void kth_init_kernel(uint32_t* ws, long long k) {
+  for (int i = threadIdx.x; i < 4 * 256 + 8; i += blockDim.x) ws[i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ws[4 * 256 + 1] = (uint32_t)(k & 0xffffffffu);
+    ws[4 * 256 + 2] = (uint32_t)((unsigned long long)k >> 32);
+  }
+}
+
+__global__ void kth_hist_kernel(const float* __restrict__ x, long long n, int pass, uint32_t* ws) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;     // blockDim.x == 256
+  __syncthreads();
+  const uint32_t prefix = ws[4 * 256 + 0];
+  const int shift = 24 - 8 * pass;
+  const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t key = float_key(x[i]);
+    if ((key & mask) == (prefix & mask)) atomicAdd(&h[(key >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(&ws[pass * 256 + threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void kth_pick_kernel(int pass, uint32_t* ws, float* out) {
+  if (threadIdx.x != 0) return;
+  unsigned long long k = (unsigned long long)ws[4 * 256 + 1] | ((unsigned long long)ws[4 * 256 + 2] << 32);
+  const int shift = 24 - 8 * pass;
+  unsigned long long cum = 0;
+  int bin = 255;
+  for (int b = 0; b < 256; ++b) {
+    unsigned long long c = ws[pass * 256 + b];
+    if (k < cum + c) { bin = b; break; }
+    cum += c;
+  }
+  k -= cum;
+  uint32_t prefix = ws[4 * 256 + 0] | ((uint32_t)bin << shift);
+  ws[4 * 256 + 0] = prefix;
+  ws[4 * 256 + 1] = (uint32_t)(k & 0xffffffffu);
+  ws[4 * 256 + 2] = (uint32_t)(k >> 32);
+  if (pass == 3) {
+    uint32_t u = (prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix;
+    *out = __uint_as_float(u);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------
+__global__ void weight_clamp_pack_kernel(const float* __restrict__ w, int O, int C, int taps,
+                                         const float* __restrict__ lo, const float* __restrict__ hi,
+                                         float* __restrict__ w_eff) {
+  long long n = (long long)O * C * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int tap = (int)((i / C) % taps);
+    int o = (int)(i / ((long long)C * taps));
+    float v = w[((long long)o * C + c) * taps + tap];
+    float l = lo[o], h = hi[o];
+    // 0.5 * ((-w + lo).abs() - (w - hi).abs() + lo + hi), utils/quant_util.py:293-300
+    float a = fabsf(__fadd_rn(-v, l));
+    float b = fabsf(__fsub_rn(v, h));
+    float t = __fadd_rn(__fadd_rn(__fsub_rn(a, b), l), h);
+    w_eff[i] = __fmul_rn(0.5f, t);
+  }
+}
+
+__global__ void weight_to_i8_kernel(const float* __restrict__ w_eff, int O, int C, int taps,
+                                    const float* __restrict__ ws, const float* __restrict__ wz, int w_bit,
+                                    int8_t* __restrict__ qw, int Cp, int32_t* __restrict__ wsum, int* on_grid) {
+  const int o = blockIdx.x;
+  const float s = ws[o], z = wz[o];
+  const float qlo = -(float)(1 << (w_bit - 1)), qhi = (float)((1 << (w_bit - 1)) - 1);
+  int acc = 0;
+  bool ok = isfinite(s) && s > 0.f;
+  const int K = taps * Cp;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    int tap = i / Cp, c = i - tap * Cp;
+    int q = 0;
+    if (c < C) {
+      float v = w_eff[((long long)o * taps + tap) * C + c];
+      float qf = rintf(__fsub_rn(__fmul_rn(s, v), z));
+      if (qf < qlo || qf > qhi) ok = false;
+      qf = fminf(fmaxf(qf, qlo), qhi);
+      // on the grid if within 1e-3 of a quantization step (the reference clamp
+      // identity perturbs on-grid weights by ~1 ulp)
+      float back = __fsub_rn(__fmul_rn(s, v), z);
+      if (fabsf(back - qf) > 1e-3f) ok = false;
+      q = (int)qf;
+    }
+    qw[(long long)o * K + i] = (int8_t)q;
+    acc += q;
+  }
+  __shared__ int s_acc[32];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+  if (!ok) atomicAnd(on_grid, 0);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_acc[i];
+    wsum[o] = t;
+  }
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+}  // namespace attndm
+
+using namespace attndm;
+
+extern "C" {
+
+int attndm_act_quant(const float* x, int B, int H, int W, int C, const float* scale, const float* zp,
+                     int a_bit, int pre_op, const double* gn_stats, const float* gn_gamma,
+                     const float* gn_beta, float gn_eps, int8_t* codes, int32_t* rowsum,
+                     int rows_layout, float* y_f32, void* stream) {
+  ATTNDM_CHECK_ARG(codes || y_f32, "act_quant: no output requested");
+  return act_quant_impl(x, B, H, W, C, scale, zp, a_bit, pre_op, gn_stats, gn_gamma, gn_beta, gn_eps, codes,
+                        rowsum, rows_layout, y_f32, true, (cudaStream_t)stream);
+}
+
+int attndm_gn_silu(const float* x, int B, int H, int W, int C, const double* gn_stats, const float* gamma,
+                   const float* beta, float eps, float* y, void* stream) {
+  ATTNDM_CHECK_ARG(y, "gn_silu: y is NULL");
+  return act_quant_impl(x, B, H, W, C, nullptr, nullptr, 0, ATTNDM_PRE_GN_SILU, gn_stats, gamma, beta, eps,
+                        nullptr, nullptr, ATTNDM_ROWS_PLAIN, y, false, (cudaStream_t)stream);
+}
+
+int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, void* stream) {
+  ATTNDM_CHECK_ARG(x && stats && B > 0 && H > 0 && W > 0, "gn_stats: bad args");
+  ATTNDM_CHECK_ARG(C % kGnGroups == 0 && C % 4 == 0 && C <= 4096, "gn_stats: C must be a multiple of 32, <= 4096");
+  const int Q = C / 4, HW = H * W;
+  int P = Q >= 256 ? 1 : 256 / Q;
+  if (P > HW) P = HW;
+  int threads = round_up(Q * P, 32);
+  int splits = cdiv(2 * kNumSMs, B);
+  int max_splits = cdiv(HW, P * 4);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int rows_per_block = cdiv(HW, splits);
+  splits = cdiv(HW, rows_per_block);
+  dim3 grid(splits, B);
+  gn_stats_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, HW, C, P, rows_per_block, stats);
+  ATTNDM_CUDA_LAUNCH_CHECK("gn_stats");
+  return ATTNDM_OK;
+}
+
+int attndm_minmax_workspace_blocks(void) { return kMinMaxBlocks; }
+
+int attndm_minmax_c(const float* x, long long rows, int C, float* min_c, float* max_c, float* workspace,
+                    void* stream) {
+  ATTNDM_CHECK_ARG(x && min_c && max_c && workspace && rows > 0 && C > 0 && C <= 4096, "minmax_c: bad args");
+  int P, threads;
+  if ((C & 3) == 0) {
+    int Q = C / 4;
+    P = Q >= 256 ? 1 : 256 / Q;
+    threads = round_up(Q * P, 32);
+  } else {
+    P = C >= 256 ? 1 : 256 / C;
+    threads = round_up(C * P, 32);
+  }
+  long long rpb = (rows + kMinMaxBlocks - 1) / kMinMaxBlocks;
+  if (rpb < P) rpb = P;
+  int nblk = (int)((rows + rpb - 1) / rpb);
+  size_t smem = 2 * (size_t)C * sizeof(float);
+  minmax_partial_kernel<<<nblk, threads, smem, (cudaStream_t)stream>>>(x, rows, C, P, rpb, workspace);
+  ATTNDM_CUDA_LAUNCH_CHECK("minmax_partial");
+  minmax_final_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(workspace, nblk, C, min_c, max_c);
+  ATTNDM_CUDA_LAUNCH_CHECK("minmax_final");
+  return ATTNDM_OK;
+}
+
+int attndm_group_ranges(const float* min_c, const float* max_c, int C, int G, float init_min, float init_max,
+                        float* groups_range_t, float* xq_min, float* xq_max, void* stream) {
+  ATTNDM_CHECK_ARG(min_c && max_c && groups_range_t && C > 0 && C <= 4096 && G >= 1 && G <= 64,
+                   "group_ranges: bad args");
+  size_t smem = 2 * (size_t)C * sizeof(float);
+  group_ranges_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(min_c, max_c, C, G, init_min, init_max,
+                                                             groups_range_t, xq_min, xq_max);
+  ATTNDM_CUDA_LAUNCH_CHECK("group_ranges");
+  return ATTNDM_OK;
+}
+
+int attndm_calib_mix(const float* x, long long rows, int C, int G, const float* groups_range_t, const float* sw,
+                     int a_bit, float* y, double* lp_sum, float lp_p, void* stream) {
+  ATTNDM_CHECK_ARG(x && y && groups_range_t && sw && rows > 0 && C > 0, "calib_mix: bad args");
+  ATTNDM_CHECK_ARG(G >= 1 && G <= kMaxGroups && a_bit >= 2 && a_bit <= 8, "calib_mix: G <= 16, 2 <= a_bit <= 8");
+  long long max_warps = (long long)kNumSMs * 8 * 8;
+  long long warps = rows < max_warps ? rows : max_warps;
+  long long rpw = (rows + warps - 1) / warps;
+  warps = (rows + rpw - 1) / rpw;
+  calib_mix_kernel<<<cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, C, G, groups_range_t, sw, a_bit, y,
+                                                                    lp_sum, lp_p, rpw);
+  ATTNDM_CUDA_LAUNCH_CHECK("calib_mix");
+  return ATTNDM_OK;
+}
+
+int attndm_kth_value(const float* x, long long n, long long k, float* out, uint32_t* workspace, void* stream) {
+  ATTNDM_CHECK_ARG(x && out && workspace && n > 0 && k >= 0 && k < n, "kth_value: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  kth_init_kernel<<<1, 256, 0, st>>>(workspace, k);
+  int blocks = cdiv(n, 256 * 8);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  for (int pass = 0; pass < 4; ++pass) {
+    kth_hist_kernel<<<blocks, 256, 0, st>>>(x, n, pass, workspace);
+    kth_pick_kernel<<<1, 32, 0, st>>>(pass, workspace, out);
+  }
+  ATTNDM_CUDA_LAUNCH_CHECK("kth_value");
+  return ATTNDM_OK;
+}
+
+int attndm_weight_clamp_pack(const float* w, int O, int C, int KH, int KW, const float* lo, const float* hi,
+                             float* w_eff, void* stream) {
+  ATTNDM_CHECK_ARG(w && lo && hi && w_eff && O > 0 && C > 0 && KH > 0 && KW > 0, "weight_clamp_pack: bad args");
+  long long n = (long long)O * C * KH * KW;
+  int blocks = cdiv(n, 256);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  weight_clamp_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, O, C, KH * KW, lo, hi, w_eff);
+  ATTNDM_CUDA_LAUNCH_CHECK("weight_clamp_pack");
+  return ATTNDM_OK;
+}
+
+int attndm_weight_to_i8(const float* w_eff, int O, int C, int taps, const float* w_scale, const float* w_zp,
+                        int w_bit, int8_t* qw, int Cp, int32_t* wsum, int* on_grid, void* stream) {
+  ATTNDM_CHECK_ARG(w_eff && w_scale && w_zp && qw && wsum && on_grid, "weight_to_i8: null pointer");
+  ATTNDM_CHECK_ARG(Cp >= C && Cp % 16 == 0 && w_bit >= 2 && w_bit <= 8, "weight_to_i8: bad Cp / w_bit");
+  set_int_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(on_grid, 1);
+  weight_to_i8_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(w_eff, O, C, taps, w_scale, w_zp, w_bit, qw, Cp, wsum,
+                                                          on_grid);
+  ATTNDM_CUDA_LAUNCH_CHECK("weight_to_i8");
+  return ATTNDM_OK;
+}
+
+}  // extern "C"

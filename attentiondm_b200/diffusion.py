@@ -1,0 +1,259 @@
+"""Drop-in for models/diffusion.py: the fake-quantized UNet (`Model`) and its
+blocks, same constructor arguments, module names and state_dict keys.
+
+Internally activations are NHWC fp32 and each block drives the fused kernels:
+GroupNorm statistics -> (GroupNorm+SiLU+quantize) -> int8 conv with the residual
+and time-embedding adds in its epilogue.  `forward(x, t)` keeps the reference
+signature (x logical NCHW, t float [B]).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .quant_util import QConv2d
+from .self_attention import EnhancedQSelfAttention
+
+
+def get_timestep_embedding(timesteps, embedding_dim):
+    """models/diffusion.py:11-29."""
+    assert len(timesteps.shape) == 1
+    return ops.timestep_embedding(timesteps, embedding_dim)
+
+
+def _need_quant(quantization, sequence):
+    if not (quantization and sequence is not None):
+        raise NotImplementedError(
+            "attentiondm_b200 implements the fake-quantized path (quantization=True, sequence given); "
+            "the FP model of the reference is outside the hot path")
+
+
+def _gn_args(norm: nn.GroupNorm, x):
+    return ops.GnArgs(stats=ops.gn_stats(x), gamma=norm.weight.detach(), beta=norm.bias.detach(), eps=norm.eps)
+
+
+class ResidualBlock(nn.Module):
+    """models/diffusion.py:82-136."""
+
+    def __init__(self, in_channels, out_channels=None, conv_shortcut=False, dropout=0.1, quantization=False,
+                 sequence=None, args=None):
+        super().__init__()
+        _need_quant(quantization, sequence)
+        self.in_channels = in_channels
+        self.out_channels = in_channels if out_channels is None else out_channels
+        out_channels = self.out_channels
+        self.use_conv_shortcut = conv_shortcut
+        q = dict(w_bit=args.bitwidth, a_bit=args.bitwidth, sequence=sequence, args=args)
+        self.norm1 = nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6)
+        self.conv1 = QConv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1, **q)
+        self.norm2 = nn.GroupNorm(num_groups=32, num_channels=out_channels, eps=1e-6)
+        self.dropout = nn.Dropout(dropout)
+        self.conv2 = QConv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1, **q)
+        if self.in_channels != self.out_channels:
+            if self.use_conv_shortcut:
+                self.conv_shortcut = QConv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1, **q)
+            else:
+                self.nin_shortcut = QConv2d(in_channels, out_channels, kernel_size=1, stride=1, padding=0, **q)
+
+    def forward_fused(self, x, temb=None):
+        """x NHWC.  temb [B, out_channels] (optional) is the block's `x + time_mlp(t_emb)`
+        (models/diffusion.py:175-177), applied after the residual add, fused in conv2's epilogue."""
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("attentiondm_b200 runs the eval-mode path (model.eval()); dropout is identity")
+        h = self.conv1.forward_fused(x, ops.PRE_GN_SILU, _gn_args(self.norm1, x))
+        gn2 = _gn_args(self.norm2, h)
+        if self.in_channels != self.out_channels:
+            sc = (self.conv_shortcut if self.use_conv_shortcut else self.nin_shortcut).forward_fused(x)
+        else:
+            sc = x
+        return self.conv2.forward_fused(h, ops.PRE_GN_SILU, gn2, residual=sc, temb=temb)
+
+    def forward(self, x):
+        return ops.to_nchw(self.forward_fused(ops.to_nhwc(x)))
+
+
+def _time_mlp(time_emb_dim, out_channels, sequence, args):
+    return nn.Sequential(
+        nn.SiLU(),
+        QConv2d(time_emb_dim, out_channels, kernel_size=1, stride=1, padding=0, w_bit=args.bitwidth,
+                a_bit=args.bitwidth, sequence=sequence, args=args))
+
+
+class _TimeBlock(nn.Module):
+    def _temb(self, time_emb):
+        """SiLU -> QConv2d 1x1 on [B,1,1,temb] -> [B, out] (models/diffusion.py:157-161)."""
+        if self.time_mlp is None or time_emb is None:
+            return None
+        y = self.time_mlp[1].forward_fused(time_emb, ops.PRE_SILU)
+        return y.view(y.shape[0], -1)
+
+    def _tail(self, x, time_emb):
+        x = self.res1.forward_fused(x, self._temb(time_emb))
+        x = self.res2.forward_fused(x)
+        if isinstance(self.attn, EnhancedQSelfAttention):
+            x = self.attn.forward_fused(x)
+        return x
+
+
+class DownBlock(_TimeBlock):
+    """models/diffusion.py:139-190."""
+
+    def __init__(self, in_channels, out_channels, time_emb_dim=None, dropout=0.1, quantization=False, sequence=None,
+                 args=None, use_attention=True):
+        super().__init__()
+        _need_quant(quantization, sequence)
+        self.maxpool = nn.MaxPool2d(2)
+        kw = dict(dropout=dropout, quantization=quantization, sequence=sequence, args=args)
+        self.res1 = ResidualBlock(in_channels, out_channels, **kw)
+        self.res2 = ResidualBlock(out_channels, out_channels, **kw)
+        self.attn = (EnhancedQSelfAttention(out_channels, quantization=quantization, sequence=sequence, args=args)
+                     if use_attention else nn.Identity())
+        self.time_mlp = _time_mlp(time_emb_dim, out_channels, sequence, args) if time_emb_dim is not None else None
+
+    def forward_fused(self, x, time_emb=None):
+        if not (x.shape[1] <= 1 or x.shape[2] <= 1):       # :172 (NHWC: dims 1,2 are H,W)
+            x = ops.maxpool2(x)
+        return self._tail(x, time_emb)
+
+    def forward(self, x, time_emb=None):
+        te = ops.to_nhwc(time_emb) if time_emb is not None else None
+        return ops.to_nchw(self.forward_fused(ops.to_nhwc(x), te))
+
+
+class UpBlock(_TimeBlock):
+    """models/diffusion.py:193-252."""
+
+    def __init__(self, in_channels, out_channels, time_emb_dim=None, dropout=0.1, quantization=False, sequence=None,
+                 args=None, use_attention=True):
+        super().__init__()
+        _need_quant(quantization, sequence)
+        self.upsample = nn.Upsample(scale_factor=2, mode='nearest')
+        kw = dict(dropout=dropout, quantization=quantization, sequence=sequence, args=args)
+        self.res1 = ResidualBlock(in_channels + out_channels, out_channels, **kw)
+        self.res2 = ResidualBlock(out_channels, out_channels, **kw)
+        self.attn = (EnhancedQSelfAttention(out_channels, quantization=quantization, sequence=sequence, args=args)
+                     if use_attention else nn.Identity())
+        self.time_mlp = _time_mlp(time_emb_dim, out_channels, sequence, args) if time_emb_dim is not None else None
+
+    def forward_fused(self, x, skip_x, time_emb=None):
+        combined = ops.upsample_concat(x, skip_x)            # :225-229 + cat
+        expected = self.res1.in_channels
+        actual = combined.shape[-1]
+        if actual != expected:
+            if not hasattr(self, 'channel_proj'):             # lazily created, fresh RNG (:238-241)
+                self.channel_proj = nn.Conv2d(actual, expected, kernel_size=1, stride=1, padding=0).to(x.device)
+            # un-quantized fp32 1x1 conv == a plain GEMM over the NHWC rows (library call)
+            B, H, W, _ = combined.shape
+            w = self.channel_proj.weight.detach().view(expected, actual)
+            combined = F.linear(combined.view(-1, actual), w, self.channel_proj.bias.detach()).view(B, H, W, expected)
+        return self._tail(combined, time_emb)
+
+    def forward(self, x, skip_x, time_emb=None):
+        te = ops.to_nhwc(time_emb) if time_emb is not None else None
+        return ops.to_nchw(self.forward_fused(ops.to_nhwc(x), ops.to_nhwc(skip_x), te))
+
+
+class Model(nn.Module):
+    """models/diffusion.py:255-382."""
+
+    def __init__(self, config, quantization=False, sequence=None, args=None):
+        super().__init__()
+        _need_quant(quantization, sequence)
+        self.config = config
+        self.quantization = quantization
+        self.sequence = sequence
+        self.args = args
+        if not hasattr(config.model, 'time_embed_dim'):
+            config.model.time_embed_dim = 256
+        if not hasattr(config.model, 'attention_resolutions'):
+            config.model.attention_resolutions = 1
+        ted = config.model.time_embed_dim
+        self.time_embed = nn.Sequential(nn.Linear(ted, ted * 4), nn.SiLU(), nn.Linear(ted * 4, ted * 4))
+        ch = config.model.ch
+        q = dict(w_bit=args.bitwidth, a_bit=args.bitwidth, sequence=sequence, args=args)
+        self.init_conv = QConv2d(config.data.channels, ch, kernel_size=3, stride=1, padding=1, **q)
+        kw = dict(time_emb_dim=ted * 4, dropout=config.model.dropout, quantization=quantization, sequence=sequence,
+                  args=args)
+        self.down_blocks = nn.ModuleList()
+        ch_mult = config.model.ch_mult
+        now_ch = ch
+        for i, mult in enumerate(ch_mult):
+            out_ch = ch * mult
+            for _ in range(config.model.num_res_blocks):
+                self.down_blocks.append(DownBlock(now_ch, out_ch, use_attention=(i >= config.model.attention_resolutions), **kw))
+                now_ch = out_ch
+            if i < len(ch_mult) - 1:
+                self.down_blocks.append(DownBlock(now_ch, now_ch, use_attention=False, **kw))
+        rk = dict(dropout=config.model.dropout, quantization=quantization, sequence=sequence, args=args)
+        self.middle_block1 = ResidualBlock(now_ch, now_ch, **rk)
+        self.middle_attn = EnhancedQSelfAttention(now_ch, quantization=quantization, sequence=sequence, args=args)
+        self.middle_block2 = ResidualBlock(now_ch, now_ch, **rk)
+        self.up_blocks = nn.ModuleList()
+        for i, mult in reversed(list(enumerate(ch_mult))):
+            out_ch = ch * mult
+            for j in range(config.model.num_res_blocks + 1):
+                blk_in = now_ch + ch * mult if j == 0 else now_ch
+                self.up_blocks.append(UpBlock(blk_in, out_ch, use_attention=(i >= config.model.attention_resolutions), **kw))
+                now_ch = out_ch
+        self.norm_out = nn.GroupNorm(num_groups=32, num_channels=now_ch, eps=1e-6)
+        self.conv_out = QConv2d(now_ch, config.data.channels, kernel_size=3, stride=1, padding=1, **q)
+
+    # ---- helpers over all quantized layers ----
+    def qconvs(self):
+        return [(n, m) for n, m in self.named_modules() if isinstance(m, QConv2d)]
+
+    def set_calibrate(self, flag=True, first=False):
+        for _, m in self.qconvs():
+            m.set_calibrate(flag)
+            m.first_calibrate(first)
+
+    def reset_index_seq(self, value=0):
+        for _, m in self.qconvs():
+            m.index_seq = value
+
+    def init_weight_ranges(self):
+        for _, m in self.qconvs():
+            m.init_weight_range()
+
+    def snap_weights_(self):
+        for _, m in self.qconvs():
+            m.snap_weights_()
+
+    def materialize_lazy_layers(self):
+        """Create the `channel_proj` 1x1 convs that UpBlock.forward would create lazily on its first
+        call (models/diffusion.py:235-242), so that a full state_dict can be loaded before any forward.
+        Channel bookkeeping follows Model.forward: skips = [init_conv] + every down block."""
+        skips = [self.init_conv.out_channels] + [b.res2.out_channels for b in self.down_blocks]
+        now = self.middle_block2.out_channels
+        dev = self.init_conv.weight.device
+        for blk in self.up_blocks:
+            sk = skips.pop() if skips else now
+            actual, expected = now + sk, blk.res1.in_channels
+            if actual != expected and not hasattr(blk, 'channel_proj'):
+                blk.channel_proj = nn.Conv2d(actual, expected, kernel_size=1, stride=1, padding=0).to(dev)
+            now = blk.res2.out_channels
+        return self
+
+    def forward_nhwc(self, x, t):
+        """x NHWC [B,H,W,C]; t float [B].  models/diffusion.py:347-382."""
+        B = x.shape[0]
+        t_emb = ops.timestep_embedding(t, self.config.model.time_embed_dim)
+        t_emb = self.time_embed(t_emb)                     # two un-quantized Linears (library GEMM)
+        t_emb = t_emb.view(B, 1, 1, -1).contiguous()
+        h = self.init_conv.forward_fused(x)
+        skips = [h]
+        for layer in self.down_blocks:
+            h = layer.forward_fused(h, t_emb)
+            skips.append(h)
+        h = self.middle_block1.forward_fused(h)
+        h = self.middle_attn.forward_fused(h)
+        h = self.middle_block2.forward_fused(h)
+        for layer in self.up_blocks:
+            skip = skips.pop() if len(skips) else torch.zeros_like(h)
+            h = layer.forward_fused(h, skip, t_emb)
+        gn = _gn_args(self.norm_out, h)
+        return self.conv_out.forward_fused(h, ops.PRE_GN_SILU, gn)
+
+    def forward(self, x, t):
+        with torch.no_grad():
+            return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x), t))

@@ -1,0 +1,203 @@
+"""CUDA-graph sampler engine: one captured denoising step, replayed T times.
+
+The reference's quantizer tables are indexed by a per-module Python counter
+(index_seq, utils/quant_util.py:228-229,281).  Here every layer's scale / zero-
+point / multiplier rows for all T steps live in ONE [T, total] device table; at
+the start of each step `attndm_stage_tables` copies row `step` into a fixed
+"current" buffer that every kernel reads, and advances the device-side step
+counter -- so a single graph serves all steps with no host work in the loop.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .denoising import ddim_coefficients
+
+
+class SamplerEngine:
+    _cache = {}
+
+    @classmethod
+    def for_model(cls, model, seq, betas, eta, x_shape):
+        key = (id(model), tuple(seq), float(eta), tuple(x_shape), betas.data_ptr())
+        eng = cls._cache.get(key)
+        if eng is None or not eng.still_valid():
+            cls._cache.clear()            # one live engine: graphs pin a lot of memory
+            eng = cls(model, seq, betas, eta, x_shape)
+            cls._cache[key] = eng
+        return eng
+
+    def __init__(self, model, seq, betas, eta, x_shape, use_graph=True):
+        self.model = model
+        self.seq = list(seq)
+        self.T = len(self.seq)
+        self.eta = float(eta)
+        self.B, self.C, self.H, self.W = x_shape
+        dev = next(model.parameters()).device
+        self.dev = dev
+        self.layers = [m for _, m in model.qconvs()]
+        idx = {m.index_seq % max(1, m.args.timesteps) for m in self.layers}
+        if len(idx) != 1:
+            raise RuntimeError("SamplerEngine: QConv2d.index_seq counters are out of step with each other; "
+                               "call model.reset_index_seq() (utils/quant_util.py:228-229 wraps per module)")
+        self.start_index = idx.pop()
+        if any(m.len_seq != self.T or m.args.timesteps != self.T for m in self.layers):
+            raise RuntimeError("SamplerEngine: len(seq) must equal every layer's len_seq and args.timesteps")
+        # ---- pack every layer's per-step rows + the DDIM coefficients + t into one table ----
+        cols, off = [], 0
+        self.slices = []
+        for m in self.layers:
+            tb = m._tables()
+            w = tb["lay"]["width"]
+            cols.append(tb["tab"])
+            self.slices.append((off, w))
+            off += w
+        coef = ddim_coefficients(self.seq, betas, self.eta).to(dev)        # [T,8]
+        self.coef_off = off
+        off += 8
+        tcol = coef[:, 5:6].expand(self.T, self.B).contiguous()             # t repeated B times
+        self.t_off = off
+        bq = (self.B + 3) // 4 * 4
+        tpad = torch.zeros(self.T, bq, device=dev)
+        tpad[:, :self.B] = tcol
+        off += bq
+        # the DDIM/t columns are indexed by the sampler step k, the layer tables by index_seq;
+        # both advance together, offset by start_index
+        layer_tab = torch.cat(cols, dim=1)
+        if self.start_index:
+            layer_tab = torch.roll(layer_tab, shifts=-self.start_index, dims=0)
+        self._table_roll = self.start_index
+        self.table = torch.cat([layer_tab, coef, tpad], dim=1).contiguous()
+        self.cur = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.versions = self._versions()
+        self.x_cur = torch.zeros(self.B, self.H, self.W, self.C, device=dev)
+        self.x0 = torch.zeros_like(self.x_cur)
+        self.noise = torch.zeros_like(self.x_cur) if self.eta != 0 else None
+        self.ext_noise = False
+        self.graph = None
+        self.use_graph = use_graph
+        self.launches_per_step = 0
+
+    def _versions(self):
+        return tuple((m._tab_key, m._pack_key) for m in self.layers)
+
+    def still_valid(self):
+        try:
+            for m in self.layers:
+                m._tables()
+        except Exception:
+            return False
+        return self._versions() == self.versions
+
+    # ---- one denoising step on the current stream ----
+    def _step_body(self):
+        ops.stage_tables(self.table, self.step, self.cur, advance=True)
+        t_cur = self.cur[self.t_off:self.t_off + self.B]
+        eps = self.model.forward_nhwc(self.x_cur, t_cur)
+        noise = None
+        if self.noise is not None:
+            if not self.ext_noise:
+                self.noise.normal_()
+            noise = self.noise
+        ops.ddim_step(self.x_cur, eps, self.cur[self.coef_off:], noise, x_next=self.x_cur, x0_out=self.x0)
+        return eps
+
+    def _with_staged(self, fn):
+        for m, (o, w) in zip(self.layers, self.slices):
+            m.use_staged_row(self.cur[o:o + w])
+        saved = [m.index_seq for m in self.layers]
+        try:
+            return fn()
+        finally:
+            for m, s in zip(self.layers, saved):
+                m.use_staged_row(None)
+                m.index_seq = s
+
+    def _capture(self):
+        from . import _ffi
+        # warm-up on a side stream (lazy channel_proj, cuBLAS workspaces, weight packs), state restored after
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        x_save = self.x_cur.clone()
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.step.zero_()
+                self._with_staged(self._step_body)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.x_cur.copy_(x_save)
+        self.step.zero_()
+        g = torch.cuda.CUDAGraph()
+        before = _ffi.launches
+        with torch.cuda.graph(g):
+            self._with_staged(self._step_body)
+        self.launches_per_step = _ffi.launches - before
+        self.graph = g
+        self.x_cur.copy_(x_save)
+        self.step.zero_()
+
+    def load_input(self, x):
+        """x: logical NCHW tensor (CUDA, or pinned host memory for the end-to-end path)."""
+        self.x_cur.copy_(x.permute(0, 2, 3, 1), non_blocking=True)
+        self.step.zero_()
+        self.start_index = self.layers[0].index_seq % self.T
+        self.done = 0
+        if self.start_index != self._table_roll:
+            raise RuntimeError("SamplerEngine: index_seq moved since the engine was built; rebuild it "
+                               "(SamplerEngine.for_model) or call model.reset_index_seq()")
+
+    def run_loaded(self, steps=None):
+        """Replay `steps` (default T) denoising steps on the already loaded input; async."""
+        n = self.T if steps is None else steps
+        if n <= 0:
+            return
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            for _ in range(n):
+                self.graph.replay()
+        else:
+            for _ in range(n):
+                self._with_staged(self._step_body)
+        # mirror the reference's per-module counter: wrap at the START of a call, +1 at its end
+        self.done = getattr(self, "done", 0) + n
+        final = (self.start_index + self.done - 1) % self.T + 1
+        for m in self.layers:
+            m.index_seq = final
+
+    def run(self, x, keep="all", noise_fn=None):
+        """Reference-shaped result: (xs, x0_preds) lists of CPU tensors."""
+        if tuple(x.shape) != (self.B, self.C, self.H, self.W):
+            raise RuntimeError("SamplerEngine: input shape differs from the captured one")
+        self.ext_noise = noise_fn is not None
+        if self.ext_noise and self.noise is None:
+            self.noise = torch.zeros_like(self.x_cur)
+            self.graph = None
+        if self.use_graph and self.graph is None:
+            self.load_input(x)
+            self._capture()
+        self.load_input(x)
+        host_x, host_x0 = [], []
+        if keep == "last" and not self.ext_noise:
+            self.run_loaded()
+            host_x.append(_pinned_copy(self.x_cur))
+            host_x0.append(_pinned_copy(self.x0))
+        else:
+            for k in range(self.T):
+                if self.ext_noise:
+                    self.noise.copy_(noise_fn(k, ops.to_nchw(self.x_cur)).permute(0, 2, 3, 1))
+                self.run_loaded(1)
+                if keep == "all" or k == self.T - 1:
+                    host_x.append(_pinned_copy(self.x_cur))
+                    host_x0.append(_pinned_copy(self.x0))
+        torch.cuda.current_stream().synchronize()
+        xs = [x] + [ops.to_nchw(h) for h in host_x]
+        return xs, [ops.to_nchw(h) for h in host_x0]
+
+
+def _pinned_copy(t):
+    h = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    return h

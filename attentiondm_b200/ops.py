@@ -1,0 +1,262 @@
+"""Tensor-level wrappers over the C-ABI (attentiondm_b200/_ffi.py).
+
+All activations here are NHWC fp32 CUDA tensors of shape [B, H, W, C]; the
+nn.Module layer converts from/to the reference's logical NCHW at its boundary
+(a channels_last tensor IS this layout, so the conversion is a view).
+torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _ffi as F_
+from ._ffi import (CONV_SIMT, CONV_TCGEN05, PRE_GN_SILU, PRE_NONE, PRE_SILU, ROWS_HALO, ROWS_PLAIN, AttnQuant,
+                   call, ptr, stream)
+
+GN_GROUPS = 32
+
+# which int8 conv kernel the modules use; tests flip it to cross-check the two
+DEFAULT_CONV_IMPL = CONV_TCGEN05
+
+
+def _chk(x: torch.Tensor, what="tensor"):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise RuntimeError(f"attentiondm_b200: {what} must be a CUDA tensor (no CPU fallback on this path)")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"attentiondm_b200: {what} must be float32, got {x.dtype}")
+    if not x.is_contiguous():
+        raise RuntimeError(f"attentiondm_b200: {what} must be contiguous NHWC")
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """logical NCHW -> contiguous [B,H,W,C] (a view when x is channels_last)."""
+    if x.dim() != 4:
+        raise RuntimeError("attentiondm_b200: expected a 4-D NCHW tensor")
+    if not x.is_cuda:
+        raise RuntimeError("attentiondm_b200: CUDA tensor required; this path has no CPU fallback")
+    y = x.permute(0, 2, 3, 1)
+    if y.dtype != torch.float32:
+        y = y.float()
+    return y.contiguous()
+
+
+def to_nchw(y: torch.Tensor) -> torch.Tensor:
+    """[B,H,W,C] -> logical NCHW view (channels_last memory)."""
+    return y.permute(0, 3, 1, 2)
+
+
+def cp_of(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+@dataclass
+class GnArgs:
+    stats: torch.Tensor      # double [B, 32, 2] sums
+    gamma: torch.Tensor
+    beta: torch.Tensor
+    eps: float
+
+
+def gn_stats(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x, "gn_stats input")
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.zeros(B, GN_GROUPS, 2, dtype=torch.float64, device=x.device)
+    else:
+        out.zero_()
+    call("attndm_gn_stats", ptr(x), B, H, W, Cc, ptr(out), stream())
+    return out
+
+
+def gn_silu(x: torch.Tensor, gn: GnArgs) -> torch.Tensor:
+    _chk(x, "gn_silu input")
+    B, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    call("attndm_gn_silu", ptr(x), B, H, W, Cc, ptr(gn.stats), ptr(gn.gamma), ptr(gn.beta), float(gn.eps), ptr(y),
+         stream())
+    return y
+
+
+def act_quant(x: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, a_bit: int, pre: int = PRE_NONE,
+              gn: Optional[GnArgs] = None, want_codes: bool = True, halo: bool = False, want_f32: bool = False):
+    """Returns (codes int8 [rows, Cp] | None, rowsum int32 [rows] | None, y fp32 NHWC | None)."""
+    _chk(x, "act_quant input")
+    B, H, W, Cc = x.shape
+    Cp = cp_of(Cc)
+    codes = rowsum = y = None
+    if want_codes:
+        rows = B * (H + 2) * (W + 2) if halo else B * H * W
+        alloc = torch.zeros if Cp != Cc else torch.empty
+        codes = alloc(rows, Cp, dtype=torch.int8, device=x.device)
+        rowsum = torch.empty(rows, dtype=torch.int32, device=x.device)
+    if want_f32:
+        y = torch.empty_like(x)
+    call("attndm_act_quant", ptr(x), B, H, W, Cc, ptr(scale), ptr(zp), int(a_bit), int(pre),
+         ptr(gn.stats) if gn else None, ptr(gn.gamma) if gn else None, ptr(gn.beta) if gn else None,
+         float(gn.eps) if gn else 0.0, ptr(codes), ptr(rowsum), ROWS_HALO if halo else ROWS_PLAIN, ptr(y), stream())
+    return codes, rowsum, y
+
+
+def minmax_c(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _chk(x, "minmax_c input")
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    nblk = F_.lib().attndm_minmax_workspace_blocks()
+    ws = torch.empty(nblk * 2 * Cc, dtype=torch.float32, device=x.device)
+    mn = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    mx = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    call("attndm_minmax_c", ptr(x), rows, Cc, ptr(mn), ptr(mx), ptr(ws), stream())
+    return mn, mx
+
+
+def group_ranges(min_c, max_c, G: int, init_min: float, init_max: float, out_gr_t: torch.Tensor):
+    """Writes out_gr_t [G,2] in place; returns (xq_min, xq_max) [C]."""
+    Cc = min_c.numel()
+    if not (out_gr_t.is_cuda and out_gr_t.is_contiguous() and out_gr_t.shape == (G, 2)):
+        raise RuntimeError("group_ranges: out_gr_t must be a contiguous CUDA [G,2] tensor")
+    xq_min = torch.empty_like(min_c)
+    xq_max = torch.empty_like(max_c)
+    call("attndm_group_ranges", ptr(min_c), ptr(max_c), Cc, G, float(init_min), float(init_max), ptr(out_gr_t),
+         ptr(xq_min), ptr(xq_max), stream())
+    return xq_min, xq_max
+
+
+def calib_mix(x: torch.Tensor, gr_t: torch.Tensor, sw: torch.Tensor, a_bit: int, lp_p: Optional[float] = None):
+    """Returns y (and the lp sum as a 1-element double tensor when lp_p is given)."""
+    _chk(x, "calib_mix input")
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    G = gr_t.shape[0]
+    y = torch.empty_like(x)
+    lp = torch.zeros(1, dtype=torch.float64, device=x.device) if lp_p is not None else None
+    call("attndm_calib_mix", ptr(x), rows, Cc, G, ptr(gr_t.contiguous()), ptr(sw.contiguous()), int(a_bit), ptr(y),
+         ptr(lp), float(lp_p or 0.0), stream())
+    return (y, lp) if lp_p is not None else y
+
+
+def kth_value(x: torch.Tensor, k: int) -> torch.Tensor:
+    xf = x.reshape(-1)
+    _chk(xf, "kth_value input")
+    ws = torch.empty(4 * 256 + 8, dtype=torch.int32, device=x.device)
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    call("attndm_kth_value", ptr(xf), xf.numel(), int(k), ptr(out), ptr(ws), stream())
+    return out
+
+
+def weight_clamp_pack(w: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor) -> torch.Tensor:
+    """w [O,C,kh,kw] -> clamped w_eff [O, taps, C]."""
+    O, Cc, KH, KW = w.shape
+    w = w.detach().float().contiguous()
+    w_eff = torch.empty(O, KH * KW, Cc, dtype=torch.float32, device=w.device)
+    call("attndm_weight_clamp_pack", ptr(w), O, Cc, KH, KW, ptr(lo.float().contiguous()),
+         ptr(hi.float().contiguous()), ptr(w_eff), stream())
+    return w_eff
+
+
+@dataclass
+class I8Pack:
+    qw: torch.Tensor        # int8 [O, taps*Cp]
+    wsum: torch.Tensor      # int32 [O]
+    w_zp: torch.Tensor      # int32 [O]
+    w_scale: torch.Tensor   # float32 [O]
+    on_grid: bool
+
+
+def weight_to_i8(w_eff: torch.Tensor, w_bit: int) -> I8Pack:
+    """Grid = AsymmetricQuantFunction's on the per-out-channel min/max of w_eff
+    (utils/quantization_utils/quant_utils.py:109-133)."""
+    O, taps, Cc = w_eff.shape
+    Cp = cp_of(Cc)
+    flat = w_eff.reshape(O, -1)
+    lo, hi = flat.min(1)[0], flat.max(1)[0]
+    n = 2 ** w_bit - 1
+    w_scale = n / (hi - lo)
+    w_zp = (w_scale * lo).round() + 2 ** (w_bit - 1)
+    qw = torch.empty(O, taps * Cp, dtype=torch.int8, device=w_eff.device)
+    wsum = torch.empty(O, dtype=torch.int32, device=w_eff.device)
+    flag = torch.empty(1, dtype=torch.int32, device=w_eff.device)
+    call("attndm_weight_to_i8", ptr(w_eff), O, Cc, taps, ptr(w_scale.contiguous()), ptr(w_zp.contiguous()),
+         int(w_bit), ptr(qw), Cp, ptr(wsum), ptr(flag), stream())
+    on_grid = bool(flag.item() == 1) and bool(torch.isfinite(w_scale).all().item())
+    return I8Pack(qw=qw, wsum=wsum, w_zp=w_zp.to(torch.int32), w_scale=w_scale, on_grid=on_grid)
+
+
+def qconv_i8(codes, rowsum, B: int, H: int, W: int, Cc: int, pack: I8Pack, taps: int, mult, act_zp, bias,
+             residual=None, temb=None, impl: Optional[int] = None, out: Optional[torch.Tensor] = None):
+    O = pack.qw.shape[0]
+    if out is None:
+        out = torch.empty(B, H, W, O, dtype=torch.float32, device=codes.device)
+    call("attndm_qconv_i8", ptr(codes), ptr(rowsum), B, H, W, Cc, ptr(pack.qw), ptr(pack.wsum), ptr(pack.w_zp), O,
+         taps, ptr(mult), ptr(act_zp), ptr(bias), ptr(residual), ptr(temb), ptr(out), None,
+         DEFAULT_CONV_IMPL if impl is None else impl, stream())
+    return out
+
+
+def conv_f32(x: torch.Tensor, w_eff: torch.Tensor, bias, residual=None, temb=None):
+    _chk(x, "conv_f32 input")
+    B, H, W, Cc = x.shape
+    O, taps, _ = w_eff.shape
+    out = torch.empty(B, H, W, O, dtype=torch.float32, device=x.device)
+    call("attndm_conv_f32", ptr(x), B, H, W, Cc, ptr(w_eff), O, taps, ptr(bias), ptr(residual), ptr(temb), ptr(out),
+         stream())
+    return out
+
+
+def attention(q, k, v, scale: float, heads: int = 1, softmax_scale: float = 1.0, qk_q=None, p_q=None):
+    """q,k [B,N,d]; v [B,N,dv] -> [B,N,dv]."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, "attention " + n)
+    B, N, d = q.shape
+    dv = v.shape[-1]
+    out = torch.empty_like(v)
+    zq = AttnQuant(1.0, 0.0, 0)
+    call("attndm_attention", ptr(q), ptr(k), ptr(v), ptr(out), B, N, d, dv, float(scale), int(heads),
+         float(softmax_scale), AttnQuant(*qk_q) if qk_q else zq, AttnQuant(*p_q) if p_q else zq, stream())
+    return out
+
+
+def scale_add(a, x, gamma):
+    out = torch.empty_like(x)
+    call("attndm_scale_add", ptr(a), ptr(x), ptr(gamma), ptr(out), x.numel(), stream())
+    return out
+
+
+def maxpool2(x):
+    _chk(x, "maxpool2 input")
+    B, H, W, Cc = x.shape
+    y = torch.empty(B, H // 2, W // 2, Cc, dtype=torch.float32, device=x.device)
+    call("attndm_maxpool2", ptr(x), B, H, W, Cc, ptr(y), stream())
+    return y
+
+
+def upsample_concat(x, skip):
+    _chk(x, "upsample_concat x")
+    _chk(skip, "upsample_concat skip")
+    B, H, W, Cx = x.shape
+    _, Hs, Ws, Cs = skip.shape
+    out = torch.empty(B, Hs, Ws, Cx + Cs, dtype=torch.float32, device=x.device)
+    call("attndm_upsample_concat", ptr(x), B, H, W, Cx, ptr(skip), Hs, Ws, Cs, ptr(out), stream())
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int):
+    t = t.float().contiguous()
+    emb = torch.empty(t.numel(), dim, dtype=torch.float32, device=t.device)
+    call("attndm_timestep_embedding", ptr(t), t.numel(), dim, ptr(emb), stream())
+    return emb
+
+
+def ddim_step(xt, eps, coef, noise=None, x_next=None, x0_out=None, want_x0=False):
+    if x_next is None:
+        x_next = torch.empty_like(xt)
+    x0 = x0_out if x0_out is not None else (torch.empty_like(xt) if want_x0 else None)
+    call("attndm_ddim_step", ptr(xt), ptr(eps), ptr(coef), ptr(noise), ptr(x_next), ptr(x0), xt.numel(), stream())
+    return x_next, x0
+
+
+def stage_tables(table: torch.Tensor, step: torch.Tensor, dst: torch.Tensor, advance: bool = True):
+    T, n = table.shape
+    call("attndm_stage_tables", ptr(table), n, T, ptr(step), 1 if advance else 0, ptr(dst), stream())

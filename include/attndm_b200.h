@@ -1,0 +1,214 @@
+/*
+ * attndm_b200.h -- C-ABI of the B200-native hot path of PTQ-AttnDM.
+ *
+ * The reference (aqilmarwan/attentionDM) is pure Python/PyTorch and has no FFI;
+ * its "operator API" is the nn.Module surface.  Each entry point below replaces
+ * the eager op chain of one reference method; the citation is the reference
+ * file:line whose arithmetic the kernel reproduces.  attentiondm_b200/_ffi.py is
+ * the ctypes binding; INTEGRATION.md shows the same binding as a patch to the
+ * reference's own modules.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (raw cudaMalloc /
+ *     torch storage); the library allocates nothing and keeps no global state
+ *     except a mutex-guarded TMA-descriptor cache;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are stream-ordered and
+ *     never synchronise;
+ *   - fp32 activations are NHWC ("channels last"): x[((b*H + h)*W + w)*C + c];
+ *   - int8 activation codes come in two row layouts, both with row pitch
+ *     Cp = round_up(C, 16) bytes (pad channels are 0):
+ *        ATTNDM_ROWS_PLAIN : row = (b*H + h)*W + w
+ *        ATTNDM_ROWS_HALO  : row = (b*(H+2) + h+1)*(W+2) + w+1, with a one-pixel
+ *                            ring holding the code of 0.0 (= -zero_point), so a
+ *                            3x3/pad-1 convolution is nine row-shifted GEMMs;
+ *     each code tensor travels with rowsum[row] = sum_c code (int32, same rows);
+ *   - return value: 0 = ok, negative = error (attndm_last_error() has the text).
+ *     No exception crosses the boundary and there is no CPU fallback.
+ */
+#ifndef ATTNDM_B200_H
+#define ATTNDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATTNDM_OK 0
+#define ATTNDM_ERR_ARG (-1)
+#define ATTNDM_ERR_CUDA (-2)
+#define ATTNDM_ERR_UNSUPPORTED (-3)
+
+#define ATTNDM_ROWS_PLAIN 0
+#define ATTNDM_ROWS_HALO 1
+
+#define ATTNDM_PRE_NONE 0      /* quantize x as is                               */
+#define ATTNDM_PRE_SILU 1      /* quantize silu(x)            (time_mlp)         */
+#define ATTNDM_PRE_GN_SILU 2   /* quantize silu(groupnorm(x)) (ResidualBlock)    */
+
+#define ATTNDM_CONV_SIMT 0     /* CUDA-core dp4a implicit GEMM (any shape)       */
+#define ATTNDM_CONV_TCGEN05 1  /* tcgen05 kind::i8 + TMA + TMEM implicit GEMM    */
+
+const char* attndm_last_error(void);
+int attndm_version(void);
+/* 1 if the current device is sm_100 (tcgen05 usable), 0 otherwise, <0 on error */
+int attndm_device_supported(void);
+
+/* ---- activation quantizers (HBM-bound) ---------------------------------- */
+
+/* QModule._quantize_activation, inference branch: utils/quant_util.py:260-282
+ * with scale/zero_point from asymmetric_linear_quantization_params,
+ * utils/quantization_utils/quant_utils.py:109-133 (computed by the host on the
+ * tiny [C] vectors and passed in).  Optional pre-op fuses the producer:
+ * GroupNorm(32, eps)+SiLU of ResidualBlock.forward (models/diffusion.py:119-127)
+ * or the SiLU of time_mlp (models/diffusion.py:157-161).
+ *   code = clamp(rne(scale[c]*v - zp[c]), -2^(a-1), 2^(a-1)-1)
+ *   y    = (code + zp[c]) / scale[c]
+ * Outputs (any may be NULL): codes/rowsum in `rows_layout`, y_f32 NHWC.
+ * gn_stats: per (b, group) {sum, sumsq} as double[B*32*2] from attndm_gn_stats. */
+int attndm_act_quant(const float* x, int B, int H, int W, int C,
+                     const float* scale, const float* zp, int a_bit,
+                     int pre_op, const double* gn_stats, const float* gn_gamma,
+                     const float* gn_beta, float gn_eps,
+                     int8_t* codes, int32_t* rowsum, int rows_layout,
+                     float* y_f32, void* stream);
+
+/* GroupNorm statistics (32 groups) of an NHWC tensor: stats[b][g] = {sum, sumsq}
+ * accumulated in double.  `stats` must be zeroed by the caller (it is an
+ * accumulation target so that a conv epilogue may also feed it).
+ * models/diffusion.py:36-37 (Normalize), 91,94 (GroupNorm eps 1e-6). */
+int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, void* stream);
+
+/* silu(groupnorm(x)) -> fp32 (used by the calibration branch, which needs the
+ * un-quantized activation).  models/diffusion.py:121-122,125-126. */
+int attndm_gn_silu(const float* x, int B, int H, int W, int C, const double* gn_stats,
+                   const float* gamma, const float* beta, float eps, float* y, void* stream);
+
+/* ---- calibration collectors --------------------------------------------- */
+
+/* Per-channel min / max over (B,H,W): utils/quant_util.py:187-191.
+ * workspace: float[2 * C * attndm_minmax_workspace_blocks()]. */
+int attndm_minmax_workspace_blocks(void);
+int attndm_minmax_c(const float* x, long long rows, int C, float* min_c, float* max_c,
+                    float* workspace, void* stream);
+
+/* Floor to the init range then GroupWise_Quantizaion of both vectors, on device:
+ * utils/quant_util.py:193-205 and 403-437 (equal-width bins evaluated as
+ * min + (div*(m+1))/G in fp32, later bins win ties, empty bin -> upper edge,
+ * unassigned channel -> 0).  Writes groups_range_t[G][2] = {gmin[g], gmax[g]} and
+ * the per-channel snapped vectors xq_min/xq_max[C] (activation_range_min1/max1). */
+int attndm_group_ranges(const float* min_c, const float* max_c, int C, int G,
+                        float init_min, float init_max, float* groups_range_t,
+                        float* xq_min, float* xq_max, void* stream);
+
+/* Calibration output y = sum_g softmax(alpha)[g,c] * FQ(x; gmin[g], gmax[g], a_bit):
+ * utils/quant_util.py:207-224 with Quant.forward :54-66.  sw = softmax weights
+ * [G][C]; groups_range_t as written by attndm_group_ranges.  Optionally also
+ * accumulates sum |y-x|^p into lp_sum (double, caller-zeroed) for the
+ * first-calibrate search, utils/quant_util.py:37-44,237-254. */
+int attndm_calib_mix(const float* x, long long rows, int C, int G, const float* groups_range_t,
+                     const float* sw, int a_bit, float* y, double* lp_sum, float lp_p,
+                     void* stream);
+
+/* find_scale_by_percentile_min/max: utils/quant_util.py:440-450.  k-th smallest
+ * of x[n] (k = int(n*(1-p)) or int(n*p)), exact, by 4-pass radix select.
+ * workspace: uint32[4*256 + 8]. */
+int attndm_kth_value(const float* x, long long n, long long k, float* out,
+                     uint32_t* workspace, void* stream);
+
+/* ---- weights -------------------------------------------------------------- */
+
+/* QModule._quantize_weight clamp, utils/quant_util.py:284-303, applied once:
+ * w_eff[o][tap][c] (tap-major, channels innermost) from w[o][c][kh][kw]. */
+int attndm_weight_clamp_pack(const float* w, int O, int C, int KH, int KW, const float* lo,
+                             const float* hi, float* w_eff, void* stream);
+
+/* If every clamped weight sits on the per-out-channel w_bit grid of
+ * AsymmetricQuantFunction (utils/quantization_utils/quant_utils.py:136-162)
+ * emit int8 codes qw[o][tap*Cp + c], wsum[o] = sum qw, and set *on_grid = 1;
+ * otherwise *on_grid = 0.  w_scale/w_zp[O] are the grid parameters. */
+int attndm_weight_to_i8(const float* w_eff, int O, int C, int taps, const float* w_scale,
+                        const float* w_zp, int w_bit, int8_t* qw, int Cp, int32_t* wsum,
+                        int* on_grid, void* stream);
+
+/* ---- convolutions --------------------------------------------------------- */
+
+/* QConv2d.forward -> F.conv2d (utils/quant_util.py:383-385) for 3x3/s1/p1 and 1x1
+ * on integer codes.  out[pix][o] = float(I) * mult[o] + bias[o] (+ residual[pix][o])
+ * (+ temb[b][o]) with the exact integer
+ *   I = sum code*qw + zp*wsum[o] + w_zp[o]*(sum_window rowsum + zp*taps*C).
+ * codes/rowsum: HALO rows for taps = 9, PLAIN rows for taps = 1.
+ * mult[o] = 1/(act_scale*w_scale[o]); act_zp: int32[1] on device.
+ * residual (NHWC fp32, same shape as out) and temb ([B][O]) may be NULL:
+ * they fuse ResidualBlock's `x + h` (models/diffusion.py:136) and the block's
+ * `x + time_mlp(t_emb)` (models/diffusion.py:175-177).
+ * gn_stats_out (double[B*32*2], caller-zeroed) may be NULL: accumulates the
+ * GroupNorm statistics of `out` for the next layer.
+ * impl: ATTNDM_CONV_SIMT or ATTNDM_CONV_TCGEN05. */
+int attndm_qconv_i8(const int8_t* codes, const int32_t* rowsum, int B, int H, int W, int C,
+                    const int8_t* qw, const int32_t* wsum, const int32_t* w_zp, int O, int taps,
+                    const float* mult, const int32_t* act_zp, const float* bias,
+                    const float* residual, const float* temb, float* out,
+                    double* gn_stats_out, int impl, void* stream);
+
+/* fp32 convolution on NHWC (3x3/s1/p1 or 1x1) with the same fused epilogue; used
+ * by the calibration branch (its input is a G-way mix, not on one integer grid),
+ * by layers whose per-channel scales differ (trained alpha_activ) and by weights
+ * that are not on the integer grid.  w_eff[o][tap][c]. */
+int attndm_conv_f32(const float* x, int B, int H, int W, int C, const float* w_eff, int O,
+                    int taps, const float* bias, const float* residual, const float* temb,
+                    float* out, void* stream);
+
+/* ---- attention ------------------------------------------------------------ */
+
+/* EnhancedQSelfAttention core (models/self_attention.py:132-144):
+ *   out = softmax(q k^T * scale) v   per sample; q,k: [B][N][d], v,out: [B][N][dv].
+ * heads > 1 selects MixedPrecisionAttention's head split and optional
+ * fake-quant of logits / probabilities (utils/attention_quant_utils.py:30-38,
+ * 65-107): qk_q / p_q = {scale, zero_point, bits} on the host, bits 0 = off;
+ * softmax_scale multiplies the logits before softmax (:91). */
+typedef struct {
+  float scale;
+  float zero_point;
+  int bits;
+} attndm_attn_quant;
+int attndm_attention(const float* q, const float* k, const float* v, float* out, int B, int N,
+                     int d, int dv, float scale, int heads, float softmax_scale,
+                     attndm_attn_quant qk_q, attndm_attn_quant p_q, void* stream);
+
+/* out = gamma[0] * a + x  (models/self_attention.py:151) */
+int attndm_scale_add(const float* a, const float* x, const float* gamma, float* out,
+                     long long n, void* stream);
+
+/* ---- UNet glue ------------------------------------------------------------ */
+
+/* nn.MaxPool2d(2) on NHWC (models/diffusion.py:143,183). */
+int attndm_maxpool2(const float* x, int B, int H, int W, int C, float* y, void* stream);
+
+/* UpBlock.forward resize + concat (models/diffusion.py:225-244): nearest x2, then
+ * nearest-resize to the skip's (Hs, Ws), written to out[..., 0:Cx]; skip copied to
+ * out[..., Cx:Cx+Cs].  out is NHWC [B][Hs][Ws][Cx+Cs]. */
+int attndm_upsample_concat(const float* x, int B, int H, int W, int Cx, const float* skip,
+                           int Hs, int Ws, int Cs, float* out, void* stream);
+
+/* get_timestep_embedding (models/diffusion.py:11-29): emb[b] = [sin(t f), cos(t f)]. */
+int attndm_timestep_embedding(const float* t, int B, int dim, float* emb, void* stream);
+
+/* ---- sampler -------------------------------------------------------------- */
+
+/* One generalized (DDIM) update, functions/denoising.py:33-39.
+ * coef (device float[5]) = {sqrt(1-at), sqrt(at), sqrt(at_next), c1, c2};
+ * noise may be NULL when c1 == 0 (eta = 0).  x0_out may be NULL. */
+int attndm_ddim_step(const float* xt, const float* eps, const float* coef, const float* noise,
+                     float* x_next, float* x0_out, long long n, void* stream);
+
+/* Copy row `*step` of a [T][n] table into `dst` and (if advance) increment *step
+ * modulo T: lets one captured CUDA graph serve every denoising step, mirroring
+ * the per-module index_seq counter (utils/quant_util.py:228-229,281). */
+int attndm_stage_tables(const float* table, long long n, int T, int* step, int advance,
+                        float* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATTNDM_B200_H */

@@ -1,0 +1,522 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the golden
+fixtures generated from the unmodified reference and against the CPU oracle
+(oracle/restate.py) on the same seeded inputs.
+
+Bars: integer codes / clip indices / group tables bit-exact given identical fp32
+inputs and identical (scale, zero_point) tables; floating-point results within
+1e-3 relative L2 (the north_star tolerance), most far tighter (stated per test).
+Weights are on the w_bit grid (H1): both sides consume the same
+snapped tensor.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restate as R
+from oracle import synth as S
+from tests.util import T, build_cuda_model, make_qconv, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    from attentiondm_b200 import _ffi
+    assert _ffi.lib().attndm_device_supported() == 1, "these tests need an sm_100 (B200) device"
+    yield
+
+
+# ---------------------------------------------------------------------------
+# a1: activation fake-quant (inference branch)
+# ---------------------------------------------------------------------------
+def test_act_quant_codes_bit_exact_vs_reference(golden):
+    """Given the reference's own (scale, zp) tables the kernel's codes / outputs are bit-exact."""
+    from attentiondm_b200 import ops
+    g = golden("quant_unit.npz")
+    for ci in range(5):
+        for mode in ("uniform", "random"):
+            k = f"inf{ci}_{mode}"
+            C, a_bit, G, Tn = [int(v) for v in g[k + "_meta"]]
+            gr, alpha, x = T(g[k + "_gr"]), T(g[k + "_alpha"]), T(g[k + "_x"])
+            xn = ops.to_nhwc(x.to(DEV))
+            for t in range(Tn):
+                lo, hi = R.mixed_range(gr[t], alpha[t])
+                s, z = R.asym_params(a_bit, lo, hi)
+                codes, rowsum, y = ops.act_quant(xn, s.to(DEV).contiguous(), z.to(DEV).contiguous(), a_bit,
+                                                 want_codes=True, want_f32=True)
+                want = T(g[k + "_y"][t])
+                assert torch.equal(ops.to_nchw(y).cpu(), want), (k, t)
+                _, wc, _, _ = R.act_fake_quant(x, gr[t], alpha[t], a_bit, return_codes=True)
+                B, _, H, W = x.shape
+                got = codes[:, :C].reshape(B, H, W, C).permute(0, 3, 1, 2).cpu().float()
+                assert torch.equal(got, wc), (k, t)
+                assert torch.equal(rowsum.reshape(B, H, W).cpu().float(), wc.sum(1)), (k, t)
+                n = 2 ** (a_bit - 1)
+                assert got.min() >= -n and got.max() <= n - 1
+
+
+def test_qconv_module_quantizer_and_index_wrap(golden):
+    """QConv2d's own table build + index_seq wrap; uniform alpha gives bit-exact tables on any device."""
+    g = golden("quant_unit.npz")
+    for ci in range(5):
+        k = f"inf{ci}_uniform"
+        C, a_bit, G, Tn = [int(v) for v in g[k + "_meta"]]
+        q = make_qconv(C, 8, 1, a_bit, Tn, G)
+        q.groups_range.data.copy_(T(g[k + "_gr"]))
+        q.invalidate_cache()
+        q.init_weight_range()
+        x = T(g[k + "_x"]).to(DEV)
+        for t in range(Tn + 1):
+            _, y, _ = q.quantize_activation_codes(x)
+            assert torch.equal(y.cpu(), T(g[k + "_y"][t])), (k, t)
+            q(x)                                   # advances index_seq like the reference
+        assert q.index_seq == 1
+        # random alpha: tables come from the device softmax (ulp-level differences allowed)
+        k = f"inf{ci}_random"
+        q = make_qconv(C, 8, 1, a_bit, Tn, G)
+        q.groups_range.data.copy_(T(g[k + "_gr"]))
+        q.alpha_activ.data.copy_(T(g[k + "_alpha"]))
+        q.invalidate_cache()
+        _, y, _ = q.quantize_activation_codes(T(g[k + "_x"]).to(DEV))
+        want = T(g[k + "_y"][0])
+        assert rel_l2(y, want) < 1e-3
+        assert (y.cpu() != want).float().mean() < 0.02
+
+
+# ---------------------------------------------------------------------------
+# a4-a6: calibration collectors
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("first", [0, 1])
+def test_calibration_vs_reference(golden, first):
+    g = golden("quant_unit.npz")
+    for ci in range(4):
+        k = f"cal{ci}_{first}"
+        C, a_bit, G, Tn = [int(v) for v in g[k + "_meta"]]
+        q = make_qconv(C, 8, 1, a_bit, Tn, G)
+        q.alpha_activ.data.copy_(T(g[k + "_alpha"]))
+        q.invalidate_cache()
+        q.init_weight_range()
+        q.set_calibrate(True)
+        q.first_calibrate(bool(first))
+        from attentiondm_b200 import ops
+        x = T(g[k + "_x"])
+        y0 = q._calibrate_step(ops.to_nhwc(x.to(DEV)))
+        q.index_seq += 1
+        y1 = q._calibrate_step(ops.to_nhwc((x * 0.7).to(DEV)))
+        q.index_seq += 1
+        # group tables: bit-exact (min/max and the fp32 bin-edge arithmetic are order independent)
+        assert torch.equal(q.groups_range.data.cpu(), T(g[k + "_gr"])), k
+        init = torch.stack([q.init_range_min, q.init_range_max])
+        assert torch.equal(init, T(g[k + "_init"])), k
+        # mix output: the G-term fp32 sum may associate differently -> 1e-6
+        assert rel_l2(ops.to_nchw(y0), T(g[k + "_y0"])) < 1e-6, k
+        assert rel_l2(ops.to_nchw(y1), T(g[k + "_y1"])) < 1e-6, k
+
+
+def test_minmax_ragged_shapes():
+    from attentiondm_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for shape in [(1, 1, 1, 3), (2, 5, 7, 3), (3, 4, 4, 32), (2, 1, 1, 1024), (5, 9, 3, 96), (2, 16, 16, 256),
+                  (1, 3, 3, 1536)]:
+        x = torch.randn(*shape, generator=g).to(DEV) * 5
+        mn, mx = ops.minmax_c(x)
+        flat = x.reshape(-1, shape[-1])
+        assert torch.equal(mn, flat.min(0)[0]) and torch.equal(mx, flat.max(0)[0]), shape
+
+
+def test_group_wise_bit_exact(golden):
+    import attentiondm_b200 as A
+    g = golden("quant_unit.npz")
+    for vi in range(int(g["gw_count"][0])):
+        x = T(g[f"gw{vi}_x"]).to(DEV)
+        for G in (4, 8):
+            for mm in ("max", "min"):
+                xq, gm = A.GroupWise_Quantizaion(x.clone(), dim=x.numel(), group_n=G, maxmin=mm)
+                assert torch.equal(xq.cpu(), T(g[f"gw{vi}_{G}_{mm}_xq"])), (vi, G, mm)
+                assert torch.equal(gm.cpu(), T(g[f"gw{vi}_{G}_{mm}_gm"])), (vi, G, mm)
+
+
+def test_percentile_collectors(golden):
+    import attentiondm_b200 as A
+    g = golden("quant_unit.npz")
+    x = T(g["pct_x"]).to(DEV)
+    assert A.find_scale_by_percentile_min(x) == float(g["pct_min"][0])
+    assert A.find_scale_by_percentile_max(x) == float(g["pct_max"][0])
+    # ragged / tied / signed-zero inputs against numpy
+    gen = torch.Generator().manual_seed(3)
+    for n in (1, 2, 257, 100003):
+        v = torch.randn(n, generator=gen)
+        v[::3] = 0.0
+        v[1::7] = -0.0
+        for p in (0.9999, 0.5, 0.01):
+            kk = int(n * p)
+            if kk >= n:
+                continue
+            from attentiondm_b200 import ops
+            got = ops.kth_value(v.to(DEV), kk).item()
+            want = float(np.partition(v.numpy(), kk)[kk])
+            assert got == want, (n, p)
+
+
+# ---------------------------------------------------------------------------
+# a2: weights
+# ---------------------------------------------------------------------------
+def test_weight_clamp_and_grid(golden):
+    from attentiondm_b200 import ops
+    g = golden("quant_unit.npz")
+    for wi in range(3):
+        w = T(g[f"wc{wi}_w"]).to(DEV)
+        lo, hi = T(g[f"wc{wi}_lo"]).to(DEV), T(g[f"wc{wi}_hi"]).to(DEV)
+        w_eff = ops.weight_clamp_pack(w, lo, hi)                     # [O, taps, C]
+        O, C, KH, KW = w.shape
+        got = w_eff.reshape(O, KH, KW, C).permute(0, 3, 1, 2).cpu()
+        assert torch.equal(got, T(g[f"wc{wi}_out"])), wi
+        bits = int(g[f"wc{wi}_bits"][0])
+        snapped = T(g[f"wc{wi}_snap"]).to(DEV)
+        flat = snapped.reshape(O, -1)
+        w_eff2 = ops.weight_clamp_pack(snapped, flat.min(1)[0], flat.max(1)[0])
+        pack = ops.weight_to_i8(w_eff2, bits)
+        assert pack.on_grid
+        _, qref, _, zref = R.snap_weight(T(g[f"wc{wi}_w"]), bits)
+        Cp = ops.cp_of(C)
+        qw = pack.qw.reshape(O, KH * KW, Cp)[:, :, :C].reshape(O, KH, KW, C).permute(0, 3, 1, 2).cpu().float()
+        # codes are defined up to the per-channel zero-point shift: compare de-biased integers
+        assert torch.equal(qw + pack.w_zp.cpu().float().view(-1, 1, 1, 1), qref + zref.view(-1, 1, 1, 1))
+        assert torch.equal(pack.wsum.cpu().float(), qw.reshape(O, -1).sum(1))
+        # off-grid weights are detected
+        assert not ops.weight_to_i8(ops.weight_clamp_pack(w, flat.min(1)[0] * 0 - 10, flat.max(1)[0] * 0 + 10), bits).on_grid
+
+
+def test_attention_quantize_tensor(golden):
+    import attentiondm_b200 as A
+    g = golden("quant_unit.npz")
+    mpa = A.MixedPrecisionAttention(head_dim=4, num_heads=8, bit_width=4).to(DEV)
+    for ai in range(4):
+        bits, sc, zp = g[f"aq{ai}_p"]
+        y = mpa.quantize_tensor(T(g[f"aq{ai}_x"]).to(DEV), torch.tensor([sc], dtype=torch.float32),
+                                torch.tensor([zp], dtype=torch.float32), int(bits))
+        assert torch.equal(y.cpu(), T(g[f"aq{ai}_y"]))
+
+
+# ---------------------------------------------------------------------------
+# a3: convolutions
+# ---------------------------------------------------------------------------
+CONV_SHAPES = [
+    # B, H, W, C, O, k
+    (2, 8, 8, 32, 32, 3), (1, 5, 7, 64, 48, 3), (3, 4, 4, 128, 128, 3), (2, 16, 16, 256, 128, 3),
+    (2, 1, 1, 256, 256, 3), (4, 2, 2, 96, 64, 3), (2, 8, 8, 3, 32, 3), (2, 8, 8, 32, 3, 3),
+    (5, 1, 1, 1024, 64, 1), (2, 4, 4, 64, 8, 1), (2, 6, 6, 160, 512, 1), (1, 32, 32, 128, 128, 3),
+    (130, 1, 1, 32, 16, 1), (1, 9, 9, 384, 272, 3),
+]
+
+
+def _conv_case(B, H, W, C, O, k, a_bit=8, w_bit=8, seed=0):
+    from attentiondm_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, H, W, generator=g) * 3
+    w = (torch.rand(O, C, k, k, generator=g) * 2 - 1) / (C * k * k) ** 0.5
+    w = R.snap_weight(w, w_bit)[0]
+    bias = torch.randn(O, generator=g) * 0.1
+    lo, hi = torch.tensor(-4.3), torch.tensor(6.1)
+    s, z = R.asym_params(a_bit, lo, hi)
+    return x, w, bias, s, z
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_qconv_i8_simt_and_tcgen05_vs_oracle(shape):
+    """Both int8 kernels: bit-identical to each other, and equal to F.conv2d on the
+    de-quantized operands up to fp32 summation order (1e-5)."""
+    from attentiondm_b200 import ops
+    B, H, W, C, O, k = shape
+    a_bit = 8
+    x, w, bias, s, z = _conv_case(B, H, W, C, O, k)
+    taps = k * k
+    xn = ops.to_nhwc(x.to(DEV))
+    sv = torch.full((C,), float(s), device=DEV)
+    zv = torch.full((C,), float(z), device=DEV)
+    codes, rowsum, y = ops.act_quant(xn, sv, zv, a_bit, want_codes=True, halo=(k == 3), want_f32=True)
+    flat = w.reshape(O, -1)
+    w_eff = ops.weight_clamp_pack(w.to(DEV), flat.min(1)[0].to(DEV), flat.max(1)[0].to(DEV))
+    pack = ops.weight_to_i8(w_eff, 8)
+    assert pack.on_grid
+    mult = (1.0 / (float(s) * pack.w_scale.double())).float().contiguous()
+    azp = torch.tensor([int(z)], dtype=torch.int32, device=DEV)
+    g = torch.Generator().manual_seed(1)
+    res = torch.randn(B, H, W, O, generator=g).to(DEV)
+    temb = torch.randn(B, O, generator=g).to(DEV)
+    outs = {}
+    for impl in (ops.CONV_SIMT, ops.CONV_TCGEN05):
+        outs[impl] = ops.qconv_i8(codes, rowsum, B, H, W, C, pack, taps, mult, azp, bias.to(DEV), res, temb, impl=impl)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[ops.CONV_SIMT], outs[ops.CONV_TCGEN05]), "tcgen05 and dp4a kernels disagree"
+    xq = R.act_fake_quant(x, torch.tensor([[-4.3, 6.1]]), torch.zeros(1, C), a_bit)
+    want = F.conv2d(xq.double(), w.double(), bias.double(), padding=k // 2)
+    want = want + res.cpu().double().permute(0, 3, 1, 2) + temb.cpu().double()[:, :, None, None]
+    assert rel_l2(ops.to_nchw(outs[ops.CONV_TCGEN05]), want) < 1e-5
+    # fp32 kernel on the de-quantized activations
+    of = ops.conv_f32(y, w_eff, bias.to(DEV), res, temb)
+    assert rel_l2(ops.to_nchw(of), want) < 1e-5
+
+
+@pytest.mark.parametrize("bits", [(4, 4), (6, 8), (8, 4)])
+def test_qconv_low_bit(bits):
+    from attentiondm_b200 import ops
+    a_bit, w_bit = bits
+    q = make_qconv(64, 32, 3, a_bit, 4, 8, w_bit=w_bit)
+    g = torch.Generator().manual_seed(2)
+    q.weight.data.copy_(torch.randn(32, 64, 3, 3, generator=g) * 0.05)
+    q.snap_weights_()
+    q.groups_range.data[..., 0] = -4.0
+    q.groups_range.data[..., 1] = 6.0
+    q.invalidate_cache()
+    assert q.int8_ok_all_steps()
+    x = torch.randn(2, 64, 6, 6, generator=g) * 3
+    y = q(x.to(DEV))
+    xq = R.act_fake_quant(x, torch.tensor([[-4.0, 6.0]] * 8), torch.full((8, 64), 0.01), a_bit)
+    want = F.conv2d(xq.double(), q.weight.data.cpu().double(), q.bias.data.cpu().double(), padding=1)
+    assert rel_l2(y, want) < 1e-5
+
+
+def test_qconv_falls_back_to_f32_when_not_integer_exact():
+    """Non-uniform alpha (per-channel scales, H2) and off-grid weights take the fp32 kernel and
+    still match the reference arithmetic."""
+    g = torch.Generator().manual_seed(4)
+    for case in ("alpha", "weights"):
+        q = make_qconv(32, 16, 1, 8, 4, 8)
+        q.groups_range.data[..., 0] = -4.0 - torch.rand(4, 8, generator=g).to(DEV)
+        q.groups_range.data[..., 1] = 6.0 + torch.rand(4, 8, generator=g).to(DEV)
+        if case == "alpha":
+            q.alpha_activ.data.copy_(torch.randn(4, 8, 32, generator=g))
+            q.snap_weights_()
+        else:
+            q.init_weight_range()
+        q.invalidate_cache()
+        assert not q.int8_ok_all_steps()
+        x = torch.randn(3, 32, 5, 5, generator=g) * 3
+        y = q(x.to(DEV))
+        xq = R.act_fake_quant(x, q.groups_range.data[0].cpu(), q.alpha_activ.data[0].cpu(), 8)
+        want = F.conv2d(xq.double(), q.weight.data.cpu().double(), q.bias.data.cpu().double())
+        assert rel_l2(y, want) < 1e-4, case
+
+
+# ---------------------------------------------------------------------------
+# a8-a10, a13: blocks
+# ---------------------------------------------------------------------------
+def test_groupnorm_silu_quant_fused():
+    from attentiondm_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for (B, H, W, C) in [(2, 8, 8, 32), (3, 4, 4, 64), (2, 16, 16, 128), (2, 1, 1, 256), (1, 3, 5, 96), (2, 2, 2, 768)]:
+        x = torch.randn(B, C, H, W, generator=g) * 2 + 0.5
+        gamma = 1 + 0.2 * torch.randn(C, generator=g)
+        beta = 0.2 * torch.randn(C, generator=g)
+        want = F.silu(F.group_norm(x, 32, gamma, beta, eps=1e-6))
+        xn = ops.to_nhwc(x.to(DEV))
+        gn = ops.GnArgs(ops.gn_stats(xn), gamma.to(DEV), beta.to(DEV), 1e-6)
+        y = ops.gn_silu(xn, gn)
+        assert rel_l2(ops.to_nchw(y), want) < 2e-6, (B, H, W, C)
+        s, z = R.asym_params(8, torch.tensor(-4.0), torch.tensor(6.0))
+        sv, zv = torch.full((C,), float(s), device=DEV), torch.full((C,), float(z), device=DEV)
+        codes, rowsum, yq = ops.act_quant(xn, sv, zv, 8, ops.PRE_GN_SILU, gn, want_codes=True, halo=True, want_f32=True)
+        # fused == unfused on the kernel's own GN+SiLU output (bit-exact), and within a code of torch's
+        c2, r2, y2 = ops.act_quant(y, sv, zv, 8, want_codes=True, halo=True, want_f32=True)
+        assert torch.equal(codes, c2) and torch.equal(rowsum, r2) and torch.equal(yq, y2)
+        wq = R.act_fake_quant(want, torch.tensor([[-4.0, 6.0]]), torch.zeros(1, C), 8)
+        diff = (ops.to_nchw(yq).cpu() - wq).abs()
+        assert diff.max() <= 10.0 / 255 * 1.001 and (diff > 0).float().mean() < 2e-3
+        # halo ring holds the code of 0.0
+        ring = codes.reshape(B, H + 2, W + 2, -1)[:, 0, :, :C]
+        assert (ring.float() == -float(z)).all()
+
+
+def test_attention_core():
+    from attentiondm_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    for (B, N, d, dv) in [(2, 16, 16, 128), (3, 64, 32, 256), (1, 1, 4, 32), (2, 1024, 16, 128), (2, 4, 8, 64)]:
+        q = torch.randn(B, N, d, generator=g)
+        k = torch.randn(B, N, d, generator=g)
+        v = torch.randn(B, N, dv, generator=g)
+        att = F.softmax(torch.bmm(q.double(), k.double().transpose(1, 2)) * d ** -0.5, dim=-1)
+        want = torch.bmm(att, v.double())
+        got = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), d ** -0.5)
+        assert rel_l2(got, want) < 2e-6, (B, N, d, dv)
+
+
+def test_mixed_precision_attention_vs_restatement():
+    import attentiondm_b200 as A
+    g = torch.Generator().manual_seed(7)
+    for bits in (4, 6, 8):
+        B, N, C = 2, 16, 256
+        kc = C // 8
+        mpa = A.MixedPrecisionAttention(head_dim=kc // 8, num_heads=8, bit_width=bits, scaling_factor=kc ** -0.5).to(DEV)
+        mpa.update_quantization_params(-3.0, 4.0, 0.0, 1.0)
+        q = torch.randn(B, N, kc, generator=g)
+        k = torch.randn(B, kc, N, generator=g)
+        v = torch.randn(B, N, C, generator=g)
+        st = dict(num_heads=8, base_bits=bits, scaling_factor=kc ** -0.5, scale_qk=mpa.quant_scale_qk.cpu(),
+                  zero_qk=mpa.quant_zero_qk.cpu(), scale_attn=mpa.quant_scale_attn.cpu(),
+                  zero_attn=mpa.quant_zero_attn.cpu(), softmax_scale=torch.ones(1))
+        want = R.mixed_precision_attention(q, k, v, st)
+        got = mpa(q.to(DEV), k.to(DEV), v.to(DEV))
+        # quantized logits/probabilities: a rounding flip moves one probability by one step
+        assert rel_l2(got, want) < (2e-2 if bits <= 6 else 2e-6), bits
+
+
+def test_unet_glue_ops():
+    from attentiondm_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 32, 8, 6, generator=g)
+    assert torch.equal(ops.to_nchw(ops.maxpool2(ops.to_nhwc(x.to(DEV)))).cpu(), F.max_pool2d(x, 2))
+    for (h, w, hs, ws) in [(4, 4, 8, 8), (1, 1, 1, 1), (2, 2, 3, 3), (1, 1, 2, 2), (3, 5, 4, 7)]:
+        a = torch.randn(2, 16, h, w, generator=g)
+        sk = torch.randn(2, 8, hs, ws, generator=g)
+        up = F.interpolate(a, scale_factor=2, mode="nearest")
+        if up.shape[2:] != sk.shape[2:]:
+            up = F.interpolate(up, size=sk.shape[2:], mode="nearest")
+        want = torch.cat([up, sk], dim=1)
+        got = ops.upsample_concat(ops.to_nhwc(a.to(DEV)), ops.to_nhwc(sk.to(DEV)))
+        assert torch.equal(ops.to_nchw(got).cpu(), want), (h, w, hs, ws)
+    t = torch.tensor([0.0, 1.0, 10.0, 500.0, 990.0])
+    emb = ops.timestep_embedding(t.to(DEV), 256)
+    assert (emb.cpu() - R.timestep_embedding(t, 256)).abs().max() < 1e-4
+    a, b = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
+    gam = torch.tensor([0.37])
+    assert torch.equal(ops.scale_add(a.to(DEV), b.to(DEV), gam.to(DEV)).cpu(), gam * a + b)
+
+
+# ---------------------------------------------------------------------------
+# a12: sampler
+# ---------------------------------------------------------------------------
+def test_ddim_loop_bit_exact_vs_reference(golden):
+    import attentiondm_b200 as A
+    g = golden("ddim_unit.npz")
+    betas = R.beta_schedule_linear().to(DEV)
+    for ci in range(4):
+        Tn, eta = g[f"d{ci}_meta"]
+        seq = range(0, 1000, 1000 // int(Tn))
+
+        def model(xt, t):
+            return (0.3 * xt.cpu() + torch.sin(t.cpu() / 100.0).view(-1, 1, 1, 1) * 0.1).to(DEV)
+
+        torch.manual_seed(77)                     # the reference draws randn_like(x) on the CPU every step
+
+        def noise_fn(k, like):
+            return torch.randn(like.shape).to(DEV)
+
+        xs, x0s = A.generalized_steps(T(g[f"d{ci}_x"]).to(DEV), seq, model, betas, eta=float(eta), noise_fn=noise_fn)
+        assert len(xs) == int(Tn) + 1 and len(x0s) == int(Tn)
+        assert all(not t.is_cuda for t in xs[1:]) and all(not t.is_cuda for t in x0s)
+        assert torch.equal(torch.stack([t.cpu() for t in xs]), T(g[f"d{ci}_xs"]))
+        assert torch.equal(torch.stack(x0s), T(g[f"d{ci}_x0"]))
+
+
+# ---------------------------------------------------------------------------
+# end to end: tiny UNet against the reference fixtures
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,bw,alpha,gain,first", [
+    ("tiny_unet_w8.npz", 8, "uniform", 1.0, False),
+    ("tiny_unet_w8_scaled.npz", 8, "uniform", 0.5, True),
+    ("tiny_unet_w4_attn.npz", 4, "attn_random", 1.0, False),
+])
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_tiny_unet_vs_reference_fixture(golden, name, bw, alpha, gain, first, impl):
+    import attentiondm_b200 as A
+    from attentiondm_b200 import ops
+    ops.DEFAULT_CONV_IMPL = ops.CONV_TCGEN05 if impl == "tcgen05" else ops.CONV_SIMT
+    try:
+        g = golden(name)
+        Tn = int(g["meta"][0])
+        spec = S.tiny_spec(T=Tn, bitwidth=bw)
+        sd = S.synth_state_dict(spec, seed=3, weight_gain=gain, alpha_mode=alpha)
+        m = build_cuda_model(spec, sd)
+        betas = R.beta_schedule_linear().to(DEV)
+        x = T(g["x"]).to(DEV)
+        # --- calibration pass, teacher-forced by construction (same x0, eta = 0) ---
+        eps_c = []
+        hook = m.register_forward_hook(lambda mod, i, o: eps_c.append(o.detach().float().cpu().contiguous()))
+        m.set_calibrate(True, first=first)
+        A.generalized_steps(x, spec.seq, m, betas, eta=0.0)
+        m.set_calibrate(False)
+        for t in range(Tn):
+            assert rel_l2(eps_c[t], T(g["calib_eps"][t])) < 1e-3, ("calib eps", t)
+        worst = 0.0
+        for n, q in m.qconvs():
+            worst = max(worst, rel_l2(q.groups_range.data, T(g["gr/" + n])))
+            if first:
+                init = torch.stack([q.init_range_min, q.init_range_max])
+                assert torch.allclose(init, T(g["init/" + n])), n
+        assert worst < 1e-3, worst
+        # --- quantized sampling with the REFERENCE's calibrated tables (isolates the sampler) ---
+        for n, q in m.qconvs():
+            q.groups_range.data.copy_(T(g["gr/" + n]))
+            q.invalidate_cache(weights=False)
+        m.reset_index_seq()
+        eps_c.clear()
+        xs, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, use_graph=False)
+        hook.remove()
+        for t in range(Tn):
+            assert rel_l2(eps_c[t], T(g["eps"][t])) < 1e-3, ("eps", t)
+        assert rel_l2(torch.stack([t.cpu() for t in xs]), T(g["xs"])) < 1e-3
+        # --- same thing through the CUDA-graph engine: identical to the eager kernels ---
+        m.reset_index_seq()
+        xs_g, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, use_graph=True)
+        assert torch.equal(torch.stack(xs_g[1:]), torch.stack(xs[1:]))
+        assert all(q.index_seq == Tn for _, q in m.qconvs())
+    finally:
+        ops.DEFAULT_CONV_IMPL = ops.CONV_TCGEN05
+
+
+def test_per_layer_trace_vs_reference_fixture(golden):
+    """Teacher-forced per-layer check: feed the reference's recorded layer input, compare the output."""
+    g = golden("tiny_unet_w8.npz")
+    spec = S.tiny_spec(T=int(g["meta"][0]), bitwidth=8)
+    sd = S.synth_state_dict(spec, seed=3)
+    m = build_cuda_model(spec, sd)
+    mods = dict(m.qconvs())
+    for key in g.files:
+        if not key.startswith("trace_in/"):
+            continue
+        n = key[len("trace_in/"):]
+        q = mods[n]
+        q.groups_range.data.copy_(T(g["gr/" + n]))
+        q.invalidate_cache(weights=False)
+        q.index_seq = 0
+        assert q.int8_ok_all_steps(), n
+        y = q(T(g[key]).to(DEV))
+        assert rel_l2(y, T(g["trace_out/" + n])) < 1e-5, n
+
+
+# ---------------------------------------------------------------------------
+# full-size properties (oracle too slow): CIFAR config, batch 8
+# ---------------------------------------------------------------------------
+def test_cifar_full_size_properties():
+    import attentiondm_b200 as A
+    from attentiondm_b200 import ops
+    spec = S.cifar_spec(T=4)
+    sd = S.synth_state_dict(spec, seed=1)
+    m = build_cuda_model(spec, sd)
+    assert len(m.qconvs()) == 198
+    betas = R.beta_schedule_linear().to(DEV)
+    x = torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(9)).to(DEV)
+    m.set_calibrate(True)
+    A.generalized_steps(x, spec.seq, m, betas, eta=0.0, keep="last")
+    m.set_calibrate(False)
+    m.reset_index_seq()
+    assert all(q.int8_ok_all_steps() for _, q in m.qconvs())
+    xs, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, keep="last")
+    assert torch.isfinite(xs[-1]).all()
+    # samples are independent: a batch of 8 equals two batches of 4 (what batch sharding relies on)
+    m.reset_index_seq()
+    xa, _ = A.generalized_steps(x[:4].contiguous(), spec.seq, m, betas, eta=0.0, keep="last")
+    m.reset_index_seq()
+    xb, _ = A.generalized_steps(x[4:].contiguous(), spec.seq, m, betas, eta=0.0, keep="last")
+    assert torch.equal(torch.cat([xa[-1], xb[-1]]), xs[-1])
+    # the dp4a twin gives the same images bit-for-bit
+    ops.DEFAULT_CONV_IMPL = ops.CONV_SIMT
+    try:
+        m.reset_index_seq()
+        xs2, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, keep="last", use_graph=False)
+    finally:
+        ops.DEFAULT_CONV_IMPL = ops.CONV_TCGEN05
+    assert torch.equal(xs2[-1], xs[-1])
