@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActQuantParams p) {
             int g0 = c / cpg, g1 = (c + 1) / cpg, g2 = (c + 2) / cpg, g3 = (c + 3) / cpg;
             float m0 = __shfl_sync(0xffffffffu, mean, g0), r0_ = __shfl_sync(0xffffffffu, rstd, g0);
             float m1 = m0, r1_ = r0_, m2 = m0, r2_ = r0_, m3 = m0, r3_ = r0_;
-            if (cpg < 4) {   // warp-uniform branch (cpg is a kernel-wide constant)
+            if (cpg & 3) {   // a float4 may straddle groups; warp-uniform branch (cpg is kernel-wide)
               m1 = __shfl_sync(0xffffffffu, mean, g1); r1_ = __shfl_sync(0xffffffffu, rstd, g1);
               m2 = __shfl_sync(0xffffffffu, mean, g2); r2_ = __shfl_sync(0xffffffffu, rstd, g2);
               m3 = __shfl_sync(0xffffffffu, mean, g3); r3_ = __shfl_sync(0xffffffffu, rstd, g3);
@@ -256,7 +256,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int 
       a3 += v.w; q3 += (double)v.w * v.w;
     }
     const int c = q << 2;
-    if (cpg >= 4) {
+    if ((cpg & 3) == 0) {   // all four channels of the quad are in one group
       int g = c / cpg;
       atomicAdd(&s_sum[g], (a0 + a1) + (a2 + a3));
       atomicAdd(&s_sq[g], (q0 + q1) + (q2 + q3));
@@ -633,6 +633,11 @@ int attndm_act_quant(const float* x, int B, int H, int W, int C, const float* sc
                      const float* gn_beta, float gn_eps, int8_t* codes, int32_t* rowsum,
                      int rows_layout, float* y_f32, void* stream) {
   ATTNDM_CHECK_ARG(codes || y_f32, "act_quant: no output requested");
+  if (a_bit == 0) {   // quantizer off: y = pre_op(x) (the calibration branch needs the un-quantized producer)
+    ATTNDM_CHECK_ARG(y_f32 && !codes, "act_quant: a_bit == 0 only produces y_f32");
+    return act_quant_impl(x, B, H, W, C, nullptr, nullptr, 0, pre_op, gn_stats, gn_gamma, gn_beta, gn_eps, nullptr,
+                          nullptr, ATTNDM_ROWS_PLAIN, y_f32, false, (cudaStream_t)stream);
+  }
   return act_quant_impl(x, B, H, W, C, scale, zp, a_bit, pre_op, gn_stats, gn_gamma, gn_beta, gn_eps, codes,
                         rowsum, rows_layout, y_f32, true, (cudaStream_t)stream);
 }

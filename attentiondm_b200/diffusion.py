@@ -142,10 +142,11 @@ class UpBlock(_TimeBlock):
         if actual != expected:
             if not hasattr(self, 'channel_proj'):             # lazily created, fresh RNG (:238-241)
                 self.channel_proj = nn.Conv2d(actual, expected, kernel_size=1, stride=1, padding=0).to(x.device)
-            # un-quantized fp32 1x1 conv == a plain GEMM over the NHWC rows (library call)
-            B, H, W, _ = combined.shape
-            w = self.channel_proj.weight.detach().view(expected, actual)
-            combined = F.linear(combined.view(-1, actual), w, self.channel_proj.bias.detach()).view(B, H, W, expected)
+            # un-quantized fp32 1x1 conv.  Our own fp32 kernel rather than a cuBLAS GEMM: its per-output
+            # summation order does not depend on the batch size, which keeps every sample's result
+            # independent of how the batch is sharded over GPUs.
+            w = self.channel_proj.weight.detach().view(expected, 1, actual)
+            combined = ops.conv_f32(combined, w.contiguous(), self.channel_proj.bias.detach())
         return self._tail(combined, time_emb)
 
     def forward(self, x, skip_x, time_emb=None):
@@ -237,9 +238,12 @@ class Model(nn.Module):
     def forward_nhwc(self, x, t):
         """x NHWC [B,H,W,C]; t float [B].  models/diffusion.py:347-382."""
         B = x.shape[0]
-        t_emb = ops.timestep_embedding(t, self.config.model.time_embed_dim)
-        t_emb = self.time_embed(t_emb)                     # two un-quantized Linears (library GEMM)
-        t_emb = t_emb.view(B, 1, 1, -1).contiguous()
+        t_emb = ops.timestep_embedding(t, self.config.model.time_embed_dim).view(B, 1, 1, -1)
+        # the two un-quantized Linears (models/diffusion.py:273-277) as batch-invariant fp32 1x1 convs
+        l0, l2 = self.time_embed[0], self.time_embed[2]
+        t_emb = ops.conv_f32(t_emb, l0.weight.detach().unsqueeze(1).contiguous(), l0.bias.detach())
+        t_emb = ops.silu(t_emb)
+        t_emb = ops.conv_f32(t_emb, l2.weight.detach().unsqueeze(1).contiguous(), l2.bias.detach())
         h = self.init_conv.forward_fused(x)
         skips = [h]
         for layer in self.down_blocks:

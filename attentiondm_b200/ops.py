@@ -218,6 +218,17 @@ def attention(q, k, v, scale: float, heads: int = 1, softmax_scale: float = 1.0,
     return out
 
 
+def silu(x: torch.Tensor) -> torch.Tensor:
+    """x / (1 + exp(-x)) through the act_quant kernel's SiLU producer with the quantizer off."""
+    _chk(x, "silu input")
+    x4 = x if x.dim() == 4 else x.reshape(1, 1, -1, x.shape[-1])
+    B, H, W, Cc = x4.shape
+    y = torch.empty_like(x4)
+    call("attndm_act_quant", ptr(x4), B, H, W, Cc, None, None, 0, PRE_SILU, None, None, None, 0.0, None, None,
+         ROWS_PLAIN, ptr(y), stream())
+    return y.view(x.shape)
+
+
 def scale_add(a, x, gamma):
     out = torch.empty_like(x)
     call("attndm_scale_add", ptr(a), ptr(x), ptr(gamma), ptr(out), x.numel(), stream())

@@ -384,7 +384,7 @@ class QConv2d(QModule):
             if pre == ops.PRE_GN_SILU:
                 xa = ops.gn_silu(x, gn)
             elif pre == ops.PRE_SILU:
-                xa = F.silu(x)           # [B,1,1,1024] time-embedding vector only
+                xa = ops.silu(x)
             else:
                 xa = x
             y = self._calibrate_step(xa)

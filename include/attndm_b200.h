@@ -65,6 +65,7 @@ int attndm_device_supported(void);
  *   code = clamp(rne(scale[c]*v - zp[c]), -2^(a-1), 2^(a-1)-1)
  *   y    = (code + zp[c]) / scale[c]
  * Outputs (any may be NULL): codes/rowsum in `rows_layout`, y_f32 NHWC.
+ * a_bit == 0 switches the quantizer off: y_f32 = pre_op(x), scale/zp ignored.
  * gn_stats: per (b, group) {sum, sumsq} as double[B*32*2] from attndm_gn_stats. */
 int attndm_act_quant(const float* x, int B, int H, int W, int C,
                      const float* scale, const float* zp, int a_bit,

@@ -114,7 +114,7 @@ def state_digest(sd: Dict[str, torch.Tensor]) -> str:
     return h.hexdigest()
 
 
-def tiny_spec(T=4, bitwidth=8, ch=32, ch_mult=(1, 2), num_res_blocks=1, image_size=8, channels=3):
+def tiny_spec(T=4, bitwidth=8, ch=32, ch_mult=(1, 2), num_res_blocks=1, image_size=16, channels=3):
     seq = tuple(range(0, 1000, 1000 // T))
     return R.UNetSpec(ch=ch, ch_mult=tuple(ch_mult), num_res_blocks=num_res_blocks, channels=channels,
                       image_size=image_size, bitwidth=bitwidth, timesteps=T, seq=seq)

@@ -82,7 +82,8 @@ def test_qconv_module_quantizer_and_index_wrap(golden):
         _, y, _ = q.quantize_activation_codes(T(g[k + "_x"]).to(DEV))
         want = T(g[k + "_y"][0])
         assert rel_l2(y, want) < 1e-3
-        assert (y.cpu() != want).float().mean() < 0.02
+        # a 1-ulp scale difference moves every element of that channel by an ulp; real code flips are rare
+        assert (~torch.isclose(y.cpu(), want, rtol=1e-5, atol=1e-6)).float().mean() < 0.02
 
 
 # ---------------------------------------------------------------------------
@@ -307,7 +308,8 @@ def test_qconv_falls_back_to_f32_when_not_integer_exact():
 def test_groupnorm_silu_quant_fused():
     from attentiondm_b200 import ops
     g = torch.Generator().manual_seed(5)
-    for (B, H, W, C) in [(2, 8, 8, 32), (3, 4, 4, 64), (2, 16, 16, 128), (2, 1, 1, 256), (1, 3, 5, 96), (2, 2, 2, 768)]:
+    for (B, H, W, C) in [(2, 8, 8, 32), (3, 4, 4, 64), (2, 16, 16, 128), (2, 1, 1, 256), (1, 3, 5, 96), (2, 2, 2, 768),
+                         (2, 1, 1, 192), (2, 3, 3, 160)]:   # 192/160: 6 / 5 channels per group, quads straddle groups
         x = torch.randn(B, C, H, W, generator=g) * 2 + 0.5
         gamma = 1 + 0.2 * torch.randn(C, generator=g)
         beta = 0.2 * torch.randn(C, generator=g)
@@ -379,7 +381,7 @@ def test_unet_glue_ops():
         assert torch.equal(ops.to_nchw(got).cpu(), want), (h, w, hs, ws)
     t = torch.tensor([0.0, 1.0, 10.0, 500.0, 990.0])
     emb = ops.timestep_embedding(t.to(DEV), 256)
-    assert (emb.cpu() - R.timestep_embedding(t, 256)).abs().max() < 1e-4
+    assert (emb.cpu() - R.timestep_embedding(t, 256)).abs().max() < 5e-4   # |t*f| ~ 1e3: one ulp of f moves sin by ~1e-4
     a, b = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
     gam = torch.tensor([0.37])
     assert torch.equal(ops.scale_add(a.to(DEV), b.to(DEV), gam.to(DEV)).cpu(), gam * a + b)
@@ -451,13 +453,19 @@ def test_tiny_unet_vs_reference_fixture(golden, name, bw, alpha, gain, first, im
         for n, q in m.qconvs():
             q.groups_range.data.copy_(T(g["gr/" + n]))
             q.invalidate_cache(weights=False)
-        m.reset_index_seq()
-        eps_c.clear()
-        xs, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, use_graph=False)
         hook.remove()
+        # step level, teacher-forced x_t (SURVEY.md section 8c acceptance): eps of every step within 1e-3
+        xs_gold = T(g["xs"])
+        rseq = list(reversed(spec.seq))
         for t in range(Tn):
-            assert rel_l2(eps_c[t], T(g["eps"][t])) < 1e-3, ("eps", t)
-        assert rel_l2(torch.stack([t.cpu() for t in xs]), T(g["xs"])) < 1e-3
+            m.reset_index_seq(t)
+            tt = torch.full((x.shape[0],), float(rseq[t]), device=DEV)
+            eps = m(xs_gold[t].to(DEV), tt)
+            assert rel_l2(eps, T(g["eps"][t])) < 1e-3, ("eps", t)
+        # run level, free running: every x_t of the trajectory within 1e-3
+        m.reset_index_seq()
+        xs, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, use_graph=False)
+        assert rel_l2(torch.stack([t.cpu() for t in xs]), xs_gold) < 1e-3
         # --- same thing through the CUDA-graph engine: identical to the eager kernels ---
         m.reset_index_seq()
         xs_g, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, use_graph=True)
