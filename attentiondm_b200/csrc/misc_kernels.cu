@@ -130,14 +130,18 @@ __global__ void upsample_concat_kernel(const float* __restrict__ x, int B, int H
 }
 
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, float* __restrict__ emb) {
+  // The reference evaluates exp / sin / cos in fp32 on fp32 arguments.  |t * f| reaches ~1e3, so one
+  // ulp of f moves sin/cos by ~1e-4 -- enough to flip 8-bit codes in the time MLP.  We therefore
+  // evaluate each transcendental in double on the SAME fp32 argument and round once: that is the
+  // correctly rounded fp32 result, which is what an accurate fp32 libm (the CPU reference) returns.
   const int half = dim / 2;
   const float coef = -(float)(log(10000.0) / (double)(half - 1));
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
     int b = i / half, e = i - b * half;
-    float f = expf(__fmul_rn((float)e, coef));
+    float f = (float)exp((double)__fmul_rn((float)e, coef));
     float a = __fmul_rn(t[b], f);
-    emb[(long long)b * dim + e] = sinf(a);
-    emb[(long long)b * dim + half + e] = cosf(a);
+    emb[(long long)b * dim + e] = (float)sin((double)a);
+    emb[(long long)b * dim + half + e] = (float)cos((double)a);
     if ((dim & 1) && e == 0) emb[(long long)b * dim + dim - 1] = 0.f;
   }
 }

@@ -44,7 +44,7 @@ class AsymmetricQuantFunction(Function):
 
     @staticmethod
     def forward(ctx, x, k, x_min=None, x_max=None):
-        if x_min is None or x_max is None or (sum(x_min == x_max) == 1 and x_min.numel() == 1):
+        if x_min is None or x_max is None or (x_min.numel() == 1 and bool((x_min == x_max).all())):
             x_min, x_max = x.min(), x.max()
         scale, zero_point = asymmetric_linear_quantization_params(k, x_min, x_max)
         q = linear_quantize(x, scale, zero_point)

@@ -37,11 +37,14 @@ with torch.no_grad():
         _ffi.call = timed
         ops.call = timed
     w0 = torch.cuda.Event(enable_timing=True); w1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
     w0.record()
     for _ in range(a.steps):
         m(x, t)
     w1.record()
     torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
 print(f"eager wall per forward: {w0.elapsed_time(w1)/a.steps:.3f} ms, C-ABI calls per forward: {len(rec)//max(1,a.steps)}")
 agg = collections.defaultdict(lambda: [0, 0.0])
 for name, ints, e0, e1 in rec:
