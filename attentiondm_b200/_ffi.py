@@ -35,7 +35,7 @@ SIGNATURES = {
     "attndm_calib_mix": [vp, i64, i32, i32, vp, vp, i32, vp, vp, f32, vp],
     "attndm_kth_value": [vp, i64, i64, vp, vp, vp],
     "attndm_weight_clamp_pack": [vp, i32, i32, i32, i32, vp, vp, vp, vp],
-    "attndm_weight_to_i8": [vp, i32, i32, i32, vp, vp, i32, vp, i32, vp, vp, vp],
+    "attndm_weight_to_i8": [vp, i32, i32, i32, vp, vp, i32, vp, i32, vp, vp, vp, vp],
     "attndm_qconv_i8": [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "attndm_conv_f32": [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp],
     "attndm_attention": [vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, f32, AttnQuant, AttnQuant, vp],

@@ -57,19 +57,19 @@ __global__ void __launch_bounds__(256) qconv_i8_simt_kernel(ConvI8Params p) {
   }
   // epilogue
   const int zp = *p.act_zp;
-  const long long ktot = (long long)p.taps * p.C;
+  const int ktot = p.taps * p.C;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long long row = m0 + ty * 4 + i;
     long long pix;
     int b;
     if (!conv_row_to_pixel(p, row, pix, b)) continue;
-    const long long cs = conv_window_rowsum(p, row) + (long long)zp * ktot;
+    const int cs = (int)conv_window_rowsum(p, row) + zp * ktot;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int o = n0 + tx * 4 + j;
       if (o >= p.O) continue;
-      float v = conv_i8_finish(p, acc[i][j], zp, cs, o);
+      float v = conv_i8_value(acc[i][j], zp * p.wsum[o], p.w_zp[o], cs, p.mult[o], p.bias ? p.bias[o] : 0.f);
       p.out[pix * p.O + o] = conv_epilogue_add(p.residual, p.temb, v, pix, b, o, p.O);
     }
   }

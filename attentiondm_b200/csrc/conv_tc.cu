@@ -84,18 +84,28 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                           // layout type SWIZZLE_128B
   return d;
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- kernel -------------------------------------------------------------------
+struct __align__(16) ColConst {
+  int A;        // zp * wsum[o]
+  int B;        // w_zp[o]
+  float m;      // 1 / (act_scale * w_scale[o])
+  float bias;
+};
+
 struct TcGeom {
   int BN;            // outputs per tile (multiple of 16, <= 256)
   int stages;
@@ -112,6 +122,9 @@ qconv_i8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ ColConst colc[256];            // per-output-column epilogue constants
+  __shared__ long long row_pix[4][32];      // output pixel of each tile row (-1 = not an output)
+  __shared__ int row_b[4][32];              // its sample index
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024-B alignment
@@ -185,42 +198,54 @@ qconv_i8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tcgen05_commit(smem_u32(&tmem_full_bar));      // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> fused scale/bias/residual/temb -> NHWC fp32 =====
+    // ===== epilogue: TMEM -> registers -> exact integer finish -> smem transpose -> coalesced NHWC rows =====
     const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
+    const int zp = *p.act_zp;
+    // (a) while the main loop runs: stage the per-column constants and the per-row geometry
+    for (int c = (warp - 2) * 32 + lane; c < g.BN; c += 128) {
+      const int o = n0 + c;
+      ColConst cc = {0, 0, 0.f, 0.f};
+      if (o < p.O) {
+        cc.A = zp * p.wsum[o];
+        cc.B = p.w_zp[o];
+        cc.m = p.mult[o];
+        cc.bias = p.bias ? p.bias[o] : 0.f;
+      }
+      colc[c] = cc;
+    }
     const long long row = m0 + quarter * 32 + lane;
     long long pix = 0;
     int b = 0;
     const bool valid = conv_row_to_pixel(p, row, pix, b);
-    const int zp = *p.act_zp;
-    long long cs = 0;
-    if (valid) cs = conv_window_rowsum(p, row) + (long long)zp * ((long long)p.taps * p.C);
+    int cs = 0;
+    if (valid) cs = (int)conv_window_rowsum(p, row) + zp * (p.taps * p.C);
+    row_pix[quarter][lane] = valid ? pix : -1;
+    row_b[quarter][lane] = b;
+    asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps only
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tcgen05_fence_after();
-    const bool vec_ok = (p.O & 3) == 0;
-    for (int c0 = 0; c0 < g.BN; c0 += 16) {
-      uint32_t v[16];
-      __syncwarp();                                   // tcgen05.ld is .sync.aligned: whole warp, converged
-      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+    // every MMA has retired, so the pipeline buffers are free: reuse them as the transpose stage
+    float* stg = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw))) + quarter * (32 * 33);
+    for (int c0 = 0; c0 < g.BN; c0 += 32) {
+      uint32_t v[32];
+      __syncwarp();                                   // tcgen05.ld is .sync.aligned; also fences stg reuse
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      const int o0 = n0 + c0;
-      if (valid && o0 < p.O) {
-        float* orow = p.out + pix * p.O;
-        if (vec_ok && o0 + 16 <= p.O) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 r;
-            r.x = conv_epilogue_add(p.residual, p.temb, conv_i8_finish(p, (int)v[j + 0], zp, cs, o0 + j + 0), pix, b, o0 + j + 0, p.O);
-            r.y = conv_epilogue_add(p.residual, p.temb, conv_i8_finish(p, (int)v[j + 1], zp, cs, o0 + j + 1), pix, b, o0 + j + 1, p.O);
-            r.z = conv_epilogue_add(p.residual, p.temb, conv_i8_finish(p, (int)v[j + 2], zp, cs, o0 + j + 2), pix, b, o0 + j + 2, p.O);
-            r.w = conv_epilogue_add(p.residual, p.temb, conv_i8_finish(p, (int)v[j + 3], zp, cs, o0 + j + 3), pix, b, o0 + j + 3, p.O);
-            *reinterpret_cast<float4*>(orow + o0 + j) = r;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int o = o0 + j;
-            if (o < p.O) orow[o] = conv_epilogue_add(p.residual, p.temb, conv_i8_finish(p, (int)v[j], zp, cs, o), pix, b, o, p.O);
-          }
+      for (int j = 0; j < 32; ++j) {
+        const ColConst cc = colc[(c0 + j) & 255];
+        stg[lane * 33 + j] = conv_i8_value((int)v[j], cc.A, cc.B, cs, cc.m, cc.bias);
+      }
+      __syncwarp();
+      const int o = n0 + c0 + lane;                   // lane <-> output channel, loop over the 32 rows
+      if (c0 + lane < g.BN && o < p.O) {
+        for (int r = 0; r < 32; ++r) {
+          const long long pr = row_pix[quarter][r];
+          if (pr < 0) continue;                       // warp-uniform
+          float val = stg[r * 33 + lane];
+          if (p.residual) val = __fadd_rn(val, p.residual[pr * p.O + o]);
+          if (p.temb) val = __fadd_rn(val, p.temb[(long long)row_b[quarter][r] * p.O + o]);
+          p.out[pr * p.O + o] = val;
         }
       }
     }
@@ -273,13 +298,16 @@ int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st) {
   ATTNDM_CHECK_ARG(p.rows + 2LL * p.Wp + 2 + TC_BM < 0x7fffffffLL, "qconv_i8_tc: too many rows for 32-bit TMA coordinates");
   TcGeom g;
   g.BN = p.O <= 256 ? round_up(p.O, 16) : 256;
+  // small problems: split N over more CTAs (idle SMs are free; the epilogue is serial per CTA)
+  const long long mtiles = (p.rows + TC_BM - 1) / TC_BM;
+  while (g.BN > 32 && (g.BN / 2) % 16 == 0 && mtiles * cdiv(p.O, g.BN) < 120) g.BN /= 2;
   g.stage_bytes = TC_BM * TC_BK + g.BN * TC_BK;
   g.stages = TC_SMEM_BUDGET / g.stage_bytes;
   if (g.stages > TC_MAX_STAGES) g.stages = TC_MAX_STAGES;
   if (g.stages < 2) g.stages = 2;
   g.ncb = cdiv(p.Cp, TC_BK);
   g.tmem_cols = 32;
-  while (g.tmem_cols < g.BN) g.tmem_cols <<= 1;
+  while (g.tmem_cols < g.BN) g.tmem_cols <<= 1;      // power of two >= 32, so 32-column loads stay in bounds
   CUtensorMap tmA, tmB;
   int rc = make_map_2d(&tmA, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, TC_BM);
   if (rc) return rc;

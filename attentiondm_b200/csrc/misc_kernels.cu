@@ -98,34 +98,36 @@ __global__ void maxpool2_kernel(const float* __restrict__ x, int B, int H, int W
   }
 }
 
+template <int V>   // V = 4: float4 over channels (Cx % 4 == 0 && Cs % 4 == 0), V = 1: scalar
 __global__ void upsample_concat_kernel(const float* __restrict__ x, int B, int H, int W, int Cx,
                                        const float* __restrict__ skip, int Hs, int Ws, int Cs,
                                        float* __restrict__ out) {
-  const int Ct = Cx + Cs;
-  const long long n = (long long)B * Hs * Ws * Ct;
+  const int Ct = Cx + Cs, Cv = Ct / V;
+  const long long n = (long long)B * Hs * Ws * Cv;
   // nearest x2 (src = dst/2) followed, when sizes differ, by nearest resize 2H x 2W -> Hs x Ws
   // (src = min(floor(dst * in/out), in-1) in fp32, as ATen's nearest kernel computes it)
   const bool same = (2 * H == Hs) && (2 * W == Ws);
   const float sh = (float)(2 * H) / (float)Hs, sw = (float)(2 * W) / (float)Ws;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % Ct);
-    long long t = i / Ct;
-    int ws = (int)(t % Ws);
+    const int c = (int)(i % Cv) * V;
+    long long t = i / Cv;
+    const int ws = (int)(t % Ws);
     t /= Ws;
-    int hs = (int)(t % Hs);
-    int b = (int)(t / Hs);
-    float v;
+    const int hs = (int)(t % Hs);
+    const int b = (int)(t / Hs);
+    const float* src;
     if (c < Cx) {
       int uh = hs, uw = ws;
       if (!same) {
         uh = min((int)floorf(__fmul_rn((float)hs, sh)), 2 * H - 1);
         uw = min((int)floorf(__fmul_rn((float)ws, sw)), 2 * W - 1);
       }
-      v = x[(((long long)b * H + (uh >> 1)) * W + (uw >> 1)) * Cx + c];
+      src = x + (((long long)b * H + (uh >> 1)) * W + (uw >> 1)) * Cx + c;
     } else {
-      v = skip[(((long long)b * Hs + hs) * Ws + ws) * Cs + (c - Cx)];
+      src = skip + (((long long)b * Hs + hs) * Ws + ws) * Cs + (c - Cx);
     }
-    out[i] = v;
+    if (V == 4) *reinterpret_cast<float4*>(out + i * 4) = *reinterpret_cast<const float4*>(src);
+    else out[i] = *src;
   }
 }
 
@@ -179,7 +181,7 @@ __global__ void stage_advance_kernel(int* step, int T) {
 
 static inline int ew_blocks(long long n) {
   long long b = (n + 255) / 256;
-  long long cap = (long long)kNumSMs * 16;
+  long long cap = (long long)kNumSMs * 32;
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
@@ -230,7 +232,10 @@ int attndm_upsample_concat(const float* x, int B, int H, int W, int Cx, const fl
   ATTNDM_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0 && Cx > 0 && Hs > 0 && Ws > 0 && Cs >= 0, "upsample_concat: bad args");
   ATTNDM_CHECK_ARG(Cs == 0 || skip, "upsample_concat: skip is NULL");
   long long n = (long long)B * Hs * Ws * (Cx + Cs);
-  upsample_concat_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, Cx, skip, Hs, Ws, Cs, out);
+  if ((Cx & 3) == 0 && (Cs & 3) == 0)
+    upsample_concat_kernel<4><<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, Cx, skip, Hs, Ws, Cs, out);
+  else
+    upsample_concat_kernel<1><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, Cx, skip, Hs, Ws, Cs, out);
   ATTNDM_CUDA_LAUNCH_CHECK("upsample_concat");
   return ATTNDM_OK;
 }

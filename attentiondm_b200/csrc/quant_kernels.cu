@@ -183,11 +183,145 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActQuantParams p) {
   }
 }
 
+// Fast path for the shapes that carry the traffic (C = 128 or 256, i.e. NQ = 1 or 2 float4 per lane):
+// per-lane quantizer / GroupNorm constants live in registers across rows, the row index is advanced
+// incrementally (no 64-bit division per row) and the next row's load is issued before the current row
+// is processed (two 512-B requests in flight per warp).
+template <int PRE, bool QUANT, int NQ>
+__global__ void __launch_bounds__(256) act_quant_fast_kernel(ActQuantParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long r0 = warp * p.rows_per_warp;
+  long long r1 = r0 + p.rows_per_warp;
+  if (r1 > p.rows) r1 = p.rows;
+  if (r0 >= r1) return;
+  const int Hp = p.halo ? p.H + 2 : p.H, Wp = p.halo ? p.W + 2 : p.W;
+  const int cpg = p.C / kGnGroups;
+  const double inv_n = (PRE == ATTNDM_PRE_GN_SILU) ? 1.0 / ((double)p.H * p.W * cpg) : 0.0;
+  const long long per = (long long)Hp * Wp;
+  int b = (int)(r0 / per);
+  int rem = (int)(r0 - (long long)b * per);
+  int hp = rem / Wp, wp = rem - hp * Wp;
+  float4 s4[NQ], z4[NQ], g4[NQ], be4[NQ], ga[NQ], gb[NQ], pad[NQ];
+  int grp[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int c = (i * 32 + lane) << 2;
+    s4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (QUANT) {
+      s4[i] = *reinterpret_cast<const float4*>(p.scale + c);
+      z4[i] = *reinterpret_cast<const float4*>(p.zp + c);
+    }
+    pad[i].x = fminf(fmaxf(-z4[i].x, p.qlo), p.qhi);
+    pad[i].y = fminf(fmaxf(-z4[i].y, p.qlo), p.qhi);
+    pad[i].z = fminf(fmaxf(-z4[i].z, p.qlo), p.qhi);
+    pad[i].w = fminf(fmaxf(-z4[i].w, p.qlo), p.qhi);
+    if (PRE == ATTNDM_PRE_GN_SILU) {
+      g4[i] = *reinterpret_cast<const float4*>(p.gamma + c);
+      be4[i] = *reinterpret_cast<const float4*>(p.beta + c);
+      grp[i] = c / cpg;                       // cpg % 4 == 0 on this path: one group per float4
+    }
+    ga[i] = gb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int cur_b = -1;
+  auto interior_of = [&](int hh, int ww) { return !p.halo || (hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W); };
+  auto pix_of = [&](int bb, int hh, int ww) {
+    return p.halo ? ((long long)bb * p.H + (hh - 1)) * p.W + (ww - 1) : ((long long)bb * p.H + hh) * p.W + ww;
+  };
+  float4 cur[NQ], nxt[NQ];
+  bool cur_in = interior_of(hp, wp);
+  long long cur_pix = cur_in ? pix_of(b, hp, wp) : 0;
+  if (cur_in) {
+#pragma unroll
+    for (int i = 0; i < NQ; ++i)
+      cur[i] = ldg_stream(reinterpret_cast<const float4*>(p.x + cur_pix * p.C + ((i * 32 + lane) << 2)));
+  }
+  for (long long r = r0; r < r1; ++r) {
+    // coordinates of the next row + prefetch
+    int nb = b, nhp = hp, nwp = wp + 1;
+    if (nwp == Wp) { nwp = 0; if (++nhp == Hp) { nhp = 0; ++nb; } }
+    const bool nxt_in = (r + 1 < r1) && interior_of(nhp, nwp);
+    const long long nxt_pix = nxt_in ? pix_of(nb, nhp, nwp) : 0;
+    if (nxt_in) {
+#pragma unroll
+      for (int i = 0; i < NQ; ++i)
+        nxt[i] = ldg_stream(reinterpret_cast<const float4*>(p.x + nxt_pix * p.C + ((i * 32 + lane) << 2)));
+    }
+    if (PRE == ATTNDM_PRE_GN_SILU && cur_in && b != cur_b) {
+      float mean, rstd;
+      gn_refresh(p.gn_stats, b, lane, inv_n, p.eps, mean, rstd);
+      cur_b = b;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const float m = __shfl_sync(0xffffffffu, mean, grp[i]), rs = __shfl_sync(0xffffffffu, rstd, grp[i]);
+        ga[i].x = rs * g4[i].x; gb[i].x = fmaf(-m, ga[i].x, be4[i].x);
+        ga[i].y = rs * g4[i].y; gb[i].y = fmaf(-m, ga[i].y, be4[i].y);
+        ga[i].z = rs * g4[i].z; gb[i].z = fmaf(-m, ga[i].z, be4[i].z);
+        ga[i].w = rs * g4[i].w; gb[i].w = fmaf(-m, ga[i].w, be4[i].w);
+      }
+    }
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const int c = (i * 32 + lane) << 2;
+      float4 cd;
+      if (cur_in) {
+        float4 v = cur[i];
+        v.x = pre_op<PRE>(v.x, ga[i].x, gb[i].x);
+        v.y = pre_op<PRE>(v.y, ga[i].y, gb[i].y);
+        v.z = pre_op<PRE>(v.z, ga[i].z, gb[i].z);
+        v.w = pre_op<PRE>(v.w, ga[i].w, gb[i].w);
+        if (QUANT) {
+          cd.x = quant_code(v.x, s4[i].x, z4[i].x, p.qlo, p.qhi);
+          cd.y = quant_code(v.y, s4[i].y, z4[i].y, p.qlo, p.qhi);
+          cd.z = quant_code(v.z, s4[i].z, z4[i].z, p.qlo, p.qhi);
+          cd.w = quant_code(v.w, s4[i].w, z4[i].w, p.qlo, p.qhi);
+          if (p.y) {
+            float4 o;
+            o.x = dequant(cd.x, s4[i].x, z4[i].x);
+            o.y = dequant(cd.y, s4[i].y, z4[i].y);
+            o.z = dequant(cd.z, s4[i].z, z4[i].z);
+            o.w = dequant(cd.w, s4[i].w, z4[i].w);
+            *reinterpret_cast<float4*>(p.y + cur_pix * p.C + c) = o;
+          }
+        } else {
+          if (p.y) *reinterpret_cast<float4*>(p.y + cur_pix * p.C + c) = v;
+          cd = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        cd = pad[i];
+      }
+      if (QUANT && p.codes) {
+        const int ix = (int)cd.x, iy = (int)cd.y, iz = (int)cd.z, iw = (int)cd.w;
+        acc += ix + iy + iz + iw;
+        *reinterpret_cast<char4*>(p.codes + r * p.Cp + c) =
+            make_char4((signed char)ix, (signed char)iy, (signed char)iz, (signed char)iw);
+      }
+    }
+    if (QUANT && p.rowsum) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) p.rowsum[r] = acc;
+    }
+    b = nb; hp = nhp; wp = nwp;
+    cur_in = nxt_in;
+    cur_pix = nxt_pix;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) cur[i] = nxt[i];
+  }
+}
+
 template <int PRE, bool QUANT>
 static void launch_act_quant(const ActQuantParams& p, int blocks, cudaStream_t st) {
   // the GN shuffle in the scalar path needs all lanes converged per channel step;
   // it is only used for C % 4 != 0 (the 3-channel latent), which never has a GN.
-  if ((p.C & 3) == 0)
+  const bool gn_ok = (PRE != ATTNDM_PRE_GN_SILU) || ((p.C / kGnGroups) % 4 == 0);
+  if (p.C == 128 && gn_ok)
+    act_quant_fast_kernel<PRE, QUANT, 1><<<blocks, 256, 0, st>>>(p);
+  else if (p.C == 256 && gn_ok)
+    act_quant_fast_kernel<PRE, QUANT, 2><<<blocks, 256, 0, st>>>(p);
+  else if ((p.C & 3) == 0)
     act_quant_kernel<PRE, QUANT, true><<<blocks, 256, 0, st>>>(p);
   else
     act_quant_kernel<PRE, QUANT, false><<<blocks, 256, 0, st>>>(p);
@@ -583,40 +717,80 @@ __global__ void weight_clamp_pack_kernel(const float* __restrict__ w, int O, int
 
 __global__ void weight_to_i8_kernel(const float* __restrict__ w_eff, int O, int C, int taps,
                                     const float* __restrict__ ws, const float* __restrict__ wz, int w_bit,
-                                    int8_t* __restrict__ qw, int Cp, int32_t* __restrict__ wsum, int* on_grid) {
+                                    int8_t* __restrict__ qw, int Cp, int32_t* __restrict__ wsum,
+                                    int32_t* __restrict__ wzp_out, int* on_grid) {
+  // One block per output channel.  Codes are only defined up to the shift (q, zp) -> (q - d, zp + d):
+  // if rounding the zero point one way pushed the code range to [-127, 128] it is slid back into the
+  // signed range instead of declaring the channel off-grid.
   const int o = blockIdx.x;
   const float s = ws[o], z = wz[o];
-  const float qlo = -(float)(1 << (w_bit - 1)), qhi = (float)((1 << (w_bit - 1)) - 1);
-  int acc = 0;
-  bool ok = isfinite(s) && s > 0.f;
+  const int qlo = -(1 << (w_bit - 1)), qhi = (1 << (w_bit - 1)) - 1;
+  bool ok = isfinite(s) && s > 0.f && isfinite(z);
   const int K = taps * Cp;
+  __shared__ int s_red[32];
+  __shared__ int s_shift;
+  int mn = 1 << 30, mx = -(1 << 30);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    int tap = i / Cp, c = i - tap * Cp;
+    if (c < C) {
+      float back = __fsub_rn(__fmul_rn(s, w_eff[((long long)o * taps + tap) * C + c]), z);
+      float qf = rintf(back);
+      // on the grid if within 1e-3 of a quantization step (the reference clamp identity perturbs
+      // on-grid weights by ~1 ulp)
+      if (!(fabsf(back - qf) <= 1e-3f) || fabsf(qf) > 1e6f) ok = false;
+      int q = ok ? (int)qf : 0;
+      mn = min(mn, q);
+      mx = max(mx, q);
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) s_red[wid] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = s_red[0]; for (int i = 1; i < nw; ++i) t = min(t, s_red[i]); s_shift = t; }
+  __syncthreads();
+  mn = s_shift;
+  __syncthreads();
+  if (lane == 0) s_red[wid] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = s_red[0];
+    for (int i = 1; i < nw; ++i) t = max(t, s_red[i]);
+    int shift = 0;
+    if (t > qhi) shift = t - qhi;          // slide down
+    else if (mn < qlo) shift = mn - qlo;   // slide up (negative shift)
+    s_shift = shift;
+    if (t - shift > qhi || mn - shift < qlo) s_shift = 1 << 20;   // range wider than the grid: off-grid
+  }
+  __syncthreads();
+  const int shift = s_shift;
+  if (shift == (1 << 20)) ok = false;
+  int acc = 0;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     int tap = i / Cp, c = i - tap * Cp;
     int q = 0;
-    if (c < C) {
-      float v = w_eff[((long long)o * taps + tap) * C + c];
-      float qf = rintf(__fsub_rn(__fmul_rn(s, v), z));
-      if (qf < qlo || qf > qhi) ok = false;
-      qf = fminf(fmaxf(qf, qlo), qhi);
-      // on the grid if within 1e-3 of a quantization step (the reference clamp
-      // identity perturbs on-grid weights by ~1 ulp)
-      float back = __fsub_rn(__fmul_rn(s, v), z);
-      if (fabsf(back - qf) > 1e-3f) ok = false;
-      q = (int)qf;
+    if (c < C && ok) {
+      float qf = rintf(__fsub_rn(__fmul_rn(s, w_eff[((long long)o * taps + tap) * C + c]), z));
+      q = (int)qf - shift;
+      q = max(qlo, min(qhi, q));
     }
     qw[(long long)o * K + i] = (int8_t)q;
     acc += q;
   }
-  __shared__ int s_acc[32];
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (lane == 0) s_red[wid] = acc;
   if (!ok) atomicAnd(on_grid, 0);
   __syncthreads();
   if (threadIdx.x == 0) {
     int t = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_acc[i];
+    for (int i = 0; i < nw; ++i) t += s_red[i];
     wsum[o] = t;
+    wzp_out[o] = (ok && shift != (1 << 20)) ? (int)z + shift : 0;
   }
 }
 
@@ -744,12 +918,13 @@ int attndm_weight_clamp_pack(const float* w, int O, int C, int KH, int KW, const
 }
 
 int attndm_weight_to_i8(const float* w_eff, int O, int C, int taps, const float* w_scale, const float* w_zp,
-                        int w_bit, int8_t* qw, int Cp, int32_t* wsum, int* on_grid, void* stream) {
-  ATTNDM_CHECK_ARG(w_eff && w_scale && w_zp && qw && wsum && on_grid, "weight_to_i8: null pointer");
+                        int w_bit, int8_t* qw, int Cp, int32_t* wsum, int32_t* w_zp_i32, int* on_grid,
+                        void* stream) {
+  ATTNDM_CHECK_ARG(w_eff && w_scale && w_zp && qw && wsum && w_zp_i32 && on_grid, "weight_to_i8: null pointer");
   ATTNDM_CHECK_ARG(Cp >= C && Cp % 16 == 0 && w_bit >= 2 && w_bit <= 8, "weight_to_i8: bad Cp / w_bit");
   set_int_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(on_grid, 1);
   weight_to_i8_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(w_eff, O, C, taps, w_scale, w_zp, w_bit, qw, Cp, wsum,
-                                                          on_grid);
+                                                          w_zp_i32, on_grid);
   ATTNDM_CUDA_LAUNCH_CHECK("weight_to_i8");
   return ATTNDM_OK;
 }

@@ -238,6 +238,16 @@ class Model(nn.Module):
     def forward_nhwc(self, x, t):
         """x NHWC [B,H,W,C]; t float [B].  models/diffusion.py:347-382."""
         B = x.shape[0]
+        if not hasattr(self, "_n_gn"):
+            self._n_gn = sum(1 for mm in self.modules() if isinstance(mm, nn.GroupNorm))
+        ops.gn_pool_begin(self._n_gn, B, x.device)
+        try:
+            return self._forward_nhwc(x, t)
+        finally:
+            ops.gn_pool_end()
+
+    def _forward_nhwc(self, x, t):
+        B = x.shape[0]
         t_emb = ops.timestep_embedding(t, self.config.model.time_embed_dim).view(B, 1, 1, -1)
         # the two un-quantized Linears (models/diffusion.py:273-277) as batch-invariant fp32 1x1 convs
         l0, l2 = self.time_embed[0], self.time_embed[2]

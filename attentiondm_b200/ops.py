@@ -60,11 +60,33 @@ class GnArgs:
     eps: float
 
 
+# One zero-filled [n, B, 32, 2] double buffer per UNet forward, handed out slice by slice, instead of
+# one memset per GroupNorm (97 of them on the CIFAR model).
+_gn_pool = None
+_gn_pool_next = 0
+
+
+def gn_pool_begin(n: int, B: int, device):
+    global _gn_pool, _gn_pool_next
+    _gn_pool = torch.zeros(n, B, GN_GROUPS, 2, dtype=torch.float64, device=device)
+    _gn_pool_next = 0
+
+
+def gn_pool_end():
+    global _gn_pool
+    _gn_pool = None
+
+
 def gn_stats(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global _gn_pool_next
     _chk(x, "gn_stats input")
     B, H, W, Cc = x.shape
     if out is None:
-        out = torch.zeros(B, GN_GROUPS, 2, dtype=torch.float64, device=x.device)
+        if _gn_pool is not None and _gn_pool_next < _gn_pool.shape[0] and _gn_pool.shape[1] == B:
+            out = _gn_pool[_gn_pool_next]
+            _gn_pool_next += 1
+        else:
+            out = torch.zeros(B, GN_GROUPS, 2, dtype=torch.float64, device=x.device)
     else:
         out.zero_()
     call("attndm_gn_stats", ptr(x), B, H, W, Cc, ptr(out), stream())
@@ -165,23 +187,31 @@ class I8Pack:
     on_grid: bool
 
 
-def weight_to_i8(w_eff: torch.Tensor, w_bit: int) -> I8Pack:
-    """Grid = AsymmetricQuantFunction's on the per-out-channel min/max of w_eff
-    (utils/quantization_utils/quant_utils.py:109-133)."""
-    O, taps, Cc = w_eff.shape
-    Cp = cp_of(Cc)
-    flat = w_eff.reshape(O, -1)
+def weight_grid(w_eff: torch.Tensor, w_bit: int):
+    """(scale[O], zero_point[O]) of AsymmetricQuantFunction's grid on the per-out-channel min/max of
+    w_eff (utils/quantization_utils/quant_utils.py:109-133)."""
+    flat = w_eff.reshape(w_eff.shape[0], -1)
     lo, hi = flat.min(1)[0], flat.max(1)[0]
     n = 2 ** w_bit - 1
     w_scale = n / (hi - lo)
     w_zp = (w_scale * lo).round() + 2 ** (w_bit - 1)
+    return w_scale, w_zp
+
+
+def weight_to_i8(w_eff: torch.Tensor, w_bit: int, grid=None) -> I8Pack:
+    """Integer codes of w_eff [O, taps, C] on `grid` (default: the grid of w_eff itself)."""
+    O, taps, Cc = w_eff.shape
+    Cp = cp_of(Cc)
+    w_eff = w_eff.contiguous()
+    w_scale, w_zp = grid if grid is not None else weight_grid(w_eff, w_bit)
     qw = torch.empty(O, taps * Cp, dtype=torch.int8, device=w_eff.device)
     wsum = torch.empty(O, dtype=torch.int32, device=w_eff.device)
     flag = torch.empty(1, dtype=torch.int32, device=w_eff.device)
+    wzp_i = torch.empty(O, dtype=torch.int32, device=w_eff.device)
     call("attndm_weight_to_i8", ptr(w_eff), O, Cc, taps, ptr(w_scale.contiguous()), ptr(w_zp.contiguous()),
-         int(w_bit), ptr(qw), Cp, ptr(wsum), ptr(flag), stream())
+         int(w_bit), ptr(qw), Cp, ptr(wsum), ptr(wzp_i), ptr(flag), stream())
     on_grid = bool(flag.item() == 1) and bool(torch.isfinite(w_scale).all().item())
-    return I8Pack(qw=qw, wsum=wsum, w_zp=w_zp.to(torch.int32), w_scale=w_scale, on_grid=on_grid)
+    return I8Pack(qw=qw, wsum=wsum, w_zp=wzp_i, w_scale=w_scale, on_grid=on_grid)
 
 
 def qconv_i8(codes, rowsum, B: int, H: int, W: int, Cc: int, pack: I8Pack, taps: int, mult, act_zp, bias,

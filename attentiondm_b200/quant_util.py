@@ -113,6 +113,7 @@ class QModule(nn.Module):
         self._tab = None            # per-step tables, see _tables()
         self._tab_key = None
         self._pack = None           # packed weights, see _packed()
+        self._pack_center = None    # centre-tap pack of a 3x3 conv (1x1 feature maps)
         self._pack_key = None
         self._state_version = 0     # bumped when a kernel writes groups_range in place
         self._staged = None         # engine-provided "current step" table row (CUDA-graph mode)
@@ -216,8 +217,15 @@ class QModule(nn.Module):
         key = (w.data_ptr(), w._version, lo.data_ptr(), lo._version, hi.data_ptr(), hi._version, self._w_bit)
         if self._pack is None or self._pack_key != key:
             w_eff = ops.weight_clamp_pack(w.detach(), lo, hi)
-            i8 = ops.weight_to_i8(w_eff, self._w_bit)
+            grid = ops.weight_grid(w_eff, self._w_bit)
+            i8 = ops.weight_to_i8(w_eff, self._w_bit, grid)
             self._pack = (w_eff, i8)
+            self._pack_center = None
+            if w_eff.shape[1] == 9:
+                # On a 1x1 feature map a 3x3/pad-1 conv only ever sees its centre tap (the other eight
+                # multiply zero padding), so it is exactly the 1x1 conv with w[:, :, 1, 1] on the same grid.
+                wc = w_eff[:, 4:5, :].contiguous()
+                self._pack_center = (wc, ops.weight_to_i8(wc, self._w_bit, grid))
             self._pack_key = key
             self._tab = None
         return self._pack
@@ -379,6 +387,10 @@ class QConv2d(QModule):
         if Cc != self.in_channels:
             raise RuntimeError(f"QConv2d: expected {self.in_channels} input channels, got {Cc}")
         w_eff, i8 = self._packed()
+        taps = self.taps
+        if taps == 9 and H == 1 and W == 1:
+            w_eff, i8 = self._pack_center
+            taps = 1
         bias = self.bias.detach() if self.bias is not None else None
         if self._calibrate:
             if pre == ops.PRE_GN_SILU:
@@ -402,9 +414,8 @@ class QConv2d(QModule):
         scale = row[lay["scale"]:]
         zp = row[lay["zp"]:]
         if use_i8:
-            codes, rowsum, _ = ops.act_quant(x, scale, zp, self._a_bit, pre, gn, want_codes=True,
-                                             halo=(self.taps == 9))
-            out = ops.qconv_i8(codes, rowsum, B, H, W, Cc, i8, self.taps, row[lay["mult"]:], row[lay["act_zp"]:],
+            codes, rowsum, _ = ops.act_quant(x, scale, zp, self._a_bit, pre, gn, want_codes=True, halo=(taps == 9))
+            out = ops.qconv_i8(codes, rowsum, B, H, W, Cc, i8, taps, row[lay["mult"]:], row[lay["act_zp"]:],
                                bias, residual, temb)
         else:
             _, _, y = ops.act_quant(x, scale, zp, self._a_bit, pre, gn, want_codes=False, want_f32=True)

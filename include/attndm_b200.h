@@ -126,11 +126,14 @@ int attndm_weight_clamp_pack(const float* w, int O, int C, int KH, int KW, const
 
 /* If every clamped weight sits on the per-out-channel w_bit grid of
  * AsymmetricQuantFunction (utils/quantization_utils/quant_utils.py:136-162)
- * emit int8 codes qw[o][tap*Cp + c], wsum[o] = sum qw, and set *on_grid = 1;
- * otherwise *on_grid = 0.  w_scale/w_zp[O] are the grid parameters. */
+ * emit int8 codes qw[o][tap*Cp + c], wsum[o] = sum qw, the integer zero points
+ * w_zp_i32[o] that go with those codes, and set *on_grid = 1; otherwise
+ * *on_grid = 0.  w_scale/w_zp[O] are the grid parameters computed by the host
+ * (codes are defined up to the shift (q, zp) -> (q-d, zp+d); the kernel slides a
+ * channel whose codes came out as [-127, 128] back into the signed range). */
 int attndm_weight_to_i8(const float* w_eff, int O, int C, int taps, const float* w_scale,
                         const float* w_zp, int w_bit, int8_t* qw, int Cp, int32_t* wsum,
-                        int* on_grid, void* stream);
+                        int32_t* w_zp_i32, int* on_grid, void* stream);
 
 /* ---- convolutions --------------------------------------------------------- */
 
