@@ -224,28 +224,68 @@ qconv_i8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps only
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tcgen05_fence_after();
-    // every MMA has retired, so the pipeline buffers are free: reuse them as the transpose stage
-    float* stg = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw))) + quarter * (32 * 33);
+    // every MMA has retired, so the pipeline buffers are free: reuse them as the transpose stage.
+    // Stage = 32 rows x 128 B per warp, 16-B chunks XOR-swizzled by (row & 7): the per-thread row writes
+    // (STS.128) and the per-row reads (LDS.128, 8 lanes per row) are both bank-conflict free.
+    float4* stg = reinterpret_cast<float4*>(smem_raw + (tiles - smem_u32(smem_raw))) + quarter * (32 * 8);
+    const bool vec_ok = (p.O & 3) == 0;
+    const int sub = lane >> 3, ch = lane & 7;          // read phase: 4 rows per instruction, 8 chunks per row
     for (int c0 = 0; c0 < g.BN; c0 += 32) {
       uint32_t v[32];
       __syncwarp();                                   // tcgen05.ld is .sync.aligned; also fences stg reuse
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const ColConst cc = colc[(c0 + j) & 255];
-        stg[lane * 33 + j] = conv_i8_value((int)v[j], cc.A, cc.B, cs, cc.m, cc.bias);
+      for (int j = 0; j < 8; ++j) {
+        float4 f;
+        ColConst cc = colc[(c0 + 4 * j + 0) & 255];
+        f.x = conv_i8_value((int)v[4 * j + 0], cc.A, cc.B, cs, cc.m, cc.bias);
+        cc = colc[(c0 + 4 * j + 1) & 255];
+        f.y = conv_i8_value((int)v[4 * j + 1], cc.A, cc.B, cs, cc.m, cc.bias);
+        cc = colc[(c0 + 4 * j + 2) & 255];
+        f.z = conv_i8_value((int)v[4 * j + 2], cc.A, cc.B, cs, cc.m, cc.bias);
+        cc = colc[(c0 + 4 * j + 3) & 255];
+        f.w = conv_i8_value((int)v[4 * j + 3], cc.A, cc.B, cs, cc.m, cc.bias);
+        stg[lane * 8 + (j ^ (lane & 7))] = f;
       }
       __syncwarp();
-      const int o = n0 + c0 + lane;                   // lane <-> output channel, loop over the 32 rows
-      if (c0 + lane < g.BN && o < p.O) {
-        for (int r = 0; r < 32; ++r) {
-          const long long pr = row_pix[quarter][r];
-          if (pr < 0) continue;                       // warp-uniform
-          float val = stg[r * 33 + lane];
-          if (p.residual) val = __fadd_rn(val, p.residual[pr * p.O + o]);
-          if (p.temb) val = __fadd_rn(val, p.temb[(long long)row_b[quarter][r] * p.O + o]);
-          p.out[pr * p.O + o] = val;
+      const int o = n0 + c0 + 4 * ch;                  // this lane's 4 output channels
+      const bool col_ok = (c0 + 4 * ch < g.BN) && (o < p.O);
+#pragma unroll
+      for (int rb = 0; rb < 32; rb += 16) {            // 4 groups of 4 rows per batch: loads first, then stores
+        long long pr[4];
+        float4 val[4], rs[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = rb + 4 * i + sub;
+          pr[i] = row_pix[quarter][r];
+          val[i] = stg[r * 8 + (ch ^ (r & 7))];
+          rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.residual && vec_ok && col_ok && pr[i] >= 0)
+            rs[i] = *reinterpret_cast<const float4*>(p.residual + pr[i] * p.O + o);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!col_ok || pr[i] < 0) continue;
+          const int r = rb + 4 * i + sub;
+          float* dst = p.out + pr[i] * p.O + o;
+          if (vec_ok) {
+            float4 t = val[i];
+            if (p.residual) { t.x = __fadd_rn(t.x, rs[i].x); t.y = __fadd_rn(t.y, rs[i].y); t.z = __fadd_rn(t.z, rs[i].z); t.w = __fadd_rn(t.w, rs[i].w); }
+            if (p.temb) {
+              const float4 te = *reinterpret_cast<const float4*>(p.temb + (long long)row_b[quarter][r] * p.O + o);
+              t.x = __fadd_rn(t.x, te.x); t.y = __fadd_rn(t.y, te.y); t.z = __fadd_rn(t.z, te.z); t.w = __fadd_rn(t.w, te.w);
+            }
+            *reinterpret_cast<float4*>(dst) = t;
+          } else {                                     // O % 4 != 0 (the 3-channel eps output): scalar tail
+            const float e[4] = {val[i].x, val[i].y, val[i].z, val[i].w};
+            for (int k = 0; k < 4 && o + k < p.O; ++k) {
+              float t = e[k];
+              if (p.residual) t = __fadd_rn(t, p.residual[pr[i] * p.O + o + k]);
+              if (p.temb) t = __fadd_rn(t, p.temb[(long long)row_b[quarter][r] * p.O + o + k]);
+              dst[k] = t;
+            }
+          }
         }
       }
     }

@@ -187,23 +187,23 @@ class I8Pack:
     on_grid: bool
 
 
-def weight_grid(w_eff: torch.Tensor, w_bit: int):
-    """(scale[O], zero_point[O]) of AsymmetricQuantFunction's grid on the per-out-channel min/max of
-    w_eff (utils/quantization_utils/quant_utils.py:109-133)."""
+def weight_grid(w_eff: torch.Tensor, w_bit: int, slack: int = 0):
+    """(scale[O], zero_point[O]) of AsymmetricQuantFunction's grid (utils/quantization_utils/
+    quant_utils.py:109-133) as recovered from the per-out-channel min/max of on-grid weights.
+    `slack` = number of grid steps by which the attained extremes fall short of the full 2^b - 1 span
+    (a channel whose original min/max tie at a rounding boundary never attains its top code)."""
     flat = w_eff.reshape(w_eff.shape[0], -1)
     lo, hi = flat.min(1)[0], flat.max(1)[0]
-    n = 2 ** w_bit - 1
+    n = 2 ** w_bit - 1 - slack
     w_scale = n / (hi - lo)
     w_zp = (w_scale * lo).round() + 2 ** (w_bit - 1)
     return w_scale, w_zp
 
 
-def weight_to_i8(w_eff: torch.Tensor, w_bit: int, grid=None) -> I8Pack:
-    """Integer codes of w_eff [O, taps, C] on `grid` (default: the grid of w_eff itself)."""
+def _weight_to_i8_on(w_eff, w_bit, grid) -> I8Pack:
     O, taps, Cc = w_eff.shape
     Cp = cp_of(Cc)
-    w_eff = w_eff.contiguous()
-    w_scale, w_zp = grid if grid is not None else weight_grid(w_eff, w_bit)
+    w_scale, w_zp = grid
     qw = torch.empty(O, taps * Cp, dtype=torch.int8, device=w_eff.device)
     wsum = torch.empty(O, dtype=torch.int32, device=w_eff.device)
     flag = torch.empty(1, dtype=torch.int32, device=w_eff.device)
@@ -212,6 +212,32 @@ def weight_to_i8(w_eff: torch.Tensor, w_bit: int, grid=None) -> I8Pack:
          int(w_bit), ptr(qw), Cp, ptr(wsum), ptr(wzp_i), ptr(flag), stream())
     on_grid = bool(flag.item() == 1) and bool(torch.isfinite(w_scale).all().item())
     return I8Pack(qw=qw, wsum=wsum, w_zp=wzp_i, w_scale=w_scale, on_grid=on_grid)
+
+
+def weight_to_i8(w_eff: torch.Tensor, w_bit: int, grid=None) -> I8Pack:
+    """Integer codes of w_eff [O, taps, C].  With grid=None the per-channel grid is recovered from the
+    weights themselves: per channel, the first span in {2^b-1, 2^b-2, 2^b-3} steps that puts every
+    weight of that channel on an integer."""
+    w_eff = w_eff.contiguous()
+    if grid is not None:
+        return _weight_to_i8_on(w_eff, w_bit, grid)
+    pack = _weight_to_i8_on(w_eff, w_bit, weight_grid(w_eff, w_bit, 0))
+    if pack.on_grid:
+        return pack
+    # rare: some channels do not attain their extreme codes -> choose the span per channel
+    O = w_eff.shape[0]
+    flat = w_eff.reshape(O, -1)
+    best_s, best_z = weight_grid(w_eff, w_bit, 0)
+    done = torch.zeros(O, dtype=torch.bool, device=w_eff.device)
+    for slack in (0, 1, 2):
+        s_k, z_k = weight_grid(w_eff, w_bit, slack)
+        back = s_k[:, None] * flat - z_k[:, None]
+        ok = ((back - back.round()).abs().amax(1) <= 1e-3) & torch.isfinite(s_k)
+        take = ok & ~done
+        best_s = torch.where(take, s_k, best_s)
+        best_z = torch.where(take, z_k, best_z)
+        done |= ok
+    return _weight_to_i8_on(w_eff, w_bit, (best_s, best_z))
 
 
 def qconv_i8(codes, rowsum, B: int, H: int, W: int, Cc: int, pack: I8Pack, taps: int, mult, act_zp, bias,

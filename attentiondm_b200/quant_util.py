@@ -217,8 +217,8 @@ class QModule(nn.Module):
         key = (w.data_ptr(), w._version, lo.data_ptr(), lo._version, hi.data_ptr(), hi._version, self._w_bit)
         if self._pack is None or self._pack_key != key:
             w_eff = ops.weight_clamp_pack(w.detach(), lo, hi)
-            grid = ops.weight_grid(w_eff, self._w_bit)
-            i8 = ops.weight_to_i8(w_eff, self._w_bit, grid)
+            i8 = ops.weight_to_i8(w_eff, self._w_bit)
+            grid = (i8.w_scale, i8.w_zp.float())     # the recovered grid (zero points as finally used)
             self._pack = (w_eff, i8)
             self._pack_center = None
             if w_eff.shape[1] == 9:
@@ -275,6 +275,13 @@ class QModule(nn.Module):
                          i8_ok=[i8.on_grid and z for z in zero_ok])
         self._tab_key = key
         return self._tab
+
+    def int8_status(self) -> dict:
+        """Why (not) the integer path: weights on the w_bit grid, per-step scale uniform over channels,
+        and 0.0 representable (the halo ring needs the code of zero)."""
+        tb = self._tables()
+        return dict(on_grid=self._pack[1].on_grid, uniform=all(tb["uniform"]), zero_ok=all(tb["zero_ok"]),
+                    forced_f32=self.force_f32)
 
     def int8_ok_all_steps(self) -> bool:
         return (not self.force_f32) and all(self._tables()["i8_ok"])

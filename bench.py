@@ -235,6 +235,10 @@ def run_ours(args):
         m.set_calibrate(False)
         m.reset_index_seq()
         n_i8 = sum(1 for _, q in m.qconvs() if q.int8_ok_all_steps())
+        if rank == 0:
+            for nm, q in m.qconvs():
+                if not q.int8_ok_all_steps():
+                    print(f"[bench] fp32 fallback layer {nm}: {q.int8_status()}", file=sys.stderr)
         eng = SamplerEngine.for_model(m, seq, betas, 0.0, (BATCH, 3, 32, 32))
         x_dev = x_host.to(dev)
 

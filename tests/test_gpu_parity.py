@@ -186,6 +186,19 @@ def test_weight_clamp_and_grid(golden):
         # codes are defined up to the per-channel zero-point shift: compare de-biased integers
         assert torch.equal(qw + pack.w_zp.cpu().float().view(-1, 1, 1, 1), qref + zref.view(-1, 1, 1, 1))
         assert torch.equal(pack.wsum.cpu().float(), qw.reshape(O, -1).sum(1))
+        # a channel with exactly symmetric extremes ties at a rounding boundary when snapped and never
+        # attains its top code; the grid must still be recovered (span 2^b - 2 steps)
+        wt = T(g[f"wc{wi}_w"]).clone()
+        b0 = wt[1].abs().max()
+        wt[1].clamp_(-b0, b0)
+        wt[1].view(-1)[0] = b0
+        wt[1].view(-1)[1] = -b0
+        st, _, _, _ = R.snap_weight(wt, bits)
+        fs = st.reshape(O, -1)
+        pk = ops.weight_to_i8(ops.weight_clamp_pack(st.to(DEV), fs.min(1)[0].to(DEV), fs.max(1)[0].to(DEV)), bits)
+        assert pk.on_grid
+        deq = (pk.qw.reshape(O, KH * KW, Cp)[:, :, :C].float() + pk.w_zp.float().view(-1, 1, 1)) / pk.w_scale.view(-1, 1, 1)
+        assert rel_l2(deq.reshape(O, KH, KW, C).permute(0, 3, 1, 2), st) < 1e-6
         # off-grid weights are detected
         assert not ops.weight_to_i8(ops.weight_clamp_pack(w, flat.min(1)[0] * 0 - 10, flat.max(1)[0] * 0 + 10), bits).on_grid
 
@@ -406,7 +419,8 @@ def test_unet_glue_ops():
     t = torch.tensor([0.0, 1.0, 10.0, 500.0, 990.0])
     emb = ops.timestep_embedding(t.to(DEV), 256)
     d = (emb.cpu() - R.timestep_embedding(t, 256)).abs()
-    assert d.max() < 2e-7 and (d > 0).float().mean() < 0.05      # correctly rounded vs the CPU's 1-ulp libm
+    # correctly rounded here vs the CPU's 1-ulp exp: a 1-ulp frequency moves sin(t*f) by up to |t*f| * 6e-8
+    assert d.max() < 1e-4 and (d > 1e-6).float().mean() < 0.05
     a, b = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
     gam = torch.tensor([0.37])
     assert torch.equal(ops.scale_add(a.to(DEV), b.to(DEV), gam.to(DEV)).cpu(), gam * a + b)
@@ -456,7 +470,7 @@ def test_ddim_loop_bit_exact_vs_reference(golden):
                                            (4, "attn_random", "sample"), (6, "uniform", "sample")])
 def test_unet_operator_parity_in_situ(bw, alpha, mode):
     import attentiondm_b200 as A
-    spec = S.tiny_spec(T=3, bitwidth=bw)
+    spec = S.tiny_spec(T=4, bitwidth=bw)          # 1000 // 4 = 250 -> exactly 4 steps (len_seq == timesteps)
     sd = S.synth_state_dict(spec, seed=5, alpha_mode=alpha)
     m = build_cuda_model(spec, sd)
     mods = dict(m.qconvs())
