@@ -28,6 +28,8 @@ class AttnQuant(C.Structure):
 SIGNATURES = {
     "attndm_act_quant": [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, f32, vp, vp, i32, vp, vp],
     "attndm_gn_stats": [vp, i32, i32, i32, i32, vp, vp],
+    "attndm_gn_act_quant_fits": [i32, i32, i32],
+    "attndm_gn_act_quant": [vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp, vp, i32, vp, vp],
     "attndm_gn_silu": [vp, i32, i32, i32, i32, vp, vp, vp, f32, vp, vp],
     "attndm_minmax_workspace_blocks": [],
     "attndm_minmax_c": [vp, i64, i32, vp, vp, vp, vp],

@@ -366,6 +366,142 @@ static int act_quant_impl(const float* x, int B, int H, int W, int C, const floa
 }
 
 // ---------------------------------------------------------------------------
+// Fused GroupNorm(32) + SiLU + quantize, one CTA per sample, the sample's [HW][C] tile resident in
+// shared memory (one HBM read, no separate statistics kernel).  Used for every feature map whose
+// per-sample tile fits (<= 16x16x128 fp32); that is ~80 of the 97 GroupNorms of the CIFAR model.
+// ---------------------------------------------------------------------------
+struct GnActParams {
+  const float* x;
+  int B, H, W, C, Cp;
+  const float* scale;
+  const float* zp;
+  float qlo, qhi;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int8_t* codes;
+  int32_t* rowsum;
+  int halo;
+  float* y;
+  int quant;
+};
+
+__global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p) {
+  extern __shared__ float4 tile4[];                 // [HW][C/4]
+  __shared__ double s_sum[kGnGroups], s_sq[kGnGroups];
+  __shared__ float s_mean[kGnGroups], s_rstd[kGnGroups];
+  const int b = blockIdx.x;
+  const int HW = p.H * p.W, Q = p.C >> 2, cpg = p.C / kGnGroups;
+  const int n4 = HW * Q;
+  const float4* src = reinterpret_cast<const float4*>(p.x + (long long)b * HW * p.C);
+  if (threadIdx.x < kGnGroups) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+  __syncthreads();
+  // phase 1: load + per-group sums (double).  Consecutive float4s of a thread's stride-256 walk hit
+  // varying groups, so accumulate per element into a small register cache keyed by the last group.
+  {
+    int gcur = -1;
+    double a = 0.0, q = 0.0;
+    for (int e = threadIdx.x; e < n4; e += blockDim.x) {
+      const float4 v = ldg_stream(src + e);
+      tile4[e] = v;
+      const int c = (e % Q) << 2;
+      if ((cpg & 3) == 0) {
+        const int g = c / cpg;
+        if (g != gcur) {
+          if (gcur >= 0) { atomicAdd(&s_sum[gcur], a); atomicAdd(&s_sq[gcur], q); }
+          gcur = g; a = 0.0; q = 0.0;
+        }
+        a += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+        q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+      } else {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          atomicAdd(&s_sum[(c + k) / cpg], (double)vv[k]);
+          atomicAdd(&s_sq[(c + k) / cpg], (double)vv[k] * vv[k]);
+        }
+      }
+    }
+    if (gcur >= 0) { atomicAdd(&s_sum[gcur], a); atomicAdd(&s_sq[gcur], q); }
+  }
+  __syncthreads();
+  if (threadIdx.x < kGnGroups) {
+    const double inv_n = 1.0 / ((double)HW * cpg);
+    const double m = s_sum[threadIdx.x] * inv_n;
+    double var = s_sq[threadIdx.x] * inv_n - m * m;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)m;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
+  }
+  __syncthreads();
+  // phase 2: apply, one warp per output row of this sample (halo rows included)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int Hp = p.halo ? p.H + 2 : p.H, Wp = p.halo ? p.W + 2 : p.W;
+  const long long row0 = (long long)b * Hp * Wp;
+  for (int rr = wid; rr < Hp * Wp; rr += nw) {
+    const int hp = rr / Wp, wp = rr - hp * Wp;
+    bool interior = true;
+    int h = hp, w = wp;
+    if (p.halo) { interior = (hp >= 1 && hp <= p.H && wp >= 1 && wp <= p.W); h = hp - 1; w = wp - 1; }
+    const int px = h * p.W + w;
+    const long long r = row0 + rr;
+    int acc = 0;
+    for (int q0 = 0; q0 < Q; q0 += 32) {
+      const int q = q0 + lane;
+      if (q >= Q) break;
+      const int c = q << 2;
+      float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.quant) {
+        s4 = *reinterpret_cast<const float4*>(p.scale + c);
+        z4 = *reinterpret_cast<const float4*>(p.zp + c);
+      }
+      float4 cd;
+      if (interior) {
+        float4 v = tile4[px * Q + q];
+        const float4 g4 = *reinterpret_cast<const float4*>(p.gamma + c);
+        const float4 b4 = *reinterpret_cast<const float4*>(p.beta + c);
+        const int g0 = c / cpg, g1 = (c + 1) / cpg, g2 = (c + 2) / cpg, g3 = (c + 3) / cpg;
+        float a0 = s_rstd[g0] * g4.x, a1 = s_rstd[g1] * g4.y, a2 = s_rstd[g2] * g4.z, a3 = s_rstd[g3] * g4.w;
+        v.x = silu_f(fmaf(v.x, a0, fmaf(-s_mean[g0], a0, b4.x)));
+        v.y = silu_f(fmaf(v.y, a1, fmaf(-s_mean[g1], a1, b4.y)));
+        v.z = silu_f(fmaf(v.z, a2, fmaf(-s_mean[g2], a2, b4.z)));
+        v.w = silu_f(fmaf(v.w, a3, fmaf(-s_mean[g3], a3, b4.w)));
+        const long long pix = (long long)b * HW + px;
+        if (p.quant) {
+          cd.x = quant_code(v.x, s4.x, z4.x, p.qlo, p.qhi);
+          cd.y = quant_code(v.y, s4.y, z4.y, p.qlo, p.qhi);
+          cd.z = quant_code(v.z, s4.z, z4.z, p.qlo, p.qhi);
+          cd.w = quant_code(v.w, s4.w, z4.w, p.qlo, p.qhi);
+          if (p.y) {
+            float4 o;
+            o.x = dequant(cd.x, s4.x, z4.x); o.y = dequant(cd.y, s4.y, z4.y);
+            o.z = dequant(cd.z, s4.z, z4.z); o.w = dequant(cd.w, s4.w, z4.w);
+            *reinterpret_cast<float4*>(p.y + pix * p.C + c) = o;
+          }
+        } else {
+          if (p.y) *reinterpret_cast<float4*>(p.y + pix * p.C + c) = v;
+          cd = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        cd.x = fminf(fmaxf(-z4.x, p.qlo), p.qhi); cd.y = fminf(fmaxf(-z4.y, p.qlo), p.qhi);
+        cd.z = fminf(fmaxf(-z4.z, p.qlo), p.qhi); cd.w = fminf(fmaxf(-z4.w, p.qlo), p.qhi);
+      }
+      if (p.quant && p.codes) {
+        const int ix = (int)cd.x, iy = (int)cd.y, iz = (int)cd.z, iw = (int)cd.w;
+        acc += ix + iy + iz + iw;
+        *reinterpret_cast<char4*>(p.codes + r * p.Cp + c) =
+            make_char4((signed char)ix, (signed char)iy, (signed char)iz, (signed char)iw);
+      }
+    }
+    if (p.quant && p.rowsum) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) p.rowsum[r] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // GroupNorm statistics
 // ---------------------------------------------------------------------------
 // block = (C/4 channel quads) x P pixel lanes, fixed quad per thread; grid = (splits, B)
@@ -814,6 +950,42 @@ int attndm_act_quant(const float* x, int B, int H, int W, int C, const float* sc
   }
   return act_quant_impl(x, B, H, W, C, scale, zp, a_bit, pre_op, gn_stats, gn_gamma, gn_beta, gn_eps, codes,
                         rowsum, rows_layout, y_f32, true, (cudaStream_t)stream);
+}
+
+int attndm_gn_act_quant_fits(int H, int W, int C) {
+  return (C % kGnGroups == 0) && (C % 4 == 0) && ((long long)H * W * C * 4 <= 160 * 1024) ? 1 : 0;
+}
+
+int attndm_gn_act_quant(const float* x, int B, int H, int W, int C, const float* gamma, const float* beta,
+                        float eps, const float* scale, const float* zp, int a_bit, int8_t* codes,
+                        int32_t* rowsum, int rows_layout, float* y_f32, void* stream) {
+  ATTNDM_CHECK_ARG(x && gamma && beta && B > 0 && H > 0 && W > 0 && C > 0, "gn_act_quant: bad args");
+  ATTNDM_CHECK_ARG(codes || y_f32, "gn_act_quant: no output requested");
+  ATTNDM_CHECK_ARG(a_bit == 0 || (scale && zp && a_bit >= 2 && a_bit <= 8), "gn_act_quant: bad quant params");
+  ATTNDM_CHECK_ARG(a_bit != 0 || (y_f32 && !codes), "gn_act_quant: a_bit == 0 only produces y_f32");
+  if (!attndm_gn_act_quant_fits(H, W, C)) {
+    set_error("gn_act_quant: per-sample tile %dx%dx%d does not fit in shared memory", H, W, C);
+    return ATTNDM_ERR_UNSUPPORTED;
+  }
+  GnActParams p;
+  p.x = x; p.B = B; p.H = H; p.W = W; p.C = C; p.Cp = round_up(C, 16);
+  p.scale = scale; p.zp = zp; p.quant = a_bit != 0;
+  p.qlo = p.quant ? -(float)(1 << (a_bit - 1)) : 0.f;
+  p.qhi = p.quant ? (float)((1 << (a_bit - 1)) - 1) : 0.f;
+  p.gamma = gamma; p.beta = beta; p.eps = eps; p.codes = codes; p.rowsum = rowsum;
+  p.halo = (rows_layout == ATTNDM_ROWS_HALO && codes) ? 1 : 0;
+  p.y = y_f32;
+  const size_t smem = (size_t)H * W * C * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(gn_act_quant_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         160 * 1024);
+    if (e != cudaSuccess) { set_error("gn_act_quant: smem attr: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
+    smem_set = 160 * 1024;
+  }
+  gn_act_quant_sample_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(p);
+  ATTNDM_CUDA_LAUNCH_CHECK("gn_act_quant");
+  return ATTNDM_OK;
 }
 
 int attndm_gn_silu(const float* x, int B, int H, int W, int C, const double* gn_stats, const float* gamma,

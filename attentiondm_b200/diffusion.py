@@ -29,7 +29,11 @@ def _need_quant(quantization, sequence):
 
 
 def _gn_args(norm: nn.GroupNorm, x):
-    return ops.GnArgs(stats=ops.gn_stats(x), gamma=norm.weight.detach(), beta=norm.bias.detach(), eps=norm.eps)
+    """GroupNorm arguments for the consumer conv.  Small feature maps use the fused per-sample kernel
+    (statistics computed in-kernel, stats=None); large ones get a separate statistics pass."""
+    _, H, W, C = x.shape
+    stats = None if ops.gn_fits_fused(H, W, C) else ops.gn_stats(x)
+    return ops.GnArgs(stats=stats, gamma=norm.weight.detach(), beta=norm.bias.detach(), eps=norm.eps)
 
 
 class ResidualBlock(nn.Module):

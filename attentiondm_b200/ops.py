@@ -54,10 +54,14 @@ def cp_of(c: int) -> int:
 
 @dataclass
 class GnArgs:
-    stats: torch.Tensor      # double [B, 32, 2] sums
+    stats: Optional[torch.Tensor]   # double [B, 32, 2] sums; None = compute in the fused per-sample kernel
     gamma: torch.Tensor
     beta: torch.Tensor
     eps: float
+
+
+def gn_fits_fused(H: int, W: int, Cc: int) -> bool:
+    return bool(F_.lib().attndm_gn_act_quant_fits(H, W, Cc))
 
 
 # One zero-filled [n, B, 32, 2] double buffer per UNet forward, handed out slice by slice, instead of
@@ -97,6 +101,10 @@ def gn_silu(x: torch.Tensor, gn: GnArgs) -> torch.Tensor:
     _chk(x, "gn_silu input")
     B, H, W, Cc = x.shape
     y = torch.empty_like(x)
+    if gn.stats is None:
+        call("attndm_gn_act_quant", ptr(x), B, H, W, Cc, ptr(gn.gamma), ptr(gn.beta), float(gn.eps), None, None, 0,
+             None, None, ROWS_PLAIN, ptr(y), stream())
+        return y
     call("attndm_gn_silu", ptr(x), B, H, W, Cc, ptr(gn.stats), ptr(gn.gamma), ptr(gn.beta), float(gn.eps), ptr(y),
          stream())
     return y
@@ -116,6 +124,10 @@ def act_quant(x: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, a_bit: int
         rowsum = torch.empty(rows, dtype=torch.int32, device=x.device)
     if want_f32:
         y = torch.empty_like(x)
+    if pre == PRE_GN_SILU and gn.stats is None:
+        call("attndm_gn_act_quant", ptr(x), B, H, W, Cc, ptr(gn.gamma), ptr(gn.beta), float(gn.eps), ptr(scale),
+             ptr(zp), int(a_bit), ptr(codes), ptr(rowsum), ROWS_HALO if halo else ROWS_PLAIN, ptr(y), stream())
+        return codes, rowsum, y
     call("attndm_act_quant", ptr(x), B, H, W, Cc, ptr(scale), ptr(zp), int(a_bit), int(pre),
          ptr(gn.stats) if gn else None, ptr(gn.gamma) if gn else None, ptr(gn.beta) if gn else None,
          float(gn.eps) if gn else 0.0, ptr(codes), ptr(rowsum), ROWS_HALO if halo else ROWS_PLAIN, ptr(y), stream())

@@ -80,6 +80,16 @@ int attndm_act_quant(const float* x, int B, int H, int W, int C,
  * models/diffusion.py:36-37 (Normalize), 91,94 (GroupNorm eps 1e-6). */
 int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, void* stream);
 
+/* GroupNorm(32)+SiLU+quantize in ONE kernel (statistics computed in-kernel, one CTA per sample with
+ * the sample's [H*W][C] tile resident in shared memory): same outputs as attndm_gn_stats followed by
+ * attndm_act_quant(pre_op = ATTNDM_PRE_GN_SILU).  Only for tiles that fit (attndm_gn_act_quant_fits);
+ * returns ATTNDM_ERR_UNSUPPORTED otherwise.  a_bit == 0: y_f32 = silu(groupnorm(x)).
+ * models/diffusion.py:119-127 + utils/quant_util.py:260-282. */
+int attndm_gn_act_quant_fits(int H, int W, int C);
+int attndm_gn_act_quant(const float* x, int B, int H, int W, int C, const float* gamma,
+                        const float* beta, float eps, const float* scale, const float* zp, int a_bit,
+                        int8_t* codes, int32_t* rowsum, int rows_layout, float* y_f32, void* stream);
+
 /* silu(groupnorm(x)) -> fp32 (used by the calibration branch, which needs the
  * un-quantized activation).  models/diffusion.py:121-122,125-126. */
 int attndm_gn_silu(const float* x, int B, int H, int W, int C, const double* gn_stats,

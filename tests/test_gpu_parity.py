@@ -367,6 +367,15 @@ def test_groupnorm_silu_quant_fused():
         # halo ring holds the code of 0.0
         ring = codes.reshape(B, H + 2, W + 2, -1)[:, 0, :, :C]
         assert (ring.float() == -float(z)).all()
+        # the one-kernel variant (statistics in-kernel, sample tile in shared memory) agrees with the
+        # two-kernel path up to the last bit of the fp64 statistics (a rare +-1 code)
+        if ops.gn_fits_fused(H, W, C):
+            gl = ops.GnArgs(None, gamma.to(DEV), beta.to(DEV), 1e-6)
+            c3, r3, y3 = ops.act_quant(xn, sv, zv, 8, ops.PRE_GN_SILU, gl, want_codes=True, halo=True, want_f32=True)
+            dc = (c3.int() - codes.int()).abs()
+            assert dc.max() <= 1 and (dc > 0).float().mean() < 1e-4
+            assert torch.equal(r3.long() - rowsum.long(), (c3.long() - codes.long()).sum(1))
+            assert rel_l2(ops.gn_silu(xn, gl), ops.gn_silu(xn, gn)) < 1e-6
 
 
 def test_attention_core():
