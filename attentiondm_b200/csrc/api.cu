@@ -1,5 +1,6 @@
 // C-ABI plumbing: error text, version/device probes and the int8 conv dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -8,6 +9,15 @@
 namespace attndm {
 
 static thread_local char g_err[512] = "";
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ATTNDM_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/attndm_b200.h"
 
 namespace attndm {
@@ -68,6 +70,33 @@ __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Every kernel of the sampling graph starts with pdl_enter(): it lets the NEXT kernel of the stream be
+// launched early (its CTAs are scheduled and run their own prologue while this grid drains) and then
+// waits until the PREVIOUS grid has completed and its writes are visible.  Nothing that a predecessor
+// writes may be touched before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
+
+bool pdl_enabled();   // ATTNDM_PDL=0 in the environment switches the launch attribute off
+
+template <typename... ExpTypes, typename... ActTypes>
+inline cudaError_t launch_pdl(void (*kernel)(ExpTypes...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              ActTypes&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr = {};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<ExpTypes>(args)...);
 }
 
 // streaming 128-bit global accesses (activations are touched once per kernel)

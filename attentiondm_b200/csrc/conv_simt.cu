@@ -14,6 +14,7 @@ namespace attndm {
 constexpr int BM = 64, BN = 64, KCB = 64;   // KCB bytes of K per smem chunk
 
 __global__ void __launch_bounds__(256) qconv_i8_simt_kernel(ConvI8Params p) {
+  pdl_enter();
   __shared__ int As[BM][KCB / 4 + 1];
   __shared__ int Bs[BN][KCB / 4 + 1];
   const int tid = threadIdx.x;
@@ -93,6 +94,7 @@ struct ConvF32Params {
 constexpr int KCF = 16;
 
 __global__ void __launch_bounds__(256) conv_f32_simt_kernel(ConvF32Params p) {
+  pdl_enter();
   __shared__ float As[BM][KCF + 1];
   __shared__ float Bs[BN][KCF + 1];
   const int tid = threadIdx.x;
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(256) conv_f32_simt_kernel(ConvF32Params p) {
 
 int launch_qconv_i8_simt(const ConvI8Params& p, cudaStream_t st) {
   dim3 grid(cdiv(p.rows, BM), cdiv(p.O, BN));
-  qconv_i8_simt_kernel<<<grid, 256, 0, st>>>(p);
+  launch_pdl(qconv_i8_simt_kernel, dim3(grid), dim3(256), 0, st, p);
   ATTNDM_CUDA_LAUNCH_CHECK("qconv_i8_simt");
   return ATTNDM_OK;
 }
@@ -190,7 +192,7 @@ extern "C" int attndm_conv_f32(const float* x, int B, int H, int W, int C, const
   p.bias = bias; p.residual = residual; p.temb = temb; p.out = out;
   p.rows = (long long)B * H * W;
   dim3 grid(cdiv(p.rows, BM), cdiv(O, BN));
-  conv_f32_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  launch_pdl(conv_f32_simt_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p);
   ATTNDM_CUDA_LAUNCH_CHECK("conv_f32");
   return ATTNDM_OK;
 }

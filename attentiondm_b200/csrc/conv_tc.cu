@@ -126,6 +126,7 @@ qconv_i8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __shared__ long long row_pix[4][32];      // output pixel of each tile row (-1 = not an output)
   __shared__ int row_b[4][32];              // its sample index
 
+  pdl_launch_dependents();     // the next kernel may start its own prologue while this grid runs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024-B alignment
   const long long m0 = (long long)blockIdx.x * TC_BM;
@@ -153,6 +154,9 @@ qconv_i8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // everything above (TMEM allocation, barrier init, descriptor prefetch) overlapped the previous
+  // kernel's tail; from here on we read what it wrote (codes, row sums, staged tables)
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -361,7 +365,7 @@ int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st) {
   });
   if (attr_err != cudaSuccess) { set_error("qconv_i8_tc: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
   dim3 grid(cdiv(p.rows, TC_BM), cdiv(p.O, g.BN));
-  qconv_i8_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p, g);
+  launch_pdl(qconv_i8_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, p, g);
   ATTNDM_CUDA_LAUNCH_CHECK("qconv_i8_tc");
   return ATTNDM_OK;
 }

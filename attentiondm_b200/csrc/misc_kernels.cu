@@ -25,6 +25,7 @@ __device__ __forceinline__ float attn_fake_quant(float x, float s, float zp, flo
 }
 
 __global__ void __launch_bounds__(128) attention_kernel(AttnParams p) {
+  pdl_enter();
   extern __shared__ float sm[];                       // [4 warps][N]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* sc = sm + (long long)w * p.N;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(128) attention_kernel(AttnParams p) {
 
 __global__ void scale_add_kernel(const float* __restrict__ a, const float* __restrict__ x, const float* __restrict__ gamma,
                                  float* __restrict__ out, long long n) {
+  pdl_enter();
   const float g = *gamma;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __fadd_rn(__fmul_rn(g, a[i]), x[i]);
@@ -83,6 +85,7 @@ __global__ void scale_add_kernel(const float* __restrict__ a, const float* __res
 // UNet glue (NHWC)
 // ---------------------------------------------------------------------------
 __global__ void maxpool2_kernel(const float* __restrict__ x, int B, int H, int W, int C, float* __restrict__ y) {
+  pdl_enter();
   const int Ho = H / 2, Wo = W / 2;
   const long long n = (long long)B * Ho * Wo * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -102,6 +105,7 @@ template <int V>   // V = 4: float4 over channels (Cx % 4 == 0 && Cs % 4 == 0), 
 __global__ void upsample_concat_kernel(const float* __restrict__ x, int B, int H, int W, int Cx,
                                        const float* __restrict__ skip, int Hs, int Ws, int Cs,
                                        float* __restrict__ out) {
+  pdl_enter();
   const int Ct = Cx + Cs, Cv = Ct / V;
   const long long n = (long long)B * Hs * Ws * Cv;
   // nearest x2 (src = dst/2) followed, when sizes differ, by nearest resize 2H x 2W -> Hs x Ws
@@ -132,6 +136,7 @@ __global__ void upsample_concat_kernel(const float* __restrict__ x, int B, int H
 }
 
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, float* __restrict__ emb) {
+  pdl_enter();
   // The reference evaluates exp / sin / cos in fp32 on fp32 arguments.  |t * f| reaches ~1e3, so one
   // ulp of f moves sin/cos by ~1e-4 -- enough to flip 8-bit codes in the time MLP.  We therefore
   // evaluate each transcendental in double on the SAME fp32 argument and round once: that is the
@@ -154,6 +159,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
 __global__ void ddim_step_kernel(const float* __restrict__ xt, const float* __restrict__ eps,
                                  const float* __restrict__ coef, const float* __restrict__ noise,
                                  float* __restrict__ x_next, float* __restrict__ x0_out, long long n) {
+  pdl_enter();
   const float s1mat = coef[0], sat = coef[1], satn = coef[2], c1 = coef[3], c2 = coef[4];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float x = xt[i], e = eps[i];
@@ -170,11 +176,13 @@ __global__ void ddim_step_kernel(const float* __restrict__ xt, const float* __re
 
 __global__ void stage_copy_kernel(const float* __restrict__ table, long long n, const int* __restrict__ step,
                                   float* __restrict__ dst) {
+  pdl_enter();
   const float* src = table + (long long)(*step) * n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[i];
 }
 __global__ void stage_advance_kernel(int* step, int T) {
+  pdl_enter();
   int s = *step + 1;
   *step = s >= T ? 0 : s;
 }
@@ -207,14 +215,14 @@ int attndm_attention(const float* q, const float* k, const float* v, float* out,
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("attention: smem attr: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
   }
-  attention_kernel<<<cdiv(total, 4), 128, smem, (cudaStream_t)stream>>>(p);
+  launch_pdl(attention_kernel, dim3(cdiv(total, 4)), dim3(128), smem, (cudaStream_t)stream, p);
   ATTNDM_CUDA_LAUNCH_CHECK("attention");
   return ATTNDM_OK;
 }
 
 int attndm_scale_add(const float* a, const float* x, const float* gamma, float* out, long long n, void* stream) {
   ATTNDM_CHECK_ARG(a && x && gamma && out && n > 0, "scale_add: bad args");
-  scale_add_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, x, gamma, out, n);
+  launch_pdl(scale_add_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, a, x, gamma, out, n);
   ATTNDM_CUDA_LAUNCH_CHECK("scale_add");
   return ATTNDM_OK;
 }
@@ -222,7 +230,7 @@ int attndm_scale_add(const float* a, const float* x, const float* gamma, float* 
 int attndm_maxpool2(const float* x, int B, int H, int W, int C, float* y, void* stream) {
   ATTNDM_CHECK_ARG(x && y && B > 0 && H >= 2 && W >= 2 && C > 0, "maxpool2: bad args");
   long long n = (long long)B * (H / 2) * (W / 2) * C;
-  maxpool2_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, y);
+  launch_pdl(maxpool2_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, x, B, H, W, C, y);
   ATTNDM_CUDA_LAUNCH_CHECK("maxpool2");
   return ATTNDM_OK;
 }
@@ -233,16 +241,16 @@ int attndm_upsample_concat(const float* x, int B, int H, int W, int Cx, const fl
   ATTNDM_CHECK_ARG(Cs == 0 || skip, "upsample_concat: skip is NULL");
   long long n = (long long)B * Hs * Ws * (Cx + Cs);
   if ((Cx & 3) == 0 && (Cs & 3) == 0)
-    upsample_concat_kernel<4><<<ew_blocks(n / 4), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, Cx, skip, Hs, Ws, Cs, out);
+    launch_pdl(upsample_concat_kernel<4>, dim3(ew_blocks(n / 4)), dim3(256), 0, (cudaStream_t)stream, x, B, H, W, Cx, skip, Hs, Ws, Cs, out);
   else
-    upsample_concat_kernel<1><<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, Cx, skip, Hs, Ws, Cs, out);
+    launch_pdl(upsample_concat_kernel<1>, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, x, B, H, W, Cx, skip, Hs, Ws, Cs, out);
   ATTNDM_CUDA_LAUNCH_CHECK("upsample_concat");
   return ATTNDM_OK;
 }
 
 int attndm_timestep_embedding(const float* t, int B, int dim, float* emb, void* stream) {
   ATTNDM_CHECK_ARG(t && emb && B > 0 && dim >= 4, "timestep_embedding: bad args");
-  timestep_embedding_kernel<<<cdiv((long long)B * (dim / 2), 256), 256, 0, (cudaStream_t)stream>>>(t, B, dim, emb);
+  launch_pdl(timestep_embedding_kernel, dim3(cdiv((long long)B * (dim / 2), 256)), dim3(256), 0, (cudaStream_t)stream, t, B, dim, emb);
   ATTNDM_CUDA_LAUNCH_CHECK("timestep_embedding");
   return ATTNDM_OK;
 }
@@ -250,15 +258,15 @@ int attndm_timestep_embedding(const float* t, int B, int dim, float* emb, void* 
 int attndm_ddim_step(const float* xt, const float* eps, const float* coef, const float* noise, float* x_next,
                      float* x0_out, long long n, void* stream) {
   ATTNDM_CHECK_ARG(xt && eps && coef && x_next && n > 0, "ddim_step: bad args");
-  ddim_step_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(xt, eps, coef, noise, x_next, x0_out, n);
+  launch_pdl(ddim_step_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, xt, eps, coef, noise, x_next, x0_out, n);
   ATTNDM_CUDA_LAUNCH_CHECK("ddim_step");
   return ATTNDM_OK;
 }
 
 int attndm_stage_tables(const float* table, long long n, int T, int* step, int advance, float* dst, void* stream) {
   ATTNDM_CHECK_ARG(table && step && dst && n > 0 && T > 0, "stage_tables: bad args");
-  stage_copy_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(table, n, step, dst);
-  if (advance) stage_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, T);
+  launch_pdl(stage_copy_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, table, n, step, dst);
+  if (advance) launch_pdl(stage_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step, T);
   ATTNDM_CUDA_LAUNCH_CHECK("stage_tables");
   return ATTNDM_OK;
 }

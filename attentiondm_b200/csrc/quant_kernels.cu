@@ -56,6 +56,7 @@ __device__ __forceinline__ void gn_refresh(const double* stats, int b, int lane,
 
 template <int PRE, bool QUANT, bool VEC>
 __global__ void __launch_bounds__(256) act_quant_kernel(ActQuantParams p) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   long long r0 = warp * p.rows_per_warp;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActQuantParams p) {
 // is processed (two 512-B requests in flight per warp).
 template <int PRE, bool QUANT, int NQ>
 __global__ void __launch_bounds__(256) act_quant_fast_kernel(ActQuantParams p) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long r0 = warp * p.rows_per_warp;
@@ -318,13 +320,13 @@ static void launch_act_quant(const ActQuantParams& p, int blocks, cudaStream_t s
   // it is only used for C % 4 != 0 (the 3-channel latent), which never has a GN.
   const bool gn_ok = (PRE != ATTNDM_PRE_GN_SILU) || ((p.C / kGnGroups) % 4 == 0);
   if (p.C == 128 && gn_ok)
-    act_quant_fast_kernel<PRE, QUANT, 1><<<blocks, 256, 0, st>>>(p);
+    launch_pdl(act_quant_fast_kernel<PRE, QUANT, 1>, dim3(blocks), dim3(256), 0, st, p);
   else if (p.C == 256 && gn_ok)
-    act_quant_fast_kernel<PRE, QUANT, 2><<<blocks, 256, 0, st>>>(p);
+    launch_pdl(act_quant_fast_kernel<PRE, QUANT, 2>, dim3(blocks), dim3(256), 0, st, p);
   else if ((p.C & 3) == 0)
-    act_quant_kernel<PRE, QUANT, true><<<blocks, 256, 0, st>>>(p);
+    launch_pdl(act_quant_kernel<PRE, QUANT, true>, dim3(blocks), dim3(256), 0, st, p);
   else
-    act_quant_kernel<PRE, QUANT, false><<<blocks, 256, 0, st>>>(p);
+    launch_pdl(act_quant_kernel<PRE, QUANT, false>, dim3(blocks), dim3(256), 0, st, p);
 }
 
 static int act_quant_impl(const float* x, int B, int H, int W, int C, const float* scale,
@@ -368,7 +370,7 @@ static int act_quant_impl(const float* x, int B, int H, int W, int C, const floa
 // ---------------------------------------------------------------------------
 // Fused GroupNorm(32) + SiLU + quantize, one CTA per sample, the sample's [HW][C] tile resident in
 // shared memory (one HBM read, no separate statistics kernel).  Used for every feature map whose
-// per-sample tile fits (<= 16x16x128 fp32); that is ~80 of the 97 GroupNorms of the CIFAR model.
+// per-sample tile fits in 64 KB (up to 8x8x256 fp32): ~75 of the 97 GroupNorms of the CIFAR model.
 // ---------------------------------------------------------------------------
 struct GnActParams {
   const float* x;
@@ -387,51 +389,40 @@ struct GnActParams {
 };
 
 __global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p) {
+  pdl_enter();
   extern __shared__ float4 tile4[];                 // [HW][C/4]
-  __shared__ double s_sum[kGnGroups], s_sq[kGnGroups];
   __shared__ float s_mean[kGnGroups], s_rstd[kGnGroups];
   const int b = blockIdx.x;
   const int HW = p.H * p.W, Q = p.C >> 2, cpg = p.C / kGnGroups;
   const int n4 = HW * Q;
   const float4* src = reinterpret_cast<const float4*>(p.x + (long long)b * HW * p.C);
-  if (threadIdx.x < kGnGroups) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+  // phase 1: stream the sample's tile into shared memory (coalesced float4)
+  for (int e = threadIdx.x; e < n4; e += blockDim.x) tile4[e] = ldg_stream(src + e);
   __syncthreads();
-  // phase 1: load + per-group sums (double).  Consecutive float4s of a thread's stride-256 walk hit
-  // varying groups, so accumulate per element into a small register cache keyed by the last group.
+  // phase 1b: one warp per group at a time, double accumulation from shared memory, shuffle reduction
   {
-    int gcur = -1;
-    double a = 0.0, q = 0.0;
-    for (int e = threadIdx.x; e < n4; e += blockDim.x) {
-      const float4 v = ldg_stream(src + e);
-      tile4[e] = v;
-      const int c = (e % Q) << 2;
-      if ((cpg & 3) == 0) {
-        const int g = c / cpg;
-        if (g != gcur) {
-          if (gcur >= 0) { atomicAdd(&s_sum[gcur], a); atomicAdd(&s_sq[gcur], q); }
-          gcur = g; a = 0.0; q = 0.0;
-        }
-        a += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
-        q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
-      } else {
-        const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          atomicAdd(&s_sum[(c + k) / cpg], (double)vv[k]);
-          atomicAdd(&s_sq[(c + k) / cpg], (double)vv[k] * vv[k]);
-        }
+    const int lane_ = threadIdx.x & 31, wid_ = threadIdx.x >> 5, nw_ = blockDim.x >> 5;
+    const float* tile = reinterpret_cast<const float*>(tile4);
+    const int per_group = HW * cpg;
+    const double inv_n = 1.0 / (double)per_group;
+    for (int g = wid_; g < kGnGroups; g += nw_) {
+      double a = 0.0, q = 0.0;
+      for (int i = lane_; i < per_group; i += 32) {
+        const int px = i / cpg, k = i - px * cpg;
+        const double v = (double)tile[px * p.C + g * cpg + k];
+        a += v;
+        q += v * v;
+      }
+      a = warp_sum_d(a);
+      q = warp_sum_d(q);
+      if (lane_ == 0) {
+        const double m = a * inv_n;
+        double var = q * inv_n - m * m;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = (float)m;
+        s_rstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
       }
     }
-    if (gcur >= 0) { atomicAdd(&s_sum[gcur], a); atomicAdd(&s_sq[gcur], q); }
-  }
-  __syncthreads();
-  if (threadIdx.x < kGnGroups) {
-    const double inv_n = 1.0 / ((double)HW * cpg);
-    const double m = s_sum[threadIdx.x] * inv_n;
-    double var = s_sq[threadIdx.x] * inv_n - m * m;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = (float)m;
-    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
   }
   __syncthreads();
   // phase 2: apply, one warp per output row of this sample (halo rows included)
@@ -507,6 +498,7 @@ __global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p)
 // block = (C/4 channel quads) x P pixel lanes, fixed quad per thread; grid = (splits, B)
 __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int P, int rows_per_block,
                                 double* __restrict__ stats) {
+  pdl_enter();
   __shared__ double s_sum[kGnGroups], s_sq[kGnGroups];
   const int b = blockIdx.y;
   const int Q = C >> 2;
@@ -953,7 +945,7 @@ int attndm_act_quant(const float* x, int B, int H, int W, int C, const float* sc
 }
 
 int attndm_gn_act_quant_fits(int H, int W, int C) {
-  return (C % kGnGroups == 0) && (C % 4 == 0) && ((long long)H * W * C * 4 <= 160 * 1024) ? 1 : 0;
+  return (C % kGnGroups == 0) && (C % 4 == 0) && ((long long)H * W * C * 4 <= 64 * 1024) ? 1 : 0;
 }
 
 int attndm_gn_act_quant(const float* x, int B, int H, int W, int C, const float* gamma, const float* beta,
@@ -979,11 +971,11 @@ int attndm_gn_act_quant(const float* x, int B, int H, int W, int C, const float*
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(gn_act_quant_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         160 * 1024);
+                                         64 * 1024);
     if (e != cudaSuccess) { set_error("gn_act_quant: smem attr: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
-    smem_set = 160 * 1024;
+    smem_set = 64 * 1024;
   }
-  gn_act_quant_sample_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(p);
+  launch_pdl(gn_act_quant_sample_kernel, dim3(B), dim3(256), smem, (cudaStream_t)stream, p);
   ATTNDM_CUDA_LAUNCH_CHECK("gn_act_quant");
   return ATTNDM_OK;
 }
@@ -1009,7 +1001,7 @@ int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, v
   int rows_per_block = cdiv(HW, splits);
   splits = cdiv(HW, rows_per_block);
   dim3 grid(splits, B);
-  gn_stats_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, HW, C, P, rows_per_block, stats);
+  launch_pdl(gn_stats_kernel, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, x, HW, C, P, rows_per_block, stats);
   ATTNDM_CUDA_LAUNCH_CHECK("gn_stats");
   return ATTNDM_OK;
 }
