@@ -17,6 +17,8 @@
 // columns each) so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -303,6 +305,236 @@ qconv_i8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// ---- persistent variant ------------------------------------------------------------------
+// One CTA per SM loops over output tiles (static round-robin).  The accumulator is double-buffered in
+// TMEM (2 x BN columns), so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1, the smem
+// ring keeps running across tile boundaries, and TMEM allocation / barrier init / descriptor fetch are
+// paid once per SM instead of once per tile.
+struct TcGeomP {
+  int BN, stages, stage_bytes, ncb, tmem_cols;
+  int ntn;            // tiles along N
+  long long ntiles;   // total tiles
+  int stg_off;        // byte offset of the epilogue staging area inside dynamic smem (after the ring)
+  int acc_stride;     // TMEM columns between the two accumulators (BN rounded up to 32: loads are 32 wide)
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                              const ConvI8Params p, const TcGeomP g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ ColConst colc[256];
+  __shared__ long long row_pix[4][32];
+  __shared__ int row_b[4][32];
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int num_kb = p.taps * g.ncb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 4);      // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+        const long long m0 = (tile / g.ntn) * TC_BM;
+        const int n0 = (int)(tile % g.ntn) * g.BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
+          const long long shift = p.taps == 9 ? (long long)(tap / 3) * p.Wp + (tap % 3) : 0;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          const uint32_t a_dst = tiles + (uint32_t)s * g.stage_bytes;
+          const uint32_t b_dst = a_dst + TC_BM * TC_BK;
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          mbar_expect_tx(bar, (uint32_t)g.stage_bytes);
+          tma_load_2d(a_dst, &tmA, bar, cb * TC_BK, (int)(m0 + shift));
+          tma_load_2d(b_dst, &tmB, bar, tap * p.Cp + cb * TC_BK, n0);
+          if (++s == g.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained it-2
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int cb = kb % g.ncb;
+          int ksteps = (p.Cp - cb * TC_BK + TC_UMMA_K - 1) / TC_UMMA_K;
+          if (ksteps > TC_BK / TC_UMMA_K) ksteps = TC_BK / TC_UMMA_K;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = tiles + (uint32_t)s * g.stage_bytes;
+          const uint32_t b_addr = a_addr + TC_BM * TC_BK;
+          for (int k = 0; k < ksteps; ++k)
+            umma_i8(d_tmem, umma_desc_sw128(a_addr + k * TC_UMMA_K), umma_desc_sw128(b_addr + k * TC_UMMA_K), idesc,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+          tcgen05_commit(smem_u32(&empty_bar[s]));
+          if (++s == g.stages) { s = 0; ph ^= 1; }
+        }
+        tcgen05_commit(smem_u32(&tmem_full_bar[acc]));
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int quarter = warp & 3;
+    const int zp = *p.act_zp;
+    float4* stg = reinterpret_cast<float4*>(smem_raw + (tiles - smem_u32(smem_raw)) + g.stg_off) + quarter * (32 * 8);
+    const bool vec_ok = (p.O & 3) == 0;
+    const int sub = lane >> 3, ch = lane & 7;
+    int last_nt = -1;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const long long m0 = (tile / g.ntn) * TC_BM;
+      const int nt = (int)(tile % g.ntn);
+      const int n0 = nt * g.BN;
+      if (nt != last_nt) {                             // warp-uniform across the four epilogue warps
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // nobody still reads the old constants
+        for (int c = (warp - 2) * 32 + lane; c < g.BN; c += 128) {
+          const int o = n0 + c;
+          ColConst cc = {0, 0, 0.f, 0.f};
+          if (o < p.O) {
+            cc.A = zp * p.wsum[o];
+            cc.B = p.w_zp[o];
+            cc.m = p.mult[o];
+            cc.bias = p.bias ? p.bias[o] : 0.f;
+          }
+          colc[c] = cc;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        last_nt = nt;
+      }
+      const long long row = m0 + quarter * 32 + lane;
+      long long pix = 0;
+      int b = 0;
+      const bool valid = conv_row_to_pixel(p, row, pix, b);
+      int cs = 0;
+      if (valid) cs = (int)conv_window_rowsum(p, row) + zp * (p.taps * p.C);
+      __syncwarp();                                    // previous tile's readers of row_pix are done
+      row_pix[quarter][lane] = valid ? pix : -1;
+      row_b[quarter][lane] = b;
+      __syncwarp();
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
+      tcgen05_fence_after();
+      const uint32_t t_acc = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+      for (int c0 = 0; c0 < g.BN; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(t_acc + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= g.BN) {                         // last TMEM read of this tile: hand the buffer back
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 f;
+          ColConst cc = colc[(c0 + 4 * j + 0) & 255];
+          f.x = conv_i8_value((int)v[4 * j + 0], cc.A, cc.B, cs, cc.m, cc.bias);
+          cc = colc[(c0 + 4 * j + 1) & 255];
+          f.y = conv_i8_value((int)v[4 * j + 1], cc.A, cc.B, cs, cc.m, cc.bias);
+          cc = colc[(c0 + 4 * j + 2) & 255];
+          f.z = conv_i8_value((int)v[4 * j + 2], cc.A, cc.B, cs, cc.m, cc.bias);
+          cc = colc[(c0 + 4 * j + 3) & 255];
+          f.w = conv_i8_value((int)v[4 * j + 3], cc.A, cc.B, cs, cc.m, cc.bias);
+          stg[lane * 8 + (j ^ (lane & 7))] = f;
+        }
+        __syncwarp();
+        const int o = n0 + c0 + 4 * ch;
+        const bool col_ok = (c0 + 4 * ch < g.BN) && (o < p.O);
+#pragma unroll
+        for (int rb = 0; rb < 32; rb += 16) {
+          long long pr[4];
+          float4 val[4], rs[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = rb + 4 * i + sub;
+            pr[i] = row_pix[quarter][r];
+            val[i] = stg[r * 8 + (ch ^ (r & 7))];
+            rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.residual && vec_ok && col_ok && pr[i] >= 0)
+              rs[i] = *reinterpret_cast<const float4*>(p.residual + pr[i] * p.O + o);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!col_ok || pr[i] < 0) continue;
+            const int r = rb + 4 * i + sub;
+            float* dst = p.out + pr[i] * p.O + o;
+            if (vec_ok) {
+              float4 t = val[i];
+              if (p.residual) { t.x = __fadd_rn(t.x, rs[i].x); t.y = __fadd_rn(t.y, rs[i].y); t.z = __fadd_rn(t.z, rs[i].z); t.w = __fadd_rn(t.w, rs[i].w); }
+              if (p.temb) {
+                const float4 te = *reinterpret_cast<const float4*>(p.temb + (long long)row_b[quarter][r] * p.O + o);
+                t.x = __fadd_rn(t.x, te.x); t.y = __fadd_rn(t.y, te.y); t.z = __fadd_rn(t.z, te.z); t.w = __fadd_rn(t.w, te.w);
+              }
+              *reinterpret_cast<float4*>(dst) = t;
+            } else {
+              const float e[4] = {val[i].x, val[i].y, val[i].z, val[i].w};
+              for (int k = 0; k < 4 && o + k < p.O; ++k) {
+                float t = e[k];
+                if (p.residual) t = __fadd_rn(t, p.residual[pr[i] * p.O + o + k]);
+                if (p.temb) t = __fadd_rn(t, p.temb[(long long)row_b[quarter][r] * p.O + o + k]);
+                dst[k] = t;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+  }
+}
+
 // ---- host side --------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -337,9 +569,57 @@ static int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_
   return ATTNDM_OK;
 }
 
+static bool tc_persistent_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ATTNDM_TC_PERSISTENT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static int launch_qconv_i8_tc_persistent(const ConvI8Params& p, cudaStream_t st) {
+  TcGeomP g;
+  g.BN = p.O <= 256 ? round_up(p.O, 16) : 256;
+  const long long mtiles = (p.rows + TC_BM - 1) / TC_BM;
+  while (g.BN > 32 && (g.BN / 2) % 16 == 0 && mtiles * cdiv(p.O, g.BN) < 120) g.BN /= 2;
+  g.ntn = cdiv(p.O, g.BN);
+  g.ntiles = mtiles * g.ntn;
+  g.ncb = cdiv(p.Cp, TC_BK);
+  g.stage_bytes = TC_BM * TC_BK + g.BN * TC_BK;
+  const int grid = (int)(g.ntiles < kNumSMs ? g.ntiles : kNumSMs);
+  const long long tiles_per_cta = (g.ntiles + grid - 1) / grid;
+  const int num_kb = p.taps * g.ncb;
+  int want = (int)(tiles_per_cta > 1 ? 2LL * num_kb : num_kb);       // no point in a ring deeper than the work
+  g.stages = (196 * 1024) / g.stage_bytes;
+  if (g.stages > TC_MAX_STAGES) g.stages = TC_MAX_STAGES;
+  if (g.stages > want) g.stages = want;
+  if (g.stages < 2) g.stages = 2;
+  g.acc_stride = round_up(g.BN, 32);
+  g.tmem_cols = 32;
+  while (g.tmem_cols < 2 * g.acc_stride) g.tmem_cols <<= 1;         // two accumulators
+  g.stg_off = g.stages * g.stage_bytes;
+  CUtensorMap tmA, tmB;
+  int rc = make_map_2d(&tmA, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, TC_BM);
+  if (rc) return rc;
+  rc = make_map_2d(&tmB, p.qw, (uint64_t)p.taps * p.Cp, (uint64_t)p.O, TC_BK, (uint32_t)g.BN);
+  if (rc) return rc;
+  const int smem = g.stages * g.stage_bytes + 4 * 32 * 8 * 16 + 1024;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(qconv_i8_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  if (attr_err != cudaSuccess) { set_error("qconv_i8_tc: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
+  launch_pdl(qconv_i8_tc_persistent_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, p, g);
+  ATTNDM_CUDA_LAUNCH_CHECK("qconv_i8_tc_persistent");
+  return ATTNDM_OK;
+}
+
 int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st) {
   ATTNDM_CHECK_ARG(((uintptr_t)p.codes & 15) == 0 && ((uintptr_t)p.qw & 15) == 0, "qconv_i8_tc: operands must be 16-byte aligned");
   ATTNDM_CHECK_ARG(p.rows + 2LL * p.Wp + 2 + TC_BM < 0x7fffffffLL, "qconv_i8_tc: too many rows for 32-bit TMA coordinates");
+  if (tc_persistent_enabled()) return launch_qconv_i8_tc_persistent(p, st);
   TcGeom g;
   g.BN = p.O <= 256 ? round_up(p.O, 16) : 256;
   // small problems: split N over more CTAs (idle SMs are free; the epilogue is serial per CTA)
