@@ -53,6 +53,7 @@ int attndm_qconv_i8(const int8_t* codes, const int32_t* rowsum, int B, int H, in
   ATTNDM_CHECK_ARG(codes && rowsum && qw && wsum && w_zp && mult && act_zp && out, "qconv_i8: null pointer");
   ATTNDM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && O > 0, "qconv_i8: bad shape");
   ATTNDM_CHECK_ARG(taps == 1 || taps == 9, "qconv_i8: only 1x1 and 3x3/s1/p1 are on the hot path");
+  ATTNDM_CHECK_ARG((long long)taps * round_up(C, 16) < 32768, "qconv_i8: K = taps*C must stay below 2^15 (int32 epilogue)");
   ConvI8Params p;
   p.codes = codes; p.rowsum = rowsum; p.B = B; p.H = H; p.W = W; p.C = C; p.Cp = round_up(C, 16);
   p.Hp = taps == 9 ? H + 2 : H;

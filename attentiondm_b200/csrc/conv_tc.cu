@@ -30,6 +30,8 @@ constexpr int TC_BM = 128;        // rows per tile  (UMMA M)
 constexpr int TC_BK = 128;        // bytes of K per stage (one SWIZZLE_128B row)
 constexpr int TC_UMMA_K = 32;     // K per tcgen05.mma for 8-bit operands
 constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS_P = 8;                       // persistent kernel: epilogue warps
+constexpr int TC_THREADS_P = 64 + 32 * TC_EPI_WARPS_P;
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_BUDGET = 110 * 1024;   // per CTA, so that two CTAs share an SM
 
@@ -322,7 +324,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS_P, 1)
 qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                               const ConvI8Params p, const TcGeomP g) {
   extern __shared__ uint8_t smem_raw[];
@@ -332,8 +334,8 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ ColConst colc[256];
-  __shared__ long long row_pix[4][32];
-  __shared__ int row_b[4][32];
+  __shared__ long long row_pix[TC_EPI_WARPS_P][32];
+  __shared__ int row_b[TC_EPI_WARPS_P][32];
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -356,7 +358,7 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), 4);      // one arrival per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[a]), TC_EPI_WARPS_P);   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -420,9 +422,13 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     }
   } else {
     // ===== epilogue warps =====
+    // eight warps: warp w reads TMEM lanes [32*(w%4), +32); the two warps of a lane quarter take
+    // alternate 32-column chunks, so every SM sub-partition has two epilogue warps to interleave
     const int quarter = warp & 3;
+    const int ew = warp - 2;                           // 0..7
+    const int half = ew >> 2;
     const int zp = *p.act_zp;
-    float4* stg = reinterpret_cast<float4*>(smem_raw + (tiles - smem_u32(smem_raw)) + g.stg_off) + quarter * (32 * 8);
+    float4* stg = reinterpret_cast<float4*>(smem_raw + (tiles - smem_u32(smem_raw)) + g.stg_off) + ew * (32 * 8);
     const bool vec_ok = (p.O & 3) == 0;
     const int sub = lane >> 3, ch = lane & 7;
     int last_nt = -1;
@@ -433,8 +439,8 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       const int nt = (int)(tile % g.ntn);
       const int n0 = nt * g.BN;
       if (nt != last_nt) {                             // warp-uniform across the four epilogue warps
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // nobody still reads the old constants
-        for (int c = (warp - 2) * 32 + lane; c < g.BN; c += 128) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // nobody still reads the old constants
+        for (int c = ew * 32 + lane; c < g.BN; c += 32 * TC_EPI_WARPS_P) {
           const int o = n0 + c;
           ColConst cc = {0, 0, 0.f, 0.f};
           if (o < p.O) {
@@ -445,7 +451,7 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
           }
           colc[c] = cc;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         last_nt = nt;
       }
       const long long row = m0 + quarter * 32 + lane;
@@ -455,18 +461,24 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       int cs = 0;
       if (valid) cs = (int)conv_window_rowsum(p, row) + zp * (p.taps * p.C);
       __syncwarp();                                    // previous tile's readers of row_pix are done
-      row_pix[quarter][lane] = valid ? pix : -1;
-      row_b[quarter][lane] = b;
+      row_pix[ew][lane] = valid ? pix : -1;
+      row_b[ew][lane] = b;
       __syncwarp();
       mbar_wait(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
       tcgen05_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-      for (int c0 = 0; c0 < g.BN; c0 += 32) {
+      const int nchunks = (g.BN + 31) >> 5;
+      if (half >= nchunks) {                           // nothing to read for this warp: release at once
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      }
+      for (int ci = half; ci < nchunks; ci += 2) {
+        const int c0 = ci << 5;
         uint32_t v[32];
         __syncwarp();
         tmem_ld32(t_acc + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (c0 + 32 >= g.BN) {                         // last TMEM read of this tile: hand the buffer back
+        if (ci + 2 >= nchunks) {                       // this warp's last TMEM read of the tile: hand it back
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
@@ -494,7 +506,7 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = rb + 4 * i + sub;
-            pr[i] = row_pix[quarter][r];
+            pr[i] = row_pix[ew][r];
             val[i] = stg[r * 8 + (ch ^ (r & 7))];
             rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.residual && vec_ok && col_ok && pr[i] >= 0)
@@ -509,7 +521,7 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
               float4 t = val[i];
               if (p.residual) { t.x = __fadd_rn(t.x, rs[i].x); t.y = __fadd_rn(t.y, rs[i].y); t.z = __fadd_rn(t.z, rs[i].z); t.w = __fadd_rn(t.w, rs[i].w); }
               if (p.temb) {
-                const float4 te = *reinterpret_cast<const float4*>(p.temb + (long long)row_b[quarter][r] * p.O + o);
+                const float4 te = *reinterpret_cast<const float4*>(p.temb + (long long)row_b[ew][r] * p.O + o);
                 t.x = __fadd_rn(t.x, te.x); t.y = __fadd_rn(t.y, te.y); t.z = __fadd_rn(t.z, te.z); t.w = __fadd_rn(t.w, te.w);
               }
               *reinterpret_cast<float4*>(dst) = t;
@@ -518,7 +530,7 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
               for (int k = 0; k < 4 && o + k < p.O; ++k) {
                 float t = e[k];
                 if (p.residual) t = __fadd_rn(t, p.residual[pr[i] * p.O + o + k]);
-                if (p.temb) t = __fadd_rn(t, p.temb[(long long)row_b[quarter][r] * p.O + o + k]);
+                if (p.temb) t = __fadd_rn(t, p.temb[(long long)row_b[ew][r] * p.O + o + k]);
                 dst[k] = t;
               }
             }
@@ -591,7 +603,7 @@ static int launch_qconv_i8_tc_persistent(const ConvI8Params& p, cudaStream_t st)
   const long long tiles_per_cta = (g.ntiles + grid - 1) / grid;
   const int num_kb = p.taps * g.ncb;
   int want = (int)(tiles_per_cta > 1 ? 2LL * num_kb : num_kb);       // no point in a ring deeper than the work
-  g.stages = (196 * 1024) / g.stage_bytes;
+  g.stages = (180 * 1024) / g.stage_bytes;
   if (g.stages > TC_MAX_STAGES) g.stages = TC_MAX_STAGES;
   if (g.stages > want) g.stages = want;
   if (g.stages < 2) g.stages = 2;
@@ -604,14 +616,14 @@ static int launch_qconv_i8_tc_persistent(const ConvI8Params& p, cudaStream_t st)
   if (rc) return rc;
   rc = make_map_2d(&tmB, p.qw, (uint64_t)p.taps * p.Cp, (uint64_t)p.O, TC_BK, (uint32_t)g.BN);
   if (rc) return rc;
-  const int smem = g.stages * g.stage_bytes + 4 * 32 * 8 * 16 + 1024;
+  const int smem = g.stages * g.stage_bytes + TC_EPI_WARPS_P * 32 * 8 * 16 + 1024;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(qconv_i8_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_err = cudaFuncSetAttribute(qconv_i8_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("qconv_i8_tc: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
-  launch_pdl(qconv_i8_tc_persistent_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, p, g);
+  launch_pdl(qconv_i8_tc_persistent_kernel, dim3(grid), dim3(TC_THREADS_P), smem, st, tmA, tmB, p, g);
   ATTNDM_CUDA_LAUNCH_CHECK("qconv_i8_tc_persistent");
   return ATTNDM_OK;
 }
