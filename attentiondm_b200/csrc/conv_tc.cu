@@ -65,6 +65,66 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// The issuing warps run their loops converged (all 32 lanes) and only the instruction itself is
+// predicated on an elected lane.  Issuing from inside an `if (lane == 0)` branch makes the compiler
+// wrap every UTCIMMA / UTMALDG (which take uniform registers) in a per-thread "waterfall" loop with
+// R2UR moves: measured ~200 cycles per MMA issue instead of the ~64 the tensor pipe needs.
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// leader-predicated variants: the elected lane is chosen ONCE per warp (elect.sync costs ~20 cycles each)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t is_leader;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(is_leader));
+  return is_leader;
+}
+__device__ __forceinline__ void umma_i8_if(uint32_t leader, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_if(uint32_t leader, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -97,6 +157,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// 16 lanes x 256 bit, repeated 4x along columns: 16 registers covering 16 TMEM lanes x 32 columns.
+// Measured layout (tools/umma_shift_test.cu): thread t, register j holds
+//   lane = t/4 + 8*((j>>1)&1),  column = 2*(t%4) + (j&1) + 8*(j>>2)
+// i.e. four consecutive threads hold 8 consecutive columns (32 B) of one row: a warp-wide float2 store
+// writes full 32-byte sectors and no shared-memory transpose is needed.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -547,6 +621,409 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   }
 }
 
+// ---- optional timeline trace (debug): CTA 0 records globaltimer at pipeline events ----------------
+__device__ unsigned long long* g_tc_trace = nullptr;    // [role 0..3][it 0..31][event 0..3]
+__device__ __forceinline__ void tc_trace(int role, int it, int ev) {
+  unsigned long long* t = g_tc_trace;
+  if (t != nullptr && blockIdx.x == 0 && it < 32) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    t[(role * 32 + it) * 4 + ev] = now;
+  }
+}
+
+// ---- halo-reuse variant ------------------------------------------------------------------
+// Measured on B200 (tools/umma_shift_test.cu): a K-major SWIZZLE_128B matrix descriptor may start at ANY
+// 128-byte row of a TMA-written tile (base_offset = 0) -- the swizzle is keyed on absolute shared-memory
+// address bits.  So a 3x3 conv loads ONE halo tile per output tile (128 + 2*(W+2) + 2 rows, once per
+// 128-channel block) and feeds all nine taps from it by sliding the A descriptor by (kh*(W+2)+kw)*128 B:
+// L2->smem traffic for the activations drops 9x -> ~1.5x.  When the layer's whole weight matrix fits it
+// is loaded once per SM and stays resident; otherwise it streams through a ring as before.
+// Warps: 0 = activation (halo) producer, 1 = MMA issuer, 2 = weight producer, 3..10 = epilogue.
+constexpr int TC_H_EPI0 = 4;                           // first epilogue warp (multiple of 4: quarter = warp % 4)
+constexpr int TC_H_EPI_WARPS = 8;                      // 2 per TMEM lane quarter
+constexpr int TC_H_EPI_GROUPS = TC_H_EPI_WARPS / 4;    // warps sharing a quarter split the 32-column chunks
+constexpr int TC_THREADS_H = 32 * (TC_H_EPI0 + TC_H_EPI_WARPS);
+constexpr int TC_H_MAXB = 8;                           // weight ring depth (streamed mode)
+
+__device__ __forceinline__ void tile_geometry(const ConvI8Params& p, long long row, int zp, long long& pix_o,
+                                              int& b_o, int& cs_o) {
+  long long pix = 0;
+  int b = 0;
+  pix_o = -1;
+  b_o = 0;
+  cs_o = 0;
+  if (conv_row_to_pixel(p, row, pix, b)) {
+    pix_o = pix;
+    b_o = b;
+    cs_o = (int)conv_window_rowsum(p, row) + zp * (p.taps * p.C);
+  }
+}
+
+struct TcGeomH {
+  int BN, ncb, tmem_cols, acc_stride, ntn;
+  long long ntiles;
+  int hr;             // halo rows per tile (128 for a 1x1 conv)
+  int hr_stride;      // bytes per (halo, channel block) in smem, multiple of 1024
+  int na;             // halo buffers (ring)
+  int b_resident;     // 1: weights loaded once; 0: streamed
+  int nb;             // weight ring depth (streamed)
+  int a_off, b_off, stg_off;   // byte offsets inside the 1024-aligned dynamic smem
+};
+
+
+// One 32-row x 32-column block of a tile, held in the 16x256b fragment layout: thread (tr = lane/4,
+// tq = lane%4) owns rows tr + 8k (k = 0..3; k < 2 from v0, k >= 2 from v1) and the column pairs
+// 8i + 2tq + {0,1} (i = 0..3).  Register j of a load: row bit = (j>>1)&1, column group i = j>>2, parity j&1.
+// Everything is statically indexed (registers only); stores are float2, four lanes per 32-byte sector.
+template <bool RES, bool TEMB>
+__device__ __forceinline__ void epi_block(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
+                                          int c0, int tq, int BN, int n0, int O, const int (&cs_r)[4],
+                                          const long long (&pix_r)[4], float* const (&out_row)[4],
+                                          const float* const (&res_row)[4], const float* const (&te_row)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cl = c0 + 8 * i + 2 * tq;
+    const bool col_ok = (cl < BN) && (n0 + cl < O);
+    const ColConst ca = colc[cl & 255], cb = colc[(cl + 1) & 255];
+    bool ok[4];
+    float2 rs[4], te[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                  // all loads first: independent, predicated, no branches
+      ok[k] = col_ok && pix_r[k] >= 0;
+      if (RES) rs[k] = ok[k] ? __ldg(reinterpret_cast<const float2*>(res_row[k] + c0 + 8 * i)) : make_float2(0.f, 0.f);
+      if (TEMB) te[k] = ok[k] ? __ldg(reinterpret_cast<const float2*>(te_row[k] + c0 + 8 * i)) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = (i << 2) | ((k & 1) << 1);
+      const int a0 = (int)(k < 2 ? v0[j] : v1[j]), a1 = (int)(k < 2 ? v0[j | 1] : v1[j | 1]);
+      float f0 = conv_i8_value(a0, ca.A, ca.B, cs_r[k], ca.m, ca.bias);
+      float f1 = conv_i8_value(a1, cb.A, cb.B, cs_r[k], cb.m, cb.bias);
+      if (RES) { f0 = __fadd_rn(f0, rs[k].x); f1 = __fadd_rn(f1, rs[k].y); }
+      if (TEMB) { f0 = __fadd_rn(f0, te[k].x); f1 = __fadd_rn(f1, te[k].y); }
+      if (ok[k]) *reinterpret_cast<float2*>(out_row[k] + c0 + 8 * i) = make_float2(f0, f1);
+    }
+  }
+}
+
+// odd channel counts (the 3-channel eps output): scalar loads/stores, same static indexing
+__device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
+                                                 int c0, int tq, int BN, int n0, int O, const int (&cs_r)[4],
+                                                 const long long (&pix_r)[4], float* const (&out_row)[4],
+                                                 const float* const (&res_row)[4], const float* const (&te_row)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+      const int cl = c0 + 8 * i + 2 * tq + par;
+      const bool col_ok = (cl < BN) && (n0 + cl < O);
+      const ColConst cc = colc[cl & 255];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = (i << 2) | ((k & 1) << 1) | par;
+        float f = conv_i8_value((int)(k < 2 ? v0[j] : v1[j]), cc.A, cc.B, cs_r[k], cc.m, cc.bias);
+        if (col_ok && pix_r[k] >= 0) {
+          if (res_row[k]) f = __fadd_rn(f, res_row[k][c0 + 8 * i + par]);
+          if (te_row[k]) f = __fadd_rn(f, te_row[k][c0 + 8 * i + par]);
+          out_row[k][c0 + 8 * i + par] = f;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS_H, 1)
+qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                     const __grid_constant__ CUtensorMap tmB, const ConvI8Params p, const TcGeomH g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[4], a_empty[4];
+  __shared__ __align__(8) uint64_t b_full[TC_H_MAXB], b_empty[TC_H_MAXB];
+  __shared__ __align__(8) uint64_t b_res_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ ColConst colc[256];
+  __shared__ __align__(8) uint64_t geo_full[2], geo_empty[2];
+  __shared__ long long geo_pix[2][TC_BM];          // output pixel of each tile row (-1: not an output)
+  __shared__ int geo_b[2][TC_BM], geo_cs[2][TC_BM];  // sample index, window row-sum + zp*K
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nkb = p.taps * g.ncb;
+  const int b_tile_bytes = g.BN * TC_BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < g.na; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
+    for (int i = 0; i < g.nb; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+    mbar_init(smem_u32(&b_res_bar), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), TC_H_EPI_WARPS);
+      mbar_init(smem_u32(&geo_full[a]), 1);
+      mbar_init(smem_u32(&geo_empty[a]), TC_H_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 2) {
+    {
+      // ===== weight producer (weights are static: no need to wait for the previous kernel) =====
+      if (g.b_resident) {
+        const int ntn_tiles_here = 1;   // resident mode is only chosen when ntn == 1
+        (void)ntn_tiles_here;
+        mbar_expect_tx_elect(smem_u32(&b_res_bar), (uint32_t)(nkb * b_tile_bytes));
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
+          tma_load_2d_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK, 0);
+        }
+      } else {
+        int s = 0;
+        uint32_t ph = 0;
+        for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+          const int n0 = (int)(tile % g.ntn) * g.BN;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
+            mbar_wait(smem_u32(&b_empty[s]), ph ^ 1);
+            mbar_expect_tx_elect(smem_u32(&b_full[s]), (uint32_t)b_tile_bytes);
+            tma_load_2d_elect(base + g.b_off + (uint32_t)s * b_tile_bytes, &tmB, smem_u32(&b_full[s]), tap * p.Cp + cb * TC_BK, n0);
+            if (++s == g.nb) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
+    pdl_wait();                                        // the codes come from the previous kernel
+    {
+      // ===== activation (halo) producer: one halo per (tile, channel block) =====
+      const int hr1 = g.hr > 256 ? 256 : g.hr;          // a TMA box holds at most 256 rows
+      const int hr2 = g.hr - hr1;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
+        const long long m0 = (tile / g.ntn) * TC_BM;
+        const int buf = it % g.na;
+        if (lane == 0) tc_trace(0, it, 0);
+        mbar_wait(smem_u32(&a_empty[buf]), (uint32_t)(((it / g.na) & 1) ^ 1));
+        if (lane == 0) tc_trace(0, it, 1);
+        const uint32_t bar = smem_u32(&a_full[buf]);
+        mbar_expect_tx_elect(bar, (uint32_t)(g.ncb * g.hr * TC_BK));
+        for (int cb = 0; cb < g.ncb; ++cb) {
+          const uint32_t dst = base + g.a_off + (uint32_t)(buf * g.ncb + cb) * g.hr_stride;
+          tma_load_2d_elect(dst, &tmA, bar, cb * TC_BK, (int)m0);
+          if (hr2 > 0) tma_load_2d_elect(dst + 256 * TC_BK, &tmA2, bar, cb * TC_BK, (int)m0 + 256);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    pdl_wait();
+    {
+      // ===== MMA issuer =====
+      // The issue loop is scalar code on one warp: anything slow between two tcgen05.mma shows up as idle
+      // tensor-pipe time (an integer division per k-block cost ~200 cycles per MMA).  So: nested loops with
+      // additive address updates only, and descriptors assembled from a constant high word plus a 14-bit
+      // (address >> 4) low field that is simply incremented (+2 per 32-byte K step).
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+                               ((uint64_t)2 << 61);
+      const int kdim = p.taps == 9 ? 3 : 1;
+      const int ksteps_last = ((p.Cp - (g.ncb - 1) * TC_BK) + TC_UMMA_K - 1) / TC_UMMA_K;   // 1..4
+      const uint32_t leader = elect_one();
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1, buf = it % g.na;
+        if (lane == 0) tc_trace(1, it, 0);
+        mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((it >> 1) & 1) ^ 1));
+        if (lane == 0) tc_trace(1, it, 1);
+        mbar_wait(smem_u32(&a_full[buf]), (uint32_t)((it / g.na) & 1));
+        if (g.b_resident && it == 0) mbar_wait(smem_u32(&b_res_bar), 0);
+        tcgen05_fence_after();
+        if (lane == 0) tc_trace(1, it, 2);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
+        const uint32_t a_buf0 = base + g.a_off + (uint32_t)(buf * g.ncb) * g.hr_stride;
+        uint32_t b_res = base + g.b_off;               // resident mode: walks through the whole weight block
+        uint32_t accumulate = 0;
+        for (int kh = 0; kh < kdim; ++kh) {
+          for (int kw = 0; kw < kdim; ++kw) {
+            uint32_t a_addr = a_buf0 + (uint32_t)(kh * p.Wp + kw) * TC_BK;
+            for (int cb = 0; cb < g.ncb; ++cb) {
+              uint32_t b_addr;
+              if (g.b_resident) {
+                b_addr = b_res;
+                b_res += (uint32_t)b_tile_bytes;
+              } else {
+                mbar_wait(smem_u32(&b_full[s]), ph);
+                tcgen05_fence_after();
+                b_addr = base + g.b_off + (uint32_t)s * b_tile_bytes;
+              }
+              const int ksteps = (cb == g.ncb - 1) ? ksteps_last : TC_BK / TC_UMMA_K;
+              uint64_t ad = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+              uint64_t bd = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFF);
+              for (int k = 0; k < ksteps; ++k) {
+                umma_i8_if(leader, d_tmem, ad, bd, idesc, accumulate);
+                accumulate = 1;
+                ad += TC_UMMA_K >> 4;
+                bd += TC_UMMA_K >> 4;
+              }
+              if (!g.b_resident) {
+                tcgen05_commit_if(leader, smem_u32(&b_empty[s]));
+                if (++s == g.nb) { s = 0; ph ^= 1; }
+              }
+              a_addr += (uint32_t)g.hr_stride;
+            }
+          }
+        }
+        tcgen05_commit_if(leader, smem_u32(&a_empty[buf]));
+        tcgen05_commit_if(leader, smem_u32(&tmem_full_bar[acc]));
+        if (lane == 0) tc_trace(1, it, 3);
+      }
+    }
+  } else if (warp == 3) {
+    // ===== geometry warp: per-row output pixel / sample / window row-sum for the NEXT tiles, so the
+    // epilogue never waits on the nine dependent-latency row-sum loads or the index divisions =====
+    pdl_wait();
+    const int zp = *p.act_zp;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const long long m0 = (tile / g.ntn) * TC_BM;
+      mbar_wait(smem_u32(&geo_empty[buf]), (uint32_t)(((it >> 1) & 1) ^ 1));
+      long long px[4];
+      int bb[4], cc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tile_geometry(p, m0 + lane + 32 * j, zp, px[j], bb[j], cc[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        geo_pix[buf][lane + 32 * j] = px[j];
+        geo_b[buf][lane + 32 * j] = bb[j];
+        geo_cs[buf][lane + 32 * j] = cc[j];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&geo_full[buf]));
+    }
+  } else if (warp >= TC_H_EPI0) {
+    // ===== epilogue warps (16): quarter = warp % 4, the four warps of a quarter take 32-column chunks round robin.
+    // No shared-memory staging: the 16x256b TMEM load shape already hands four consecutive threads 32
+    // contiguous bytes of one output row, so results go TMEM -> registers -> global (float2 per lane).
+    // Keeping the epilogue off shared memory matters: an SS-mode M=128,N=128 MMA reads 8 KB of operands
+    // per 64 cycles, i.e. the SM's whole 128 B/clk shared-memory bandwidth.
+    pdl_wait();
+    const int quarter = warp & 3;
+    const int ew = warp - TC_H_EPI0;                   // 0..15
+    const int half = ew >> 2;                          // which of the quarter's four warps (chunk phase)
+    const int zp = *p.act_zp;
+    const bool pair_ok = (p.O & 1) == 0;               // float2 stores need an even channel count
+    const int tq = lane & 3, tr = lane >> 2;           // fragment coordinates of this thread
+    int last_nt = -1;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const long long m0 = (tile / g.ntn) * TC_BM;
+      const int nt = (int)(tile % g.ntn);
+      const int n0 = nt * g.BN;
+      if (nt != last_nt) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_H_EPI_WARPS) : "memory");
+        for (int c = ew * 32 + lane; c < g.BN; c += 32 * TC_H_EPI_WARPS) {
+          const int o = n0 + c;
+          ColConst cc = {0, 0, 0.f, 0.f};
+          if (o < p.O) {
+            cc.A = zp * p.wsum[o];
+            cc.B = p.w_zp[o];
+            cc.m = p.mult[o];
+            cc.bias = p.bias ? p.bias[o] : 0.f;
+          }
+          colc[c] = cc;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_H_EPI_WARPS) : "memory");
+        last_nt = nt;
+      }
+      // row geometry of this thread's four fragment rows (tr, tr+8, tr+16, tr+24 of the quarter), prepared
+      // by the geometry warp
+      const int gb = it & 1;
+      mbar_wait(smem_u32(&geo_full[gb]), (uint32_t)((it >> 1) & 1));
+      long long pix_r[4];
+      int b_r[4], cs_r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = quarter * 32 + tr + 8 * k;
+        pix_r[k] = geo_pix[gb][r];
+        b_r[k] = geo_b[gb][r];
+        cs_r[k] = geo_cs[gb][r];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&geo_empty[gb]));
+      if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 0);
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
+      tcgen05_fence_after();
+      if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 1);
+      const uint32_t t_acc = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+      const int nchunks = (g.BN + 31) >> 5;
+      if (half >= nchunks) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      }
+      // row bases of this thread's four fragment rows (element offsets; invalid rows are predicated off)
+      const float* res_row[4];
+      const float* te_row[4];
+      float* out_row[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long off = (pix_r[k] < 0 ? 0 : pix_r[k]) * p.O + n0 + 2 * tq;
+        out_row[k] = p.out + off;
+        res_row[k] = p.residual ? p.residual + off : nullptr;
+        te_row[k] = p.temb ? p.temb + (long long)b_r[k] * p.O + n0 + 2 * tq : nullptr;
+      }
+      for (int ci = half; ci < nchunks; ci += TC_H_EPI_GROUPS) {
+        const int c0 = ci << 5;
+        uint32_t v0[16], v1[16];
+        __syncwarp();
+        tmem_ld_16x256b_x4(t_acc + (uint32_t)c0, v0);                      // tile rows 32q + 0..15
+        tmem_ld_16x256b_x4(t_acc + (16u << 16) + (uint32_t)c0, v1);        // tile rows 32q + 16..31
+        tmem_ld_wait();
+        if (ci + TC_H_EPI_GROUPS >= nchunks) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+          if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 2);
+        }
+        if (pair_ok) {
+          if (p.residual) {
+            if (p.temb) epi_block<true, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
+            else        epi_block<true, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
+          } else {
+            if (p.temb) epi_block<false, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
+            else        epi_block<false, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
+          }
+        } else {
+          epi_block_scalar(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
+        }
+      }
+      if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 3);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+  }
+}
+
 // ---- host side --------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -628,9 +1105,93 @@ static int launch_qconv_i8_tc_persistent(const ConvI8Params& p, cudaStream_t st)
   return ATTNDM_OK;
 }
 
+}  // namespace attndm
+extern "C" int attndm_debug_set_tc_trace(unsigned long long* buf) {
+  cudaError_t e = cudaMemcpyToSymbol(attndm::g_tc_trace, &buf, sizeof(buf));
+  return e == cudaSuccess ? 0 : -2;
+}
+namespace attndm {
+
+static bool tc_halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ATTNDM_TC_HALO");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// returns 1 if the halo kernel was launched, 0 if the shape does not fit it, <0 on error
+static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
+  constexpr int kBudget = 214 * 1024;                   // dynamic smem we allow ourselves (227 KB - static - slack)
+  TcGeomH g;
+  g.BN = p.O <= 256 ? round_up(p.O, 16) : 256;
+  const long long mtiles = (p.rows + TC_BM - 1) / TC_BM;
+  while (g.BN > 32 && (g.BN / 2) % 16 == 0 && mtiles * cdiv(p.O, g.BN) < 120) g.BN /= 2;
+  g.ntn = cdiv(p.O, g.BN);
+  g.ntiles = mtiles * g.ntn;
+  g.ncb = cdiv(p.Cp, TC_BK);
+  g.hr = p.taps == 9 ? TC_BM + 2 * p.Wp + 2 : TC_BM;
+  if (g.hr > 512) return 0;
+  g.hr_stride = round_up(g.hr * TC_BK, 1024);
+  const int nkb = p.taps * g.ncb;
+  const int b_tile = g.BN * TC_BK;
+  const int stg_bytes = 0;                              // the epilogue does not stage through shared memory
+  const int a_buf = g.ncb * g.hr_stride;
+  const int grid = (int)(g.ntiles < kNumSMs ? g.ntiles : kNumSMs);
+  const long long tiles_per_cta = (g.ntiles + grid - 1) / grid;
+  g.na = tiles_per_cta > 1 ? 2 : 1;
+  // weights resident when they fit next to two halo buffers (and there is a single N tile)
+  g.b_resident = (g.ntn == 1 && (long long)nkb * b_tile + (long long)g.na * a_buf + stg_bytes <= kBudget) ? 1 : 0;
+  if (g.b_resident) {
+    g.nb = 1;
+  } else {
+    long long left = (long long)kBudget - (long long)g.na * a_buf - stg_bytes;
+    if (left < 2LL * b_tile && g.na == 2) { g.na = 1; left += a_buf; }
+    if (left < 2LL * b_tile) return 0;
+    g.nb = (int)(left / b_tile);
+    if (g.nb > TC_H_MAXB) g.nb = TC_H_MAXB;
+    if (g.nb > nkb * 2) g.nb = nkb * 2;
+    if (g.nb < 2) g.nb = 2;
+  }
+  g.a_off = 0;
+  g.b_off = g.na * a_buf;
+  g.stg_off = g.b_off + (g.b_resident ? nkb : g.nb) * b_tile;
+  g.acc_stride = round_up(g.BN, 32);
+  g.tmem_cols = 32;
+  while (g.tmem_cols < 2 * g.acc_stride) g.tmem_cols <<= 1;
+  const int smem = g.stg_off + stg_bytes + 1024;
+  CUtensorMap tmA, tmA2, tmB;
+  const int hr1 = g.hr > 256 ? 256 : g.hr;
+  int rc = make_map_2d(&tmA, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, (uint32_t)hr1);
+  if (rc) return rc;
+  tmA2 = tmA;
+  if (g.hr > 256) {
+    rc = make_map_2d(&tmA2, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, (uint32_t)(g.hr - 256));
+    if (rc) return rc;
+  }
+  rc = make_map_2d(&tmB, p.qw, (uint64_t)p.taps * p.Cp, (uint64_t)p.O, TC_BK, (uint32_t)g.BN);
+  if (rc) return rc;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+  });
+  if (attr_err != cudaSuccess) { set_error("qconv_i8_halo: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
+  launch_pdl(qconv_i8_halo_kernel, dim3(grid), dim3(TC_THREADS_H), smem, st, tmA, tmA2, tmB, p, g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("qconv_i8_halo: launch failed: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
+  return 1;
+}
+
 int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st) {
   ATTNDM_CHECK_ARG(((uintptr_t)p.codes & 15) == 0 && ((uintptr_t)p.qw & 15) == 0, "qconv_i8_tc: operands must be 16-byte aligned");
   ATTNDM_CHECK_ARG(p.rows + 2LL * p.Wp + 2 + TC_BM < 0x7fffffffLL, "qconv_i8_tc: too many rows for 32-bit TMA coordinates");
+  if (tc_halo_enabled()) {
+    int rc = launch_qconv_i8_halo(p, st);
+    if (rc < 0) return rc;
+    if (rc == 1) return ATTNDM_OK;
+  }
   if (tc_persistent_enabled()) return launch_qconv_i8_tc_persistent(p, st);
   TcGeom g;
   g.BN = p.O <= 256 ? round_up(p.O, 16) : 256;
