@@ -47,6 +47,10 @@ SIGNATURES = {
     "attndm_timestep_embedding": [vp, i32, i32, vp, vp],
     "attndm_ddim_step": [vp, vp, vp, vp, vp, vp, i64, vp],
     "attndm_stage_tables": [vp, i64, i32, vp, i32, vp, vp],
+    "attndm_rowprog": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp],
+    "attndm_rowprog_smem_bytes": [i32, i32, i32, i32],
+    "attndm_rowprog_packed_weight_bytes": [i32, i32],
+    "attndm_rowprog_pack_weights": [vp, i32, i32, vp, vp],
     "attndm_version": [],
     "attndm_device_supported": [],
 }
@@ -67,6 +71,7 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = C.c_int
+        L.attndm_rowprog_packed_weight_bytes.restype = C.c_longlong
         L.attndm_last_error.restype = C.c_char_p
         L.attndm_last_error.argtypes = []
         _lib = L

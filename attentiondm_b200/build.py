@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libattndm_b200.so")
-SOURCES = ["api.cu", "quant_kernels.cu", "conv_simt.cu", "conv_tc.cu", "misc_kernels.cu"]
+SOURCES = ["api.cu", "quant_kernels.cu", "conv_simt.cu", "conv_tc.cu", "misc_kernels.cu", "rowprog.cu"]
 HEADERS = ["common.cuh", "conv_common.cuh", os.path.join("..", "..", "include", "attndm_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-cudart", "static"]

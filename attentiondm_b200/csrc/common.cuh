@@ -51,6 +51,22 @@ __device__ __forceinline__ float silu_f(float v) {
   return __fdiv_rn(v, __fadd_rn(1.0f, expf(-v)));
 }
 
+
+// GroupNorm(32) finalisation and application, shared by every kernel that normalises (so that the fused
+// and the stand-alone paths agree bit for bit): mean / rstd from double sums, each step separately rounded.
+__device__ __forceinline__ void gn_mean_rstd(double s, double ss, double inv_n, float eps, float& mean, float& rstd) {
+  const double m = __dmul_rn(s, inv_n);
+  double var = __dsub_rn(__dmul_rn(ss, inv_n), __dmul_rn(m, m));
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(__dadd_rn(var, (double)eps)));
+}
+// silu(groupnorm(v)) with a = rstd*gamma, b = beta - mean*a  (models/diffusion.py:121-122)
+__device__ __forceinline__ float gn_silu_apply(float v, float mean, float rstd, float gamma, float beta) {
+  const float a = __fmul_rn(rstd, gamma);
+  return silu_f(fmaf(v, a, fmaf(-mean, a, beta)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

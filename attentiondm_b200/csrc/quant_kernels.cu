@@ -47,11 +47,7 @@ __device__ __forceinline__ void gn_refresh(const double* stats, int b, int lane,
   // lane g owns group g
   double s = stats[((long long)b * kGnGroups + lane) * 2 + 0];
   double ss = stats[((long long)b * kGnGroups + lane) * 2 + 1];
-  double m = s * inv_n;
-  double var = ss * inv_n - m * m;
-  if (var < 0.0) var = 0.0;
-  mean = (float)m;
-  rstd = (float)(1.0 / sqrt(var + (double)eps));
+  gn_mean_rstd(s, ss, inv_n, eps, mean, rstd);
 }
 
 template <int PRE, bool QUANT, bool VEC>
@@ -415,13 +411,7 @@ __global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p)
       }
       a = warp_sum_d(a);
       q = warp_sum_d(q);
-      if (lane_ == 0) {
-        const double m = a * inv_n;
-        double var = q * inv_n - m * m;
-        if (var < 0.0) var = 0.0;
-        s_mean[g] = (float)m;
-        s_rstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
-      }
+      if (lane_ == 0) gn_mean_rstd(a, q, inv_n, p.eps, s_mean[g], s_rstd[g]);
     }
   }
   __syncthreads();
@@ -452,11 +442,10 @@ __global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p)
         const float4 g4 = *reinterpret_cast<const float4*>(p.gamma + c);
         const float4 b4 = *reinterpret_cast<const float4*>(p.beta + c);
         const int g0 = c / cpg, g1 = (c + 1) / cpg, g2 = (c + 2) / cpg, g3 = (c + 3) / cpg;
-        float a0 = s_rstd[g0] * g4.x, a1 = s_rstd[g1] * g4.y, a2 = s_rstd[g2] * g4.z, a3 = s_rstd[g3] * g4.w;
-        v.x = silu_f(fmaf(v.x, a0, fmaf(-s_mean[g0], a0, b4.x)));
-        v.y = silu_f(fmaf(v.y, a1, fmaf(-s_mean[g1], a1, b4.y)));
-        v.z = silu_f(fmaf(v.z, a2, fmaf(-s_mean[g2], a2, b4.z)));
-        v.w = silu_f(fmaf(v.w, a3, fmaf(-s_mean[g3], a3, b4.w)));
+        v.x = gn_silu_apply(v.x, s_mean[g0], s_rstd[g0], g4.x, b4.x);
+        v.y = gn_silu_apply(v.y, s_mean[g1], s_rstd[g1], g4.y, b4.y);
+        v.z = gn_silu_apply(v.z, s_mean[g2], s_rstd[g2], g4.z, b4.z);
+        v.w = gn_silu_apply(v.w, s_mean[g3], s_rstd[g3], g4.w, b4.w);
         const long long pix = (long long)b * HW + px;
         if (p.quant) {
           cd.x = quant_code(v.x, s4.x, z4.x, p.qlo, p.qhi);

@@ -88,6 +88,9 @@ class _TimeBlock(nn.Module):
         """SiLU -> QConv2d 1x1 on [B,1,1,temb] -> [B, out] (models/diffusion.py:157-161)."""
         if self.time_mlp is None or time_emb is None:
             return None
+        pre = getattr(self, "_temb_fused", None)        # written by the fused time_mlp launch (rowprog.py)
+        if pre is not None:
+            return pre
         y = self.time_mlp[1].forward_fused(time_emb, ops.PRE_SILU)
         return y.view(y.shape[0], -1)
 
@@ -258,15 +261,27 @@ class Model(nn.Module):
         t_emb = ops.conv_f32(t_emb, l0.weight.detach().unsqueeze(1).contiguous(), l0.bias.detach())
         t_emb = ops.silu(t_emb)
         t_emb = ops.conv_f32(t_emb, l2.weight.detach().unsqueeze(1).contiguous(), l2.bias.detach())
+        fp = getattr(self, "_fused", None)                 # rowprog.FusedPlans, set by the CUDA-graph engine
+        if fp is not None:
+            fp.run_time_mlps(t_emb, self._fused_cur)
         h = self.init_conv.forward_fused(x)
         skips = [h]
-        for layer in self.down_blocks:
-            h = layer.forward_fused(h, t_emb)
-            skips.append(h)
-        h = self.middle_block1.forward_fused(h)
-        h = self.middle_attn.forward_fused(h)
-        h = self.middle_block2.forward_fused(h)
-        for layer in self.up_blocks:
+        if fp is not None and fp.trunk_plan is not None:
+            # every block that works on a 1x1 map runs inside ONE kernel (attndm_rowprog)
+            for layer in self.down_blocks[:fp.first_down]:
+                h = layer.forward_fused(h, t_emb)
+                skips.append(h)
+            h = fp.run_trunk(h, self._fused_cur)
+            rest = self.up_blocks[fp.n_up:]
+        else:
+            for layer in self.down_blocks:
+                h = layer.forward_fused(h, t_emb)
+                skips.append(h)
+            h = self.middle_block1.forward_fused(h)
+            h = self.middle_attn.forward_fused(h)
+            h = self.middle_block2.forward_fused(h)
+            rest = self.up_blocks
+        for layer in rest:
             skip = skips.pop() if len(skips) else torch.zeros_like(h)
             h = layer.forward_fused(h, skip, t_emb)
         gn = _gn_args(self.norm_out, h)

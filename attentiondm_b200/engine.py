@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from . import rowprog
 from .denoising import ddim_coefficients
 
 
@@ -79,6 +80,12 @@ class SamplerEngine:
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = 0
+        # fused per-sample programs (time_mlp of every block; all blocks on 1x1 maps): graph mode only
+        self.fused = None
+        if use_graph and hasattr(model, "down_blocks"):
+            if hasattr(model, "materialize_lazy_layers"):
+                model.materialize_lazy_layers()
+            self.fused = rowprog.build(model, self.B, {id(m): sl for m, sl in zip(self.layers, self.slices)}, dev)
 
     def _versions(self):
         return tuple((m._tab_key, m._pack_key) for m in self.layers)
@@ -108,12 +115,22 @@ class SamplerEngine:
         for m, (o, w) in zip(self.layers, self.slices):
             m.use_staged_row(self.cur[o:o + w])
         saved = [m.index_seq for m in self.layers]
+        blocks = []
+        if self.fused is not None:
+            self.model._fused, self.model._fused_cur = self.fused, self.cur
+            blocks = list(self.model.down_blocks) + list(self.model.up_blocks)
+            for b in blocks:
+                b._temb_fused = self.fused.temb.get(id(b))
         try:
             return fn()
         finally:
             for m, s in zip(self.layers, saved):
                 m.use_staged_row(None)
                 m.index_seq = s
+            if self.fused is not None:
+                self.model._fused = None
+                for b in blocks:
+                    b._temb_fused = None
 
     def _capture(self):
         from . import _ffi

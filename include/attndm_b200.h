@@ -222,6 +222,79 @@ int attndm_ddim_step(const float* xt, const float* eps, const float* coef, const
 int attndm_stage_tables(const float* table, long long n, int T, int* step, int advance,
                         float* dst, void* stream);
 
+
+/* ---- fused per-sample layer programs (1x1 feature maps) ------------------- */
+
+/* On a 1x1 feature map every op of the UNet is row-local: GroupNorm reduces over the channels of ONE
+ * sample, a 3x3/pad-1 conv is its centre tap, attention over a single position is the identity on V.
+ * So a run of blocks at 1x1 (11 DownBlock/UpBlock/middle blocks, ~150 of the 198 QConv2d of the CIFAR
+ * model: models/diffusion.py:119-136,170-190,224-252, models/self_attention.py:127-151) is executed by
+ * ONE kernel: each CTA owns `ns` samples, keeps their activations in shared memory and interprets a
+ * list of ops.  The tiny GEMMs run as warp-level int8 tensor-core MMAs whose weight fragments (and the
+ * per-channel parameter vectors) of the NEXT conv are fetched while the current one finishes.
+ * Every op reproduces the arithmetic of the stand-alone kernel it replaces bit for bit
+ * (attndm_gn_act_quant, attndm_act_quant, attndm_qconv_i8 with taps = 1, attndm_conv_f32,
+ * attndm_attention with N = 1, attndm_scale_add, attndm_maxpool2), which is how it is tested.
+ *
+ * Activation buffers live in a per-CTA fp32 arena; a buffer reference is (offset, leading dimension):
+ * element (sample n, channel c) = arena[off + n*ld + c].  Offsets and lds are multiples of 4.
+ *
+ * A CONV op reads its parameters from shared memory, where the PREVIOUS conv of the program (or the
+ * program's first op, which must not be a CONV) has put them: the nx_* fields of those ops describe the
+ * next CONV -- nx_qw its weights (attndm_rowprog_pack_weights order), nx_tab_off its row of the staged
+ * table ([scale Cq | zero point Cq | mult Oq | act_zp 4], Cq = round_up(C, 4)), nx_stat its static block
+ * (floats: gamma[C] beta[C] bias[O], then int32 wsum[O] w_zp[O]; gamma/beta unused without GroupNorm,
+ * bias zero when the layer has none). */
+#define ATTNDM_ROWOP_END 0
+#define ATTNDM_ROWOP_LOAD 1        /* dst[n][0..C) = g0[(s0+n)*g_ld + c]                                   */
+#define ATTNDM_ROWOP_LOAD_POOL 2   /* dst[n][c] = max over the 2x2 pixels of g0 viewed as [B][2][2][C]      */
+#define ATTNDM_ROWOP_STORE 3       /* g0[(s0+n)*g_ld + c] = src[n][c]                                       */
+#define ATTNDM_ROWOP_COPY 4        /* dst = src                                                             */
+#define ATTNDM_ROWOP_CONV 5        /* dst = qconv1x1(quant(pre(src))) + bias (+ add0) (+ g1[(s0+n)*O + o]) */
+#define ATTNDM_ROWOP_FCONV 6       /* dst = fp32 1x1 conv: g0 = w^T [C][O], g1 = bias[O]                    */
+#define ATTNDM_ROWOP_ATTN1 7       /* dst = softmax(q.k * scale) v for one position: src = q, add0 = k, aux = v */
+#define ATTNDM_ROWOP_SCALE_ADD 8   /* dst = g0[0] * src + add0                                              */
+
+typedef struct {
+  int32_t type;
+  int32_t C, O;                    /* input / output channels                                               */
+  int32_t src_off, src_ld;
+  int32_t dst_off, dst_ld;
+  int32_t add0_off, add0_ld;       /* -1 = none                                                             */
+  int32_t aux_off, aux_ld;
+  int32_t pre, a_bit;              /* CONV: ATTNDM_PRE_*, activation bits                                   */
+  int32_t tab_off;                 /* CONV: float offset of this layer's row in the staged table            */
+  int32_t nx_C, nx_O, nx_tab_off;  /* the next CONV of the program (see above)                              */
+  int32_t g_ld;                    /* LOAD/STORE: row pitch of g0 in floats                                 */
+  float fparam;                    /* CONV: GroupNorm eps; ATTN1: logit scale                               */
+  int32_t g0_ext;                  /* >= 0: g0 is taken from ext[g0_ext] of the launch instead (LOAD/STORE) */
+  const void* g0;                  /* LOAD/STORE/FCONV/SCALE_ADD global pointer                             */
+  const void* g1;                  /* CONV: temb [B][O] or NULL; FCONV: bias                                */
+  const void* qw;                  /* CONV: int8 weights in attndm_rowprog_pack_weights order               */
+  const void* stat;                /* CONV: this layer's static block (informational)                       */
+  const void* nx_qw;               /* next CONV: weights, or NULL when there is none                        */
+  const void* nx_stat;             /* next CONV: static block                                               */
+  const void* rsv0;
+  const void* rsv1;
+} attndm_rowop;
+
+/* ops: device array of attndm_rowop; prog_start: device int32[nprog], index of each program's first op
+ * (a program ends at ATTNDM_ROWOP_END).  Grid = ceil(B/ns) x nprog CTAs; ns in {2,4,8}.
+ * arena_floats: per-CTA arena size; cp_max: largest input channel count of any CONV (multiple of 16);
+ * pbuf_floats: largest parameter block over the CONV ops: (2*Cq + Oq + 4) + (2*C + 3*O) floats.
+ * cur: the staged per-step table (attndm_stage_tables).
+ * ext: host array of n_ext (<= 4) device pointers bound at launch time, for tensors whose address is
+ * only known per call (the program's input and output activations). */
+int attndm_rowprog(const attndm_rowop* ops, const int32_t* prog_start, int nprog, int B, int ns,
+                   int arena_floats, int cp_max, int pbuf_floats, const float* cur,
+                   const void* const* ext, int n_ext, void* stream);
+/* shared memory the kernel would need (bytes), for the host-side planner */
+int attndm_rowprog_smem_bytes(int ns, int arena_floats, int cp_max, int pbuf_floats);
+/* int8 weights [O][Cp] -> MMA-fragment order [ceil(O/16)][ceil(Cp/32)][32 lanes][16 B] (zero padded);
+ * `out` needs attndm_rowprog_packed_weight_bytes(O, Cp) bytes. */
+long long attndm_rowprog_packed_weight_bytes(int O, int Cp);
+int attndm_rowprog_pack_weights(const int8_t* qw, int O, int Cp, int8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

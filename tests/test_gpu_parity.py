@@ -586,6 +586,41 @@ def test_per_layer_trace_vs_reference_fixture(golden):
 
 
 # ---------------------------------------------------------------------------
+# fused per-sample programs (attndm_rowprog): the CUDA-graph engine runs every time_mlp and every block
+# that works on a 1x1 map inside one kernel each; the result must equal the layer-by-layer kernels
+# (which the in-situ tests above pin to the oracle) bit for bit.
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("ch,ch_mult,size,bw,alpha,B", [
+    (32, (1, 2), 4, 8, "uniform", 3),          # 4 -> 2 -> 1 -> 1: pooled trunk input, 32/64 channels (1-2 per group)
+    (64, (1, 2, 2), 8, 8, "uniform", 9),       # 8 -> 4 -> 2 -> 1 ..., 128 channels, ragged sample tile
+    (32, (1, 2), 4, 6, "uniform", 2),          # 6-bit activations (4-bit key projection)
+    (32, (1, 2), 4, 4, "attn_random", 2),      # trained attention alphas -> those layers leave the integer path
+])
+def test_fused_rowprog_equals_layerwise(ch, ch_mult, size, bw, alpha, B):
+    import attentiondm_b200 as A
+    from attentiondm_b200.engine import SamplerEngine
+    spec = S.tiny_spec(T=4, bitwidth=bw, ch=ch, ch_mult=ch_mult, image_size=size)
+    sd = S.synth_state_dict(spec, seed=11, alpha_mode=alpha)
+    m = build_cuda_model(spec, sd)
+    betas = R.beta_schedule_linear().to(DEV)
+    x = torch.randn(B, 3, size, size, generator=torch.Generator().manual_seed(4)).to(DEV)
+    m.set_calibrate(True)
+    A.generalized_steps(x, spec.seq, m, betas, eta=0.0, keep="last")
+    m.set_calibrate(False)
+    m.reset_index_seq()
+    xs_e, x0_e = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, use_graph=False)
+    m.reset_index_seq()
+    xs_g, x0_g = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, use_graph=True)
+    eng = SamplerEngine.for_model(m, spec.seq, betas, 0.0, tuple(x.shape))
+    if alpha == "uniform":
+        assert eng.fused is not None and eng.fused.trunk_plan is not None, "the fused plan was not built"
+        assert eng.fused.n_up >= 1
+    assert torch.isfinite(xs_g[-1]).all()
+    assert torch.equal(torch.stack(xs_g[1:]), torch.stack(xs_e[1:]))
+    assert torch.equal(torch.stack(x0_g), torch.stack(x0_e))
+
+
+# ---------------------------------------------------------------------------
 # full-size properties (oracle too slow): CIFAR config, batch 8
 # ---------------------------------------------------------------------------
 def test_cifar_full_size_properties():
