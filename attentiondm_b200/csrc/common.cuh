@@ -47,8 +47,12 @@ __device__ __forceinline__ float dequant(float code, float s, float zp) {
 }
 
 __device__ __forceinline__ float silu_f(float v) {
-  // x * sigmoid(x) == x / (1 + exp(-x)); accurate expf (no fast-math)
-  return __fdiv_rn(v, __fadd_rn(1.0f, expf(-v)));
+  // x * sigmoid(x) == x / (1 + exp(-x)) on the special-function unit: ex2.approx for the exponential and
+  // rcp.approx for the quotient (<= ~3 ulp in total, i.e. well inside what separates two fp32 SiLU
+  // implementations -- torch's CPU and CUDA kernels differ by as much).  The IEEE divide + accurate expf
+  // version cost ~40 instructions per element and made every GroupNorm+SiLU+quantize pass
+  // instruction-bound at a third of the HBM rate.  Every kernel shares this one definition.
+  return __fdividef(v, __fadd_rn(1.0f, __expf(-v)));
 }
 
 

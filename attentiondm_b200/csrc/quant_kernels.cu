@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActQuantParams p) {
 // incrementally (no 64-bit division per row) and the next row's load is issued before the current row
 // is processed (two 512-B requests in flight per warp).
 template <int PRE, bool QUANT, int NQ>
-__global__ void __launch_bounds__(256) act_quant_fast_kernel(ActQuantParams p) {
+__global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) act_quant_fast_kernel(ActQuantParams p) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -200,8 +200,7 @@ __global__ void __launch_bounds__(256) act_quant_fast_kernel(ActQuantParams p) {
   int b = (int)(r0 / per);
   int rem = (int)(r0 - (long long)b * per);
   int hp = rem / Wp, wp = rem - hp * Wp;
-  float4 s4[NQ], z4[NQ], g4[NQ], be4[NQ], ga[NQ], gb[NQ], pad[NQ];
-  int grp[NQ];
+  float4 s4[NQ], z4[NQ], ga[NQ], gb[NQ];       // per-lane quantizer and GroupNorm constants, in registers across rows
 #pragma unroll
   for (int i = 0; i < NQ; ++i) {
     const int c = (i * 32 + lane) << 2;
@@ -211,102 +210,224 @@ __global__ void __launch_bounds__(256) act_quant_fast_kernel(ActQuantParams p) {
       s4[i] = *reinterpret_cast<const float4*>(p.scale + c);
       z4[i] = *reinterpret_cast<const float4*>(p.zp + c);
     }
-    pad[i].x = fminf(fmaxf(-z4[i].x, p.qlo), p.qhi);
-    pad[i].y = fminf(fmaxf(-z4[i].y, p.qlo), p.qhi);
-    pad[i].z = fminf(fmaxf(-z4[i].z, p.qlo), p.qhi);
-    pad[i].w = fminf(fmaxf(-z4[i].w, p.qlo), p.qhi);
-    if (PRE == ATTNDM_PRE_GN_SILU) {
-      g4[i] = *reinterpret_cast<const float4*>(p.gamma + c);
-      be4[i] = *reinterpret_cast<const float4*>(p.beta + c);
-      grp[i] = c / cpg;                       // cpg % 4 == 0 on this path: one group per float4
-    }
     ga[i] = gb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   int cur_b = -1;
   auto interior_of = [&](int hh, int ww) { return !p.halo || (hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W); };
   auto pix_of = [&](int bb, int hh, int ww) {
-    return p.halo ? ((long long)bb * p.H + (hh - 1)) * p.W + (ww - 1) : ((long long)bb * p.H + hh) * p.W + ww;
+    return p.halo ? (bb * p.H + (hh - 1)) * p.W + (ww - 1) : (bb * p.H + hh) * p.W + ww;
   };
-  float4 cur[NQ], nxt[NQ];
-  bool cur_in = interior_of(hp, wp);
-  long long cur_pix = cur_in ? pix_of(b, hp, wp) : 0;
-  if (cur_in) {
+  // R rows per iteration: all their loads are issued before any arithmetic (R x NQ independent 512-byte
+  // requests in flight per warp), and the per-row bookkeeping (coordinates, code-sum reduction, row-sum store)
+  // is paid once per group.
+  constexpr int R = 4;
+  for (long long r = r0; r < r1; r += R) {
+    bool in[R];
+    unsigned pix[R];                   // element offset of the pixel row (the launcher checks it fits 32 bits)
+    int bb[R];
+    float4 v[R][NQ];
 #pragma unroll
-    for (int i = 0; i < NQ; ++i)
-      cur[i] = ldg_stream(reinterpret_cast<const float4*>(p.x + cur_pix * p.C + ((i * 32 + lane) << 2)));
-  }
-  for (long long r = r0; r < r1; ++r) {
-    // coordinates of the next row + prefetch
-    int nb = b, nhp = hp, nwp = wp + 1;
-    if (nwp == Wp) { nwp = 0; if (++nhp == Hp) { nhp = 0; ++nb; } }
-    const bool nxt_in = (r + 1 < r1) && interior_of(nhp, nwp);
-    const long long nxt_pix = nxt_in ? pix_of(nb, nhp, nwp) : 0;
-    if (nxt_in) {
+    for (int k = 0; k < R; ++k) {
+      in[k] = (r + k < r1) && interior_of(hp, wp);
+      pix[k] = in[k] ? (unsigned)pix_of(b, hp, wp) * (unsigned)p.C : 0u;
+      bb[k] = b;
+      if (in[k]) {
 #pragma unroll
-      for (int i = 0; i < NQ; ++i)
-        nxt[i] = ldg_stream(reinterpret_cast<const float4*>(p.x + nxt_pix * p.C + ((i * 32 + lane) << 2)));
+        for (int i = 0; i < NQ; ++i)
+          v[k][i] = ldg_stream(reinterpret_cast<const float4*>(p.x + pix[k] + ((i * 32 + lane) << 2)));
+      }
+      if (++wp == Wp) { wp = 0; if (++hp == Hp) { hp = 0; ++b; } }
     }
-    if (PRE == ATTNDM_PRE_GN_SILU && cur_in && b != cur_b) {
+    int sums[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (PRE == ATTNDM_PRE_GN_SILU && in[k] && bb[k] != cur_b) {        // warp-uniform
+        float mean, rstd;
+        gn_refresh(p.gn_stats, bb[k], lane, inv_n, p.eps, mean, rstd);
+        cur_b = bb[k];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {                        // once per sample: gamma / beta come from L1/L2
+          const int c = (i * 32 + lane) << 2;
+          const int gi = c / cpg;                              // cpg % 4 == 0 on this path: one group per float4
+          const float4 g4 = *reinterpret_cast<const float4*>(p.gamma + c);
+          const float4 be4 = *reinterpret_cast<const float4*>(p.beta + c);
+          const float m = __shfl_sync(0xffffffffu, mean, gi), rs = __shfl_sync(0xffffffffu, rstd, gi);
+          ga[i].x = rs * g4.x; gb[i].x = fmaf(-m, ga[i].x, be4.x);
+          ga[i].y = rs * g4.y; gb[i].y = fmaf(-m, ga[i].y, be4.y);
+          ga[i].z = rs * g4.z; gb[i].z = fmaf(-m, ga[i].z, be4.z);
+          ga[i].w = rs * g4.w; gb[i].w = fmaf(-m, ga[i].w, be4.w);
+        }
+      }
+      int acc = 0;
+      if (r + k < r1) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const int c = (i * 32 + lane) << 2;
+          float4 cd;
+          if (in[k]) {
+            float4 t = v[k][i];
+            t.x = pre_op<PRE>(t.x, ga[i].x, gb[i].x);
+            t.y = pre_op<PRE>(t.y, ga[i].y, gb[i].y);
+            t.z = pre_op<PRE>(t.z, ga[i].z, gb[i].z);
+            t.w = pre_op<PRE>(t.w, ga[i].w, gb[i].w);
+            if (QUANT) {
+              cd.x = quant_code(t.x, s4[i].x, z4[i].x, p.qlo, p.qhi);
+              cd.y = quant_code(t.y, s4[i].y, z4[i].y, p.qlo, p.qhi);
+              cd.z = quant_code(t.z, s4[i].z, z4[i].z, p.qlo, p.qhi);
+              cd.w = quant_code(t.w, s4[i].w, z4[i].w, p.qlo, p.qhi);
+              if (p.y) {
+                float4 o;
+                o.x = dequant(cd.x, s4[i].x, z4[i].x);
+                o.y = dequant(cd.y, s4[i].y, z4[i].y);
+                o.z = dequant(cd.z, s4[i].z, z4[i].z);
+                o.w = dequant(cd.w, s4[i].w, z4[i].w);
+                *reinterpret_cast<float4*>(p.y + pix[k] + c) = o;
+              }
+            } else {
+              if (p.y) *reinterpret_cast<float4*>(p.y + pix[k] + c) = t;
+              cd = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          } else {                                             // halo ring: the code of 0.0
+            cd.x = fminf(fmaxf(-z4[i].x, p.qlo), p.qhi);
+            cd.y = fminf(fmaxf(-z4[i].y, p.qlo), p.qhi);
+            cd.z = fminf(fmaxf(-z4[i].z, p.qlo), p.qhi);
+            cd.w = fminf(fmaxf(-z4[i].w, p.qlo), p.qhi);
+          }
+          if (QUANT && p.codes) {
+            const int ix = (int)cd.x, iy = (int)cd.y, iz = (int)cd.z, iw = (int)cd.w;
+            acc += ix + iy + iz + iw;
+            *reinterpret_cast<char4*>(p.codes + (r + k) * p.Cp + c) =
+                make_char4((signed char)ix, (signed char)iy, (signed char)iz, (signed char)iw);
+          }
+        }
+      }
+      sums[k] = acc;
+    }
+    if (QUANT && p.rowsum) {
+      int mine = 0;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int t = __reduce_add_sync(0xffffffffu, sums[k]);
+        if (lane == k) mine = t;
+      }
+      if (lane < R && r + lane < r1) p.rowsum[r + lane] = mine;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The int8 hot path at the large feature maps (codes + row sums only, C = 128 or 256, W % 4 == 0):
+// warps walk INTERIOR image rows, four pixels per step with all loads issued first; the halo ring is
+// written by the warp that owns the adjacent image row, so the inner loop has no border logic.
+// Quantizer: clamp before round (bounds are integers, so it equals round-then-clamp, NaN -> lo as before)
+// and one F2I.RNI instead of rint + cvt.  ~15 instructions per element instead of ~25.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int quant_code_i(float v, float s, float zp, float lo, float hi) {
+  const float t = __fsub_rn(__fmul_rn(s, v), zp);
+  return __float2int_rn(fminf(fmaxf(t, lo), hi));
+}
+
+template <int PRE, int NQ>
+__global__ void __launch_bounds__(256, NQ == 1 ? 4 : 3) act_quant_rows_kernel(ActQuantParams p) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nimg = p.B * p.H;                           // interior image rows
+  const int ir0 = warp * (int)p.rows_per_warp;
+  int ir1 = ir0 + (int)p.rows_per_warp;
+  if (ir1 > nimg) ir1 = nimg;
+  if (ir0 >= ir1) return;
+  const int W = p.W, C = p.C, Cp = p.Cp;
+  const int Hp = p.halo ? p.H + 2 : p.H, Wp = p.halo ? W + 2 : W;
+  const int cpg = C / kGnGroups;
+  const double inv_n = (PRE == ATTNDM_PRE_GN_SILU) ? 1.0 / ((double)p.H * W * cpg) : 0.0;
+  float4 s4[NQ], z4[NQ], ga[NQ], gb[NQ];
+  int padw[NQ], padsum = 0;                              // the ring code (packed) and its row sum
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int c = (i * 32 + lane) << 2;
+    s4[i] = *reinterpret_cast<const float4*>(p.scale + c);
+    z4[i] = *reinterpret_cast<const float4*>(p.zp + c);
+    const int a = (int)fminf(fmaxf(-z4[i].x, p.qlo), p.qhi), b2 = (int)fminf(fmaxf(-z4[i].y, p.qlo), p.qhi);
+    const int c2 = (int)fminf(fmaxf(-z4[i].z, p.qlo), p.qhi), d = (int)fminf(fmaxf(-z4[i].w, p.qlo), p.qhi);
+    padw[i] = (a & 0xff) | ((b2 & 0xff) << 8) | ((c2 & 0xff) << 16) | ((d & 0xff) << 24);
+    padsum += a + b2 + c2 + d;
+    ga[i] = gb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  padsum = __reduce_add_sync(0xffffffffu, padsum);
+  auto ring_row = [&](long long row) {                   // one ring pixel: its codes and row sum
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) *reinterpret_cast<int*>(p.codes + row * Cp + ((i * 32 + lane) << 2)) = padw[i];
+    if (lane == 0) p.rowsum[row] = padsum;
+  };
+  int cur_b = -1;
+  constexpr int R = 4;
+  for (int ir = ir0; ir < ir1; ++ir) {
+    const int b = ir / p.H, h = ir - b * p.H;
+    if (PRE == ATTNDM_PRE_GN_SILU && b != cur_b) {       // warp-uniform, once per sample
       float mean, rstd;
       gn_refresh(p.gn_stats, b, lane, inv_n, p.eps, mean, rstd);
       cur_b = b;
 #pragma unroll
       for (int i = 0; i < NQ; ++i) {
-        const float m = __shfl_sync(0xffffffffu, mean, grp[i]), rs = __shfl_sync(0xffffffffu, rstd, grp[i]);
-        ga[i].x = rs * g4[i].x; gb[i].x = fmaf(-m, ga[i].x, be4[i].x);
-        ga[i].y = rs * g4[i].y; gb[i].y = fmaf(-m, ga[i].y, be4[i].y);
-        ga[i].z = rs * g4[i].z; gb[i].z = fmaf(-m, ga[i].z, be4[i].z);
-        ga[i].w = rs * g4[i].w; gb[i].w = fmaf(-m, ga[i].w, be4[i].w);
+        const int c = (i * 32 + lane) << 2;
+        const int gi = c / cpg;                            // cpg % 4 == 0 on this path: one group per float4
+        const float4 g4 = *reinterpret_cast<const float4*>(p.gamma + c);
+        const float4 be4 = *reinterpret_cast<const float4*>(p.beta + c);
+        const float m = __shfl_sync(0xffffffffu, mean, gi), rs = __shfl_sync(0xffffffffu, rstd, gi);
+        ga[i].x = rs * g4.x; gb[i].x = fmaf(-m, ga[i].x, be4.x);
+        ga[i].y = rs * g4.y; gb[i].y = fmaf(-m, ga[i].y, be4.y);
+        ga[i].z = rs * g4.z; gb[i].z = fmaf(-m, ga[i].z, be4.z);
+        ga[i].w = rs * g4.w; gb[i].w = fmaf(-m, ga[i].w, be4.w);
       }
     }
-    int acc = 0;
+    const float* xrow = p.x + (long long)ir * W * C + (lane << 2);
+    const long long rbase = p.halo ? ((long long)b * Hp + h + 1) * Wp + 1 : (long long)ir * W;   // code row of pixel w = 0
+    int8_t* crow = p.codes + rbase * Cp + (lane << 2);
+    for (int w0 = 0; w0 < W; w0 += R) {
+      float4 v[R][NQ];
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-      const int c = (i * 32 + lane) << 2;
-      float4 cd;
-      if (cur_in) {
-        float4 v = cur[i];
-        v.x = pre_op<PRE>(v.x, ga[i].x, gb[i].x);
-        v.y = pre_op<PRE>(v.y, ga[i].y, gb[i].y);
-        v.z = pre_op<PRE>(v.z, ga[i].z, gb[i].z);
-        v.w = pre_op<PRE>(v.w, ga[i].w, gb[i].w);
-        if (QUANT) {
-          cd.x = quant_code(v.x, s4[i].x, z4[i].x, p.qlo, p.qhi);
-          cd.y = quant_code(v.y, s4[i].y, z4[i].y, p.qlo, p.qhi);
-          cd.z = quant_code(v.z, s4[i].z, z4[i].z, p.qlo, p.qhi);
-          cd.w = quant_code(v.w, s4[i].w, z4[i].w, p.qlo, p.qhi);
-          if (p.y) {
-            float4 o;
-            o.x = dequant(cd.x, s4[i].x, z4[i].x);
-            o.y = dequant(cd.y, s4[i].y, z4[i].y);
-            o.z = dequant(cd.z, s4[i].z, z4[i].z);
-            o.w = dequant(cd.w, s4[i].w, z4[i].w);
-            *reinterpret_cast<float4*>(p.y + cur_pix * p.C + c) = o;
-          }
-        } else {
-          if (p.y) *reinterpret_cast<float4*>(p.y + cur_pix * p.C + c) = v;
-          cd = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < R; ++k)
+#pragma unroll
+        for (int i = 0; i < NQ; ++i)
+          v[k][i] = ldg_stream(reinterpret_cast<const float4*>(xrow + (long long)(w0 + k) * C + i * 128));
+      int sums[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        int acc = 0;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          float4 t = v[k][i];
+          t.x = pre_op<PRE>(t.x, ga[i].x, gb[i].x);
+          t.y = pre_op<PRE>(t.y, ga[i].y, gb[i].y);
+          t.z = pre_op<PRE>(t.z, ga[i].z, gb[i].z);
+          t.w = pre_op<PRE>(t.w, ga[i].w, gb[i].w);
+          const int ix = quant_code_i(t.x, s4[i].x, z4[i].x, p.qlo, p.qhi);
+          const int iy = quant_code_i(t.y, s4[i].y, z4[i].y, p.qlo, p.qhi);
+          const int iz = quant_code_i(t.z, s4[i].z, z4[i].z, p.qlo, p.qhi);
+          const int iw = quant_code_i(t.w, s4[i].w, z4[i].w, p.qlo, p.qhi);
+          acc += ix + iy + iz + iw;
+          *reinterpret_cast<int*>(crow + (long long)(w0 + k) * Cp + i * 128) =
+              (ix & 0xff) | ((iy & 0xff) << 8) | ((iz & 0xff) << 16) | (iw << 24);
         }
-      } else {
-        cd = pad[i];
+        sums[k] = acc;
       }
-      if (QUANT && p.codes) {
-        const int ix = (int)cd.x, iy = (int)cd.y, iz = (int)cd.z, iw = (int)cd.w;
-        acc += ix + iy + iz + iw;
-        *reinterpret_cast<char4*>(p.codes + r * p.Cp + c) =
-            make_char4((signed char)ix, (signed char)iy, (signed char)iz, (signed char)iw);
+      int mine = 0;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int t = __reduce_add_sync(0xffffffffu, sums[k]);
+        if (lane == k) mine = t;
       }
+      if (lane < R) p.rowsum[rbase + w0 + lane] = mine;
     }
-    if (QUANT && p.rowsum) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) p.rowsum[r] = acc;
+    if (p.halo) {                                        // the ring next to this image row
+      ring_row(rbase - 1);
+      ring_row(rbase + W);
+      if (h == 0)
+        for (int w = 0; w < Wp; ++w) ring_row(rbase - 1 - Wp + w);
+      if (h == p.H - 1)
+        for (int w = 0; w < Wp; ++w) ring_row(rbase - 1 + Wp + w);
     }
-    b = nb; hp = nhp; wp = nwp;
-    cur_in = nxt_in;
-    cur_pix = nxt_pix;
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) cur[i] = nxt[i];
   }
 }
 
@@ -314,7 +435,8 @@ template <int PRE, bool QUANT>
 static void launch_act_quant(const ActQuantParams& p, int blocks, cudaStream_t st) {
   // the GN shuffle in the scalar path needs all lanes converged per channel step;
   // it is only used for C % 4 != 0 (the 3-channel latent), which never has a GN.
-  const bool gn_ok = (PRE != ATTNDM_PRE_GN_SILU) || ((p.C / kGnGroups) % 4 == 0);
+  const bool gn_ok = ((PRE != ATTNDM_PRE_GN_SILU) || ((p.C / kGnGroups) % 4 == 0)) &&
+                     (long long)p.B * p.H * p.W * p.C < (1LL << 31);          // 32-bit element offsets in the fast kernel
   if (p.C == 128 && gn_ok)
     launch_pdl(act_quant_fast_kernel<PRE, QUANT, 1>, dim3(blocks), dim3(256), 0, st, p);
   else if (p.C == 256 && gn_ok)
@@ -345,11 +467,34 @@ static int act_quant_impl(const float* x, int B, int H, int W, int C, const floa
   p.y = y;
   p.rows = p.halo ? (long long)B * (H + 2) * (W + 2) : (long long)B * H * W;
   // ~8 warps per block; aim at <= 16 resident blocks per SM worth of warps, rows contiguous per warp
-  long long max_warps = (long long)kNumSMs * 8 * 8;
+  // one wave: the fast kernels keep 3 (C = 128) or 2 (C = 256) blocks of 8 warps resident per SM
+  long long max_warps = (long long)kNumSMs * 8 * (C == 128 ? 3 : C == 256 ? 2 : 8);
   long long warps = p.rows < max_warps ? p.rows : max_warps;
   p.rows_per_warp = (p.rows + warps - 1) / warps;
   warps = (p.rows + p.rows_per_warp - 1) / p.rows_per_warp;
   int blocks = cdiv(warps, 8);
+  // int8 hot path at the large maps: codes + row sums only
+  if (quant && codes && rowsum && !y && (C == 128 || C == 256) && (W & 3) == 0 &&
+      (pre != ATTNDM_PRE_GN_SILU || (C / kGnGroups) % 4 == 0) && (long long)B * H * W * C < (1LL << 31) &&
+      (((uintptr_t)x | (uintptr_t)codes | (uintptr_t)scale | (uintptr_t)zp) & 15) == 0) {
+    const int nimg = B * H;
+    int w2 = kNumSMs * 8 * (C == 128 ? 4 : 3);
+    if (w2 > nimg) w2 = nimg;
+    p.rows_per_warp = (nimg + w2 - 1) / w2;
+    w2 = (nimg + (int)p.rows_per_warp - 1) / (int)p.rows_per_warp;
+    const int nb = cdiv(w2, 8);
+#define ATTNDM_AQ_ROWS(PREV)                                                                                         \
+    do {                                                                                                              \
+      if (C == 128) launch_pdl(act_quant_rows_kernel<PREV, 1>, dim3(nb), dim3(256), 0, st, p);                        \
+      else launch_pdl(act_quant_rows_kernel<PREV, 2>, dim3(nb), dim3(256), 0, st, p);                                 \
+    } while (0)
+    if (pre == ATTNDM_PRE_GN_SILU) ATTNDM_AQ_ROWS(ATTNDM_PRE_GN_SILU);
+    else if (pre == ATTNDM_PRE_SILU) ATTNDM_AQ_ROWS(ATTNDM_PRE_SILU);
+    else ATTNDM_AQ_ROWS(ATTNDM_PRE_NONE);
+#undef ATTNDM_AQ_ROWS
+    ATTNDM_CUDA_LAUNCH_CHECK("act_quant");
+    return ATTNDM_OK;
+  }
   if (!quant) {
     if (pre == ATTNDM_PRE_GN_SILU) launch_act_quant<ATTNDM_PRE_GN_SILU, false>(p, blocks, st);
     else if (pre == ATTNDM_PRE_SILU) launch_act_quant<ATTNDM_PRE_SILU, false>(p, blocks, st);
@@ -1035,7 +1180,8 @@ int attndm_calib_mix(const float* x, long long rows, int C, int G, const float* 
                      int a_bit, float* y, double* lp_sum, float lp_p, void* stream) {
   ATTNDM_CHECK_ARG(x && y && groups_range_t && sw && rows > 0 && C > 0, "calib_mix: bad args");
   ATTNDM_CHECK_ARG(G >= 1 && G <= kMaxGroups && a_bit >= 2 && a_bit <= 8, "calib_mix: G <= 16, 2 <= a_bit <= 8");
-  long long max_warps = (long long)kNumSMs * 8 * 8;
+  // one wave: the fast kernels keep 3 (C = 128) or 2 (C = 256) blocks of 8 warps resident per SM
+  long long max_warps = (long long)kNumSMs * 8 * (C == 128 ? 3 : C == 256 ? 2 : 8);
   long long warps = rows < max_warps ? rows : max_warps;
   long long rpw = (rows + warps - 1) / warps;
   warps = (rows + rpw - 1) / rpw;

@@ -46,14 +46,37 @@ __device__ __forceinline__ void rp_mma_s8(int (&d)[4], const uint4& a, uint32_t 
       : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
       : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
-// 16-byte asynchronous global -> shared copy (LDGSTS): unlike a load into registers it holds no register
-// scoreboard, so the instructions that follow never wait for it
-__device__ __forceinline__ void rp_cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+// Bulk asynchronous global -> shared copies (TMA, cp.async.bulk) tracked by mbarriers: ONE instruction moves a
+// warp's whole 4 KB block of A fragments (or a conv's parameter block), holds no register scoreboard, and is
+// waited for only where the data is consumed.  (Per-thread 16-byte cp.async cost ~8 issue cycles each --
+// 5600 of them per conv took longer than the conv's MMAs.)
+__device__ __forceinline__ uint32_t rp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rp_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rp_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = clock64();
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && clock64() - t0 > 4000000000LL) __trap();     // a lost arrival fails the launch instead of hanging
+  } while (!done);
+}
+__device__ __forceinline__ void rp_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rp_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void rp_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void rp_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void rp_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint4 rp_ldg128(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -113,6 +136,8 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
   __shared__ float s_mean[NS * kGnGroups], s_rstd[NS * kGnGroups];
   __shared__ int s_rowsum[8];
   __shared__ float s_prob[8];
+  __shared__ __align__(8) uint64_t s_wbar[RP_WARPS];   // per warp: its staged A fragments have landed
+  __shared__ __align__(8) uint64_t s_pbar[2];          // per parameter buffer
   pdl_launch_dependents();
 
   uint8_t* const wstage = rp_smem;                                               // [16 warps][8 k32 steps][512 B]
@@ -125,6 +150,12 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
   const attndm_rowop* prog = ops + prog_start[blockIdx.y];
   constexpr int OPW = (int)(sizeof(attndm_rowop) / 4);
   if (tid < OPW) reinterpret_cast<int*>(&s_op[0])[tid] = reinterpret_cast<const int*>(prog)[tid];
+  if (tid == 0) {
+    for (int i = 0; i < RP_WARPS; ++i) rp_mbar_init(rp_smem_u32(&s_wbar[i]), 1);
+    rp_mbar_init(rp_smem_u32(&s_pbar[0]), 1);
+    rp_mbar_init(rp_smem_u32(&s_pbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   pdl_wait();                          // inputs (activations, staged table) come from earlier kernels
 
@@ -134,6 +165,7 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
 
   uint32_t nconv = 0;                  // CONV ops seen so far: parity selects the parameter buffer
   uint8_t* const wmine = wstage + (size_t)warp * (RP_KCH * 512) + lane * 16;    // this lane's slots of the staged fragments
+  uint32_t wuse = 0;                   // how many times this warp's fragment barrier has completed (parity)
 
   for (int opi = 0;; ++opi) {
     const attndm_rowop& op = s_op[opi & 1];
@@ -143,25 +175,32 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
     if (tid < OPW) next_word = reinterpret_cast<const int*>(prog + opi + 1)[tid];
     const int C = op.C, O = op.O;
     // Prefetch of the NEXT conv (described by the nx_* fields of a CONV op and of a program's first op) with
-    // cp.async: its first 256 input channels of A fragments (tile = warp) into this warp's staging slots, its
-    // parameter block into the other parameter buffer.  Nobody waits for it until that conv's phase A2.
+    // bulk copies: its first 256 input channels of A fragments (tile = warp) into this warp's staging block
+    // (one copy per warp), its parameter block into the other parameter buffer (two copies by one thread).
+    // Nobody waits for them until that conv's phase A2 / phase B.
     const bool has_next = (type == ATTNDM_ROWOP_CONV || opi == 0) && op.nx_qw != nullptr;
     const int nC = op.nx_C, nO = op.nx_O;
 #define RP_PREFETCH_ISSUE(parity)                                                                        \
     if (has_next) {                                                                                        \
       const int nk32n = (nC + 31) >> 5, ntilen = (nO + 15) >> 4;                                           \
-      if (warp < ntilen) {                                                                                 \
-        const uint8_t* wn = reinterpret_cast<const uint8_t*>(op.nx_qw) + ((size_t)warp * nk32n * 32 + lane) * 16; \
-        _Pragma("unroll") for (int j = 0; j < RP_KCH; ++j)                                                \
-          if (j < nk32n) rp_cp_async16(wmine + j * 512, wn + (size_t)j * 512);                             \
+      __syncwarp();                                                                                        \
+      if (warp < ntilen && lane == 0) {                                                                    \
+        const uint32_t nb = (uint32_t)(nk32n < RP_KCH ? nk32n : RP_KCH) * 512u;                            \
+        rp_fence_async();                                                                                  \
+        rp_mbar_expect_tx(rp_smem_u32(&s_wbar[warp]), nb);                                                 \
+        rp_bulk_g2s(rp_smem_u32(wstage + (size_t)warp * (RP_KCH * 512)),                                   \
+                    reinterpret_cast<const uint8_t*>(op.nx_qw) + (size_t)warp * nk32n * 512, nb,           \
+                    rp_smem_u32(&s_wbar[warp]));                                                           \
       }                                                                                                    \
-      const int nrow4 = rp_row_floats(nC, nO) >> 2, ntot4 = nrow4 + (rp_stat_floats(nC, nO) >> 2);         \
-      const float4* rown = reinterpret_cast<const float4*>(cur + op.nx_tab_off);                           \
-      const float4* statn = reinterpret_cast<const float4*>(op.nx_stat);                                   \
-      float4* dstp = reinterpret_cast<float4*>(params + (size_t)((parity) & 1) * pbuf_floats);             \
-      for (int i = tid; i < ntot4; i += RP_THREADS)                                                        \
-        rp_cp_async16(dstp + i, i < nrow4 ? rown + i : statn + (i - nrow4));                               \
-      rp_cp_async_commit();                                                                                \
+      if (tid == RP_THREADS - 32) {                                                                        \
+        const uint32_t nrowb = (uint32_t)rp_row_floats(nC, nO) * 4u, nstatb = (uint32_t)rp_stat_floats(nC, nO) * 4u; \
+        float* dstp = params + (size_t)((parity) & 1) * pbuf_floats;                                       \
+        const uint32_t bar = rp_smem_u32(&s_pbar[(parity) & 1]);                                           \
+        rp_fence_async();                                                                                  \
+        rp_mbar_expect_tx(bar, nrowb + nstatb);                                                            \
+        rp_bulk_g2s(rp_smem_u32(dstp), cur + op.nx_tab_off, nrowb, bar);                                   \
+        rp_bulk_g2s(rp_smem_u32(dstp) + nrowb, op.nx_stat, nstatb, bar);                                   \
+      }                                                                                                    \
     }
     rp_trace(opi, 0);
     if (type != ATTNDM_ROWOP_CONV) { RP_PREFETCH_ISSUE(nconv); }  // (only a program's first op qualifies)
@@ -243,33 +282,53 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
         break;
       }
       case ATTNDM_ROWOP_FCONV: {           // conv_f32_simt_kernel: sequential fmaf over c, then + bias
-        const float* wt = reinterpret_cast<const float*>(op.g0);     // [C][O]: lanes read consecutive o
+        // Weight-bandwidth bound per CTA (every CTA streams the whole [C][O] matrix for its few samples): each
+        // thread owns four consecutive output channels and keeps 16 independent 128-bit loads in flight.
+        const float* wt = reinterpret_cast<const float*>(op.g0);     // [C][O], O % 4 == 0
         const float* bias = reinterpret_cast<const float*>(op.g1);
         const int doff = op.dst_off, dld = op.dst_ld, ld = op.src_ld;
         const float* xs = arena + op.src_off + hh * NST * ld;
-        for (int o = ot; o < O; o += RP_OCH) {
-          float acc[NST];
+        for (int o = 4 * ot; o < O; o += 4 * RP_OCH) {
+          float acc[NST][4];
 #pragma unroll
-          for (int n = 0; n < NST; ++n) acc[n] = 0.f;
+          for (int n = 0; n < NST; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
           const float* wp = wt + o;
           int c = 0;
-          for (; c + 16 <= C; c += 16) {            // 16 independent loads in flight per thread
-            float w[16];
+          for (; c + 16 <= C; c += 16) {
+            float4 w[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) w[u] = __ldg(wp + (long long)(c + u) * O);
+            for (int u = 0; u < 16; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wp + (long long)(c + u) * O));
 #pragma unroll
             for (int u = 0; u < 16; ++u)
 #pragma unroll
-              for (int n = 0; n < NST; ++n) acc[n] = fmaf(xs[n * ld + c + u], w[u], acc[n]);
+              for (int n = 0; n < NST; ++n) {
+                const float xv = xs[n * ld + c + u];
+                acc[n][0] = fmaf(xv, w[u].x, acc[n][0]);
+                acc[n][1] = fmaf(xv, w[u].y, acc[n][1]);
+                acc[n][2] = fmaf(xv, w[u].z, acc[n][2]);
+                acc[n][3] = fmaf(xv, w[u].w, acc[n][3]);
+              }
           }
           for (; c < C; ++c) {
-            const float w = __ldg(wp + (long long)c * O);
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (long long)c * O));
 #pragma unroll
-            for (int n = 0; n < NST; ++n) acc[n] = fmaf(xs[n * ld + c], w, acc[n]);
+            for (int n = 0; n < NST; ++n) {
+              const float xv = xs[n * ld + c];
+              acc[n][0] = fmaf(xv, w.x, acc[n][0]);
+              acc[n][1] = fmaf(xv, w.y, acc[n][1]);
+              acc[n][2] = fmaf(xv, w.z, acc[n][2]);
+              acc[n][3] = fmaf(xv, w.w, acc[n][3]);
+            }
           }
-          const float bz = bias ? bias[o] : 0.f;
+          float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) bz = *reinterpret_cast<const float4*>(bias + o);
 #pragma unroll
-          for (int n = 0; n < NST; ++n) arena[doff + (hh * NST + n) * dld + o] = acc[n] + bz;
+          for (int n = 0; n < NST; ++n) {
+            float* d = arena + doff + (hh * NST + n) * dld + o;
+            d[0] = acc[n][0] + bz.x; d[1] = acc[n][1] + bz.y; d[2] = acc[n][2] + bz.z; d[3] = acc[n][3] + bz.w;
+          }
         }
         break;
       }
@@ -329,7 +388,7 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
             }
           }
         }
-        rp_cp_async_wait_all();            // this conv's parameters and fragments (prefetched long ago) have landed
+        rp_mbar_wait(rp_smem_u32(&s_pbar[nconv & 1]), (nconv >> 1) & 1);    // this conv's parameter block has landed
         rp_sync();
         rp_trace(opi, 2);
         // ---- phase A2: producer op + quantize (utils/quant_util.py:260-282), codes and per-sample code sums ----
@@ -394,6 +453,8 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
                   for (int j = 0; j < RP_KCH; ++j)
                     if (k0 + j < nk32) wf[j] = rp_ldg128(w + (size_t)(k0 + j) * 512);
                 } else {
+                  rp_mbar_wait(rp_smem_u32(&s_wbar[warp]), wuse & 1);       // prefetched by the previous conv
+                  ++wuse;
 #pragma unroll
                   for (int j = 0; j < RP_KCH; ++j)
                     if (j < nk32) wf[j] = *reinterpret_cast<const uint4*>(wmine + j * 512);
