@@ -118,42 +118,51 @@ __global__ void __launch_bounds__(256) conv_f32_simt_kernel(ConvF32Params p) {
     lw = rem - lh * p.W;
   }
   const bool vec = (p.C & 3) == 0;
-  for (int tap = 0; tap < p.taps; ++tap) {
+  // (tap, 16-channel chunk) pairs are walked as one sequence; the loads of chunk i+1 are issued before the FMAs of
+  // chunk i (register double buffering), which is what matters for the long-K, few-CTA shapes (the 1024-wide
+  // time_embed linears were pure load latency: 64 chunks x ~0.7 us)
+  const int nkc = (p.C + KCF - 1) / KCF, nchunks = p.taps * nkc;
+  float av[4], bv[4];
+  auto load_chunk = [&](int idx) {
+    const int tap = idx / nkc, kc = (idx - tap * nkc) * KCF;
     const int dh = p.taps == 9 ? tap / 3 - 1 : 0, dw = p.taps == 9 ? tap % 3 - 1 : 0;
     const int hh = lh + dh, ww = lw + dw;
     const bool inb = lvalid && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
     const float* arow = p.x + (((long long)lb * p.H + hh) * p.W + ww) * p.C;
     const float* brow = p.w + ((long long)(n0 + lrow) * p.taps + tap) * p.C;
     const bool bvalid = n0 + lrow < p.O;
-    for (int kc = 0; kc < p.C; kc += KCF) {
-      float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
-      const int k = kc + lq * 4;
-      if (vec) {
-        if (inb && k < p.C) { float4 t = *reinterpret_cast<const float4*>(arow + k); av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w; }
-        if (bvalid && k < p.C) { float4 t = *reinterpret_cast<const float4*>(brow + k); bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w; }
-      } else {
+    const int k = kc + lq * 4;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (inb && k + e < p.C) av[e] = arow[k + e];
-          if (bvalid && k + e < p.C) bv[e] = brow[k + e];
-        }
+    for (int e = 0; e < 4; ++e) { av[e] = 0.f; bv[e] = 0.f; }
+    if (vec) {
+      if (inb && k < p.C) { float4 t = *reinterpret_cast<const float4*>(arow + k); av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w; }
+      if (bvalid && k < p.C) { float4 t = *reinterpret_cast<const float4*>(brow + k); bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (inb && k + e < p.C) av[e] = arow[k + e];
+        if (bvalid && k + e < p.C) bv[e] = brow[k + e];
       }
-      __syncthreads();
+    }
+  };
+  load_chunk(0);
+  for (int idx = 0; idx < nchunks; ++idx) {
+    __syncthreads();
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { As[lrow][lq * 4 + e] = av[e]; Bs[lrow][lq * 4 + e] = bv[e]; }
-      __syncthreads();
+    for (int e = 0; e < 4; ++e) { As[lrow][lq * 4 + e] = av[e]; Bs[lrow][lq * 4 + e] = bv[e]; }
+    __syncthreads();
+    if (idx + 1 < nchunks) load_chunk(idx + 1);
 #pragma unroll
-      for (int kk = 0; kk < KCF; ++kk) {
-        float a[4], b[4];
+    for (int kk = 0; kk < KCF; ++kk) {
+      float a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[ty * 4 + i][kk];
+      for (int i = 0; i < 4; ++i) a[i] = As[ty * 4 + i][kk];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Bs[tx * 4 + j][kk];
+      for (int j = 0; j < 4; ++j) b[j] = Bs[tx * 4 + j][kk];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
   }
 #pragma unroll

@@ -59,6 +59,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!done && clock64() - t0 > 4000000000LL) __trap();
   } while (!done);
 }
+// Waits of the warps that are NOT on the critical path (epilogue, geometry, producers): back off between polls.
+// A spinning warp issues try_wait / clock / branch instructions back to back and takes issue slots away from
+// the MMA-issuing warp that shares its SM sub-partition -- measured: with eleven warps spinning the MMA warp
+// sustained one tcgen05.mma per ~130 cycles instead of the 64 the tensor pipe needs.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = clock64();
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(128);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -75,6 +95,19 @@ __device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMa
       "elect.sync _|q, 0xffffffff;\n\t"
       "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// L2 prefetch of a TMA box (no shared memory, no barrier): the halo tiles of the tiles a CTA will process two and
+// three iterations from now are pulled from HBM into L2 early, so that the real load (issued only when one of
+// the two shared-memory halo buffers frees up) pays L2 latency instead of DRAM latency.  Measured on the
+// 128->128 3x3 @32x32 layer: the MMA-only time per tile drops from 2.9 us (= DRAM latency of the halo load)
+// towards the 1.2-1.7 us the tensor pipe needs.
+__device__ __forceinline__ void tma_prefetch_2d_elect(const CUtensorMap* map, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n\t}"
+      ::"l"(map), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
@@ -115,6 +148,46 @@ __device__ __forceinline__ void umma_i8_if(uint32_t leader, uint32_t tmem_d, uin
       "setp.ne.b32 p, %4, 0;\n\t"
       "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+// Up to four K steps (32 bytes each) of one 128-byte k-block in ONE asm block: the descriptors are the constant
+// high word 0x40004040 (SBO = 1024 B, version 1, SWIZZLE_128B) over a low word ((addr >> 4) | LBO) that simply
+// advances by 2 per step, so the issuing warp executes ~6 instructions per MMA instead of a C-level loop that
+// the compiler lowers through vector registers and R2UR moves (measured: 115 cycles per MMA issued, against
+// the 64 the tensor pipe needs).
+__device__ __forceinline__ void umma_i8_x4_if(uint32_t leader, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                              uint32_t idesc, uint32_t accumulate, int nk) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q, p, tr, k2, k3, k4;\n\t"
+      ".reg .b64 ad, bd;\n\t"
+      ".reg .b32 al, bl;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.u32 tr, 0, 0;\n\t"
+      "setp.gt.and.s32 k2, %6, 1, q;\n\t"
+      "setp.gt.and.s32 k3, %6, 2, q;\n\t"
+      "setp.gt.and.s32 k4, %6, 3, q;\n\t"
+      "mov.b64 ad, {%1, %7};\n\t"
+      "mov.b64 bd, {%2, %7};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::i8 [%0], ad, bd, %3, p;\n\t"
+      "add.u32 al, %1, 2;\n\t"
+      "add.u32 bl, %2, 2;\n\t"
+      "mov.b64 ad, {al, %7};\n\t"
+      "mov.b64 bd, {bl, %7};\n\t"
+      "@k2 tcgen05.mma.cta_group::1.kind::i8 [%0], ad, bd, %3, tr;\n\t"
+      "add.u32 al, %1, 4;\n\t"
+      "add.u32 bl, %2, 4;\n\t"
+      "mov.b64 ad, {al, %7};\n\t"
+      "mov.b64 bd, {bl, %7};\n\t"
+      "@k3 tcgen05.mma.cta_group::1.kind::i8 [%0], ad, bd, %3, tr;\n\t"
+      "add.u32 al, %1, 6;\n\t"
+      "add.u32 bl, %2, 6;\n\t"
+      "mov.b64 ad, {al, %7};\n\t"
+      "mov.b64 bd, {bl, %7};\n\t"
+      "@k4 tcgen05.mma.cta_group::1.kind::i8 [%0], ad, bd, %3, tr;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(leader), "r"(nk), "r"(0x40004040u)
       : "memory");
 }
 __device__ __forceinline__ void tcgen05_commit_if(uint32_t leader, uint32_t bar) {
@@ -669,6 +742,7 @@ struct TcGeomH {
   int b_resident;     // 1: weights loaded once; 0: streamed
   int nb;             // weight ring depth (streamed)
   int a_off, b_off, stg_off;   // byte offsets inside the 1024-aligned dynamic smem
+  int dbg;            // debug experiments (ATTNDM_TC_DBG): 1 = epilogue skips the math/stores, 2 = skips the TMEM loads too
 };
 
 
@@ -797,7 +871,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int n0 = (int)(tile % g.ntn) * g.BN;
           for (int kb = 0; kb < nkb; ++kb) {
             const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
-            mbar_wait(smem_u32(&b_empty[s]), ph ^ 1);
+            mbar_wait_relaxed(smem_u32(&b_empty[s]), ph ^ 1);
             mbar_expect_tx_elect(smem_u32(&b_full[s]), (uint32_t)b_tile_bytes);
             tma_load_2d_elect(base + g.b_off + (uint32_t)s * b_tile_bytes, &tmB, smem_u32(&b_full[s]), tap * p.Cp + cb * TC_BK, n0);
             if (++s == g.nb) { s = 0; ph ^= 1; }
@@ -816,14 +890,26 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const long long m0 = (tile / g.ntn) * TC_BM;
         const int buf = it % g.na;
         if (lane == 0) tc_trace(0, it, 0);
-        mbar_wait(smem_u32(&a_empty[buf]), (uint32_t)(((it / g.na) & 1) ^ 1));
+        mbar_wait_relaxed(smem_u32(&a_empty[buf]), (uint32_t)(((it / g.na) & 1) ^ 1));
         if (lane == 0) tc_trace(0, it, 1);
         const uint32_t bar = smem_u32(&a_full[buf]);
+        if (g.dbg & 16) { mbar_expect_tx_elect(bar, 0u); continue; }       // experiment: no halo loads at all
         mbar_expect_tx_elect(bar, (uint32_t)(g.ncb * g.hr * TC_BK));
         for (int cb = 0; cb < g.ncb; ++cb) {
           const uint32_t dst = base + g.a_off + (uint32_t)(buf * g.ncb + cb) * g.hr_stride;
           tma_load_2d_elect(dst, &tmA, bar, cb * TC_BK, (int)m0);
           if (hr2 > 0) tma_load_2d_elect(dst + 256 * TC_BK, &tmA2, bar, cb * TC_BK, (int)m0 + 256);
+        }
+        // pull the halos of the tiles 2 and 3 iterations ahead into L2
+        for (int ahead = (it == 0 ? 1 : 3); ahead <= 3; ++ahead) {
+          const long long tf = tile + (long long)ahead * gridDim.x;
+          if (tf < g.ntiles) {
+            const long long mf = (tf / g.ntn) * TC_BM;
+            for (int cb = 0; cb < g.ncb; ++cb) {
+              tma_prefetch_2d_elect(&tmA, cb * TC_BK, (int)mf);
+              if (hr2 > 0) tma_prefetch_2d_elect(&tmA2, cb * TC_BK, (int)mf + 256);
+            }
+          }
         }
       }
     }
@@ -858,6 +944,24 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t a_buf0 = base + g.a_off + (uint32_t)(buf * g.ncb) * g.hr_stride;
         uint32_t b_res = base + g.b_off;               // resident mode: walks through the whole weight block
         uint32_t accumulate = 0;
+        if (g.b_resident) {
+          // no waits inside a tile: descriptor low words advance additively, four MMAs per asm block
+          const uint32_t a_lo0 = ((a_buf0 >> 4) & 0x3FFF) | 0x10000u;
+          uint32_t b_lo = ((b_res >> 4) & 0x3FFF) | 0x10000u;
+          const uint32_t a_step = (uint32_t)g.hr_stride >> 4, b_step = (uint32_t)b_tile_bytes >> 4;
+          for (int kh = 0; kh < kdim; ++kh) {
+            for (int kw = 0; kw < kdim; ++kw) {
+              uint32_t a_lo = a_lo0 + ((g.dbg & 4) ? 0u : (uint32_t)(kh * p.Wp + kw) * (TC_BK >> 4));
+              for (int cb = 0; cb < g.ncb; ++cb) {
+                umma_i8_x4_if(leader, d_tmem, a_lo, b_lo, idesc, accumulate,
+                              (cb == g.ncb - 1) ? ksteps_last : TC_BK / TC_UMMA_K);
+                accumulate = 1;
+                a_lo += a_step;
+                if (!(g.dbg & 8)) b_lo += b_step;
+              }
+            }
+          }
+        } else
         for (int kh = 0; kh < kdim; ++kh) {
           for (int kw = 0; kw < kdim; ++kw) {
             uint32_t a_addr = a_buf0 + (uint32_t)(kh * p.Wp + kw) * TC_BK;
@@ -902,7 +1006,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const long long m0 = (tile / g.ntn) * TC_BM;
-      mbar_wait(smem_u32(&geo_empty[buf]), (uint32_t)(((it >> 1) & 1) ^ 1));
+      mbar_wait_relaxed(smem_u32(&geo_empty[buf]), (uint32_t)(((it >> 1) & 1) ^ 1));
       long long px[4];
       int bb[4], cc[4];
 #pragma unroll
@@ -955,7 +1059,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // row geometry of this thread's four fragment rows (tr, tr+8, tr+16, tr+24 of the quarter), prepared
       // by the geometry warp
       const int gb = it & 1;
-      mbar_wait(smem_u32(&geo_full[gb]), (uint32_t)((it >> 1) & 1));
+      mbar_wait_relaxed(smem_u32(&geo_full[gb]), (uint32_t)((it >> 1) & 1));
       long long pix_r[4];
       int b_r[4], cs_r[4];
 #pragma unroll
@@ -968,7 +1072,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&geo_empty[gb]));
       if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 0);
-      mbar_wait(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
+      mbar_wait_relaxed(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
       tcgen05_fence_after();
       if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 1);
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(quarter * 32) << 16);
@@ -992,15 +1096,21 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int c0 = ci << 5;
         uint32_t v0[16], v1[16];
         __syncwarp();
-        tmem_ld_16x256b_x4(t_acc + (uint32_t)c0, v0);                      // tile rows 32q + 0..15
-        tmem_ld_16x256b_x4(t_acc + (16u << 16) + (uint32_t)c0, v1);        // tile rows 32q + 16..31
-        tmem_ld_wait();
+        if ((g.dbg & 3) < 2) {
+          tmem_ld_16x256b_x4(t_acc + (uint32_t)c0, v0);                      // tile rows 32q + 0..15
+          tmem_ld_16x256b_x4(t_acc + (16u << 16) + (uint32_t)c0, v1);        // tile rows 32q + 16..31
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v0[j] = 0; v1[j] = 0; }
+        }
         if (ci + TC_H_EPI_GROUPS >= nchunks) {
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
           if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 2);
         }
+        if ((g.dbg & 3) >= 1) continue;
         if (pair_ok) {
           if (p.residual) {
             if (p.temb) epi_block<true, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
@@ -1157,6 +1267,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   g.a_off = 0;
   g.b_off = g.na * a_buf;
   g.stg_off = g.b_off + (g.b_resident ? nkb : g.nb) * b_tile;
+  { const char* e = getenv("ATTNDM_TC_DBG"); g.dbg = e ? atoi(e) : 0; }
   g.acc_stride = round_up(g.BN, 32);
   g.tmem_cols = 32;
   while (g.tmem_cols < 2 * g.acc_stride) g.tmem_cols <<= 1;

@@ -177,7 +177,10 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
     // Prefetch of the NEXT conv (described by the nx_* fields of a CONV op and of a program's first op) with
     // bulk copies: its first 256 input channels of A fragments (tile = warp) into this warp's staging block
     // (one copy per warp), its parameter block into the other parameter buffer (two copies by one thread).
-    // Nobody waits for them until that conv's phase A2 / phase B.
+    // Nobody waits for them until that conv's phase A2 / phase B.  (The staging block and the parameter buffer
+    // were last READ through the generic proxy and those reads have retired -- their values fed the MMAs /
+    // the epilogue before this point -- so no proxy fence is needed before the async writes; an explicit
+    // fence.proxy.async here cost ~0.4 us per conv.)
     const bool has_next = (type == ATTNDM_ROWOP_CONV || opi == 0) && op.nx_qw != nullptr;
     const int nC = op.nx_C, nO = op.nx_O;
 #define RP_PREFETCH_ISSUE(parity)                                                                        \
@@ -186,7 +189,6 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
       __syncwarp();                                                                                        \
       if (warp < ntilen && lane == 0) {                                                                    \
         const uint32_t nb = (uint32_t)(nk32n < RP_KCH ? nk32n : RP_KCH) * 512u;                            \
-        rp_fence_async();                                                                                  \
         rp_mbar_expect_tx(rp_smem_u32(&s_wbar[warp]), nb);                                                 \
         rp_bulk_g2s(rp_smem_u32(wstage + (size_t)warp * (RP_KCH * 512)),                                   \
                     reinterpret_cast<const uint8_t*>(op.nx_qw) + (size_t)warp * nk32n * 512, nb,           \
@@ -196,7 +198,6 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
         const uint32_t nrowb = (uint32_t)rp_row_floats(nC, nO) * 4u, nstatb = (uint32_t)rp_stat_floats(nC, nO) * 4u; \
         float* dstp = params + (size_t)((parity) & 1) * pbuf_floats;                                       \
         const uint32_t bar = rp_smem_u32(&s_pbar[(parity) & 1]);                                           \
-        rp_fence_async();                                                                                  \
         rp_mbar_expect_tx(bar, nrowb + nstatb);                                                            \
         rp_bulk_g2s(rp_smem_u32(dstp), cur + op.nx_tab_off, nrowb, bar);                                   \
         rp_bulk_g2s(rp_smem_u32(dstp) + nrowb, op.nx_stat, nstatb, bar);                                   \
@@ -432,11 +433,11 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
         // ---- phase B: the GEMM on the tensor cores.  warp = one 16-channel tile (two for O > 256); the A fragments
         //      of the first 256 input channels of tile `warp` are already in registers (prefetched by the
         //      previous conv); anything beyond is loaded here ----
-        int acc[RP_MAXT][4];
+        int acc[RP_MAXT][4], acc2[RP_MAXT][4];
 #pragma unroll
         for (int t = 0; t < RP_MAXT; ++t)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[t][j] = 0;
+          for (int j = 0; j < 4; ++j) { acc[t][j] = 0; acc2[t][j] = 0; }
         {
           const int nk32 = (C + 31) >> 5, ntile = (O + 15) >> 4;
           const uint8_t* crow = reinterpret_cast<const uint8_t*>(codes) + grp * crow_bytes + tig * 4;
@@ -467,7 +468,8 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
                       b0 = *reinterpret_cast<const uint32_t*>(crow + (k0 + j) * 32);
                       b1 = *reinterpret_cast<const uint32_t*>(crow + (k0 + j) * 32 + 16);
                     }
-                    rp_mma_s8(acc[t], wf[j], b0, b1);
+                    if (j & 1) rp_mma_s8(acc2[t], wf[j], b0, b1);     // two independent accumulation chains
+                    else rp_mma_s8(acc[t], wf[j], b0, b1);
                   }
                 }
               }
@@ -490,7 +492,7 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
               for (int j = 0; j < 4; ++j) {
                 const int o = tile * 16 + grp + 8 * (j >> 1), n = 2 * tig + (j & 1);
                 if (n < NS && o < O) {
-                  float v = conv_i8_value(acc[t][j], zp * wsum[o], wzp[o], s_rowsum[n] + zp * C, mult[o], bias[o]);
+                  float v = conv_i8_value(acc[t][j] + acc2[t][j], zp * wsum[o], wzp[o], s_rowsum[n] + zp * C, mult[o], bias[o]);
                   if (aoff >= 0) v = __fadd_rn(v, arena[aoff + n * ald + o]);
                   if (temb && s0 + n < B) v = __fadd_rn(v, temb[(long long)(s0 + n) * O + o]);
                   arena[doff + n * dld + o] = v;
