@@ -750,22 +750,36 @@ struct TcGeomH {
 // tq = lane%4) owns rows tr + 8k (k = 0..3; k < 2 from v0, k >= 2 from v1) and the column pairs
 // 8i + 2tq + {0,1} (i = 0..3).  Register j of a load: row bit = (j>>1)&1, column group i = j>>2, parity j&1.
 // Everything is statically indexed (registers only); stores are float2, four lanes per 32-byte sector.
+// The residual of one 32x32 block, straight from HBM: all sixteen float2 loads are issued together -- and, for a
+// warp's first block of a tile, BEFORE it waits for the accumulator, so the round trip hides behind the MMAs.
+__device__ __forceinline__ void epi_load_residual(float2 (&rs)[4][4], int c0, int tq, int BN, int n0, int O,
+                                                  const long long (&pix_r)[4], const float* const (&res_row)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cl = c0 + 8 * i + 2 * tq;
+    const bool col_ok = (cl < BN) && (n0 + cl < O);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      rs[i][k] = (col_ok && pix_r[k] >= 0) ? __ldg(reinterpret_cast<const float2*>(res_row[k] + c0 + 8 * i))
+                                           : make_float2(0.f, 0.f);
+  }
+}
+
 template <bool RES, bool TEMB>
 __device__ __forceinline__ void epi_block(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
                                           int c0, int tq, int BN, int n0, int O, const int (&cs_r)[4],
                                           const long long (&pix_r)[4], float* const (&out_row)[4],
-                                          const float* const (&res_row)[4], const float* const (&te_row)[4]) {
+                                          const float2 (&rs)[4][4], const float* const (&te_row)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int cl = c0 + 8 * i + 2 * tq;
     const bool col_ok = (cl < BN) && (n0 + cl < O);
     const ColConst ca = colc[cl & 255], cb = colc[(cl + 1) & 255];
     bool ok[4];
-    float2 rs[4], te[4];
+    float2 te[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {                  // all loads first: independent, predicated, no branches
+    for (int k = 0; k < 4; ++k) {
       ok[k] = col_ok && pix_r[k] >= 0;
-      if (RES) rs[k] = ok[k] ? __ldg(reinterpret_cast<const float2*>(res_row[k] + c0 + 8 * i)) : make_float2(0.f, 0.f);
       if (TEMB) te[k] = ok[k] ? __ldg(reinterpret_cast<const float2*>(te_row[k] + c0 + 8 * i)) : make_float2(0.f, 0.f);
     }
 #pragma unroll
@@ -774,7 +788,7 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v0)[16], const uint32
       const int a0 = (int)(k < 2 ? v0[j] : v1[j]), a1 = (int)(k < 2 ? v0[j | 1] : v1[j | 1]);
       float f0 = conv_i8_value(a0, ca.A, ca.B, cs_r[k], ca.m, ca.bias);
       float f1 = conv_i8_value(a1, cb.A, cb.B, cs_r[k], cb.m, cb.bias);
-      if (RES) { f0 = __fadd_rn(f0, rs[k].x); f1 = __fadd_rn(f1, rs[k].y); }
+      if (RES) { f0 = __fadd_rn(f0, rs[i][k].x); f1 = __fadd_rn(f1, rs[i][k].y); }
       if (TEMB) { f0 = __fadd_rn(f0, te[k].x); f1 = __fadd_rn(f1, te[k].y); }
       if (ok[k]) *reinterpret_cast<float2*>(out_row[k] + c0 + 8 * i) = make_float2(f0, f1);
     }
@@ -1072,15 +1086,6 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&geo_empty[gb]));
       if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 0);
-      mbar_wait_relaxed(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
-      tcgen05_fence_after();
-      if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 1);
-      const uint32_t t_acc = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-      const int nchunks = (g.BN + 31) >> 5;
-      if (half >= nchunks) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-      }
       // row bases of this thread's four fragment rows (element offsets; invalid rows are predicated off)
       const float* res_row[4];
       const float* te_row[4];
@@ -1091,6 +1096,18 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         out_row[k] = p.out + off;
         res_row[k] = p.residual ? p.residual + off : nullptr;
         te_row[k] = p.temb ? p.temb + (long long)b_r[k] * p.O + n0 + 2 * tq : nullptr;
+      }
+      const int nchunks = (g.BN + 31) >> 5;
+      const bool res_vec = p.residual != nullptr && pair_ok;
+      float2 rs[4][4];
+      if (res_vec && half < nchunks) epi_load_residual(rs, half << 5, tq, g.BN, n0, p.O, pix_r, res_row);
+      mbar_wait_relaxed(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
+      tcgen05_fence_after();
+      if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 1);
+      const uint32_t t_acc = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(quarter * 32) << 16);
+      if (half >= nchunks) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
       }
       for (int ci = half; ci < nchunks; ci += TC_H_EPI_GROUPS) {
         const int c0 = ci << 5;
@@ -1111,13 +1128,14 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 2);
         }
         if ((g.dbg & 3) >= 1) continue;
+        if (res_vec && ci != half) epi_load_residual(rs, c0, tq, g.BN, n0, p.O, pix_r, res_row);
         if (pair_ok) {
           if (p.residual) {
-            if (p.temb) epi_block<true, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
-            else        epi_block<true, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
+            if (p.temb) epi_block<true, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, rs, te_row);
+            else        epi_block<true, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, rs, te_row);
           } else {
-            if (p.temb) epi_block<false, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
-            else        epi_block<false, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
+            if (p.temb) epi_block<false, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, rs, te_row);
+            else        epi_block<false, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, rs, te_row);
           }
         } else {
           epi_block_scalar(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
