@@ -198,11 +198,21 @@ def dominant_kernel_roofline(dev, pk):
     ach = flops / (res["tcgen05"] * 1e-3) / 1e12
     peak = 2.0 * pk["bf16_tflops"]
     algo_bytes = codes.numel() + rowsum.numel() * 4 + out.numel() * 4 + pack.qw.numel()
-    return {"bound": "tensor", "kernel": "qconv_i8_tc_kernel (128->128 3x3 @32x32, batch 256)", "achieved": ach,
+    hbm_s = algo_bytes / (pk["hbm_gbs"] * 1e9)               # what HBM alone would need for the algorithmic bytes
+    return {"bound": "tensor", "kernel": "qconv_i8_halo_kernel (128->128 3x3 @32x32, batch 256)", "achieved": ach,
             "peak": peak, "unit": "TOP/s", "frac": ach / peak,
-            "peak_source": f"2 x bf16_tflops of {pk['source']} (int8 tensor rate = 2 x bf16 on sm_100; no int8 entry measured)",
-            "traffic": None, "ms_per_launch": res["tcgen05"], "algorithmic_bytes": algo_bytes,
-            "hbm_gbs_at_this_time": algo_bytes / (res["tcgen05"] * 1e-3) / 1e9}
+            "peak_source": f"2 x bf16_tflops of {pk['source']}: tcgen05 kind::i8 measured at exactly 2x the bf16 "
+                           "MMA rate on this part (tools/umma_rate_test.cu: 64 cycles per 128x128x32 MMA); "
+                           "MEASURED_PEAKS.json has no int8 entry",
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/ncu_conv_r01.txt)
+            "traffic": 119.57e6, "traffic_source": "profiles/ncu_conv_r01.txt (39.3 MB read + 80.3 MB written; "
+                                                   "the rest of the 134 MB output is still in L2 at kernel end)",
+            "ms_per_launch": res["tcgen05"], "algorithmic_bytes": algo_bytes,
+            "hbm_gbs_at_this_time": algo_bytes / (res["tcgen05"] * 1e-3) / 1e9,
+            "hbm_floor_ms": hbm_s * 1e3,
+            "note": "fp32 activations between layers make this layer HBM-co-bound: 173 MB at the measured "
+                    f"{pk['hbm_gbs']:.0f} GB/s is {hbm_s * 1e6:.0f} us, i.e. at most "
+                    f"{flops / hbm_s / 1e12 / peak:.2f} of the int8 peak is reachable without changing the layout"}
 
 
 def run_ours(args):
@@ -290,6 +300,9 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms, ms_e2e = float(tt[0]), float(tt[1])
         roof = dominant_kernel_roofline(dev, pk) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     ms_per_step = ms / args.steps
