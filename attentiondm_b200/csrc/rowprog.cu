@@ -339,7 +339,6 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
         const float* scale = prm;
         const float* zpv = prm + Cq;
         const float* mult = prm + 2 * Cq;
-        const int zp = *reinterpret_cast<const int*>(prm + 2 * Cq + Oq);
         const float* stat = prm + rp_row_floats(C, O);
         const float* gamma = stat;
         const float* beta = stat + C;
@@ -391,6 +390,7 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
         }
         rp_mbar_wait(rp_smem_u32(&s_pbar[nconv & 1]), (nconv >> 1) & 1);    // this conv's parameter block has landed
         rp_sync();
+        const int zp = *reinterpret_cast<const int*>(prm + 2 * Cq + Oq);     // (nothing of `prm` may be read before the wait)
         rp_trace(opi, 2);
         // ---- phase A2: producer op + quantize (utils/quant_util.py:260-282), codes and per-sample code sums ----
         {

@@ -30,7 +30,7 @@ from ._ffi import PRE_GN_SILU, PRE_NONE, PRE_SILU
 
 OP_END, OP_LOAD, OP_LOAD_POOL, OP_STORE, OP_COPY, OP_CONV, OP_FCONV, OP_ATTN1, OP_SCALE_ADD = range(9)
 MAX_SMEM = 220 * 1024
-MAX_O = 1024          # FCONV
+MAX_O = 4096          # FCONV
 MAX_CONV_O = 512      # CONV (two MMA tiles per warp, two k16 steps per 16 KB ring slot)
 
 
@@ -51,6 +51,9 @@ assert C.sizeof(RowOp) == 144
 
 class Unfusable(Exception):
     pass
+
+
+last_unfusable = None
 
 
 @dataclass
@@ -363,9 +366,12 @@ def build(model, B: int, layer_slice: dict, device) -> Optional[FusedPlans]:
     """Plans for `model` at batch B, or None when the model/state is outside what the kernel fuses."""
     if os.environ.get("ATTNDM_FUSED", "1") == "0":
         return None
+    global last_unfusable
+    last_unfusable = None
     try:
         return _build(model, B, layer_slice, device)
-    except Unfusable:
+    except Unfusable as e:
+        last_unfusable = str(e)          # why the model / state is outside what the kernel fuses
         return None
 
 

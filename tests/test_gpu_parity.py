@@ -618,6 +618,11 @@ def test_fused_rowprog_equals_layerwise(ch, ch_mult, size, bw, alpha, B):
     assert torch.isfinite(xs_g[-1]).all()
     assert torch.equal(torch.stack(xs_g[1:]), torch.stack(xs_e[1:]))
     assert torch.equal(torch.stack(x0_g), torch.stack(x0_e))
+    # the fused kernel prefetches the next conv's parameters asynchronously: replays must not depend on timing
+    for _ in range(20):
+        m.reset_index_seq()
+        xs_r, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, keep="last", use_graph=True)
+        assert torch.equal(xs_r[-1], xs_e[-1])
 
 
 # ---------------------------------------------------------------------------
@@ -653,3 +658,50 @@ def test_cifar_full_size_properties():
     finally:
         ops.DEFAULT_CONV_IMPL = ops.CONV_TCGEN05
     assert torch.equal(xs2[-1], xs[-1])
+
+
+# ---------------------------------------------------------------------------
+# the other named configs (BASELINE.json configs 4 and 5): CelebA 64x64 and LSUN church 256x256 UNets.
+# The oracle is far too slow at these sizes, so the checks are the size-independent properties the path
+# offers: every layer stays on the integer path, the CUDA-graph engine (with the fused 1x1 programs) equals the
+# layer-by-layer kernels bit for bit, the tcgen05 conv equals its dp4a twin bit for bit, samples are independent
+# of how the batch is sharded, outputs are finite.
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,B", [("celeba", 2), ("church", 1)])
+def test_large_configs_properties(name, B):
+    import attentiondm_b200 as A
+    from attentiondm_b200 import ops
+    from attentiondm_b200.engine import SamplerEngine
+    spec = (S.celeba_spec if name == "celeba" else S.church_spec)(T=2)
+    sd = S.synth_state_dict(spec, seed=2)
+    m = build_cuda_model(spec, sd)
+    del sd
+    n_layers = {"celeba": 252, "church": 305}[name]
+    assert len(m.qconvs()) == n_layers
+    betas = R.beta_schedule_linear().to(DEV)
+    size = spec.image_size
+    x = torch.randn(B, 3, size, size, generator=torch.Generator().manual_seed(17)).to(DEV)
+    m.set_calibrate(True)
+    A.generalized_steps(x, spec.seq, m, betas, eta=0.0, keep="last")
+    m.set_calibrate(False)
+    m.reset_index_seq()
+    assert all(q.int8_ok_all_steps() for _, q in m.qconvs())
+    xs_g, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, keep="last")                  # CUDA-graph engine
+    eng = SamplerEngine.for_model(m, spec.seq, betas, 0.0, tuple(x.shape))
+    from attentiondm_b200 import rowprog
+    assert eng.fused is not None and eng.fused.trunk_plan is not None, rowprog.last_unfusable
+    assert torch.isfinite(xs_g[-1]).all()
+    m.reset_index_seq()
+    xs_e, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, keep="last", use_graph=False)
+    assert torch.equal(xs_e[-1], xs_g[-1])
+    ops.DEFAULT_CONV_IMPL = ops.CONV_SIMT
+    try:
+        m.reset_index_seq()
+        xs_s, _ = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, keep="last", use_graph=False)
+    finally:
+        ops.DEFAULT_CONV_IMPL = ops.CONV_TCGEN05
+    assert torch.equal(xs_s[-1], xs_g[-1])
+    if B > 1:
+        m.reset_index_seq()
+        xa, _ = A.generalized_steps(x[:1].contiguous(), spec.seq, m, betas, eta=0.0, keep="last")
+        assert torch.equal(xa[-1], xs_g[-1][:1])
