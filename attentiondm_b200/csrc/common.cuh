@@ -71,6 +71,18 @@ __device__ __forceinline__ float gn_silu_apply(float v, float mean, float rstd, 
   return silu_f(fmaf(v, a, fmaf(-mean, a, beta)));
 }
 
+// (c0, c1) = (a*b0 + c0, a*b1 + c1), each an IEEE fma, in one packed instruction
+__device__ __forceinline__ void fma2(float& c0, float& c1, float a, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %2};\n\t"
+      "mov.b64 rb, {%3, %4};\n\t"
+      "mov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(c0), "+f"(c1)
+      : "f"(a), "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -10,6 +10,8 @@
 // the per-pixel code sum is a warp shuffle reduction and never an atomic.  Warps
 // own contiguous row ranges so per-sample state (GroupNorm mean/rstd, held one
 // group per lane) is refreshed only when the sample index changes.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace attndm {
@@ -328,7 +330,7 @@ __device__ __forceinline__ int quant_code_i(float v, float s, float zp, float lo
 }
 
 template <int PRE, int NQ>
-__global__ void __launch_bounds__(256, NQ == 1 ? 4 : 3) act_quant_rows_kernel(ActQuantParams p) {
+__global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_rows_kernel(ActQuantParams p) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
   const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 4 : 3) act_quant_rows_kernel(Ac
     if (lane == 0) p.rowsum[row] = padsum;
   };
   int cur_b = -1;
-  constexpr int R = 4;
+  constexpr int R = NQ <= 2 ? 4 : 2;                    // pixels per step (register budget)
   for (int ir = ir0; ir < ir1; ++ir) {
     const int b = ir / p.H, h = ir - b * p.H;
     if (PRE == ATTNDM_PRE_GN_SILU && b != cur_b) {       // warp-uniform, once per sample
@@ -516,11 +518,11 @@ static int act_quant_impl(const float* x, int B, int H, int W, int C, const floa
     return ATTNDM_OK;
   }
   // int8 hot path at the large maps: codes + row sums only
-  if (quant && codes && rowsum && !y && (C == 128 || C == 256) && (W & 3) == 0 &&
+  if (quant && codes && rowsum && !y && (C == 128 || C == 256 || C == 384 || C == 512) && (W & 3) == 0 &&
       (pre != ATTNDM_PRE_GN_SILU || (C / kGnGroups) % 4 == 0) && (long long)B * H * W * C < (1LL << 31) &&
       (((uintptr_t)x | (uintptr_t)codes | (uintptr_t)scale | (uintptr_t)zp) & 15) == 0) {
     const int nimg = B * H;
-    int w2 = kNumSMs * 8 * (C == 128 ? 4 : 3);
+    int w2 = kNumSMs * 8 * (C == 128 ? 4 : C == 256 ? 3 : 2);
     if (w2 > nimg) w2 = nimg;
     p.rows_per_warp = (nimg + w2 - 1) / w2;
     w2 = (nimg + (int)p.rows_per_warp - 1) / (int)p.rows_per_warp;
@@ -528,7 +530,9 @@ static int act_quant_impl(const float* x, int B, int H, int W, int C, const floa
 #define ATTNDM_AQ_ROWS(PREV)                                                                                         \
     do {                                                                                                              \
       if (C == 128) launch_pdl(act_quant_rows_kernel<PREV, 1>, dim3(nb), dim3(256), 0, st, p);                        \
-      else launch_pdl(act_quant_rows_kernel<PREV, 2>, dim3(nb), dim3(256), 0, st, p);                                 \
+      else if (C == 256) launch_pdl(act_quant_rows_kernel<PREV, 2>, dim3(nb), dim3(256), 0, st, p);                   \
+      else if (C == 384) launch_pdl(act_quant_rows_kernel<PREV, 3>, dim3(nb), dim3(256), 0, st, p);                   \
+      else launch_pdl(act_quant_rows_kernel<PREV, 4>, dim3(nb), dim3(256), 0, st, p);                                 \
     } while (0)
     if (pre == ATTNDM_PRE_GN_SILU) ATTNDM_AQ_ROWS(ATTNDM_PRE_GN_SILU);
     else if (pre == ATTNDM_PRE_SILU) ATTNDM_AQ_ROWS(ATTNDM_PRE_SILU);
@@ -1134,7 +1138,12 @@ int attndm_act_quant(const float* x, int B, int H, int W, int C, const float* sc
 }
 
 int attndm_gn_act_quant_fits(int H, int W, int C) {
-  return (C % kGnGroups == 0) && (C % 4 == 0) && ((long long)H * W * C * 4 <= 64 * 1024) ? 1 : 0;
+  static int max_hw = -1;
+  if (max_hw < 0) {
+    const char* e = getenv("ATTNDM_GN_FUSED_MAX_HW");
+    max_hw = e ? atoi(e) : 4;     // above 2x2 the statistics kernel + the row kernel are faster (measured: 9 us vs 25 us at 8x8x128)
+  }
+  return (C % kGnGroups == 0) && (C % 4 == 0) && ((long long)H * W * C * 4 <= 64 * 1024) && H * W <= max_hw ? 1 : 0;
 }
 
 int attndm_gn_act_quant(const float* x, int B, int H, int W, int C, const float* gamma, const float* beta,

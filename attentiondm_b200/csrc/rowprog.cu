@@ -306,10 +306,8 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
 #pragma unroll
               for (int n = 0; n < NST; ++n) {
                 const float xv = xs[n * ld + c + u];
-                acc[n][0] = fmaf(xv, w[u].x, acc[n][0]);
-                acc[n][1] = fmaf(xv, w[u].y, acc[n][1]);
-                acc[n][2] = fmaf(xv, w[u].z, acc[n][2]);
-                acc[n][3] = fmaf(xv, w[u].w, acc[n][3]);
+                fma2(acc[n][0], acc[n][1], xv, w[u].x, w[u].y);      // packed fp32 FMAs: same results as fmaf
+                fma2(acc[n][2], acc[n][3], xv, w[u].z, w[u].w);
               }
           }
           for (; c < C; ++c) {
@@ -317,10 +315,8 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
 #pragma unroll
             for (int n = 0; n < NST; ++n) {
               const float xv = xs[n * ld + c];
-              acc[n][0] = fmaf(xv, w.x, acc[n][0]);
-              acc[n][1] = fmaf(xv, w.y, acc[n][1]);
-              acc[n][2] = fmaf(xv, w.z, acc[n][2]);
-              acc[n][3] = fmaf(xv, w.w, acc[n][3]);
+              fma2(acc[n][0], acc[n][1], xv, w.x, w.y);
+              fma2(acc[n][2], acc[n][3], xv, w.z, w.w);
             }
           }
           float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
