@@ -271,7 +271,7 @@ class Plan:
             raise Unfusable("program does not fit in shared memory")
         # the programs are latency-bound per CTA and every CTA re-reads the weights from L2: spread the
         # samples over enough CTAs to cover the chip, but no thinner
-        target = int(os.environ.get("ATTNDM_ROWPROG_CTAS", "64"))
+        target = int(os.environ.get("ATTNDM_ROWPROG_CTAS", "128"))
         while ns > 2 and (B + ns - 1) // ns * len(self.programs) < target:
             ns //= 2
         self.ns = ns

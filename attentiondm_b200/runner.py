@@ -77,6 +77,63 @@ def load_by_shape_match(model, states):
     return i
 
 
+# ---------------------------------------------------------------------------------------------
+# Checkpoint I/O for the quantizer state.  The reference can only persist what
+# `state_dict()` holds ({weight, bias, groups_range, alpha_activ} per QConv2d); what calibration also produces --
+# weight_range_min/max, init_range_min/max (first-calibrate search), the per-layer bit widths and the lazily
+# created channel_proj convs -- lives in plain attributes and is lost on reload.  These two helpers keep it.
+# ---------------------------------------------------------------------------------------------
+QUANT_STATE_VERSION = 1
+
+
+def quant_state(model):
+    """Everything needed to resume sampling without re-calibrating: the state_dict plus the non-state_dict
+    attributes of every QConv2d (utils/quant_util.py:88-118)."""
+    layers = {}
+    for name, q in model.qconvs():
+        layers[name] = dict(
+            weight_range_min=q.weight_range_min.detach().cpu().clone(),
+            weight_range_max=q.weight_range_max.detach().cpu().clone(),
+            init_range_min=q.init_range_min.detach().cpu().clone(),
+            init_range_max=q.init_range_max.detach().cpu().clone(),
+            a_bit=int(q._a_bit), w_bit=int(q._w_bit), group_num=int(q.group_num), index_seq=int(q.index_seq))
+    return dict(version=QUANT_STATE_VERSION,
+                state_dict={k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, layers=layers)
+
+
+def save_quant_state(model, path):
+    torch.save(quant_state(model), path)
+
+
+def load_quant_state(model, state):
+    """Inverse of quant_state(); `state` may be a path.  The model must have been built from the same config."""
+    if isinstance(state, (str, os.PathLike)):
+        state = torch.load(state, map_location="cpu")
+    if state.get("version") != QUANT_STATE_VERSION:
+        raise RuntimeError(f"quant state version {state.get('version')} not understood")
+    model.materialize_lazy_layers()
+    mods = dict(model.qconvs())
+    missing = set(state["layers"]) ^ set(mods)
+    if missing:
+        raise RuntimeError(f"quant state does not match the model's QConv2d layers: {sorted(missing)[:4]} ...")
+    for name, d in state["layers"].items():
+        q = mods[name]
+        if d["group_num"] != q.group_num:
+            raise RuntimeError(f"{name}: group_num {d['group_num']} != {q.group_num}")
+    model.load_state_dict(state["state_dict"], strict=True)
+    for name, d in state["layers"].items():
+        q = mods[name]
+        dev = q.weight.device
+        q.weight_range_min = d["weight_range_min"].to(dev)
+        q.weight_range_max = d["weight_range_max"].to(dev)
+        q.init_range_min = d["init_range_min"].clone()
+        q.init_range_max = d["init_range_max"].clone()
+        q._a_bit, q._w_bit = d["a_bit"], d["w_bit"]
+        q.index_seq = d["index_seq"]
+        q.invalidate_cache()
+    return model
+
+
 class Diffusion(object):
     def __init__(self, args, config, device=None):
         self.args = args

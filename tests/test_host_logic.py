@@ -111,3 +111,34 @@ def test_quantization_params_match_oracle():
     flat = w.reshape(8, -1)
     snapped = A.AsymmetricQuantFunction.apply(w, 8, flat.min(1)[0], flat.max(1)[0])
     assert torch.equal(snapped, R.snap_weight(w, 8)[0])
+
+
+def test_quant_state_round_trip(tmp_path):
+    """runner.quant_state / load_quant_state keep what state_dict() alone loses (weight ranges, init ranges,
+    bit widths, counters, lazily created channel_proj)."""
+    spec = S.tiny_spec()
+    mk = lambda: A.Model(config_for(spec), quantization=True, sequence=spec.seq, args=args_for(spec))
+    m = mk()
+    m.materialize_lazy_layers()
+    m.load_state_dict(S.synth_state_dict(spec, seed=3), strict=True)
+    m.init_weight_ranges()
+    names = [n for n, _ in m.qconvs()]
+    q0 = dict(m.qconvs())[names[0]]
+    q0.init_range_min[1] = -2.5
+    q0.init_range_max[2] = 3.25
+    q0.a_bit = 6
+    q0.index_seq = 3
+    path = tmp_path / "quant_state.pt"
+    runner.save_quant_state(m, path)
+    m2 = runner.load_quant_state(mk(), str(path))
+    for (n1, a), (n2, b) in zip(m.qconvs(), m2.qconvs()):
+        assert n1 == n2
+        assert torch.equal(a.weight_range_min, b.weight_range_min) and torch.equal(a.weight_range_max, b.weight_range_max)
+        assert torch.equal(a.init_range_min, b.init_range_min) and torch.equal(a.init_range_max, b.init_range_max)
+        assert (a.a_bit, a.w_bit, a.index_seq, a.group_num) == (b.a_bit, b.w_bit, b.index_seq, b.group_num)
+    sd1, sd2 = m.state_dict(), m2.state_dict()
+    assert set(sd1) == set(sd2) and all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+    bad = runner.quant_state(m)
+    bad["layers"].pop(names[0])
+    with pytest.raises(RuntimeError):
+        runner.load_quant_state(mk(), bad)
