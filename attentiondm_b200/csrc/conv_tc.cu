@@ -714,7 +714,7 @@ __device__ __forceinline__ void tc_trace(int role, int it, int ev) {
 // is loaded once per SM and stays resident; otherwise it streams through a ring as before.
 // Warps: 0 = activation (halo) producer, 1 = MMA issuer, 2 = weight producer, 3..10 = epilogue.
 constexpr int TC_H_EPI0 = 4;                           // first epilogue warp (multiple of 4: quarter = warp % 4)
-constexpr int TC_H_EPI_WARPS = 8;                      // 2 per TMEM lane quarter
+constexpr int TC_H_EPI_WARPS = 8;                      // 2 per TMEM lane quarter (16 measured slower: register spills, LSU contention)
 constexpr int TC_H_EPI_GROUPS = TC_H_EPI_WARPS / 4;    // warps sharing a quarter split the 32-column chunks
 constexpr int TC_THREADS_H = 32 * (TC_H_EPI0 + TC_H_EPI_WARPS);
 constexpr int TC_H_MAXB = 8;                           // weight ring depth (streamed mode)
@@ -750,56 +750,68 @@ struct TcGeomH {
 // tq = lane%4) owns rows tr + 8k (k = 0..3; k < 2 from v0, k >= 2 from v1) and the column pairs
 // 8i + 2tq + {0,1} (i = 0..3).  Register j of a load: row bit = (j>>1)&1, column group i = j>>2, parity j&1.
 // Everything is statically indexed (registers only); stores are float2, four lanes per 32-byte sector.
+// Per-thread row state of a tile: four fragment rows (tr + 8k), kept as 32-bit element offsets of the output
+// row (relative to p.out; the launcher checks that the output has < 2^31 elements), a validity mask, the
+// window row-sums and the sample indices.  Residual and time-embedding addresses are derived from these.
+struct EpiRows {
+  uint32_t off[4];      // pixel * O + n0 + 2*tq   (0 for an invalid row)
+  uint32_t te_off[4];   // sample * O + n0 + 2*tq
+  int cs[4];
+  uint32_t ok;          // bit k: row k is an output pixel
+};
+
 // The residual of one 32x32 block, straight from HBM: all sixteen float2 loads are issued together -- and, for a
 // warp's first block of a tile, BEFORE it waits for the accumulator, so the round trip hides behind the MMAs.
-__device__ __forceinline__ void epi_load_residual(float2 (&rs)[4][4], int c0, int tq, int BN, int n0, int O,
-                                                  const long long (&pix_r)[4], const float* const (&res_row)[4]) {
+__device__ __forceinline__ void epi_load_residual(float2 (&rs)[4][4], const float* res, const EpiRows& r, int c0, int tq,
+                                                  int BN, int n0, int O) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int cl = c0 + 8 * i + 2 * tq;
     const bool col_ok = (cl < BN) && (n0 + cl < O);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      rs[i][k] = (col_ok && pix_r[k] >= 0) ? __ldg(reinterpret_cast<const float2*>(res_row[k] + c0 + 8 * i))
-                                           : make_float2(0.f, 0.f);
+      rs[i][k] = (col_ok && ((r.ok >> k) & 1)) ? __ldg(reinterpret_cast<const float2*>(res + r.off[k] + c0 + 8 * i))
+                                               : make_float2(0.f, 0.f);
   }
 }
 
+// One 32-row x 32-column block of a tile, held in the 16x256b fragment layout: thread (tr = lane/4,
+// tq = lane%4) owns rows tr + 8k (k = 0..3; k < 2 from v0, k >= 2 from v1) and the column pairs
+// 8i + 2tq + {0,1} (i = 0..3).  Register j of a load: row bit = (j>>1)&1, column group i = j>>2, parity j&1.
+// Everything is statically indexed (registers only); stores are float2, four lanes per 32-byte sector.
 template <bool RES, bool TEMB>
 __device__ __forceinline__ void epi_block(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
-                                          int c0, int tq, int BN, int n0, int O, const int (&cs_r)[4],
-                                          const long long (&pix_r)[4], float* const (&out_row)[4],
-                                          const float2 (&rs)[4][4], const float* const (&te_row)[4]) {
+                                          int c0, int tq, int BN, int n0, int O, const EpiRows& r, float* out,
+                                          const float2 (&rs)[4][4], const float* temb) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int cl = c0 + 8 * i + 2 * tq;
     const bool col_ok = (cl < BN) && (n0 + cl < O);
     const ColConst ca = colc[cl & 255], cb = colc[(cl + 1) & 255];
-    bool ok[4];
     float2 te[4];
+    if (TEMB) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      ok[k] = col_ok && pix_r[k] >= 0;
-      if (TEMB) te[k] = ok[k] ? __ldg(reinterpret_cast<const float2*>(te_row[k] + c0 + 8 * i)) : make_float2(0.f, 0.f);
+      for (int k = 0; k < 4; ++k)
+        te[k] = (col_ok && ((r.ok >> k) & 1)) ? __ldg(reinterpret_cast<const float2*>(temb + r.te_off[k] + c0 + 8 * i))
+                                              : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j = (i << 2) | ((k & 1) << 1);
       const int a0 = (int)(k < 2 ? v0[j] : v1[j]), a1 = (int)(k < 2 ? v0[j | 1] : v1[j | 1]);
-      float f0 = conv_i8_value(a0, ca.A, ca.B, cs_r[k], ca.m, ca.bias);
-      float f1 = conv_i8_value(a1, cb.A, cb.B, cs_r[k], cb.m, cb.bias);
+      float f0 = conv_i8_value(a0, ca.A, ca.B, r.cs[k], ca.m, ca.bias);
+      float f1 = conv_i8_value(a1, cb.A, cb.B, r.cs[k], cb.m, cb.bias);
       if (RES) { f0 = __fadd_rn(f0, rs[i][k].x); f1 = __fadd_rn(f1, rs[i][k].y); }
       if (TEMB) { f0 = __fadd_rn(f0, te[k].x); f1 = __fadd_rn(f1, te[k].y); }
-      if (ok[k]) *reinterpret_cast<float2*>(out_row[k] + c0 + 8 * i) = make_float2(f0, f1);
+      if (col_ok && ((r.ok >> k) & 1)) *reinterpret_cast<float2*>(out + r.off[k] + c0 + 8 * i) = make_float2(f0, f1);
     }
   }
 }
 
 // odd channel counts (the 3-channel eps output): scalar loads/stores, same static indexing
 __device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
-                                                 int c0, int tq, int BN, int n0, int O, const int (&cs_r)[4],
-                                                 const long long (&pix_r)[4], float* const (&out_row)[4],
-                                                 const float* const (&res_row)[4], const float* const (&te_row)[4]) {
+                                                 int c0, int tq, int BN, int n0, int O, const EpiRows& r, float* out,
+                                                 const float* res, const float* temb) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
 #pragma unroll
@@ -810,11 +822,11 @@ __device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int j = (i << 2) | ((k & 1) << 1) | par;
-        float f = conv_i8_value((int)(k < 2 ? v0[j] : v1[j]), cc.A, cc.B, cs_r[k], cc.m, cc.bias);
-        if (col_ok && pix_r[k] >= 0) {
-          if (res_row[k]) f = __fadd_rn(f, res_row[k][c0 + 8 * i + par]);
-          if (te_row[k]) f = __fadd_rn(f, te_row[k][c0 + 8 * i + par]);
-          out_row[k][c0 + 8 * i + par] = f;
+        float f = conv_i8_value((int)(k < 2 ? v0[j] : v1[j]), cc.A, cc.B, r.cs[k], cc.m, cc.bias);
+        if (col_ok && ((r.ok >> k) & 1)) {
+          if (res) f = __fadd_rn(f, res[r.off[k] + c0 + 8 * i + par]);
+          if (temb) f = __fadd_rn(f, temb[r.te_off[k] + c0 + 8 * i + par]);
+          out[r.off[k] + c0 + 8 * i + par] = f;
         }
       }
     }
@@ -1074,33 +1086,24 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // by the geometry warp
       const int gb = it & 1;
       mbar_wait_relaxed(smem_u32(&geo_full[gb]), (uint32_t)((it >> 1) & 1));
-      long long pix_r[4];
-      int b_r[4], cs_r[4];
+      EpiRows rows;
+      rows.ok = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int r = quarter * 32 + tr + 8 * k;
-        pix_r[k] = geo_pix[gb][r];
-        b_r[k] = geo_b[gb][r];
-        cs_r[k] = geo_cs[gb][r];
+        const long long pix = geo_pix[gb][r];
+        rows.ok |= (pix >= 0 ? 1u : 0u) << k;
+        rows.off[k] = (uint32_t)((pix < 0 ? 0 : pix) * p.O) + (uint32_t)(n0 + 2 * tq);
+        rows.te_off[k] = (uint32_t)geo_b[gb][r] * (uint32_t)p.O + (uint32_t)(n0 + 2 * tq);
+        rows.cs[k] = geo_cs[gb][r];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&geo_empty[gb]));
       if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 0);
-      // row bases of this thread's four fragment rows (element offsets; invalid rows are predicated off)
-      const float* res_row[4];
-      const float* te_row[4];
-      float* out_row[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long long off = (pix_r[k] < 0 ? 0 : pix_r[k]) * p.O + n0 + 2 * tq;
-        out_row[k] = p.out + off;
-        res_row[k] = p.residual ? p.residual + off : nullptr;
-        te_row[k] = p.temb ? p.temb + (long long)b_r[k] * p.O + n0 + 2 * tq : nullptr;
-      }
       const int nchunks = (g.BN + 31) >> 5;
       const bool res_vec = p.residual != nullptr && pair_ok;
       float2 rs[4][4];
-      if (res_vec && half < nchunks) epi_load_residual(rs, half << 5, tq, g.BN, n0, p.O, pix_r, res_row);
+      if (res_vec && half < nchunks) epi_load_residual(rs, p.residual, rows, half << 5, tq, g.BN, n0, p.O);
       mbar_wait_relaxed(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
       tcgen05_fence_after();
       if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 1);
@@ -1128,17 +1131,17 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 2);
         }
         if ((g.dbg & 3) >= 1) continue;
-        if (res_vec && ci != half) epi_load_residual(rs, c0, tq, g.BN, n0, p.O, pix_r, res_row);
+        if (res_vec && ci != half) epi_load_residual(rs, p.residual, rows, c0, tq, g.BN, n0, p.O);
         if (pair_ok) {
           if (p.residual) {
-            if (p.temb) epi_block<true, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, rs, te_row);
-            else        epi_block<true, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, rs, te_row);
+            if (p.temb) epi_block<true, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs, p.temb);
+            else        epi_block<true, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs, p.temb);
           } else {
-            if (p.temb) epi_block<false, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, rs, te_row);
-            else        epi_block<false, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, rs, te_row);
+            if (p.temb) epi_block<false, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs, p.temb);
+            else        epi_block<false, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs, p.temb);
           }
         } else {
-          epi_block_scalar(v0, v1, colc, c0, tq, g.BN, n0, p.O, cs_r, pix_r, out_row, res_row, te_row);
+          epi_block_scalar(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, p.residual, p.temb);
         }
       }
       if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 3);
@@ -1261,6 +1264,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   g.ncb = cdiv(p.Cp, TC_BK);
   g.hr = p.taps == 9 ? TC_BM + 2 * p.Wp + 2 : TC_BM;
   if (g.hr > 512) return 0;
+  if ((long long)p.B * p.H * p.W * p.O >= (1LL << 31)) return 0;      // the epilogue keeps 32-bit output offsets
   g.hr_stride = round_up(g.hr * TC_BK, 1024);
   const int nkb = p.taps * g.ncb;
   const int b_tile = g.BN * TC_BK;

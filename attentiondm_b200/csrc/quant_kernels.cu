@@ -329,7 +329,7 @@ __device__ __forceinline__ int quant_code_i(float v, float s, float zp, float lo
   return __float2int_rn(fminf(fmaxf(t, lo), hi));
 }
 
-template <int PRE, int NQ>
+template <int PRE, int NQ, bool A8>
 __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_rows_kernel(ActQuantParams p) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
@@ -404,13 +404,27 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_
           t.y = pre_op<PRE>(t.y, ga[i].y, gb[i].y);
           t.z = pre_op<PRE>(t.z, ga[i].z, gb[i].z);
           t.w = pre_op<PRE>(t.w, ga[i].w, gb[i].w);
-          const int ix = quant_code_i(t.x, s4[i].x, z4[i].x, p.qlo, p.qhi);
-          const int iy = quant_code_i(t.y, s4[i].y, z4[i].y, p.qlo, p.qhi);
-          const int iz = quant_code_i(t.z, s4[i].z, z4[i].z, p.qlo, p.qhi);
-          const int iw = quant_code_i(t.w, s4[i].w, z4[i].w, p.qlo, p.qhi);
-          acc += ix + iy + iz + iw;
-          *reinterpret_cast<int*>(crow + (long long)(w0 + k) * Cp + i * 128) =
-              (ix & 0xff) | ((iy & 0xff) << 8) | ((iz & 0xff) << 16) | (iw << 24);
+          int word;
+          if (A8) {
+            // 8-bit codes: round to nearest even, then ONE saturating pack per two codes (cvt.pack.sat.s8.s32 clamps
+            // to [-128, 127], which is the quantizer's clamp), and the code sum as one dp4a with a vector of ones
+            const int ix = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].x, t.x), z4[i].x));
+            const int iy = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].y, t.y), z4[i].y));
+            const int iz = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].z, t.z), z4[i].z));
+            const int iw = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].w, t.w), z4[i].w));
+            int hi2;
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi2) : "r"(iw), "r"(iz));
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(word) : "r"(iy), "r"(ix), "r"(hi2));
+            acc = __dp4a(word, 0x01010101, acc);
+          } else {
+            const int ix = quant_code_i(t.x, s4[i].x, z4[i].x, p.qlo, p.qhi);
+            const int iy = quant_code_i(t.y, s4[i].y, z4[i].y, p.qlo, p.qhi);
+            const int iz = quant_code_i(t.z, s4[i].z, z4[i].z, p.qlo, p.qhi);
+            const int iw = quant_code_i(t.w, s4[i].w, z4[i].w, p.qlo, p.qhi);
+            acc += ix + iy + iz + iw;
+            word = (ix & 0xff) | ((iy & 0xff) << 8) | ((iz & 0xff) << 16) | (iw << 24);
+          }
+          *reinterpret_cast<int*>(crow + (long long)(w0 + k) * Cp + i * 128) = word;
         }
         sums[k] = acc;
       }
@@ -527,16 +541,22 @@ static int act_quant_impl(const float* x, int B, int H, int W, int C, const floa
     p.rows_per_warp = (nimg + w2 - 1) / w2;
     w2 = (nimg + (int)p.rows_per_warp - 1) / (int)p.rows_per_warp;
     const int nb = cdiv(w2, 8);
+#define ATTNDM_AQ_ROWS_N(PREV, NQV)                                                                                 \
+    do {                                                                                                              \
+      if (a_bit == 8) launch_pdl(act_quant_rows_kernel<PREV, NQV, true>, dim3(nb), dim3(256), 0, st, p);             \
+      else launch_pdl(act_quant_rows_kernel<PREV, NQV, false>, dim3(nb), dim3(256), 0, st, p);                       \
+    } while (0)
 #define ATTNDM_AQ_ROWS(PREV)                                                                                         \
     do {                                                                                                              \
-      if (C == 128) launch_pdl(act_quant_rows_kernel<PREV, 1>, dim3(nb), dim3(256), 0, st, p);                        \
-      else if (C == 256) launch_pdl(act_quant_rows_kernel<PREV, 2>, dim3(nb), dim3(256), 0, st, p);                   \
-      else if (C == 384) launch_pdl(act_quant_rows_kernel<PREV, 3>, dim3(nb), dim3(256), 0, st, p);                   \
-      else launch_pdl(act_quant_rows_kernel<PREV, 4>, dim3(nb), dim3(256), 0, st, p);                                 \
+      if (C == 128) ATTNDM_AQ_ROWS_N(PREV, 1);                                                                        \
+      else if (C == 256) ATTNDM_AQ_ROWS_N(PREV, 2);                                                                   \
+      else if (C == 384) ATTNDM_AQ_ROWS_N(PREV, 3);                                                                   \
+      else ATTNDM_AQ_ROWS_N(PREV, 4);                                                                                 \
     } while (0)
     if (pre == ATTNDM_PRE_GN_SILU) ATTNDM_AQ_ROWS(ATTNDM_PRE_GN_SILU);
     else if (pre == ATTNDM_PRE_SILU) ATTNDM_AQ_ROWS(ATTNDM_PRE_SILU);
     else ATTNDM_AQ_ROWS(ATTNDM_PRE_NONE);
+#undef ATTNDM_AQ_ROWS_N
 #undef ATTNDM_AQ_ROWS
     ATTNDM_CUDA_LAUNCH_CHECK("act_quant");
     return ATTNDM_OK;
