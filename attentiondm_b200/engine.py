@@ -9,6 +9,8 @@ counter -- so a single graph serves all steps with no host work in the loop.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -82,10 +84,22 @@ class SamplerEngine:
         self.launches_per_step = 0
         # fused per-sample programs (time_mlp of every block; all blocks on 1x1 maps): graph mode only
         self.fused = None
+        # Experiment (ATTNDM_SPLIT=2): two half-batches on two streams of the same graph, so that one half's
+        # latency-bound layers (the fused trunk above all) overlap the other half's HBM-bound layers.  Samples are
+        # independent through every op, so the result is bit-identical -- but on B200 at batch 256 it measured
+        # SLOWER (679 vs 804 images/s): the half-size kernels lose more than the overlap wins.  Off by default.
+        self.nsplit = 1
+        if (use_graph and hasattr(model, "down_blocks") and self.B % 2 == 0 and self.B >= 64
+                and os.environ.get("ATTNDM_SPLIT", "1") == "2"):
+            self.nsplit = 2
+        self.side_stream = torch.cuda.Stream(device=dev) if self.nsplit == 2 else None
+        self.fused_parts = [None] * self.nsplit
         if use_graph and hasattr(model, "down_blocks"):
             if hasattr(model, "materialize_lazy_layers"):
                 model.materialize_lazy_layers()
-            self.fused = rowprog.build(model, self.B, {id(m): sl for m, sl in zip(self.layers, self.slices)}, dev)
+            sl = {id(m): s_ for m, s_ in zip(self.layers, self.slices)}
+            self.fused_parts = [rowprog.build(model, self.B // self.nsplit, sl, dev) for _ in range(self.nsplit)]
+            self.fused = self.fused_parts[0]
 
     def _versions(self):
         return tuple((m._tab_key, m._pack_key) for m in self.layers)
@@ -99,38 +113,51 @@ class SamplerEngine:
         return self._versions() == self.versions
 
     # ---- one denoising step on the current stream ----
+    def _set_fused(self, fp):
+        self.model._fused, self.model._fused_cur = fp, self.cur
+        for b in self._blocks:
+            b._temb_fused = fp.temb.get(id(b)) if fp is not None else None
+
+    def _forward_part(self, part):
+        """UNet forward + DDIM update of one slice of the batch, on the current stream."""
+        n = self.B // self.nsplit
+        lo, hi = part * n, (part + 1) * n
+        self._set_fused(self.fused_parts[part])
+        x = self.x_cur[lo:hi]
+        eps = self.model.forward_nhwc(x, self.cur[self.t_off + lo:self.t_off + hi])
+        noise = self.noise[lo:hi] if self.noise is not None else None
+        ops.ddim_step(x, eps, self.cur[self.coef_off:], noise, x_next=x, x0_out=self.x0[lo:hi])
+        return eps
+
+    # ---- one denoising step on the current stream ----
     def _step_body(self):
         ops.stage_tables(self.table, self.step, self.cur, advance=True)
-        t_cur = self.cur[self.t_off:self.t_off + self.B]
-        eps = self.model.forward_nhwc(self.x_cur, t_cur)
-        noise = None
-        if self.noise is not None:
-            if not self.ext_noise:
-                self.noise.normal_()
-            noise = self.noise
-        ops.ddim_step(self.x_cur, eps, self.cur[self.coef_off:], noise, x_next=self.x_cur, x0_out=self.x0)
-        return eps
+        if self.noise is not None and not self.ext_noise:
+            self.noise.normal_()
+        if self.nsplit == 1:
+            return self._forward_part(0)
+        main = torch.cuda.current_stream()
+        side = self.side_stream
+        side.wait_stream(main)                         # fork after the tables are staged
+        eps0 = self._forward_part(0)
+        with torch.cuda.stream(side):
+            eps1 = self._forward_part(1)
+        main.wait_stream(side)                         # join
+        return torch.cat([eps0, eps1], dim=0) if not torch.cuda.is_current_stream_capturing() else eps0
 
     def _with_staged(self, fn):
         for m, (o, w) in zip(self.layers, self.slices):
             m.use_staged_row(self.cur[o:o + w])
         saved = [m.index_seq for m in self.layers]
-        blocks = []
-        if self.fused is not None:
-            self.model._fused, self.model._fused_cur = self.fused, self.cur
-            blocks = list(self.model.down_blocks) + list(self.model.up_blocks)
-            for b in blocks:
-                b._temb_fused = self.fused.temb.get(id(b))
+        self._blocks = (list(self.model.down_blocks) + list(self.model.up_blocks)) if hasattr(self.model, "down_blocks") else []
         try:
             return fn()
         finally:
             for m, s in zip(self.layers, saved):
                 m.use_staged_row(None)
                 m.index_seq = s
-            if self.fused is not None:
-                self.model._fused = None
-                for b in blocks:
-                    b._temb_fused = None
+            if hasattr(self.model, "down_blocks"):
+                self._set_fused(None)
 
     def _capture(self):
         from . import _ffi
