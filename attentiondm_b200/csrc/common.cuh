@@ -63,7 +63,10 @@ __device__ __forceinline__ void gn_mean_rstd(double s, double ss, double inv_n, 
   double var = __dsub_rn(__dmul_rn(ss, inv_n), __dmul_rn(m, m));
   if (var < 0.0) var = 0.0;
   mean = (float)m;
-  rstd = (float)(1.0 / sqrt(__dadd_rn(var, (double)eps)));
+  // correctly rounded fp32 reciprocal square root of the (double-accumulated) variance: <= 1 ulp from the
+  // double-precision 1/sqrt it replaces, without the ~100-instruction software double sqrt + divide that every
+  // warp of the small-map kernels paid per sample
+  rstd = __frsqrt_rn((float)__dadd_rn(var, (double)eps));
 }
 // silu(groupnorm(v)) with a = rstd*gamma, b = beta - mean*a  (models/diffusion.py:121-122)
 __device__ __forceinline__ float gn_silu_apply(float v, float mean, float rstd, float gamma, float beta) {

@@ -11,10 +11,10 @@
 // Weights are [O][taps*Cp] (K-major), tile {128, BN}.  One CTA computes a
 // 128-row x BN-output tile: M = 128 (TMEM lanes), N = BN <= 256 (TMEM columns).
 //
-// Warp roles (192 threads): warp 0 = TMEM allocator + TMA producer (one lane),
-// warp 1 = barrier init + MMA issuer (one lane), warps 2..5 = epilogue (TMEM lane
-// quarter = warp_idx % 4).  Two CTAs fit per SM (<= 112 KB smem, <= 256 TMEM
-// columns each) so one CTA's epilogue overlaps the other's main loop.
+// Two kernels: qconv_i8_halo_kernel (the default: one halo tile per output tile feeds all nine taps, weights
+// resident in shared memory when they fit) and qconv_i8_tc_persistent_kernel (ring-fed, one TMA box per
+// (tap, channel block); the fallback for feature maps whose halo tile exceeds 512 rows).  Both are persistent
+// (one CTA per SM, static round-robin over tiles) with the accumulator double-buffered in TMEM.
 #include <cuda.h>
 
 #include <stdlib.h>
@@ -29,11 +29,9 @@ namespace attndm {
 constexpr int TC_BM = 128;        // rows per tile  (UMMA M)
 constexpr int TC_BK = 128;        // bytes of K per stage (one SWIZZLE_128B row)
 constexpr int TC_UMMA_K = 32;     // K per tcgen05.mma for 8-bit operands
-constexpr int TC_THREADS = 192;
 constexpr int TC_EPI_WARPS_P = 8;                       // persistent kernel: epilogue warps
 constexpr int TC_THREADS_P = 64 + 32 * TC_EPI_WARPS_P;
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_SMEM_BUDGET = 110 * 1024;   // per CTA, so that two CTAs share an SM
 
 // ---- PTX wrappers -----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -256,203 +254,6 @@ struct __align__(16) ColConst {
   float m;      // 1 / (act_scale * w_scale[o])
   float bias;
 };
-
-struct TcGeom {
-  int BN;            // outputs per tile (multiple of 16, <= 256)
-  int stages;
-  int stage_bytes;   // 16384 + BN*128
-  int ncb;           // channel blocks of 128 per tap
-  int tmem_cols;     // power of two >= max(32, BN)
-};
-
-__global__ void __launch_bounds__(TC_THREADS, 2)
-qconv_i8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const ConvI8Params p, const TcGeom g) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
-  __shared__ uint32_t tmem_base_slot;
-  __shared__ ColConst colc[256];            // per-output-column epilogue constants
-  __shared__ long long row_pix[4][32];      // output pixel of each tile row (-1 = not an output)
-  __shared__ int row_b[4][32];              // its sample index
-
-  pdl_launch_dependents();     // the next kernel may start its own prologue while this grid runs
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024-B alignment
-  const long long m0 = (long long)blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * g.BN;
-  const int num_kb = p.taps * g.ncb;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    }
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"((uint32_t)g.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  } else if (warp == 1 && lane == 0) {
-    for (int s = 0; s < g.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
-    }
-    mbar_init(smem_u32(&tmem_full_bar), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-  // everything above (TMEM allocation, barrier init, descriptor prefetch) overlapped the previous
-  // kernel's tail; from here on we read what it wrote (codes, row sums, staged tables)
-  pdl_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
-        const long long shift = p.taps == 9 ? (long long)(tap / 3) * p.Wp + (tap % 3) : 0;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-        const uint32_t a_dst = tiles + (uint32_t)s * g.stage_bytes;
-        const uint32_t b_dst = a_dst + TC_BM * TC_BK;
-        const uint32_t bar = smem_u32(&full_bar[s]);
-        mbar_expect_tx(bar, (uint32_t)g.stage_bytes);
-        tma_load_2d(a_dst, &tmA, bar, cb * TC_BK, (int)(m0 + shift));
-        tma_load_2d(b_dst, &tmB, bar, tap * p.Cp + cb * TC_BK, n0);
-        if (++s == g.stages) { s = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      // instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = BN
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
-                             ((uint32_t)(TC_BM >> 4) << 24);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int cb = kb % g.ncb;
-        int ksteps = (p.Cp - cb * TC_BK + TC_UMMA_K - 1) / TC_UMMA_K;   // skip all-zero K tails
-        if (ksteps > TC_BK / TC_UMMA_K) ksteps = TC_BK / TC_UMMA_K;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
-        tcgen05_fence_after();
-        const uint32_t a_addr = tiles + (uint32_t)s * g.stage_bytes;
-        const uint32_t b_addr = a_addr + TC_BM * TC_BK;
-        for (int k = 0; k < ksteps; ++k) {
-          umma_i8(tmem_base, umma_desc_sw128(a_addr + k * TC_UMMA_K), umma_desc_sw128(b_addr + k * TC_UMMA_K), idesc,
-                  (kb > 0 || k > 0) ? 1u : 0u);
-        }
-        tcgen05_commit(smem_u32(&empty_bar[s]));     // frees the smem slot when these MMAs retire
-        if (++s == g.stages) { s = 0; ph ^= 1; }
-      }
-      tcgen05_commit(smem_u32(&tmem_full_bar));      // accumulator complete
-    }
-  } else {
-    // ===== epilogue: TMEM -> registers -> exact integer finish -> smem transpose -> coalesced NHWC rows =====
-    const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
-    const int zp = *p.act_zp;
-    // (a) while the main loop runs: stage the per-column constants and the per-row geometry
-    for (int c = (warp - 2) * 32 + lane; c < g.BN; c += 128) {
-      const int o = n0 + c;
-      ColConst cc = {0, 0, 0.f, 0.f};
-      if (o < p.O) {
-        cc.A = zp * p.wsum[o];
-        cc.B = p.w_zp[o];
-        cc.m = p.mult[o];
-        cc.bias = p.bias ? p.bias[o] : 0.f;
-      }
-      colc[c] = cc;
-    }
-    const long long row = m0 + quarter * 32 + lane;
-    long long pix = 0;
-    int b = 0;
-    const bool valid = conv_row_to_pixel(p, row, pix, b);
-    int cs = 0;
-    if (valid) cs = (int)conv_window_rowsum(p, row) + zp * (p.taps * p.C);
-    row_pix[quarter][lane] = valid ? pix : -1;
-    row_b[quarter][lane] = b;
-    asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps only
-    mbar_wait(smem_u32(&tmem_full_bar), 0);
-    tcgen05_fence_after();
-    // every MMA has retired, so the pipeline buffers are free: reuse them as the transpose stage.
-    // Stage = 32 rows x 128 B per warp, 16-B chunks XOR-swizzled by (row & 7): the per-thread row writes
-    // (STS.128) and the per-row reads (LDS.128, 8 lanes per row) are both bank-conflict free.
-    float4* stg = reinterpret_cast<float4*>(smem_raw + (tiles - smem_u32(smem_raw))) + quarter * (32 * 8);
-    const bool vec_ok = (p.O & 3) == 0;
-    const int sub = lane >> 3, ch = lane & 7;          // read phase: 4 rows per instruction, 8 chunks per row
-    for (int c0 = 0; c0 < g.BN; c0 += 32) {
-      uint32_t v[32];
-      __syncwarp();                                   // tcgen05.ld is .sync.aligned; also fences stg reuse
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 f;
-        ColConst cc = colc[(c0 + 4 * j + 0) & 255];
-        f.x = conv_i8_value((int)v[4 * j + 0], cc.A, cc.B, cs, cc.m, cc.bias);
-        cc = colc[(c0 + 4 * j + 1) & 255];
-        f.y = conv_i8_value((int)v[4 * j + 1], cc.A, cc.B, cs, cc.m, cc.bias);
-        cc = colc[(c0 + 4 * j + 2) & 255];
-        f.z = conv_i8_value((int)v[4 * j + 2], cc.A, cc.B, cs, cc.m, cc.bias);
-        cc = colc[(c0 + 4 * j + 3) & 255];
-        f.w = conv_i8_value((int)v[4 * j + 3], cc.A, cc.B, cs, cc.m, cc.bias);
-        stg[lane * 8 + (j ^ (lane & 7))] = f;
-      }
-      __syncwarp();
-      const int o = n0 + c0 + 4 * ch;                  // this lane's 4 output channels
-      const bool col_ok = (c0 + 4 * ch < g.BN) && (o < p.O);
-#pragma unroll
-      for (int rb = 0; rb < 32; rb += 16) {            // 4 groups of 4 rows per batch: loads first, then stores
-        long long pr[4];
-        float4 val[4], rs[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = rb + 4 * i + sub;
-          pr[i] = row_pix[quarter][r];
-          val[i] = stg[r * 8 + (ch ^ (r & 7))];
-          rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.residual && vec_ok && col_ok && pr[i] >= 0)
-            rs[i] = *reinterpret_cast<const float4*>(p.residual + pr[i] * p.O + o);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (!col_ok || pr[i] < 0) continue;
-          const int r = rb + 4 * i + sub;
-          float* dst = p.out + pr[i] * p.O + o;
-          if (vec_ok) {
-            float4 t = val[i];
-            if (p.residual) { t.x = __fadd_rn(t.x, rs[i].x); t.y = __fadd_rn(t.y, rs[i].y); t.z = __fadd_rn(t.z, rs[i].z); t.w = __fadd_rn(t.w, rs[i].w); }
-            if (p.temb) {
-              const float4 te = *reinterpret_cast<const float4*>(p.temb + (long long)row_b[quarter][r] * p.O + o);
-              t.x = __fadd_rn(t.x, te.x); t.y = __fadd_rn(t.y, te.y); t.z = __fadd_rn(t.z, te.z); t.w = __fadd_rn(t.w, te.w);
-            }
-            *reinterpret_cast<float4*>(dst) = t;
-          } else {                                     // O % 4 != 0 (the 3-channel eps output): scalar tail
-            const float e[4] = {val[i].x, val[i].y, val[i].z, val[i].w};
-            for (int k = 0; k < 4 && o + k < p.O; ++k) {
-              float t = e[k];
-              if (p.residual) t = __fadd_rn(t, p.residual[pr[i] * p.O + o + k]);
-              if (p.temb) t = __fadd_rn(t, p.temb[(long long)row_b[quarter][r] * p.O + o + k]);
-              dst[k] = t;
-            }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
-                 : "memory");
-  }
-}
 
 // ---- persistent variant ------------------------------------------------------------------
 // One CTA per SM loops over output tiles (static round-robin).  The accumulator is double-buffered in
@@ -1063,7 +864,6 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int it = 0;
     for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
-      const long long m0 = (tile / g.ntn) * TC_BM;
       const int nt = (int)(tile % g.ntn);
       const int n0 = nt * g.BN;
       if (nt != last_nt) {
@@ -1187,15 +987,6 @@ static int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("qconv_i8_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return ATTNDM_ERR_CUDA; }
   return ATTNDM_OK;
-}
-
-static bool tc_persistent_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ATTNDM_TC_PERSISTENT");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
 }
 
 static int launch_qconv_i8_tc_persistent(const ConvI8Params& p, cudaStream_t st) {
@@ -1325,35 +1116,7 @@ int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st) {
     if (rc < 0) return rc;
     if (rc == 1) return ATTNDM_OK;
   }
-  if (tc_persistent_enabled()) return launch_qconv_i8_tc_persistent(p, st);
-  TcGeom g;
-  g.BN = p.O <= 256 ? round_up(p.O, 16) : 256;
-  // small problems: split N over more CTAs (idle SMs are free; the epilogue is serial per CTA)
-  const long long mtiles = (p.rows + TC_BM - 1) / TC_BM;
-  while (g.BN > 32 && (g.BN / 2) % 16 == 0 && mtiles * cdiv(p.O, g.BN) < 120) g.BN /= 2;
-  g.stage_bytes = TC_BM * TC_BK + g.BN * TC_BK;
-  g.stages = TC_SMEM_BUDGET / g.stage_bytes;
-  if (g.stages > TC_MAX_STAGES) g.stages = TC_MAX_STAGES;
-  if (g.stages < 2) g.stages = 2;
-  g.ncb = cdiv(p.Cp, TC_BK);
-  g.tmem_cols = 32;
-  while (g.tmem_cols < g.BN) g.tmem_cols <<= 1;      // power of two >= 32, so 32-column loads stay in bounds
-  CUtensorMap tmA, tmB;
-  int rc = make_map_2d(&tmA, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, TC_BM);
-  if (rc) return rc;
-  rc = make_map_2d(&tmB, p.qw, (uint64_t)p.taps * p.Cp, (uint64_t)p.O, TC_BK, (uint32_t)g.BN);
-  if (rc) return rc;
-  const int smem = g.stages * g.stage_bytes + 1024;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(qconv_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  });
-  if (attr_err != cudaSuccess) { set_error("qconv_i8_tc: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
-  dim3 grid(cdiv(p.rows, TC_BM), cdiv(p.O, g.BN));
-  launch_pdl(qconv_i8_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmB, p, g);
-  ATTNDM_CUDA_LAUNCH_CHECK("qconv_i8_tc");
-  return ATTNDM_OK;
+  return launch_qconv_i8_tc_persistent(p, st);     // shapes the halo kernel does not take (halo > 512 rows, >= 2^31 outputs)
 }
 
 }  // namespace attndm
