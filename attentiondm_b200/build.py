@@ -18,6 +18,8 @@ SOURCES = ["api.cu", "quant_kernels.cu", "conv_simt.cu", "conv_tc.cu", "misc_ker
 HEADERS = ["common.cuh", "conv_common.cuh", os.path.join("..", "..", "include", "attndm_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-cudart", "static"]
+# debug builds only, e.g. ATTNDM_NVCC_EXTRA=-DATTNDM_TC_TRACE for tools/conv_trace.py (part of the stamp digest)
+NVCC_FLAGS += os.environ.get("ATTNDM_NVCC_EXTRA", "").split()
 
 
 def _digest():

@@ -245,6 +245,25 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) 
       : "r"(taddr)
       : "memory");
 }
+// ---- asynchronous output stores: shared -> global through the TMA unit ------------------------------
+// (measured, tools/tma_store_4d_test.cu: a tensor store clips coordinates beyond the tensor, but a NEGATIVE
+// start coordinate raises an illegal-instruction fault -- so every store below starts inside the tensor)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- kernel -------------------------------------------------------------------
@@ -496,13 +515,29 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 }
 
 // ---- optional timeline trace (debug): CTA 0 records globaltimer at pipeline events ----------------
-__device__ unsigned long long* g_tc_trace = nullptr;    // [role 0..3][it 0..31][event 0..3]
+__device__ unsigned long long* g_tc_trace = nullptr;    // [role 0..11][it 0..31][event 0..3], [1536] = CTA, [1540+it] = clock64
 __device__ __forceinline__ void tc_trace(int role, int it, int ev) {
+#ifndef ATTNDM_TC_TRACE
+  return;       // the hooks cost a global load each: compiled in only with -DATTNDM_TC_TRACE (tools/conv_trace.py)
+#endif
   unsigned long long* t = g_tc_trace;
-  if (t != nullptr && blockIdx.x == 0 && it < 32) {
+  if (t != nullptr && blockIdx.x == (unsigned)t[1536] && it < 32) {        // t[1536]: which CTA to record
     unsigned long long now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory");
     t[(role * 32 + it) * 4 + ev] = now;
+    if (role == 1 && ev == 0) t[1540 + it] = (unsigned long long)clock64();   // SM clock at each tile start
+  }
+}
+
+__device__ __forceinline__ void tc_span(int ev) {          // per-CTA kernel-level timestamps (all CTAs)
+#ifndef ATTNDM_TC_TRACE
+  return;
+#endif
+  unsigned long long* t = g_tc_trace;
+  if (t != nullptr) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory");
+    t[1600 + 4 * blockIdx.x + ev] = now;
   }
 }
 
@@ -516,6 +551,9 @@ __device__ __forceinline__ void tc_trace(int role, int it, int ev) {
 // Warps: 0 = activation (halo) producer, 1 = MMA issuer, 2 = weight producer, 3..10 = epilogue.
 constexpr int TC_H_EPI0 = 4;                           // first epilogue warp (multiple of 4: quarter = warp % 4)
 constexpr int TC_H_EPI_WARPS = 8;                      // 2 per TMEM lane quarter (16 measured slower: register spills, LSU contention)
+constexpr int TC_H_NGEO = 4;                           // row-geometry buffers (the geometry warp runs this far ahead)
+constexpr int TC_H_NBOX = 5;                           // output tensor maps: boxes of 32, 31, 30, 29, 28 pixels
+constexpr bool TC_H_WIDE = TC_H_EPI_WARPS == 16;       // half-block epilogue path (fits the 96-register cap of 640 threads)
 constexpr int TC_H_EPI_GROUPS = TC_H_EPI_WARPS / 4;    // warps sharing a quarter split the 32-column chunks
 constexpr int TC_THREADS_H = 32 * (TC_H_EPI0 + TC_H_EPI_WARPS);
 constexpr int TC_H_MAXB = 8;                           // weight ring depth (streamed mode)
@@ -543,6 +581,7 @@ struct TcGeomH {
   int b_resident;     // 1: weights loaded once; 0: streamed
   int nb;             // weight ring depth (streamed)
   int a_off, b_off, stg_off;   // byte offsets inside the 1024-aligned dynamic smem
+  int tma_store;      // 1: full 16-column pieces leave through per-warp staging + TMA tensor stores
   int dbg;            // debug experiments (ATTNDM_TC_DBG): 1 = epilogue skips the math/stores, 2 = skips the TMEM loads too
 };
 
@@ -563,16 +602,19 @@ struct EpiRows {
 
 // The residual of one 32x32 block, straight from HBM: all sixteen float2 loads are issued together -- and, for a
 // warp's first block of a tile, BEFORE it waits for the accumulator, so the round trip hides behind the MMAs.
-__device__ __forceinline__ void epi_load_residual(float2 (&rs)[4][4], const float* res, const EpiRows& r, int c0, int tq,
+__device__ __forceinline__ void epi_load_residual(float4 (&rs)[2][4], const float* res, const EpiRows& r, int c0, int tq,
                                                   int BN, int n0, int O) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int cl = c0 + 8 * i + 2 * tq;
     const bool col_ok = (cl < BN) && (n0 + cl < O);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      rs[i][k] = (col_ok && ((r.ok >> k) & 1)) ? __ldg(reinterpret_cast<const float2*>(res + r.off[k] + c0 + 8 * i))
-                                               : make_float2(0.f, 0.f);
+    for (int k = 0; k < 4; ++k) {
+      const float2 t = (col_ok && ((r.ok >> k) & 1)) ? __ldg(reinterpret_cast<const float2*>(res + r.off[k] + c0 + 8 * i))
+                                                     : make_float2(0.f, 0.f);
+      if (i & 1) { rs[i >> 1][k].z = t.x; rs[i >> 1][k].w = t.y; }      // shares its registers with the 128-bit path
+      else       { rs[i >> 1][k].x = t.x; rs[i >> 1][k].y = t.y; }
+    }
   }
 }
 
@@ -583,7 +625,7 @@ __device__ __forceinline__ void epi_load_residual(float2 (&rs)[4][4], const floa
 template <bool RES, bool TEMB>
 __device__ __forceinline__ void epi_block(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
                                           int c0, int tq, int BN, int n0, int O, const EpiRows& r, float* out,
-                                          const float2 (&rs)[4][4], const float* temb) {
+                                          const float4 (&rs)[2][4], const float* temb) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int cl = c0 + 8 * i + 2 * tq;
@@ -602,10 +644,136 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v0)[16], const uint32
       const int a0 = (int)(k < 2 ? v0[j] : v1[j]), a1 = (int)(k < 2 ? v0[j | 1] : v1[j | 1]);
       float f0 = conv_i8_value(a0, ca.A, ca.B, r.cs[k], ca.m, ca.bias);
       float f1 = conv_i8_value(a1, cb.A, cb.B, r.cs[k], cb.m, cb.bias);
-      if (RES) { f0 = __fadd_rn(f0, rs[i][k].x); f1 = __fadd_rn(f1, rs[i][k].y); }
+      if (RES) {
+        f0 = __fadd_rn(f0, (i & 1) ? rs[i >> 1][k].z : rs[i >> 1][k].x);
+        f1 = __fadd_rn(f1, (i & 1) ? rs[i >> 1][k].w : rs[i >> 1][k].y);
+      }
       if (TEMB) { f0 = __fadd_rn(f0, te[k].x); f1 = __fadd_rn(f1, te[k].y); }
       if (col_ok && ((r.ok >> k) & 1)) *reinterpret_cast<float2*>(out + r.off[k] + c0 + 8 * i) = make_float2(f0, f1);
     }
+  }
+}
+
+// ---- 128-bit variant for full blocks (all 32 columns valid, O % 4 == 0) ----
+// The LSU handles one cache line per cycle, so a float2 store of the fragment layout (8 rows x 32 B per warp
+// instruction) costs 8 line-cycles for 256 B and the epilogue of a tile is bound by ~4000 of them.  One exchange
+// with the neighbouring lane (xor 1) gives every lane FOUR consecutive columns of its rows: even lanes keep
+// their pair of column group i and receive the neighbour's, odd lanes keep group i+1 -- then stores (and the
+// residual / time-embedding loads) are 128-bit, 8 rows x 64 B per instruction: half the line-cycles.
+__device__ __forceinline__ void epi_load_residual_v4(float4 (&rs)[2][4], const float* res, const EpiRows& r, int c0, int tq) {
+  const int col4 = (tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq;        // first of this lane's four columns inside a group pair
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      rs[h][k] = ((r.ok >> k) & 1) ? __ldg(reinterpret_cast<const float4*>(res + (r.off[k] - 2 * tq) + c0 + 16 * h + col4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <bool RES, bool TEMB>
+__device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
+                                             int c0, int tq, const EpiRows& r, float* out, const float4 (&rs)[2][4],
+                                             const float* temb) {
+  const bool odd = tq & 1;
+  const int col4 = odd ? 8 + 2 * (tq - 1) : 2 * tq;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {                       // column-group pairs (0,1) and (2,3)
+    const int i0 = 2 * h, i1 = 2 * h + 1;
+    const int cl0 = c0 + 8 * i0 + 2 * tq, cl1 = c0 + 8 * i1 + 2 * tq;
+    const ColConst a0c = colc[cl0 & 255], a1c = colc[(cl0 + 1) & 255], b0c = colc[cl1 & 255], b1c = colc[(cl1 + 1) & 255];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j0 = (i0 << 2) | ((k & 1) << 1), j1 = (i1 << 2) | ((k & 1) << 1);
+      const float lo0 = conv_i8_value((int)(k < 2 ? v0[j0] : v1[j0]), a0c.A, a0c.B, r.cs[k], a0c.m, a0c.bias);
+      const float lo1 = conv_i8_value((int)(k < 2 ? v0[j0 | 1] : v1[j0 | 1]), a1c.A, a1c.B, r.cs[k], a1c.m, a1c.bias);
+      const float hi0 = conv_i8_value((int)(k < 2 ? v0[j1] : v1[j1]), b0c.A, b0c.B, r.cs[k], b0c.m, b0c.bias);
+      const float hi1 = conv_i8_value((int)(k < 2 ? v0[j1 | 1] : v1[j1 | 1]), b1c.A, b1c.B, r.cs[k], b1c.m, b1c.bias);
+      // even lanes send their group-i1 pair, odd lanes their group-i0 pair
+      const float s0 = odd ? lo0 : hi0, s1 = odd ? lo1 : hi1;
+      const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+      float4 o = odd ? make_float4(g0, g1, hi0, hi1) : make_float4(lo0, lo1, g0, g1);
+      const bool ok = (r.ok >> k) & 1;
+      if (RES) {
+        o.x = __fadd_rn(o.x, rs[h][k].x); o.y = __fadd_rn(o.y, rs[h][k].y);
+        o.z = __fadd_rn(o.z, rs[h][k].z); o.w = __fadd_rn(o.w, rs[h][k].w);
+      }
+      if (TEMB) {
+        const float4 te = ok ? __ldg(reinterpret_cast<const float4*>(temb + (r.te_off[k] - 2 * tq) + c0 + 16 * h + col4))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        o.x = __fadd_rn(o.x, te.x); o.y = __fadd_rn(o.y, te.y); o.z = __fadd_rn(o.z, te.z); o.w = __fadd_rn(o.w, te.w);
+      }
+      if (ok) *reinterpret_cast<float4*>(out + (r.off[k] - 2 * tq) + c0 + 16 * h + col4) = o;
+    }
+  }
+}
+
+// The same exchange on a 32-row x 16-column half block (two 16x256b.x2 loads): the unit of work when sixteen
+// epilogue warps share a tile and registers are scarce.
+template <bool RES, bool TEMB>
+__device__ __forceinline__ void epi_half_v4(const uint32_t (&v0)[8], const uint32_t (&v1)[8], const ColConst* colc,
+                                            int c0, int tq, const EpiRows& r, float* out, const float4 (&rs)[4],
+                                            const float* temb) {
+  const bool odd = tq & 1;
+  const int col4 = odd ? 8 + 2 * (tq - 1) : 2 * tq;
+  const int cl0 = c0 + 2 * tq, cl1 = c0 + 8 + 2 * tq;
+  const ColConst a0c = colc[cl0 & 255], a1c = colc[(cl0 + 1) & 255], b0c = colc[cl1 & 255], b1c = colc[(cl1 + 1) & 255];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int j0 = (k & 1) << 1, j1 = 4 | ((k & 1) << 1);
+    const float lo0 = conv_i8_value((int)(k < 2 ? v0[j0] : v1[j0]), a0c.A, a0c.B, r.cs[k], a0c.m, a0c.bias);
+    const float lo1 = conv_i8_value((int)(k < 2 ? v0[j0 | 1] : v1[j0 | 1]), a1c.A, a1c.B, r.cs[k], a1c.m, a1c.bias);
+    const float hi0 = conv_i8_value((int)(k < 2 ? v0[j1] : v1[j1]), b0c.A, b0c.B, r.cs[k], b0c.m, b0c.bias);
+    const float hi1 = conv_i8_value((int)(k < 2 ? v0[j1 | 1] : v1[j1 | 1]), b1c.A, b1c.B, r.cs[k], b1c.m, b1c.bias);
+    const float s0 = odd ? lo0 : hi0, s1 = odd ? lo1 : hi1;
+    const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    float4 o = odd ? make_float4(g0, g1, hi0, hi1) : make_float4(lo0, lo1, g0, g1);
+    const bool ok = (r.ok >> k) & 1;
+    if (RES) {
+      o.x = __fadd_rn(o.x, rs[k].x); o.y = __fadd_rn(o.y, rs[k].y);
+      o.z = __fadd_rn(o.z, rs[k].z); o.w = __fadd_rn(o.w, rs[k].w);
+    }
+    if (TEMB) {
+      const float4 te = ok ? __ldg(reinterpret_cast<const float4*>(temb + (r.te_off[k] - 2 * tq) + c0 + col4))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      o.x = __fadd_rn(o.x, te.x); o.y = __fadd_rn(o.y, te.y); o.z = __fadd_rn(o.z, te.z); o.w = __fadd_rn(o.w, te.w);
+    }
+    if (ok) *reinterpret_cast<float4*>(out + (r.off[k] - 2 * tq) + c0 + col4) = o;
+  }
+}
+
+// 32 rows x 16 columns of results into this warp's staging slot ([32][16] fp32, dense: a warp-wide 128-bit
+// store writes 512 contiguous bytes, conflict free).  Rows that are not output pixels are staged as they are --
+// the tensor store clips them.
+template <bool RES, bool TEMB>
+__device__ __forceinline__ void epi_piece_compute(const uint32_t (&v0)[16], const uint32_t (&v1)[16], int h, const ColConst* colc,
+                                                  int c0, int tq, const EpiRows& r, float4 (&res)[4],
+                                                  const float4 (&rs)[2][4], const float* temb) {
+  const bool odd = tq & 1;
+  const int col4 = odd ? 8 + 2 * (tq - 1) : 2 * tq;
+  const int i0 = 2 * h, i1 = 2 * h + 1;
+  const int cl0 = c0 + 8 * i0 + 2 * tq, cl1 = c0 + 8 * i1 + 2 * tq;
+  const ColConst a0c = colc[cl0 & 255], a1c = colc[(cl0 + 1) & 255], b0c = colc[cl1 & 255], b1c = colc[(cl1 + 1) & 255];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int j0 = (i0 << 2) | ((k & 1) << 1), j1 = (i1 << 2) | ((k & 1) << 1);
+    const float lo0 = conv_i8_value((int)(k < 2 ? v0[j0] : v1[j0]), a0c.A, a0c.B, r.cs[k], a0c.m, a0c.bias);
+    const float lo1 = conv_i8_value((int)(k < 2 ? v0[j0 | 1] : v1[j0 | 1]), a1c.A, a1c.B, r.cs[k], a1c.m, a1c.bias);
+    const float hi0 = conv_i8_value((int)(k < 2 ? v0[j1] : v1[j1]), b0c.A, b0c.B, r.cs[k], b0c.m, b0c.bias);
+    const float hi1 = conv_i8_value((int)(k < 2 ? v0[j1 | 1] : v1[j1 | 1]), b1c.A, b1c.B, r.cs[k], b1c.m, b1c.bias);
+    const float s0 = odd ? lo0 : hi0, s1 = odd ? lo1 : hi1;
+    const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    float4 o = odd ? make_float4(g0, g1, hi0, hi1) : make_float4(lo0, lo1, g0, g1);
+    const bool ok = (r.ok >> k) & 1;
+    if (RES) {
+      o.x = __fadd_rn(o.x, rs[h][k].x); o.y = __fadd_rn(o.y, rs[h][k].y);
+      o.z = __fadd_rn(o.z, rs[h][k].z); o.w = __fadd_rn(o.w, rs[h][k].w);
+    }
+    if (TEMB) {
+      const float4 te = ok ? __ldg(reinterpret_cast<const float4*>(temb + (r.te_off[k] - 2 * tq) + c0 + 16 * h + col4))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      o.x = __fadd_rn(o.x, te.x); o.y = __fadd_rn(o.y, te.y); o.z = __fadd_rn(o.z, te.z); o.w = __fadd_rn(o.w, te.w);
+    }
+    res[k] = o;
   }
 }
 
@@ -636,7 +804,10 @@ __device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const
 
 __global__ void __launch_bounds__(TC_THREADS_H, 1)
 qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                     const __grid_constant__ CUtensorMap tmB, const ConvI8Params p, const TcGeomH g) {
+                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
+                     const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
+                     const __grid_constant__ CUtensorMap tmO3, const __grid_constant__ CUtensorMap tmO4,
+                     const ConvI8Params p, const TcGeomH g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[4], a_empty[4];
   __shared__ __align__(8) uint64_t b_full[TC_H_MAXB], b_empty[TC_H_MAXB];
@@ -644,9 +815,12 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ ColConst colc[256];
-  __shared__ __align__(8) uint64_t geo_full[2], geo_empty[2];
-  __shared__ long long geo_pix[2][TC_BM];          // output pixel of each tile row (-1: not an output)
-  __shared__ int geo_b[2][TC_BM], geo_cs[2][TC_BM];  // sample index, window row-sum + zp*K
+  __shared__ __align__(8) uint64_t geo_full[TC_H_NGEO], geo_empty[TC_H_NGEO];
+  __shared__ int geo_pix[TC_H_NGEO][TC_BM];        // output pixel of each tile row (-1: not an output)
+  __shared__ int geo_b[TC_H_NGEO][TC_BM], geo_cs[TC_H_NGEO][TC_BM];  // sample index, window row-sum + zp*K
+  // tensor-store segments of each 32-row quarter: {first-row x coordinate, image row, sample, valid}
+  // tensor store of each 32-row quarter: {first pixel inside its sample, sample, first pixel (global), box index or -1}
+  __shared__ int4 geo_seg[TC_H_NGEO][4];
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -670,6 +844,8 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[a]), TC_H_EPI_WARPS);
+    }
+    for (int a = 0; a < TC_H_NGEO; ++a) {
       mbar_init(smem_u32(&geo_full[a]), 1);
       mbar_init(smem_u32(&geo_empty[a]), TC_H_EPI_WARPS);
     }
@@ -679,6 +855,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0) tc_span(0);
 
   if (warp == 2) {
     {
@@ -691,6 +868,16 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
           tma_load_2d_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK, 0);
         }
+#ifdef ATTNDM_TC_TRACE
+        if (g_tc_trace != nullptr && blockIdx.x == (unsigned)g_tc_trace[1536]) {
+          // trace only: this otherwise idle warp timestamps the true completion of every tile's MMAs
+          int it = 0;
+          for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
+            mbar_wait(smem_u32(&tmem_full_bar[it & 1]), (uint32_t)((it >> 1) & 1));
+            if (lane == 0) tc_trace(2, it, 0);
+          }
+        }
+#endif
       } else {
         int s = 0;
         uint32_t ph = 0;
@@ -755,16 +942,21 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int kdim = p.taps == 9 ? 3 : 1;
       const int ksteps_last = ((p.Cp - (g.ncb - 1) * TC_BK) + TC_UMMA_K - 1) / TC_UMMA_K;   // 1..4
       const uint32_t leader = elect_one();
+#ifdef ATTNDM_TC_TRACE
+      unsigned long long* const tr_all = g_tc_trace;     // debug: per-tile issue-complete timestamps of every CTA
+#else
+      unsigned long long* const tr_all = nullptr;
+#endif
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
       for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
         const int acc = it & 1, buf = it % g.na;
         if (lane == 0) tc_trace(1, it, 0);
-        mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((it >> 1) & 1) ^ 1));
+        if (!(g.dbg & 256)) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((it >> 1) & 1) ^ 1));
         if (lane == 0) tc_trace(1, it, 1);
-        mbar_wait(smem_u32(&a_full[buf]), (uint32_t)((it / g.na) & 1));
-        if (g.b_resident && it == 0) mbar_wait(smem_u32(&b_res_bar), 0);
+        if (!(g.dbg & 128)) mbar_wait(smem_u32(&a_full[buf]), (uint32_t)((it / g.na) & 1));
+        if (g.b_resident && it == 0) { mbar_wait(smem_u32(&b_res_bar), 0); if (lane == 0) tc_span(1); }
         tcgen05_fence_after();
         if (lane == 0) tc_trace(1, it, 2);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
@@ -822,27 +1014,82 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tcgen05_commit_if(leader, smem_u32(&a_empty[buf]));
         tcgen05_commit_if(leader, smem_u32(&tmem_full_bar[acc]));
         if (lane == 0) tc_trace(1, it, 3);
+        if (tr_all != nullptr && lane == 0 && it < 32) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory");
+          tr_all[4096 + blockIdx.x * 32 + it] = now;
+        }
       }
     }
   } else if (warp == 3) {
     // ===== geometry warp: per-row output pixel / sample / window row-sum for the NEXT tiles, so the
     // epilogue never waits on the nine dependent-latency row-sum loads or the index divisions =====
+    // One warp has to keep up with the tile rate, so: 32-bit index arithmetic (the launcher guarantees
+    // rows < 2^31), all 36 row-sum loads of a tile in flight together, and the wait for a free buffer only
+    // AFTER they were issued -- with four buffers the warp runs up to four tiles ahead of the epilogue.
     pdl_wait();
     const int zp = *p.act_zp;
+    const unsigned rows_u = (unsigned)p.rows, per = (unsigned)(p.Hp * p.Wp), hw = (unsigned)(p.H * p.W);
+    const int zk = zp * (p.taps * p.C);
     int it = 0;
     for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const long long m0 = (tile / g.ntn) * TC_BM;
-      mbar_wait_relaxed(smem_u32(&geo_empty[buf]), (uint32_t)(((it >> 1) & 1) ^ 1));
-      long long px[4];
-      int bb[4], cc[4];
+      const int buf = it % TC_H_NGEO;
+      const unsigned m0 = (unsigned)(tile / g.ntn) * TC_BM;
+      int px[4], bb[4], cc[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) tile_geometry(p, m0 + lane + 32 * j, zp, px[j], bb[j], cc[j]);
+      for (int j = 0; j < 4; ++j) {
+        const unsigned row = m0 + lane + 32 * j;
+        px[j] = -1;
+        bb[j] = 0;
+        cc[j] = 0;
+        if (row < rows_u) {
+          if (p.taps == 1) {
+            px[j] = (int)row;
+            bb[j] = (int)(row / hw);
+            cc[j] = __ldg(p.rowsum + row) + zk;
+          } else {
+            const unsigned b = row / per, rem = row - b * per;
+            const unsigned hp = rem / (unsigned)p.Wp, wp = rem - hp * (unsigned)p.Wp;
+            if (hp < (unsigned)p.H && wp < (unsigned)p.W) {
+              px[j] = (int)((b * (unsigned)p.H + hp) * (unsigned)p.W + wp);
+              bb[j] = (int)b;
+              const int32_t* rs = p.rowsum + row;
+              int s0 = __ldg(rs) + __ldg(rs + 1) + __ldg(rs + 2);
+              int s1 = __ldg(rs + p.Wp) + __ldg(rs + p.Wp + 1) + __ldg(rs + p.Wp + 2);
+              int s2 = __ldg(rs + 2 * p.Wp) + __ldg(rs + 2 * p.Wp + 1) + __ldg(rs + 2 * p.Wp + 2);
+              cc[j] = s0 + s1 + s2 + zk;
+            }
+          }
+        }
+      }
+      mbar_wait_relaxed(smem_u32(&geo_empty[buf]), (uint32_t)(((it / TC_H_NGEO) & 1) ^ 1));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         geo_pix[buf][lane + 32 * j] = px[j];
         geo_b[buf][lane + 32 * j] = bb[j];
         geo_cs[buf][lane + 32 * j] = cc[j];
+      }
+      if (g.tma_store) {
+        // The output pixels of a quarter (lane l holds row 32 j + l of quarter j) are consecutive in memory:
+        // the ring positions between two image rows are skipped in the padded row order, not in the output.
+        // One tensor store per 16-column piece covers them when they sit in one sample and either fill one
+        // of the box heights or run up to the end of the sample (the rest of the box is clipped).
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned okm = __ballot_sync(0xffffffffu, px[j] >= 0);
+          const unsigned pmin = __reduce_min_sync(0xffffffffu, px[j] >= 0 ? (unsigned)px[j] : 0xffffffffu);
+          const unsigned bmin = __reduce_min_sync(0xffffffffu, px[j] >= 0 ? (unsigned)bb[j] : 0xffffffffu);
+          const unsigned bmax = __reduce_max_sync(0xffffffffu, px[j] >= 0 ? (unsigned)bb[j] : 0u);
+          const int n = __popc(okm);
+          int4 sgm = make_int4(0, 0, 0, -1);
+          if (n > 0 && bmin == bmax) {
+            const unsigned in_sample = pmin - bmin * hw;
+            const bool to_end = in_sample + (unsigned)n == hw;
+            const int box = to_end ? 0 : 32 - n;               // box 0 = 32 pixels (clipped at the sample end)
+            if (box < TC_H_NBOX) sgm = make_int4((int)in_sample, (int)bmin, (int)pmin, box);
+          }
+          if (lane == 0) geo_seg[buf][j] = sgm;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&geo_full[buf]));
@@ -884,29 +1131,40 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       // row geometry of this thread's four fragment rows (tr, tr+8, tr+16, tr+24 of the quarter), prepared
       // by the geometry warp
-      const int gb = it & 1;
-      mbar_wait_relaxed(smem_u32(&geo_full[gb]), (uint32_t)((it >> 1) & 1));
+      const int gb = it % TC_H_NGEO;
+      mbar_wait_relaxed(smem_u32(&geo_full[gb]), (uint32_t)((it / TC_H_NGEO) & 1));
       EpiRows rows;
       rows.ok = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int r = quarter * 32 + tr + 8 * k;
-        const long long pix = geo_pix[gb][r];
+        const int pix = geo_pix[gb][r];
         rows.ok |= (pix >= 0 ? 1u : 0u) << k;
-        rows.off[k] = (uint32_t)((pix < 0 ? 0 : pix) * p.O) + (uint32_t)(n0 + 2 * tq);
+        rows.off[k] = (uint32_t)(pix < 0 ? 0 : pix) * (uint32_t)p.O + (uint32_t)(n0 + 2 * tq);
         rows.te_off[k] = (uint32_t)geo_b[gb][r] * (uint32_t)p.O + (uint32_t)(n0 + 2 * tq);
         rows.cs[k] = geo_cs[gb][r];
       }
+      if (g.dbg & 32) rows.ok = 0;                           // experiment: the epilogue math without loads/stores
+      int4 seg = make_int4(0, 0, 0, -1);
+      if (g.tma_store) seg = geo_seg[gb][quarter];
+      // staging row of each of this thread's rows: its rank among the quarter's output pixels
+      uint32_t srow = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) srow |= (uint32_t)((geo_pix[gb][quarter * 32 + tr + 8 * k] - seg.z) & 31) << (8 * k);
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&geo_empty[gb]));
-      if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 0);
       const int nchunks = (g.BN + 31) >> 5;
       const bool res_vec = p.residual != nullptr && pair_ok;
-      float2 rs[4][4];
-      if (res_vec && half < nchunks) epi_load_residual(rs, p.residual, rows, half << 5, tq, g.BN, n0, p.O);
+      const bool vec4 = (p.O & 3) == 0 && !(g.dbg & 64);                       // 128-bit path for blocks without ragged columns
+      float4 rs4[2][4];
+      if (!TC_H_WIDE && res_vec && half < nchunks) {
+        const int cf = half << 5;
+        if (vec4 && cf + 32 <= g.BN && n0 + cf + 32 <= p.O) epi_load_residual_v4(rs4, p.residual, rows, cf, tq);
+        else epi_load_residual(rs4, p.residual, rows, cf, tq, g.BN, n0, p.O);
+      }
       mbar_wait_relaxed(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
       tcgen05_fence_after();
-      if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 1);
+      if (lane == 0) tc_trace(4 + (ew & 7), it, 0);
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(quarter * 32) << 16);
       if (half >= nchunks) {
         __syncwarp();
@@ -914,12 +1172,46 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       for (int ci = half; ci < nchunks; ci += TC_H_EPI_GROUPS) {
         const int c0 = ci << 5;
+        if (TC_H_WIDE && vec4 && c0 + 32 <= g.BN && n0 + c0 + 32 <= p.O && (g.dbg & 3) == 0) {
+          // sixteen-warp mode: two 16-column half blocks, few live registers, residual loaded beside the TMEM read
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ch = c0 + 16 * h;
+            uint32_t a[8], b[8];
+            __syncwarp();
+            tmem_ld_16x256b_x2(t_acc + (uint32_t)ch, a);
+            tmem_ld_16x256b_x2(t_acc + (16u << 16) + (uint32_t)ch, b);
+            float4 r4[4];
+            if (p.residual) {
+              const int col4 = (tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                r4[k] = ((rows.ok >> k) & 1) ? __ldg(reinterpret_cast<const float4*>(p.residual + (rows.off[k] - 2 * tq) + ch + col4))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            tmem_ld_wait();
+            if (h == 1 && ci + TC_H_EPI_GROUPS >= nchunks) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+            }
+            if (p.residual) {
+              if (p.temb) epi_half_v4<true, true>(a, b, colc, ch, tq, rows, p.out, r4, p.temb);
+              else        epi_half_v4<true, false>(a, b, colc, ch, tq, rows, p.out, r4, p.temb);
+            } else {
+              if (p.temb) epi_half_v4<false, true>(a, b, colc, ch, tq, rows, p.out, r4, p.temb);
+              else        epi_half_v4<false, false>(a, b, colc, ch, tq, rows, p.out, r4, p.temb);
+            }
+          }
+          continue;
+        }
         uint32_t v0[16], v1[16];
         __syncwarp();
         if ((g.dbg & 3) < 2) {
           tmem_ld_16x256b_x4(t_acc + (uint32_t)c0, v0);                      // tile rows 32q + 0..15
           tmem_ld_16x256b_x4(t_acc + (16u << 16) + (uint32_t)c0, v1);        // tile rows 32q + 16..31
           tmem_ld_wait();
+          if (lane == 0 && ci == half) tc_trace(4 + (ew & 7), it, 1);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) { v0[j] = 0; v1[j] = 0; }
@@ -928,27 +1220,76 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-          if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 2);
         }
         if ((g.dbg & 3) >= 1) continue;
-        if (res_vec && ci != half) epi_load_residual(rs, p.residual, rows, c0, tq, g.BN, n0, p.O);
-        if (pair_ok) {
+        const bool use4 = vec4 && c0 + 32 <= g.BN && n0 + c0 + 32 <= p.O;
+        if (res_vec && (TC_H_WIDE || ci != half)) {
+          if (use4) epi_load_residual_v4(rs4, p.residual, rows, c0, tq);
+          else epi_load_residual(rs4, p.residual, rows, c0, tq, g.BN, n0, p.O);
+        }
+        if (use4 && seg.w >= 0) {
+          // results -> this warp's staging slot -> tensor store.  The warp never waits for the SM's store port
+          // (32 B/clk, and every SM bursts at the same time): the TMA unit drains the slot while the warp is
+          // already doing the arithmetic of the next piece.
+          float* const stage = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + g.stg_off) + ew * (32 * 16);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float4 o[4];
+            if (p.residual) {
+              if (p.temb) epi_piece_compute<true, true>(v0, v1, h, colc, c0, tq, rows, o, rs4, p.temb);
+              else        epi_piece_compute<true, false>(v0, v1, h, colc, c0, tq, rows, o, rs4, p.temb);
+            } else {
+              if (p.temb) epi_piece_compute<false, true>(v0, v1, h, colc, c0, tq, rows, o, rs4, p.temb);
+              else        epi_piece_compute<false, false>(v0, v1, h, colc, c0, tq, rows, o, rs4, p.temb);
+            }
+            if (lane == 0) bulk_wait_read0();                // the previous piece has left the slot
+            __syncwarp();
+            const int col4 = (tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if ((rows.ok >> k) & 1) *reinterpret_cast<float4*>(stage + ((srow >> (8 * k)) & 31) * 16 + col4) = o[k];
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {                                 // one thread: the tensor store takes uniform operands
+              const uint32_t src = smem_u32(stage);
+              const int col = n0 + c0 + 16 * h;
+              switch (seg.w) {
+                case 0: tma_store_3d(&tmO0, src, col, seg.x, seg.y); break;
+                case 1: tma_store_3d(&tmO1, src, col, seg.x, seg.y); break;
+                case 2: tma_store_3d(&tmO2, src, col, seg.x, seg.y); break;
+                case 3: tma_store_3d(&tmO3, src, col, seg.x, seg.y); break;
+                default: tma_store_3d(&tmO4, src, col, seg.x, seg.y); break;
+              }
+              bulk_commit();
+            }
+          }
+        } else if (use4) {
           if (p.residual) {
-            if (p.temb) epi_block<true, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs, p.temb);
-            else        epi_block<true, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs, p.temb);
+            if (p.temb) epi_block_v4<true, true>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.temb);
+            else        epi_block_v4<true, false>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.temb);
           } else {
-            if (p.temb) epi_block<false, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs, p.temb);
-            else        epi_block<false, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs, p.temb);
+            if (p.temb) epi_block_v4<false, true>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.temb);
+            else        epi_block_v4<false, false>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.temb);
+          }
+        } else if (pair_ok) {
+          if (p.residual) {
+            if (p.temb) epi_block<true, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs4, p.temb);
+            else        epi_block<true, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs4, p.temb);
+          } else {
+            if (p.temb) epi_block<false, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs4, p.temb);
+            else        epi_block<false, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs4, p.temb);
           }
         } else {
           epi_block_scalar(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, p.residual, p.temb);
         }
+        if (lane == 0) tc_trace(4 + (ew & 7), it, ci == half ? 2 : 3);
       }
-      if (lane == 0 && (ew == 0 || ew == 4)) tc_trace(2 + (ew >> 2), it, 3);
     }
   }
+  if (g.tma_store && warp >= TC_H_EPI0 && lane == 0) bulk_wait0();
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) tc_span(2);
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
                  : "memory");
@@ -1019,7 +1360,7 @@ static int launch_qconv_i8_tc_persistent(const ConvI8Params& p, cudaStream_t st)
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(qconv_i8_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    attr_err = cudaFuncSetAttribute(qconv_i8_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("qconv_i8_tc: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
   launch_pdl(qconv_i8_tc_persistent_kernel, dim3(grid), dim3(TC_THREADS_P), smem, st, tmA, tmB, p, g);
@@ -1045,7 +1386,7 @@ static bool tc_halo_enabled() {
 
 // returns 1 if the halo kernel was launched, 0 if the shape does not fit it, <0 on error
 static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
-  constexpr int kBudget = 214 * 1024;                   // dynamic smem we allow ourselves (227 KB - static - slack)
+  constexpr int kBudget = 213 * 1024;                   // dynamic smem we allow ourselves (227 KB - static - slack)
   TcGeomH g;
   g.BN = p.O <= 256 ? round_up(p.O, 16) : 256;
   const long long mtiles = (p.rows + TC_BM - 1) / TC_BM;
@@ -1056,15 +1397,28 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   g.hr = p.taps == 9 ? TC_BM + 2 * p.Wp + 2 : TC_BM;
   if (g.hr > 512) return 0;
   if ((long long)p.B * p.H * p.W * p.O >= (1LL << 31)) return 0;      // the epilogue keeps 32-bit output offsets
+  if (p.rows + TC_BM >= (1LL << 31)) return 0;                        // the geometry warp keeps 32-bit row indices
   g.hr_stride = round_up(g.hr * TC_BK, 1024);
   const int nkb = p.taps * g.ncb;
   const int b_tile = g.BN * TC_BK;
-  const int stg_bytes = 0;                              // the epilogue does not stage through shared memory
+  // output path: per-warp 2 KB staging slots + TMA tensor stores when the 128-bit path applies (O % 4 == 0)
+  // and a quarter's 32 rows meet at most TC_H_NSEG image rows
+  // Off by default: with one 2 KB slot per warp (all the shared memory left beside resident weights) the warp
+  // waits for the TMA unit to read the slot before every piece, and the 128->128 3x3 layer measured 76 us
+  // against 59 us for direct 128-bit stores.  ATTNDM_TC_TMA_STORE=1 enables it for experiments.
+  static const bool tma_store_on = [] { const char* e = getenv("ATTNDM_TC_TMA_STORE"); return e && e[0] == '1'; }();
+  g.tma_store = (tma_store_on && (p.O & 3) == 0 && g.BN % 32 == 0 && ((uintptr_t)p.out & 15) == 0) ? 1 : 0;
+  int stg_bytes = g.tma_store ? TC_H_EPI_WARPS * 32 * 16 * 4 : 0;
   const int a_buf = g.ncb * g.hr_stride;
   const int grid = (int)(g.ntiles < kNumSMs ? g.ntiles : kNumSMs);
   const long long tiles_per_cta = (g.ntiles + grid - 1) / grid;
   g.na = tiles_per_cta > 1 ? 2 : 1;
   // weights resident when they fit next to two halo buffers (and there is a single N tile)
+  if (g.tma_store && g.ntn == 1 && (long long)nkb * b_tile + (long long)g.na * a_buf <= kBudget &&
+      (long long)nkb * b_tile + (long long)g.na * a_buf + stg_bytes > kBudget) {
+    g.tma_store = 0;                                    // resident weights are worth more than the staging slots
+    stg_bytes = 0;
+  }
   g.b_resident = (g.ntn == 1 && (long long)nkb * b_tile + (long long)g.na * a_buf + stg_bytes <= kBudget) ? 1 : 0;
   if (g.b_resident) {
     g.nb = 1;
@@ -1099,10 +1453,26 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("qconv_i8_halo: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
-  launch_pdl(qconv_i8_halo_kernel, dim3(grid), dim3(TC_THREADS_H), smem, st, tmA, tmA2, tmB, p, g);
+  CUtensorMap tmO[TC_H_NBOX];
+  for (int i = 0; i < TC_H_NBOX; ++i) tmO[i] = tmA;
+  if (g.tma_store) {
+    // the output as [sample][pixel][channel]; one map per box height (32 - i pixels x 16 channels)
+    EncodeTiledFn enc = get_encode_fn();
+    const uint64_t hw = (uint64_t)p.H * p.W;
+    cuuint64_t dims[3] = {(cuuint64_t)p.O, hw, (cuuint64_t)p.B};
+    cuuint64_t strides[2] = {(cuuint64_t)p.O * 4, hw * p.O * 4};
+    cuuint32_t estr[3] = {1, 1, 1};
+    for (int i = 0; i < TC_H_NBOX; ++i) {
+      cuuint32_t box[3] = {16, (cuuint32_t)(32 - i), 1};
+      CUresult r = enc(&tmO[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("qconv_i8_halo: output tensor map failed (%d)", (int)r); return ATTNDM_ERR_CUDA; }
+    }
+  }
+  launch_pdl(qconv_i8_halo_kernel, dim3(grid), dim3(TC_THREADS_H), smem, st, tmA, tmA2, tmB, tmO[0], tmO[1], tmO[2], tmO[3], tmO[4], p, g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("qconv_i8_halo: launch failed: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
   return 1;

@@ -5,7 +5,7 @@ import torch
 import attentiondm_b200 as A
 from attentiondm_b200 import ops, _ffi
 dev = torch.device("cuda")
-shape = {"c128_32": (256, 32, 32, 128, 128, 3), "out_32": (256, 32, 32, 128, 3, 3), "c256_32": (256, 32, 32, 256, 128, 3)}[sys.argv[1] if len(sys.argv) > 1 else "c128_32"]
+shape = {"c128_32": (256, 32, 32, 128, 128, 3), "out_32": (256, 32, 32, 128, 3, 3), "c256_32": (256, 32, 32, 256, 128, 3), "n256_32": (256, 32, 32, 256, 128, 1)}[sys.argv[1] if len(sys.argv) > 1 else "c128_32"]
 B, H, W, C, O, k = shape
 g = torch.Generator().manual_seed(0)
 x = torch.randn(B, H, W, C, generator=g).to(dev)
@@ -20,18 +20,51 @@ mult = (1.0 / (25.5 * pack.w_scale.double())).float().contiguous()
 azp = torch.tensor([26], dtype=torch.int32, device=dev)
 bias = torch.zeros(O, device=dev); out = torch.empty(B, H, W, O, device=dev)
 for _ in range(3):
-    ops.qconv_i8(codes, rowsum, B, H, W, C, pack, 9, mult, azp, bias, out=out)
-tr = torch.zeros(4 * 32 * 4, dtype=torch.int64, device=dev)
+    ops.qconv_i8(codes, rowsum, B, H, W, C, pack, k * k, mult, azp, bias, out=out)
+tr = torch.zeros(4096 + 148 * 32, dtype=torch.int64, device=dev)
+tr[1536] = int(os.environ.get('TRACE_CTA', '0'))
 L = _ffi.lib(); L.attndm_debug_set_tc_trace.argtypes = [ctypes.c_void_p]
 L.attndm_debug_set_tc_trace(ctypes.c_void_p(tr.data_ptr()))
-ops.qconv_i8(codes, rowsum, B, H, W, C, pack, 9, mult, azp, bias, out=out)
+ops.qconv_i8(codes, rowsum, B, H, W, C, pack, k * k, mult, azp, bias, out=out)
 torch.cuda.synchronize()
 L.attndm_debug_set_tc_trace(None)
-t = tr.cpu().view(4, 32, 4)
+full = tr.cpu()
+t = full[:1536].view(12, 32, 4)
 t0 = int(t[t > 0].min())
-names = ["Aprod", "MMA", "epi0", "epi1"]
-evn = [["wait_empty", "got_empty", "-", "-"], ["start", "tmem_free", "a_full", "issued"], ["ready", "tmem_full", "tmem_read", "done"], ["ready", "tmem_full", "tmem_read", "done"]]
-for it in range(8):
-    for r in range(4):
+names = ["Aprod", "MMA", "MMAdone", "-"] + [f"epi{i}" for i in range(8)]
+evn = [["wait_empty", "got_empty", "-", "-"], ["start", "tmem_free", "a_full", "issued"], ["mma_done", "-", "-", "-"], []] + [["tmem_full", "c0_loaded", "c0_done", "c1_done"]] * 8
+for it in range(int(os.environ.get('TRACE_ITS', '8'))):
+    for r in (1, 2, 4, 5, 6, 7, 8, 9, 10, 11):
         row = [(int(v) - t0) / 1000.0 if v > 0 else float('nan') for v in t[r, it]]
         print(f"it={it} {names[r]:6s} " + "  ".join(f"{evn[r][e]}={row[e]:8.2f}us" for e in range(4)))
+
+v = t[t > 0]
+print(f"CTA {int(tr[1536])}: span first..last event {(int(v.max()) - int(v.min())) / 1000.0:.2f} us")
+
+ck = full[1540:1540 + 16]
+st = t[1, :16, 0]
+for i in range(1, 14):
+    if ck[i] > 0 and ck[i - 1] > 0:
+        print(f"tile {i}: {(int(ck[i]) - int(ck[i-1])) / max(1, int(st[i]) - int(st[i-1])) * 1000:.0f} MHz")
+
+sp = full[1600:1600 + 4 * 148].view(148, 4)
+ok = sp[:, 0] > 0
+k0 = int(sp[ok, 0].min())
+import statistics
+st_ = [(int(v) - k0) / 1000 for v in sp[ok, 0]]; wr = [(int(v) - k0) / 1000 for v in sp[ok, 1]]; en = [(int(v) - k0) / 1000 for v in sp[ok, 2]]
+print(f"CTAs {int(ok.sum())}: start min/med/max {min(st_):.2f}/{statistics.median(st_):.2f}/{max(st_):.2f}  weights-resident med/max {statistics.median(wr):.2f}/{max(wr):.2f}  end min/med/max {min(en):.2f}/{statistics.median(en):.2f}/{max(en):.2f} us")
+
+pt = full[4096:4096 + 148 * 32].view(148, 32)
+import numpy as np
+a = pt.numpy().astype(np.int64)
+d = np.diff(a, axis=1).astype(np.float64) / 1000.0
+valid = (a[:, 1:] > 0) & (a[:, :-1] > 0)
+if int(os.environ.get('TRACE_CTA', '0')) < 148:
+    valid[int(os.environ.get('TRACE_CTA', '0'))] = False
+print("per-tile issue-to-issue interval, all untraced CTAs: mean %.2f  p10 %.2f  p50 %.2f  p90 %.2f  max %.2f us" % (
+    d[valid].mean(), np.percentile(d[valid], 10), np.percentile(d[valid], 50), np.percentile(d[valid], 90), d[valid].max()))
+for i in range(0, 13):
+    col = d[:, i][valid[:, i]]
+    print(f"  tile {i+1}: mean {col.mean():.2f} p50 {np.percentile(col,50):.2f} max {col.max():.2f}")
+first = (a[:, 0] - k0) / 1000.0
+print("first tile issued at: mean %.2f max %.2f us" % (first.mean(), first.max()))
