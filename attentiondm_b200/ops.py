@@ -64,6 +64,11 @@ def gn_fits_fused(H: int, W: int, Cc: int) -> bool:
     return bool(F_.lib().attndm_gn_act_quant_fits(H, W, Cc))
 
 
+def gn_fits_cluster(H: int, W: int, Cc: int) -> bool:
+    """Large maps: the one-pass cluster kernel (statistics + quantize from distributed shared memory)."""
+    return bool(F_.lib().attndm_gn_quant_cluster_fits(H, W, Cc))
+
+
 # One zero-filled [n, B, 32, 2] double buffer per UNet forward, handed out slice by slice, instead of
 # one memset per GroupNorm (97 of them on the CIFAR model).
 _gn_pool = None
@@ -101,6 +106,8 @@ def gn_silu(x: torch.Tensor, gn: GnArgs) -> torch.Tensor:
     _chk(x, "gn_silu input")
     B, H, W, Cc = x.shape
     y = torch.empty_like(x)
+    if gn.stats is None and not gn_fits_fused(H, W, Cc):
+        gn = GnArgs(stats=gn_stats(x), gamma=gn.gamma, beta=gn.beta, eps=gn.eps)    # deferred statistics
     if gn.stats is None:
         call("attndm_gn_act_quant", ptr(x), B, H, W, Cc, ptr(gn.gamma), ptr(gn.beta), float(gn.eps), None, None, 0,
              None, None, ROWS_PLAIN, ptr(y), stream())
@@ -124,6 +131,13 @@ def act_quant(x: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, a_bit: int
         rowsum = torch.empty(rows, dtype=torch.int32, device=x.device)
     if want_f32:
         y = torch.empty_like(x)
+    if pre == PRE_GN_SILU and gn.stats is None and not gn_fits_fused(H, W, Cc):
+        # statistics were deferred (large map): one-pass cluster kernel for the int8 path, else compute them now
+        if want_codes and not want_f32 and gn_fits_cluster(H, W, Cc):
+            call("attndm_gn_quant_cluster", ptr(x), B, H, W, Cc, ptr(gn.gamma), ptr(gn.beta), float(gn.eps), ptr(scale),
+                 ptr(zp), int(a_bit), ptr(codes), ptr(rowsum), ROWS_HALO if halo else ROWS_PLAIN, stream())
+            return codes, rowsum, y
+        gn = GnArgs(stats=gn_stats(x), gamma=gn.gamma, beta=gn.beta, eps=gn.eps)
     if pre == PRE_GN_SILU and gn.stats is None:
         call("attndm_gn_act_quant", ptr(x), B, H, W, Cc, ptr(gn.gamma), ptr(gn.beta), float(gn.eps), ptr(scale),
              ptr(zp), int(a_bit), ptr(codes), ptr(rowsum), ROWS_HALO if halo else ROWS_PLAIN, ptr(y), stream())

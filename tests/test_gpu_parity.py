@@ -378,6 +378,44 @@ def test_groupnorm_silu_quant_fused():
             assert rel_l2(ops.gn_silu(xn, gl), ops.gn_silu(xn, gn)) < 1e-6
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,C,a_bit,halo", [(3, 32, 32, 128, 8, True), (2, 32, 32, 128, 6, False), (2, 32, 32, 256, 8, True),
+                                                 (5, 32, 32, 128, 4, True)])
+def test_groupnorm_quant_cluster_one_pass(B, H, W, C, a_bit, halo):
+    """The one-pass cluster kernel (sample in distributed shared memory) against the two-pass path
+    (attndm_gn_stats + attndm_act_quant): same codes and row sums, up to the last bit of the fp64 statistics."""
+    from attentiondm_b200 import ops, _ffi
+    assert not ops.gn_fits_cluster(H, W, C)                          # opt-in: off by default
+    old = _ffi.lib().attndm_set_gn_cluster_min_kb(512)
+    try:
+        _cluster_case(ops, B, H, W, C, a_bit, halo)
+    finally:
+        _ffi.lib().attndm_set_gn_cluster_min_kb(old)
+
+
+def _cluster_case(ops, B, H, W, C, a_bit, halo):
+    assert ops.gn_fits_cluster(H, W, C) and not ops.gn_fits_cluster(64, 64, 128) and not ops.gn_fits_cluster(16, 16, 128)
+    g = torch.Generator().manual_seed(100 + C + a_bit)
+    x = (torch.randn(B, H, W, C, generator=g) * 1.5 + 0.3).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV)
+    s, z = R.asym_params(a_bit, torch.tensor(-0.4), torch.tensor(5.0))
+    sv = torch.full((C,), float(s), device=DEV) * (1 + 0.1 * torch.rand(C, generator=g).to(DEV))
+    zv = torch.full((C,), float(z), device=DEV)
+    two = ops.GnArgs(ops.gn_stats(x), gamma, beta, 1e-6)
+    c2, r2, _ = ops.act_quant(x, sv, zv, a_bit, ops.PRE_GN_SILU, two, want_codes=True, halo=halo)
+    one = ops.GnArgs(None, gamma, beta, 1e-6)
+    c1, r1, _ = ops.act_quant(x, sv, zv, a_bit, ops.PRE_GN_SILU, one, want_codes=True, halo=halo)
+    dc = (c1.int() - c2.int()).abs()
+    assert dc.max() <= 1 and (dc > 0).float().mean() < 1e-4
+    assert torch.equal(r1.long() - r2.long(), (c1.long() - c2.long()).sum(1))
+    # deferred statistics: a consumer that wants fp32 output falls back to the two-pass path
+    _, _, y1 = ops.act_quant(x, sv, zv, a_bit, ops.PRE_GN_SILU, one, want_codes=False, want_f32=True)
+    _, _, y2 = ops.act_quant(x, sv, zv, a_bit, ops.PRE_GN_SILU, two, want_codes=False, want_f32=True)
+    assert torch.equal(y1, y2)
+    assert rel_l2(ops.gn_silu(x, one), ops.gn_silu(x, two)) < 1e-6
+
+
 def test_attention_core():
     from attentiondm_b200 import ops
     g = torch.Generator().manual_seed(6)
