@@ -258,12 +258,6 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- kernel -------------------------------------------------------------------
@@ -552,8 +546,15 @@ __device__ __forceinline__ void tc_span(int ev) {          // per-CTA kernel-lev
 constexpr int TC_H_EPI0 = 4;                           // first epilogue warp (multiple of 4: quarter = warp % 4)
 constexpr int TC_H_EPI_WARPS = 8;                      // 2 per TMEM lane quarter (16 measured slower: register spills, LSU contention)
 constexpr int TC_H_NGEO = 4;                           // row-geometry buffers (the geometry warp runs this far ahead)
+// The TMA output path (per-warp staging slot + tensor stores) is compiled out: it measured 76 us against 59 us
+// for direct stores (see launch_qconv_i8_halo) and its four epilogue instantiations cost instruction cache.
+// Build with -DATTNDM_TC_TMA_STORE (ATTNDM_NVCC_EXTRA) and set ATTNDM_TC_TMA_STORE=1 to experiment with it.
+#ifdef ATTNDM_TC_TMA_STORE
+constexpr bool TC_H_TMA_STORE = true;
+#else
+constexpr bool TC_H_TMA_STORE = false;
+#endif
 constexpr int TC_H_NBOX = 5;                           // output tensor maps: boxes of 32, 31, 30, 29, 28 pixels
-constexpr bool TC_H_WIDE = TC_H_EPI_WARPS == 16;       // half-block epilogue path (fits the 96-register cap of 640 threads)
 constexpr int TC_H_EPI_GROUPS = TC_H_EPI_WARPS / 4;    // warps sharing a quarter split the 32-column chunks
 constexpr int TC_THREADS_H = 32 * (TC_H_EPI0 + TC_H_EPI_WARPS);
 constexpr int TC_H_MAXB = 8;                           // weight ring depth (streamed mode)
@@ -600,60 +601,6 @@ struct EpiRows {
   uint32_t ok;          // bit k: row k is an output pixel
 };
 
-// The residual of one 32x32 block, straight from HBM: all sixteen float2 loads are issued together -- and, for a
-// warp's first block of a tile, BEFORE it waits for the accumulator, so the round trip hides behind the MMAs.
-__device__ __forceinline__ void epi_load_residual(float4 (&rs)[2][4], const float* res, const EpiRows& r, int c0, int tq,
-                                                  int BN, int n0, int O) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int cl = c0 + 8 * i + 2 * tq;
-    const bool col_ok = (cl < BN) && (n0 + cl < O);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 t = (col_ok && ((r.ok >> k) & 1)) ? __ldg(reinterpret_cast<const float2*>(res + r.off[k] + c0 + 8 * i))
-                                                     : make_float2(0.f, 0.f);
-      if (i & 1) { rs[i >> 1][k].z = t.x; rs[i >> 1][k].w = t.y; }      // shares its registers with the 128-bit path
-      else       { rs[i >> 1][k].x = t.x; rs[i >> 1][k].y = t.y; }
-    }
-  }
-}
-
-// One 32-row x 32-column block of a tile, held in the 16x256b fragment layout: thread (tr = lane/4,
-// tq = lane%4) owns rows tr + 8k (k = 0..3; k < 2 from v0, k >= 2 from v1) and the column pairs
-// 8i + 2tq + {0,1} (i = 0..3).  Register j of a load: row bit = (j>>1)&1, column group i = j>>2, parity j&1.
-// Everything is statically indexed (registers only); stores are float2, four lanes per 32-byte sector.
-template <bool RES, bool TEMB>
-__device__ __forceinline__ void epi_block(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
-                                          int c0, int tq, int BN, int n0, int O, const EpiRows& r, float* out,
-                                          const float4 (&rs)[2][4], const float* temb) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int cl = c0 + 8 * i + 2 * tq;
-    const bool col_ok = (cl < BN) && (n0 + cl < O);
-    const ColConst ca = colc[cl & 255], cb = colc[(cl + 1) & 255];
-    float2 te[4];
-    if (TEMB) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        te[k] = (col_ok && ((r.ok >> k) & 1)) ? __ldg(reinterpret_cast<const float2*>(temb + r.te_off[k] + c0 + 8 * i))
-                                              : make_float2(0.f, 0.f);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int j = (i << 2) | ((k & 1) << 1);
-      const int a0 = (int)(k < 2 ? v0[j] : v1[j]), a1 = (int)(k < 2 ? v0[j | 1] : v1[j | 1]);
-      float f0 = conv_i8_value(a0, ca.A, ca.B, r.cs[k], ca.m, ca.bias);
-      float f1 = conv_i8_value(a1, cb.A, cb.B, r.cs[k], cb.m, cb.bias);
-      if (RES) {
-        f0 = __fadd_rn(f0, (i & 1) ? rs[i >> 1][k].z : rs[i >> 1][k].x);
-        f1 = __fadd_rn(f1, (i & 1) ? rs[i >> 1][k].w : rs[i >> 1][k].y);
-      }
-      if (TEMB) { f0 = __fadd_rn(f0, te[k].x); f1 = __fadd_rn(f1, te[k].y); }
-      if (col_ok && ((r.ok >> k) & 1)) *reinterpret_cast<float2*>(out + r.off[k] + c0 + 8 * i) = make_float2(f0, f1);
-    }
-  }
-}
-
 // ---- 128-bit variant for full blocks (all 32 columns valid, O % 4 == 0) ----
 // The LSU handles one cache line per cycle, so a float2 store of the fragment layout (8 rows x 32 B per warp
 // instruction) costs 8 line-cycles for 256 B and the epilogue of a tile is bound by ~4000 of them.  One exchange
@@ -670,10 +617,10 @@ __device__ __forceinline__ void epi_load_residual_v4(float4 (&rs)[2][4], const f
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-template <bool RES, bool TEMB>
+template <bool ADD>
 __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
                                              int c0, int tq, const EpiRows& r, float* out, const float4 (&rs)[2][4],
-                                             const float* temb) {
+                                             bool has_res, const float* temb) {
   const bool odd = tq & 1;
   const int col4 = odd ? 8 + 2 * (tq - 1) : 2 * tq;
 #pragma unroll
@@ -693,61 +640,29 @@ __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uin
       const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
       float4 o = odd ? make_float4(g0, g1, hi0, hi1) : make_float4(lo0, lo1, g0, g1);
       const bool ok = (r.ok >> k) & 1;
-      if (RES) {
-        o.x = __fadd_rn(o.x, rs[h][k].x); o.y = __fadd_rn(o.y, rs[h][k].y);
-        o.z = __fadd_rn(o.z, rs[h][k].z); o.w = __fadd_rn(o.w, rs[h][k].w);
-      }
-      if (TEMB) {
-        const float4 te = ok ? __ldg(reinterpret_cast<const float4*>(temb + (r.te_off[k] - 2 * tq) + c0 + 16 * h + col4))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-        o.x = __fadd_rn(o.x, te.x); o.y = __fadd_rn(o.y, te.y); o.z = __fadd_rn(o.z, te.z); o.w = __fadd_rn(o.w, te.w);
+      if (ADD) {
+        if (has_res) {
+          o.x = __fadd_rn(o.x, rs[h][k].x); o.y = __fadd_rn(o.y, rs[h][k].y);
+          o.z = __fadd_rn(o.z, rs[h][k].z); o.w = __fadd_rn(o.w, rs[h][k].w);
+        }
+        if (temb != nullptr) {
+          const float4 te = ok ? __ldg(reinterpret_cast<const float4*>(temb + (r.te_off[k] - 2 * tq) + c0 + 16 * h + col4))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          o.x = __fadd_rn(o.x, te.x); o.y = __fadd_rn(o.y, te.y); o.z = __fadd_rn(o.z, te.z); o.w = __fadd_rn(o.w, te.w);
+        }
       }
       if (ok) *reinterpret_cast<float4*>(out + (r.off[k] - 2 * tq) + c0 + 16 * h + col4) = o;
     }
   }
 }
 
-// The same exchange on a 32-row x 16-column half block (two 16x256b.x2 loads): the unit of work when sixteen
-// epilogue warps share a tile and registers are scarce.
-template <bool RES, bool TEMB>
-__device__ __forceinline__ void epi_half_v4(const uint32_t (&v0)[8], const uint32_t (&v1)[8], const ColConst* colc,
-                                            int c0, int tq, const EpiRows& r, float* out, const float4 (&rs)[4],
-                                            const float* temb) {
-  const bool odd = tq & 1;
-  const int col4 = odd ? 8 + 2 * (tq - 1) : 2 * tq;
-  const int cl0 = c0 + 2 * tq, cl1 = c0 + 8 + 2 * tq;
-  const ColConst a0c = colc[cl0 & 255], a1c = colc[(cl0 + 1) & 255], b0c = colc[cl1 & 255], b1c = colc[(cl1 + 1) & 255];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int j0 = (k & 1) << 1, j1 = 4 | ((k & 1) << 1);
-    const float lo0 = conv_i8_value((int)(k < 2 ? v0[j0] : v1[j0]), a0c.A, a0c.B, r.cs[k], a0c.m, a0c.bias);
-    const float lo1 = conv_i8_value((int)(k < 2 ? v0[j0 | 1] : v1[j0 | 1]), a1c.A, a1c.B, r.cs[k], a1c.m, a1c.bias);
-    const float hi0 = conv_i8_value((int)(k < 2 ? v0[j1] : v1[j1]), b0c.A, b0c.B, r.cs[k], b0c.m, b0c.bias);
-    const float hi1 = conv_i8_value((int)(k < 2 ? v0[j1 | 1] : v1[j1 | 1]), b1c.A, b1c.B, r.cs[k], b1c.m, b1c.bias);
-    const float s0 = odd ? lo0 : hi0, s1 = odd ? lo1 : hi1;
-    const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-    float4 o = odd ? make_float4(g0, g1, hi0, hi1) : make_float4(lo0, lo1, g0, g1);
-    const bool ok = (r.ok >> k) & 1;
-    if (RES) {
-      o.x = __fadd_rn(o.x, rs[k].x); o.y = __fadd_rn(o.y, rs[k].y);
-      o.z = __fadd_rn(o.z, rs[k].z); o.w = __fadd_rn(o.w, rs[k].w);
-    }
-    if (TEMB) {
-      const float4 te = ok ? __ldg(reinterpret_cast<const float4*>(temb + (r.te_off[k] - 2 * tq) + c0 + col4))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      o.x = __fadd_rn(o.x, te.x); o.y = __fadd_rn(o.y, te.y); o.z = __fadd_rn(o.z, te.z); o.w = __fadd_rn(o.w, te.w);
-    }
-    if (ok) *reinterpret_cast<float4*>(out + (r.off[k] - 2 * tq) + c0 + col4) = o;
-  }
-}
-
 // 32 rows x 16 columns of results into this warp's staging slot ([32][16] fp32, dense: a warp-wide 128-bit
 // store writes 512 contiguous bytes, conflict free).  Rows that are not output pixels are staged as they are --
 // the tensor store clips them.
-template <bool RES, bool TEMB>
+template <bool ADD>
 __device__ __forceinline__ void epi_piece_compute(const uint32_t (&v0)[16], const uint32_t (&v1)[16], int h, const ColConst* colc,
                                                   int c0, int tq, const EpiRows& r, float4 (&res)[4],
-                                                  const float4 (&rs)[2][4], const float* temb) {
+                                                  const float4 (&rs)[2][4], bool has_res, const float* temb) {
   const bool odd = tq & 1;
   const int col4 = odd ? 8 + 2 * (tq - 1) : 2 * tq;
   const int i0 = 2 * h, i1 = 2 * h + 1;
@@ -764,11 +679,11 @@ __device__ __forceinline__ void epi_piece_compute(const uint32_t (&v0)[16], cons
     const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
     float4 o = odd ? make_float4(g0, g1, hi0, hi1) : make_float4(lo0, lo1, g0, g1);
     const bool ok = (r.ok >> k) & 1;
-    if (RES) {
+    if (ADD && has_res) {
       o.x = __fadd_rn(o.x, rs[h][k].x); o.y = __fadd_rn(o.y, rs[h][k].y);
       o.z = __fadd_rn(o.z, rs[h][k].z); o.w = __fadd_rn(o.w, rs[h][k].w);
     }
-    if (TEMB) {
+    if (ADD && temb != nullptr) {
       const float4 te = ok ? __ldg(reinterpret_cast<const float4*>(temb + (r.te_off[k] - 2 * tq) + c0 + 16 * h + col4))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
       o.x = __fadd_rn(o.x, te.x); o.y = __fadd_rn(o.y, te.y); o.z = __fadd_rn(o.z, te.z); o.w = __fadd_rn(o.w, te.w);
@@ -787,12 +702,13 @@ __device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const
     for (int par = 0; par < 2; ++par) {
       const int cl = c0 + 8 * i + 2 * tq + par;
       const bool col_ok = (cl < BN) && (n0 + cl < O);
+      if (!col_ok) continue;                 // the 3-channel output: 125 of 128 accumulator columns are padding
       const ColConst cc = colc[cl & 255];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int j = (i << 2) | ((k & 1) << 1) | par;
         float f = conv_i8_value((int)(k < 2 ? v0[j] : v1[j]), cc.A, cc.B, r.cs[k], cc.m, cc.bias);
-        if (col_ok && ((r.ok >> k) & 1)) {
+        if ((r.ok >> k) & 1) {
           if (res) f = __fadd_rn(f, res[r.off[k] + c0 + 8 * i + par]);
           if (temb) f = __fadd_rn(f, temb[r.te_off[k] + c0 + 8 * i + par]);
           out[r.off[k] + c0 + 8 * i + par] = f;
@@ -1069,7 +985,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         geo_b[buf][lane + 32 * j] = bb[j];
         geo_cs[buf][lane + 32 * j] = cc[j];
       }
-      if (g.tma_store) {
+      if (TC_H_TMA_STORE && g.tma_store) {
         // The output pixels of a quarter (lane l holds row 32 j + l of quarter j) are consecutive in memory:
         // the ring positions between two image rows are skipped in the padded row order, not in the output.
         // One tensor store per 16-column piece covers them when they sit in one sample and either fill one
@@ -1105,7 +1021,6 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int ew = warp - TC_H_EPI0;                   // 0..15
     const int half = ew >> 2;                          // which of the quarter's four warps (chunk phase)
     const int zp = *p.act_zp;
-    const bool pair_ok = (p.O & 1) == 0;               // float2 stores need an even channel count
     const int tq = lane & 3, tr = lane >> 2;           // fragment coordinates of this thread
     int last_nt = -1;
     int it = 0;
@@ -1146,7 +1061,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       if (g.dbg & 32) rows.ok = 0;                           // experiment: the epilogue math without loads/stores
       int4 seg = make_int4(0, 0, 0, -1);
-      if (g.tma_store) seg = geo_seg[gb][quarter];
+      if (TC_H_TMA_STORE && g.tma_store) seg = geo_seg[gb][quarter];
       // staging row of each of this thread's rows: its rank among the quarter's output pixels
       uint32_t srow = 0;
 #pragma unroll
@@ -1154,13 +1069,12 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&geo_empty[gb]));
       const int nchunks = (g.BN + 31) >> 5;
-      const bool res_vec = p.residual != nullptr && pair_ok;
-      const bool vec4 = (p.O & 3) == 0 && !(g.dbg & 64);                       // 128-bit path for blocks without ragged columns
+      const bool vec4 = (p.O & 3) == 0;                      // 128-bit path for full 32-column blocks
+      const bool adds = p.residual != nullptr || p.temb != nullptr;
       float4 rs4[2][4];
-      if (!TC_H_WIDE && res_vec && half < nchunks) {
+      if (p.residual != nullptr && half < nchunks) {         // first block's residual: issued before the wait below
         const int cf = half << 5;
         if (vec4 && cf + 32 <= g.BN && n0 + cf + 32 <= p.O) epi_load_residual_v4(rs4, p.residual, rows, cf, tq);
-        else epi_load_residual(rs4, p.residual, rows, cf, tq, g.BN, n0, p.O);
       }
       mbar_wait_relaxed(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
       tcgen05_fence_after();
@@ -1172,39 +1086,6 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       for (int ci = half; ci < nchunks; ci += TC_H_EPI_GROUPS) {
         const int c0 = ci << 5;
-        if (TC_H_WIDE && vec4 && c0 + 32 <= g.BN && n0 + c0 + 32 <= p.O && (g.dbg & 3) == 0) {
-          // sixteen-warp mode: two 16-column half blocks, few live registers, residual loaded beside the TMEM read
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int ch = c0 + 16 * h;
-            uint32_t a[8], b[8];
-            __syncwarp();
-            tmem_ld_16x256b_x2(t_acc + (uint32_t)ch, a);
-            tmem_ld_16x256b_x2(t_acc + (16u << 16) + (uint32_t)ch, b);
-            float4 r4[4];
-            if (p.residual) {
-              const int col4 = (tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                r4[k] = ((rows.ok >> k) & 1) ? __ldg(reinterpret_cast<const float4*>(p.residual + (rows.off[k] - 2 * tq) + ch + col4))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            tmem_ld_wait();
-            if (h == 1 && ci + TC_H_EPI_GROUPS >= nchunks) {
-              tcgen05_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-            }
-            if (p.residual) {
-              if (p.temb) epi_half_v4<true, true>(a, b, colc, ch, tq, rows, p.out, r4, p.temb);
-              else        epi_half_v4<true, false>(a, b, colc, ch, tq, rows, p.out, r4, p.temb);
-            } else {
-              if (p.temb) epi_half_v4<false, true>(a, b, colc, ch, tq, rows, p.out, r4, p.temb);
-              else        epi_half_v4<false, false>(a, b, colc, ch, tq, rows, p.out, r4, p.temb);
-            }
-          }
-          continue;
-        }
         uint32_t v0[16], v1[16];
         __syncwarp();
         if ((g.dbg & 3) < 2) {
@@ -1223,11 +1104,8 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         if ((g.dbg & 3) >= 1) continue;
         const bool use4 = vec4 && c0 + 32 <= g.BN && n0 + c0 + 32 <= p.O;
-        if (res_vec && (TC_H_WIDE || ci != half)) {
-          if (use4) epi_load_residual_v4(rs4, p.residual, rows, c0, tq);
-          else epi_load_residual(rs4, p.residual, rows, c0, tq, g.BN, n0, p.O);
-        }
-        if (use4 && seg.w >= 0) {
+        if (use4 && p.residual != nullptr && ci != half) epi_load_residual_v4(rs4, p.residual, rows, c0, tq);
+        if (TC_H_TMA_STORE && use4 && seg.w >= 0) {
           // results -> this warp's staging slot -> tensor store.  The warp never waits for the SM's store port
           // (32 B/clk, and every SM bursts at the same time): the TMA unit drains the slot while the warp is
           // already doing the arithmetic of the next piece.
@@ -1235,13 +1113,8 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float4 o[4];
-            if (p.residual) {
-              if (p.temb) epi_piece_compute<true, true>(v0, v1, h, colc, c0, tq, rows, o, rs4, p.temb);
-              else        epi_piece_compute<true, false>(v0, v1, h, colc, c0, tq, rows, o, rs4, p.temb);
-            } else {
-              if (p.temb) epi_piece_compute<false, true>(v0, v1, h, colc, c0, tq, rows, o, rs4, p.temb);
-              else        epi_piece_compute<false, false>(v0, v1, h, colc, c0, tq, rows, o, rs4, p.temb);
-            }
+            if (adds) epi_piece_compute<true>(v0, v1, h, colc, c0, tq, rows, o, rs4, p.residual != nullptr, p.temb);
+            else      epi_piece_compute<false>(v0, v1, h, colc, c0, tq, rows, o, rs4, false, nullptr);
             if (lane == 0) bulk_wait_read0();                // the previous piece has left the slot
             __syncwarp();
             const int col4 = (tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq;
@@ -1264,29 +1137,19 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
         } else if (use4) {
-          if (p.residual) {
-            if (p.temb) epi_block_v4<true, true>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.temb);
-            else        epi_block_v4<true, false>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.temb);
-          } else {
-            if (p.temb) epi_block_v4<false, true>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.temb);
-            else        epi_block_v4<false, false>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.temb);
-          }
-        } else if (pair_ok) {
-          if (p.residual) {
-            if (p.temb) epi_block<true, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs4, p.temb);
-            else        epi_block<true, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs4, p.temb);
-          } else {
-            if (p.temb) epi_block<false, true>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs4, p.temb);
-            else        epi_block<false, false>(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, rs4, p.temb);
-          }
+          // two instantiations only (the kernel's code size is felt in the instruction cache): the plain
+          // conv, and one variant that checks the residual / time-embedding pointers at run time
+          if (adds) epi_block_v4<true>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.residual != nullptr, p.temb);
+          else      epi_block_v4<false>(v0, v1, colc, c0, tq, rows, p.out, rs4, false, nullptr);
         } else {
+          // ragged last block or O % 4 != 0 (the 3-channel output): scalar, per-column checks
           epi_block_scalar(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, p.residual, p.temb);
         }
         if (lane == 0) tc_trace(4 + (ew & 7), it, ci == half ? 2 : 3);
       }
     }
   }
-  if (g.tma_store && warp >= TC_H_EPI0 && lane == 0) bulk_wait0();
+  if (TC_H_TMA_STORE && g.tma_store && warp >= TC_H_EPI0 && lane == 0) bulk_wait0();
   tcgen05_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) tc_span(2);
@@ -1407,7 +1270,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   // waits for the TMA unit to read the slot before every piece, and the 128->128 3x3 layer measured 76 us
   // against 59 us for direct 128-bit stores.  ATTNDM_TC_TMA_STORE=1 enables it for experiments.
   static const bool tma_store_on = [] { const char* e = getenv("ATTNDM_TC_TMA_STORE"); return e && e[0] == '1'; }();
-  g.tma_store = (tma_store_on && (p.O & 3) == 0 && g.BN % 32 == 0 && ((uintptr_t)p.out & 15) == 0) ? 1 : 0;
+  g.tma_store = (TC_H_TMA_STORE && tma_store_on && (p.O & 3) == 0 && g.BN % 32 == 0 && ((uintptr_t)p.out & 15) == 0) ? 1 : 0;
   int stg_bytes = g.tma_store ? TC_H_EPI_WARPS * 32 * 16 * 4 : 0;
   const int a_buf = g.ncb * g.hr_stride;
   const int grid = (int)(g.ntiles < kNumSMs ? g.ntiles : kNumSMs);
