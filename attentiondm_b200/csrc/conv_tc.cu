@@ -554,6 +554,8 @@ constexpr bool TC_H_TMA_STORE = true;
 #else
 constexpr bool TC_H_TMA_STORE = false;
 #endif
+// reading both accumulator blocks of a warp up front (plain conv) measured slower: 62.5 us vs 58.8 us
+constexpr bool TC_H_PAIR = false;
 constexpr int TC_H_NBOX = 5;                           // output tensor maps: boxes of 32, 31, 30, 29, 28 pixels
 constexpr int TC_H_EPI_GROUPS = TC_H_EPI_WARPS / 4;    // warps sharing a quarter split the 32-column chunks
 constexpr int TC_THREADS_H = 32 * (TC_H_EPI0 + TC_H_EPI_WARPS);
@@ -718,6 +720,9 @@ __device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const
   }
 }
 
+// ADDS: the epilogue adds a residual and/or a time embedding.  Two instantiations so that each carries only its
+// own epilogue code (the kernel's size is felt in the instruction cache).
+template <bool ADDS>
 __global__ void __launch_bounds__(TC_THREADS_H, 1)
 qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
@@ -1070,9 +1075,9 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lane == 0) mbar_arrive(smem_u32(&geo_empty[gb]));
       const int nchunks = (g.BN + 31) >> 5;
       const bool vec4 = (p.O & 3) == 0;                      // 128-bit path for full 32-column blocks
-      const bool adds = p.residual != nullptr || p.temb != nullptr;
+      constexpr bool adds = ADDS;
       float4 rs4[2][4];
-      if (p.residual != nullptr && half < nchunks) {         // first block's residual: issued before the wait below
+      if (ADDS && p.residual != nullptr && half < nchunks) {   // first block's residual: issued before the wait below
         const int cf = half << 5;
         if (vec4 && cf + 32 <= g.BN && n0 + cf + 32 <= p.O) epi_load_residual_v4(rs4, p.residual, rows, cf, tq);
       }
@@ -1083,6 +1088,33 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (half >= nchunks) {
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      }
+      if (TC_H_PAIR && !ADDS && !TC_H_TMA_STORE && (g.dbg & 3) == 0) {
+        for (int ci = half; ci < nchunks; ci += 2 * TC_H_EPI_GROUPS) {
+          const int ca = ci << 5, cb = (ci + TC_H_EPI_GROUPS) << 5;
+          const bool has_b = ci + TC_H_EPI_GROUPS < nchunks;
+          uint32_t va0[16], va1[16], vb0[16], vb1[16];
+          __syncwarp();
+          tmem_ld_16x256b_x4(t_acc + (uint32_t)ca, va0);
+          tmem_ld_16x256b_x4(t_acc + (16u << 16) + (uint32_t)ca, va1);
+          if (has_b) {
+            tmem_ld_16x256b_x4(t_acc + (uint32_t)cb, vb0);
+            tmem_ld_16x256b_x4(t_acc + (16u << 16) + (uint32_t)cb, vb1);
+          }
+          tmem_ld_wait();
+          if (ci + 2 * TC_H_EPI_GROUPS >= nchunks) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+          }
+          if (vec4 && ca + 32 <= g.BN && n0 + ca + 32 <= p.O) epi_block_v4<false>(va0, va1, colc, ca, tq, rows, p.out, rs4, false, nullptr);
+          else epi_block_scalar(va0, va1, colc, ca, tq, g.BN, n0, p.O, rows, p.out, nullptr, nullptr);
+          if (has_b) {
+            if (vec4 && cb + 32 <= g.BN && n0 + cb + 32 <= p.O) epi_block_v4<false>(vb0, vb1, colc, cb, tq, rows, p.out, rs4, false, nullptr);
+            else epi_block_scalar(vb0, vb1, colc, cb, tq, g.BN, n0, p.O, rows, p.out, nullptr, nullptr);
+          }
+        }
+        continue;
       }
       for (int ci = half; ci < nchunks; ci += TC_H_EPI_GROUPS) {
         const int c0 = ci << 5;
@@ -1316,7 +1348,9 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024);
+    attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("qconv_i8_halo: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
   CUtensorMap tmO[TC_H_NBOX];
@@ -1335,7 +1369,10 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
       if (r != CUDA_SUCCESS) { set_error("qconv_i8_halo: output tensor map failed (%d)", (int)r); return ATTNDM_ERR_CUDA; }
     }
   }
-  launch_pdl(qconv_i8_halo_kernel, dim3(grid), dim3(TC_THREADS_H), smem, st, tmA, tmA2, tmB, tmO[0], tmO[1], tmO[2], tmO[3], tmO[4], p, g);
+  if (p.residual != nullptr || p.temb != nullptr)
+    launch_pdl(qconv_i8_halo_kernel<true>, dim3(grid), dim3(TC_THREADS_H), smem, st, tmA, tmA2, tmB, tmO[0], tmO[1], tmO[2], tmO[3], tmO[4], p, g);
+  else
+    launch_pdl(qconv_i8_halo_kernel<false>, dim3(grid), dim3(TC_THREADS_H), smem, st, tmA, tmA2, tmB, tmO[0], tmO[1], tmO[2], tmO[3], tmO[4], p, g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("qconv_i8_halo: launch failed: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
   return 1;
