@@ -234,8 +234,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 // 16 lanes x 256 bit, repeated 4x along columns: 16 registers covering 16 TMEM lanes x 32 columns.
 // Measured layout (tools/umma_shift_test.cu): thread t, register j holds
 //   lane = t/4 + 8*((j>>1)&1),  column = 2*(t%4) + (j&1) + 8*(j>>2)
-// i.e. four consecutive threads hold 8 consecutive columns (32 B) of one row: a warp-wide float2 store
-// writes full 32-byte sectors and no shared-memory transpose is needed.
+// i.e. four consecutive threads hold 8 consecutive columns (32 B) of one row: no shared-memory transpose is
+// needed, and after one exchange with the neighbouring lane every thread stores 16 contiguous bytes.
 __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
@@ -592,7 +592,7 @@ struct TcGeomH {
 // One 32-row x 32-column block of a tile, held in the 16x256b fragment layout: thread (tr = lane/4,
 // tq = lane%4) owns rows tr + 8k (k = 0..3; k < 2 from v0, k >= 2 from v1) and the column pairs
 // 8i + 2tq + {0,1} (i = 0..3).  Register j of a load: row bit = (j>>1)&1, column group i = j>>2, parity j&1.
-// Everything is statically indexed (registers only); stores are float2, four lanes per 32-byte sector.
+// Everything is statically indexed (registers only).
 // Per-thread row state of a tile: four fragment rows (tr + 8k), kept as 32-bit element offsets of the output
 // row (relative to p.out; the launcher checks that the output has < 2^31 elements), a validity mask, the
 // window row-sums and the sample indices.  Residual and time-embedding addresses are derived from these.
@@ -1016,14 +1016,13 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lane == 0) mbar_arrive(smem_u32(&geo_full[buf]));
     }
   } else if (warp >= TC_H_EPI0) {
-    // ===== epilogue warps (16): quarter = warp % 4, the four warps of a quarter take 32-column chunks round robin.
+    // ===== epilogue warps (8): quarter = warp % 4, the two warps of a quarter take 32-column chunks round robin.
     // No shared-memory staging: the 16x256b TMEM load shape already hands four consecutive threads 32
-    // contiguous bytes of one output row, so results go TMEM -> registers -> global (float2 per lane).
-    // Keeping the epilogue off shared memory matters: an SS-mode M=128,N=128 MMA reads 8 KB of operands
-    // per 64 cycles, i.e. the SM's whole 128 B/clk shared-memory bandwidth.
+    // contiguous bytes of one output row, so results go TMEM -> registers -> global (128-bit per lane after
+    // the neighbour-lane exchange of epi_block_v4).
     pdl_wait();
     const int quarter = warp & 3;
-    const int ew = warp - TC_H_EPI0;                   // 0..15
+    const int ew = warp - TC_H_EPI0;                   // 0..7
     const int half = ew >> 2;                          // which of the quarter's four warps (chunk phase)
     const int zp = *p.act_zp;
     const int tq = lane & 3, tr = lane >> 2;           // fragment coordinates of this thread
