@@ -27,6 +27,9 @@ class AttnQuant(C.Structure):
 # name -> argtypes, in the order of include/attndm_b200.h
 SIGNATURES = {
     "attndm_act_quant": [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, f32, vp, vp, i32, vp, vp],
+    "attndm_conv_f32_tc_fits": [i64, i32, i32],
+    "attndm_split_tf32": [vp, i64, vp, vp, vp],
+    "attndm_gemm_tf32x3": [vp, vp, i64, i32, vp, vp, i32, vp, vp, vp],
     "attndm_gn_stats": [vp, i32, i32, i32, i32, vp, vp],
     "attndm_gn_act_quant_fits": [i32, i32, i32],
     "attndm_set_gn_cluster_min_kb": [i32],

@@ -72,5 +72,9 @@ __device__ __forceinline__ float conv_epilogue_add(const float* residual, const 
 
 int launch_qconv_i8_simt(const ConvI8Params& p, cudaStream_t st);
 int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st);
+int conv_f32_tc_fits(long long rows, int C, int O);
+int launch_split_tf32(const float* x, long long n, float* big, float* small, cudaStream_t st);
+int launch_gemm_tf32x3(const float* a_big, const float* a_small, long long rows, int C, const float* w_big,
+                       const float* w_small, int O, const float* bias, float* out, cudaStream_t st);
 
 }  // namespace attndm

@@ -231,3 +231,14 @@ extern "C" int attndm_conv_f32(const float* x, int B, int H, int W, int C, const
   ATTNDM_CUDA_LAUNCH_CHECK("conv_f32");
   return ATTNDM_OK;
 }
+
+/* fp32 1x1 conv (plain GEMM + bias) on the tensor cores, fp32-level accuracy by operand splitting (conv_tc.cu) */
+extern "C" int attndm_conv_f32_tc_fits(long long rows, int C, int O) { return conv_f32_tc_fits(rows, C, O); }
+extern "C" int attndm_split_tf32(const float* x, long long n, float* big, float* small, void* stream) {
+  return launch_split_tf32(x, n, big, small, (cudaStream_t)stream);
+}
+extern "C" int attndm_gemm_tf32x3(const float* a_big, const float* a_small, long long rows, int C, const float* w_big,
+                                  const float* w_small, int O, const float* bias, float* out, void* stream) {
+  ATTNDM_CHECK_ARG(a_big && a_small && w_big && w_small && out && rows > 0 && C > 0 && O > 0, "gemm_tf32x3: bad args");
+  return launch_gemm_tf32x3(a_big, a_small, rows, C, w_big, w_small, O, bias, out, (cudaStream_t)stream);
+}

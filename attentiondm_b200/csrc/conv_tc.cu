@@ -1361,4 +1361,249 @@ int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st) {
   return launch_qconv_i8_tc_persistent(p, st);     // shapes the halo kernel does not take (halo > 512 rows, >= 2^31 outputs)
 }
 
+
+// =====================================================================================================
+// fp32 GEMM on the tensor cores with fp32-level accuracy ("3xTF32"): out[M][N] = x[M][K] . w[N][K]^T + bias
+// Reference op: the lazily created fp32 `channel_proj` 1x1 conv of UpBlock (models/diffusion.py:235-242), the one
+// fp32 layer of the step that is large (M = B*H*W = 16384, K = 768, N = 512 on CIFAR: 190 us on the FP32 pipe,
+// at 95 % of its peak).
+// kind::tf32 keeps 10 mantissa bits, so each operand is split exactly, a = big + small with
+//   big = a with its 13 low mantissa bits cleared,  small = a - big  (exact, <= 13 significant bits),
+// and the product is accumulated as big*big + big*small + small*big in the fp32 TMEM accumulator; what is
+// dropped (small*small and the bits of `small` below tf32) is ~2^-21 relative per product, the size of an fp32
+// rounding.  The caller owns the split operands (weights are split once, activations by a streaming pass).
+// Kernel: persistent 128 x 128 tiles, TMA (SWIZZLE_128B, 32 floats per row) -> 3-stage ring of
+// {A big, A small, B big, B small} -> 12 tcgen05.mma per k-block -> four TMEM accumulators -> 4 epilogue warps.
+// =====================================================================================================
+constexpr int G32_STAGES = 3;
+constexpr int G32_TILE_BYTES = 128 * 128;                 // 128 rows x 32 floats
+constexpr int G32_STAGE_BYTES = 4 * G32_TILE_BYTES;
+constexpr int G32_NACC = 4;                               // TMEM accumulators per tile (4 x 128 columns)
+constexpr int G32_THREADS = 192;                          // producer, MMA issuer, 4 epilogue warps
+
+struct GemmTf32Params {
+  const float* bias;
+  float* out;
+  int M, N, K;
+  int ntn, nkb;
+  long long ntiles;
+};
+
+__global__ void f32_split_tf32_kernel(const float4* __restrict__ x, long long n4, float4* __restrict__ big,
+                                      float4* __restrict__ small) {
+  pdl_enter();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = ldg_stream(x + i);
+    float4 b, s;
+    b.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); s.x = __fsub_rn(v.x, b.x);
+    b.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); s.y = __fsub_rn(v.y, b.y);
+    b.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); s.z = __fsub_rn(v.z, b.z);
+    b.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); s.w = __fsub_rn(v.w, b.w);
+    big[i] = b;
+    small[i] = s;
+  }
+}
+
+__device__ __forceinline__ void umma_tf32_if(uint32_t leader, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(G32_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAb, const __grid_constant__ CUtensorMap tmAs,
+                   const __grid_constant__ CUtensorMap tmBb, const __grid_constant__ CUtensorMap tmBs,
+                   const GemmTf32Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[G32_STAGES], empty[G32_STAGES], tmem_full_bar, tmem_empty_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < G32_STAGES; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    mbar_init(smem_u32(&tmem_empty_bar), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  // The tensor core adds into its fp32 accumulator with truncation, so the error of one accumulator grows with
+  // the number of MMAs chained into it (measured 5.7e-6 of the output range for K = 768 in ONE accumulator,
+  // against 1.1e-6 for sequential fmaf).  The k-blocks are therefore dealt round-robin to G32_NACC accumulators
+  // (four times shorter chains) which the epilogue adds with round-to-nearest.
+  const int nacc = p.nkb < G32_NACC ? p.nkb : G32_NACC;
+  pdl_launch_dependents();
+  if (warp == 0) {
+    pdl_wait();
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int m0 = (int)(tile / p.ntn) * 128, n0 = (int)(tile % p.ntn) * 128;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait_relaxed(smem_u32(&empty[s]), ph ^ 1);
+        const uint32_t bar = smem_u32(&full[s]);
+        const uint32_t dst = base + (uint32_t)s * G32_STAGE_BYTES;
+        mbar_expect_tx_elect(bar, (uint32_t)G32_STAGE_BYTES);
+        tma_load_2d_elect(dst, &tmAb, bar, kb * 32, m0);
+        tma_load_2d_elect(dst + G32_TILE_BYTES, &tmAs, bar, kb * 32, m0);
+        tma_load_2d_elect(dst + 2 * G32_TILE_BYTES, &tmBb, bar, kb * 32, n0);
+        tma_load_2d_elect(dst + 3 * G32_TILE_BYTES, &tmBs, bar, kb * 32, n0);
+        if (++s == G32_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // c = f32, a = b = tf32, K-major, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    const uint32_t leader = elect_one();
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      mbar_wait(smem_u32(&tmem_empty_bar), (uint32_t)((it & 1) ^ 1));
+      tcgen05_fence_after();
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(smem_u32(&full[s]), ph);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)((kb % G32_NACC) * 128);
+        uint32_t accumulate = kb >= G32_NACC ? 1u : 0u;
+        const uint32_t st = base + (uint32_t)s * G32_STAGE_BYTES;
+        const uint64_t ab = desc_hi | (uint64_t)((st >> 4) & 0x3FFF), as = desc_hi | (uint64_t)(((st + G32_TILE_BYTES) >> 4) & 0x3FFF);
+        const uint64_t bb = desc_hi | (uint64_t)(((st + 2 * G32_TILE_BYTES) >> 4) & 0x3FFF),
+                       bs = desc_hi | (uint64_t)(((st + 3 * G32_TILE_BYTES) >> 4) & 0x3FFF);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                    // 8 floats (32 bytes) of K per MMA
+          umma_tf32_if(leader, d_tmem, as + 2 * k, bb + 2 * k, idesc, accumulate);   // small terms first
+          umma_tf32_if(leader, d_tmem, ab + 2 * k, bs + 2 * k, idesc, 1u);
+          umma_tf32_if(leader, d_tmem, ab + 2 * k, bb + 2 * k, idesc, 1u);
+          accumulate = 1;
+        }
+        tcgen05_commit_if(leader, smem_u32(&empty[s]));
+        if (++s == G32_STAGES) { s = 0; ph ^= 1; }
+      }
+      tcgen05_commit_if(leader, smem_u32(&tmem_full_bar));
+    }
+  } else {
+    pdl_wait();
+    const int quarter = warp & 3;
+    const int tq = lane & 3, tr = lane >> 2;
+    const bool odd = tq & 1;
+    const int col4 = odd ? 8 + 2 * (tq - 1) : 2 * tq;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int m0 = (int)(tile / p.ntn) * 128, n0 = (int)(tile % p.ntn) * 128;
+      mbar_wait_relaxed(smem_u32(&tmem_full_bar), (uint32_t)(it & 1));
+      tcgen05_fence_after();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c0 = ci << 5;
+        float f0[16], f1[16];
+        for (int a = 0; a < nacc; ++a) {
+          uint32_t v0[16], v1[16];
+          __syncwarp();
+          tmem_ld_16x256b_x4(t_acc + (uint32_t)(a * 128 + c0), v0);
+          tmem_ld_16x256b_x4(t_acc + (16u << 16) + (uint32_t)(a * 128 + c0), v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f0[j] = a == 0 ? __uint_as_float(v0[j]) : __fadd_rn(f0[j], __uint_as_float(v0[j]));
+            f1[j] = a == 0 ? __uint_as_float(v1[j]) : __fadd_rn(f1[j], __uint_as_float(v1[j]));
+          }
+        }
+        if (ci == 3) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = n0 + c0 + 16 * h + col4;
+          const float4 bi = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j0 = ((2 * h) << 2) | ((k & 1) << 1), j1 = ((2 * h + 1) << 2) | ((k & 1) << 1);
+            const float lo0 = k < 2 ? f0[j0] : f1[j0], lo1 = k < 2 ? f0[j0 | 1] : f1[j0 | 1];
+            const float hi0 = k < 2 ? f0[j1] : f1[j1], hi1 = k < 2 ? f0[j1 | 1] : f1[j1 | 1];
+            const float s0 = odd ? lo0 : hi0, s1 = odd ? lo1 : hi1;
+            const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+            float4 o = odd ? make_float4(g0, g1, hi0, hi1) : make_float4(lo0, lo1, g0, g1);
+            o.x = __fadd_rn(o.x, bi.x); o.y = __fadd_rn(o.y, bi.y); o.z = __fadd_rn(o.z, bi.z); o.w = __fadd_rn(o.w, bi.w);
+            const int row = m0 + quarter * 32 + tr + 8 * k;
+            if (row < p.M) *reinterpret_cast<float4*>(p.out + (long long)row * p.N + col) = o;
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+static int make_map_2d_f32(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("gemm_tf32: cuTensorMapEncodeTiled not available"); return ATTNDM_ERR_CUDA; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 4};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tf32: cuTensorMapEncodeTiled failed (%d)", (int)r); return ATTNDM_ERR_CUDA; }
+  return ATTNDM_OK;
+}
+
+int conv_f32_tc_fits(long long rows, int C, int O) {
+  return rows >= 1 && rows < (1LL << 31) - 256 && C >= 64 && (C & 3) == 0 && (O & 127) == 0 && O >= 128 ? 1 : 0;
+}
+
+int launch_split_tf32(const float* x, long long n, float* big, float* small, cudaStream_t st) {
+  ATTNDM_CHECK_ARG(x && big && small && n > 0 && (n & 3) == 0, "split_tf32: n must be a positive multiple of 4");
+  ATTNDM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)big & 15) == 0 && ((uintptr_t)small & 15) == 0,
+                   "split_tf32: operands must be 16-byte aligned");
+  const long long n4 = n / 4;
+  const long long blocks = cdiv(n4, 256);
+  launch_pdl(f32_split_tf32_kernel, dim3((unsigned)(blocks < 4 * kNumSMs ? blocks : 4 * kNumSMs)), dim3(256), 0, st,
+             reinterpret_cast<const float4*>(x), n4, reinterpret_cast<float4*>(big), reinterpret_cast<float4*>(small));
+  ATTNDM_CUDA_LAUNCH_CHECK("split_tf32");
+  return ATTNDM_OK;
+}
+
+int launch_gemm_tf32x3(const float* a_big, const float* a_small, long long rows, int C, const float* w_big,
+                       const float* w_small, int O, const float* bias, float* out, cudaStream_t st) {
+  if (!conv_f32_tc_fits(rows, C, O)) { set_error("gemm_tf32x3: shape %lld x %d -> %d not supported", rows, C, O); return ATTNDM_ERR_UNSUPPORTED; }
+  ATTNDM_CHECK_ARG(((uintptr_t)a_big & 15) == 0 && ((uintptr_t)a_small & 15) == 0 && ((uintptr_t)w_big & 15) == 0 &&
+                   ((uintptr_t)w_small & 15) == 0 && ((uintptr_t)out & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0),
+                   "gemm_tf32x3: operands must be 16-byte aligned");
+  CUtensorMap tmAb, tmAs, tmBb, tmBs;
+  int rc = make_map_2d_f32(&tmAb, a_big, (uint64_t)C, (uint64_t)rows); if (rc) return rc;
+  rc = make_map_2d_f32(&tmAs, a_small, (uint64_t)C, (uint64_t)rows); if (rc) return rc;
+  rc = make_map_2d_f32(&tmBb, w_big, (uint64_t)C, (uint64_t)O); if (rc) return rc;
+  rc = make_map_2d_f32(&tmBs, w_small, (uint64_t)C, (uint64_t)O); if (rc) return rc;
+  GemmTf32Params p;
+  p.bias = bias; p.out = out; p.M = (int)rows; p.N = O; p.K = C;
+  p.ntn = O / 128; p.nkb = cdiv(C, 32);
+  p.ntiles = (long long)cdiv(rows, 128) * p.ntn;
+  const int smem = G32_STAGES * G32_STAGE_BYTES + 1024;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [smem] { attr_err = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+  if (attr_err != cudaSuccess) { set_error("gemm_tf32x3: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
+  const int grid = (int)(p.ntiles < kNumSMs ? p.ntiles : kNumSMs);
+  launch_pdl(gemm_tf32x3_kernel, dim3(grid), dim3(G32_THREADS), smem, st, tmAb, tmAs, tmBb, tmBs, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("gemm_tf32x3: launch failed: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
+  return ATTNDM_OK;
+}
+
 }  // namespace attndm

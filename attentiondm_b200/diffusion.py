@@ -153,8 +153,20 @@ class UpBlock(_TimeBlock):
             # un-quantized fp32 1x1 conv.  Our own fp32 kernel rather than a cuBLAS GEMM: its per-output
             # summation order does not depend on the batch size, which keeps every sample's result
             # independent of how the batch is sharded over GPUs.
-            w = self.channel_proj.weight.detach().view(expected, 1, actual)
-            combined = ops.conv_f32(combined, w.contiguous(), self.channel_proj.bias.detach())
+            # On spatial maps it runs on the tensor cores with fp32-level accuracy (3xTF32 operand splitting, also
+            # batch-independent); 1x1 maps keep the SIMT kernel, whose order the fused programs reproduce.
+            Bc, Hc, Wc, _ = combined.shape
+            bias = self.channel_proj.bias.detach()
+            if Hc * Wc > 1 and ops.conv_f32_tc_fits(Bc * Hc * Wc, actual, expected):
+                wt = self.channel_proj.weight
+                key = (wt.data_ptr(), wt._version)
+                if getattr(self, "_proj_split_key", None) != key:
+                    self._proj_split = ops.split_tf32(wt.detach().view(expected, actual).contiguous())
+                    self._proj_split_key = key
+                combined = ops.conv1x1_f32_tc(combined, self._proj_split, bias)
+            else:
+                w = self.channel_proj.weight.detach().view(expected, 1, actual)
+                combined = ops.conv_f32(combined, w.contiguous(), bias)
         return self._tail(combined, time_emb)
 
     def forward(self, x, skip_x, time_emb=None):

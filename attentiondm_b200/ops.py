@@ -7,6 +7,8 @@ torch is used for device memory and streams only.
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -274,6 +276,32 @@ def qconv_i8(codes, rowsum, B: int, H: int, W: int, Cc: int, pack: I8Pack, taps:
     call("attndm_qconv_i8", ptr(codes), ptr(rowsum), B, H, W, Cc, ptr(pack.qw), ptr(pack.wsum), ptr(pack.w_zp), O,
          taps, ptr(mult), ptr(act_zp), ptr(bias), ptr(residual), ptr(temb), ptr(out), None,
          DEFAULT_CONV_IMPL if impl is None else impl, stream())
+    return out
+
+
+def conv_f32_tc_fits(rows: int, Cc: int, O: int) -> bool:
+    if os.environ.get("ATTNDM_F32_TC", "1") == "0":
+        return False
+    return bool(F_.lib().attndm_conv_f32_tc_fits(int(rows), int(Cc), int(O)))
+
+
+def split_tf32(x: torch.Tensor):
+    """x = big + small exactly: big has the 13 low mantissa bits cleared (a tf32 value), small is the remainder."""
+    big, small = torch.empty_like(x), torch.empty_like(x)
+    call("attndm_split_tf32", ptr(x), x.numel(), ptr(big), ptr(small), stream())
+    return big, small
+
+
+def conv1x1_f32_tc(x: torch.Tensor, w_split, bias) -> torch.Tensor:
+    """fp32 1x1 conv on the tensor cores (3xTF32).  x NHWC fp32; w_split = split_tf32 of the [O, C] weight."""
+    _chk(x, "conv1x1_f32_tc input")
+    B, H, W, Cc = x.shape
+    w_big, w_small = w_split
+    O = w_big.shape[0]
+    a_big, a_small = split_tf32(x)
+    out = torch.empty(B, H, W, O, dtype=torch.float32, device=x.device)
+    call("attndm_gemm_tf32x3", ptr(a_big), ptr(a_small), B * H * W, Cc, ptr(w_big), ptr(w_small), O, ptr(bias), ptr(out),
+         stream())
     return out
 
 

@@ -186,6 +186,18 @@ int attndm_conv_f32(const float* x, int B, int H, int W, int C, const float* w_e
                     int taps, const float* bias, const float* residual, const float* temb,
                     float* out, void* stream);
 
+/* The same fp32 1x1 conv (a GEMM, out[rows][O] = x[rows][C] . w[O][C]^T + bias) on the tensor cores with
+ * fp32-level accuracy: each operand is split exactly into a tf32 "big" part and an fp32 remainder
+ * (attndm_split_tf32: big = x with the 13 low mantissa bits cleared, small = x - big) and the product is
+ * accumulated as big*big + big*small + small*big by tcgen05.mma kind::tf32 (~2^-21 relative per product).
+ * Used for the reference's lazily created fp32 `channel_proj` (models/diffusion.py:235-242) on spatial maps;
+ * 1x1 maps keep attndm_conv_f32 (the fused programs reproduce its summation order bit for bit).
+ * attndm_conv_f32_tc_fits: rows < 2^31, C % 4 == 0, C >= 64, O % 128 == 0. */
+int attndm_conv_f32_tc_fits(long long rows, int C, int O);
+int attndm_split_tf32(const float* x, long long n, float* big, float* small, void* stream);
+int attndm_gemm_tf32x3(const float* a_big, const float* a_small, long long rows, int C, const float* w_big,
+                       const float* w_small, int O, const float* bias, float* out, void* stream);
+
 /* ---- attention ------------------------------------------------------------ */
 
 /* EnhancedQSelfAttention core (models/self_attention.py:132-144):

@@ -55,13 +55,21 @@ def oracle_layer(q, r, calibrate):
     return y
 
 
-def worst_layer_error(model, rec, calibrate):
+def layer_errors(model, rec, calibrate):
+    """[(rel-L2 error, (layer name, step))] of every recorded call against the reference arithmetic."""
     mods = dict(model.qconvs())
-    worst, where = 0.0, None
+    out = []
     for r in rec:
         want = oracle_layer(mods[r["name"]], r, calibrate)
         got = r["y"].permute(0, 3, 1, 2)
         e = float((got.double() - want.double()).norm() / want.double().norm().clamp_min(1e-30))
+        out.append((e, (r["name"], r["t"])))
+    return out
+
+
+def worst_layer_error(model, rec, calibrate):
+    worst, where = 0.0, None
+    for e, w in layer_errors(model, rec, calibrate):
         if e > worst:
-            worst, where = e, (r["name"], r["t"])
+            worst, where = e, w
     return worst, where
