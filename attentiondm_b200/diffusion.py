@@ -266,14 +266,27 @@ class Model(nn.Module):
         finally:
             ops.gn_pool_end()
 
+    def _linear_f32(self, x, lin):
+        """An un-quantized fp32 Linear on [B, 1, 1, C]: the 3xTF32 tensor-core GEMM when the shape fits (the
+        1024-wide time_embed layers are 64 CTAs of pure latency on the FP32 pipe), else the fp32 SIMT kernel."""
+        B = x.shape[0]
+        O, Cc = lin.weight.shape
+        if ops.conv_f32_tc_fits(B, Cc, O):
+            key = (lin.weight.data_ptr(), lin.weight._version)
+            cache = self.__dict__.setdefault("_lin_split", {})
+            if cache.get(id(lin), (None,))[0] != key:
+                cache[id(lin)] = (key, ops.split_tf32(lin.weight.detach().contiguous()))
+            return ops.conv1x1_f32_tc(x, cache[id(lin)][1], lin.bias.detach())
+        return ops.conv_f32(x, lin.weight.detach().unsqueeze(1).contiguous(), lin.bias.detach())
+
     def _forward_nhwc(self, x, t):
         B = x.shape[0]
         t_emb = ops.timestep_embedding(t, self.config.model.time_embed_dim).view(B, 1, 1, -1)
         # the two un-quantized Linears (models/diffusion.py:273-277) as batch-invariant fp32 1x1 convs
         l0, l2 = self.time_embed[0], self.time_embed[2]
-        t_emb = ops.conv_f32(t_emb, l0.weight.detach().unsqueeze(1).contiguous(), l0.bias.detach())
+        t_emb = self._linear_f32(t_emb, l0)
         t_emb = ops.silu(t_emb)
-        t_emb = ops.conv_f32(t_emb, l2.weight.detach().unsqueeze(1).contiguous(), l2.bias.detach())
+        t_emb = self._linear_f32(t_emb, l2)
         fp = getattr(self, "_fused", None)                 # rowprog.FusedPlans, set by the CUDA-graph engine
         if fp is not None:
             fp.run_time_mlps(t_emb, self._fused_cur)
