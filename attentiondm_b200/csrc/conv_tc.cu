@@ -585,7 +585,10 @@ struct TcGeomH {
   int nb;             // weight ring depth (streamed)
   int a_off, b_off, stg_off;   // byte offsets inside the 1024-aligned dynamic smem
   int tma_store;      // 1: full 16-column pieces leave through per-warp staging + TMA tensor stores
-  int dbg;            // debug experiments (ATTNDM_TC_DBG): 1 = epilogue skips the math/stores, 2 = skips the TMEM loads too
+  int dbg;            // debug experiments (ATTNDM_TC_DBG, bit mask): low two bits 1 = epilogue skips the math/stores,
+                      // 2 = skips the TMEM loads too; 4 = A descriptor not shifted per tap; 8 = B descriptor fixed;
+                      // 16 = no halo loads; 32 = epilogue arithmetic without loads/stores; 128 / 256 = the MMA warp
+                      // skips the halo-full / accumulator-free waits (results are garbage: timing only)
 };
 
 

@@ -1,4 +1,13 @@
-"""Debug: per-role timeline of the halo conv kernel (CTA 0, first tiles), via the trace hook."""
+"""Debug: per-role timeline of the halo conv kernel, via the trace hooks.
+
+The hooks are compiled in only with -DATTNDM_TC_TRACE (each costs a global load on the kernel's critical path):
+    ATTNDM_NVCC_EXTRA=-DATTNDM_TC_TRACE python -m attentiondm_b200.build      # trace build of the library
+    TRACE_CTA=5 TRACE_ITS=9 python tools/conv_trace.py c128_32                # on the GPU box
+    python -m attentiondm_b200.build                                          # back to the normal build
+Prints, for CTA TRACE_CTA, the globaltimer stamps of the MMA warp (start / accumulator free / halo full / issued),
+the true MMA completion (an idle warp waits on the same barrier) and the eight epilogue warps (accumulator seen /
+first block loaded / first block done / second block done); the SM clock per tile; and for ALL CTAs the start,
+weights-resident and end times and the per-tile issue intervals."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
