@@ -32,9 +32,6 @@ SIGNATURES = {
     "attndm_gemm_tf32x3": [vp, vp, i64, i32, vp, vp, i32, vp, vp, vp],
     "attndm_gn_stats": [vp, i32, i32, i32, i32, vp, vp],
     "attndm_gn_act_quant_fits": [i32, i32, i32],
-    "attndm_set_gn_cluster_min_kb": [i32],
-    "attndm_gn_quant_cluster_fits": [i32, i32, i32],
-    "attndm_gn_quant_cluster": [vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp, vp, i32, vp],
     "attndm_gn_act_quant": [vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp, vp, i32, vp, vp],
     "attndm_gn_silu": [vp, i32, i32, i32, i32, vp, vp, vp, f32, vp, vp],
     "attndm_minmax_workspace_blocks": [],

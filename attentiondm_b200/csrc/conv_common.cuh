@@ -55,9 +55,10 @@ __device__ __forceinline__ long long conv_window_rowsum(const ConvI8Params& p, l
 
 // Exact integer I = acc + A + B*cs with A = zp*wsum[o], B = w_zp[o], cs = window rowsum + zp*taps*C,
 // then one fused multiply-add: out = float(I) * mult[o] + bias[o].
-// On the integer path 0.0 is representable, so |zp| <= 2^(a-1) and |w_zp| <= 2^(w-1) <= 128; with
-// |code|, |q| <= 128 every term is bounded by K*2^16, i.e. I fits in int32 for K = taps*Cp < 2^15
-// (checked by the launcher; the largest layer of the supported models has K = 9*1536).
+// Range: on the integer path 0.0 is representable, so |zp| <= 2^(a-1) <= 128; |code|, |q| <= 128 give
+// |acc|, |A| <= K*2^14 and |cs| <= K*2^8.  |w_zp| is NOT bounded by the bit width (a channel whose weights do
+// not straddle 0 has w_zp = 2^(w-1) + round(s*lo)): attndm_weight_to_i8 declares a channel off-grid unless
+// K*2^15 + |w_zp|*K*2^8 < 2^31, and the launcher checks K = taps*Cp < 2^15, so I always fits in int32.
 // Both conv kernels call this, so they agree bit for bit.
 __device__ __forceinline__ float conv_i8_value(int acc, int A, int B, int cs, float m, float bias) {
   return fmaf((float)(acc + A + B * cs), m, bias);

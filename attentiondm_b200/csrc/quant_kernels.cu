@@ -695,195 +695,6 @@ __global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p)
 }
 
 
-// ---------------------------------------------------------------------------
-// GroupNorm + SiLU + quantize of a LARGE feature map in one pass over HBM: a thread-block cluster per sample.
-// gn_stats_kernel + act_quant_rows_kernel read the fp32 tensor twice (the 32x32x128 maps of a batch are 134 MB,
-// more than L2 keeps).  Here the CTAs of a cluster each pull 1/cs of their sample into shared memory with bulk
-// copies (128 KB per CTA), reduce the GroupNorm sums across the cluster through distributed shared memory, and
-// quantize straight from shared memory: one HBM read, one code write.
-// Statistics are double sums like gn_stats_kernel (so both paths give the same mean / rstd up to the order of
-// double additions); the per-element arithmetic is act_quant_rows_kernel's.
-// ---------------------------------------------------------------------------
-struct GnClusterParams {
-  const float* x;
-  int B, H, W, C, Cp;
-  const float* scale;
-  const float* zp;
-  float qlo, qhi;
-  const float* gamma;
-  const float* beta;
-  float eps;
-  int8_t* codes;
-  int32_t* rowsum;
-  int halo;
-  int cs;               // CTAs per sample (cluster size)
-  int rows_per_cta;     // image rows per CTA = H / cs
-};
-constexpr int kGnClusterMax = 8;
-
-__device__ __forceinline__ uint32_t gq_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int NQ, bool A8>
-__global__ void __launch_bounds__(256, 1) gn_quant_cluster_kernel(GnClusterParams p) {
-  extern __shared__ __align__(128) float gq_tile[];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ double s_sum[kGnGroups], s_sq[kGnGroups];
-  __shared__ double part[kGnClusterMax][kGnGroups][2];      // [rank] partial sums of every CTA of the cluster
-  __shared__ float s_mean[kGnGroups], s_rstd[kGnGroups];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const int b = blockIdx.x / p.cs;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int W = p.W, C = p.C, Cp = p.Cp;
-  const int npix = p.rows_per_cta * W;
-  const uint32_t bytes = (uint32_t)npix * C * 4u;
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gq_smem_u32(&bar)) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (threadIdx.x < kGnGroups) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
-  pdl_enter();                                         // x is the previous kernel's output
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const float* src = p.x + ((long long)b * p.H + (long long)rank * p.rows_per_cta) * W * C;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gq_smem_u32(&bar)), "r"(bytes) : "memory");
-    for (uint32_t off = 0; off < bytes; off += 16384u) {
-      const uint32_t n = bytes - off < 16384u ? bytes - off : 16384u;
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(gq_smem_u32(gq_tile) + off), "l"(reinterpret_cast<const char*>(src) + off), "r"(n),
-                     "r"(gq_smem_u32(&bar))
-                   : "memory");
-    }
-  }
-  {   // wait for the tile
-    uint32_t done = 0;
-    while (!done)
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(done) : "r"(gq_smem_u32(&bar)) : "memory");
-  }
-  // ---- GroupNorm sums of this CTA's pixels (channel quad q fixed per thread, P pixel lanes) ----
-  const int Q = C >> 2, P = 256 / Q, cpg = C / kGnGroups;
-  {
-    const int q = threadIdx.x % Q, pl = threadIdx.x / Q;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-    const float4* t4 = reinterpret_cast<const float4*>(gq_tile) + q;
-    for (int r = pl; r < npix; r += P) {
-      const float4 v = t4[(long long)r * Q];
-      a0 += v.x; q0 += (double)v.x * v.x;
-      a1 += v.y; q1 += (double)v.y * v.y;
-      a2 += v.z; q2 += (double)v.z * v.z;
-      a3 += v.w; q3 += (double)v.w * v.w;
-    }
-    const int g = (q << 2) / cpg;                      // cpg % 4 == 0 (host-checked): one group per quad
-    atomicAdd(&s_sum[g], (a0 + a1) + (a2 + a3));
-    atomicAdd(&s_sq[g], (q0 + q1) + (q2 + q3));
-  }
-  __syncthreads();
-  if (threadIdx.x < kGnGroups) {                        // all-gather the partial sums over the cluster
-    for (int j = 0; j < p.cs; ++j) {
-      double* dst = cluster.map_shared_rank(&part[rank][threadIdx.x][0], j);
-      dst[0] = s_sum[threadIdx.x];
-      dst[1] = s_sq[threadIdx.x];
-    }
-  }
-  cluster.sync();
-  if (threadIdx.x < kGnGroups) {
-    double S = 0.0, SS = 0.0;
-    for (int j = 0; j < p.cs; ++j) { S += part[j][threadIdx.x][0]; SS += part[j][threadIdx.x][1]; }   // rank order: every CTA agrees
-    float mean, rstd;
-    gn_mean_rstd(S, SS, 1.0 / ((double)p.H * W * cpg), p.eps, mean, rstd);
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rstd;
-  }
-  __syncthreads();
-  // ---- quantize from shared memory: warps take image rows, four pixels per step (act_quant_rows_kernel) ----
-  const int Hp = p.halo ? p.H + 2 : p.H, Wp = p.halo ? W + 2 : W;
-  float4 s4[NQ], z4[NQ], ga[NQ], gb[NQ];
-  int padw[NQ], padsum = 0;
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    const int c = (i * 32 + lane) << 2;
-    s4[i] = *reinterpret_cast<const float4*>(p.scale + c);
-    z4[i] = *reinterpret_cast<const float4*>(p.zp + c);
-    const int a = (int)fminf(fmaxf(-z4[i].x, p.qlo), p.qhi), b2 = (int)fminf(fmaxf(-z4[i].y, p.qlo), p.qhi);
-    const int c2 = (int)fminf(fmaxf(-z4[i].z, p.qlo), p.qhi), d = (int)fminf(fmaxf(-z4[i].w, p.qlo), p.qhi);
-    padw[i] = (a & 0xff) | ((b2 & 0xff) << 8) | ((c2 & 0xff) << 16) | ((d & 0xff) << 24);
-    padsum += a + b2 + c2 + d;
-    const int gi = c / cpg;
-    const float4 g4 = *reinterpret_cast<const float4*>(p.gamma + c);
-    const float4 be4 = *reinterpret_cast<const float4*>(p.beta + c);
-    const float m = s_mean[gi], rs = s_rstd[gi];
-    ga[i].x = rs * g4.x; gb[i].x = fmaf(-m, ga[i].x, be4.x);
-    ga[i].y = rs * g4.y; gb[i].y = fmaf(-m, ga[i].y, be4.y);
-    ga[i].z = rs * g4.z; gb[i].z = fmaf(-m, ga[i].z, be4.z);
-    ga[i].w = rs * g4.w; gb[i].w = fmaf(-m, ga[i].w, be4.w);
-  }
-  padsum = __reduce_add_sync(0xffffffffu, padsum);
-  auto ring_row = [&](long long row) {
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) *reinterpret_cast<int*>(p.codes + row * Cp + ((i * 32 + lane) << 2)) = padw[i];
-    if (lane == 0) p.rowsum[row] = padsum;
-  };
-  constexpr int R = 4;
-  const int steps = W / R;
-  for (int item = warp; item < p.rows_per_cta * steps; item += 8) {      // (image row, four-pixel step) pairs
-    const int lr = item / steps, w0 = (item - lr * steps) * R;
-    const int h = rank * p.rows_per_cta + lr;
-    const float* xrow = gq_tile + (long long)lr * W * C + (lane << 2);
-    const long long rbase = p.halo ? ((long long)b * Hp + h + 1) * Wp + 1 : ((long long)b * p.H + h) * W;
-    int8_t* crow = p.codes + rbase * Cp + (lane << 2);
-    {
-      int sums[R];
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        int acc = 0;
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-          float4 t = *reinterpret_cast<const float4*>(xrow + (long long)(w0 + k) * C + i * 128);
-          t.x = pre_op<ATTNDM_PRE_GN_SILU>(t.x, ga[i].x, gb[i].x);
-          t.y = pre_op<ATTNDM_PRE_GN_SILU>(t.y, ga[i].y, gb[i].y);
-          t.z = pre_op<ATTNDM_PRE_GN_SILU>(t.z, ga[i].z, gb[i].z);
-          t.w = pre_op<ATTNDM_PRE_GN_SILU>(t.w, ga[i].w, gb[i].w);
-          int word;
-          if (A8) {
-            const int ix = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].x, t.x), z4[i].x));
-            const int iy = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].y, t.y), z4[i].y));
-            const int iz = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].z, t.z), z4[i].z));
-            const int iw = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].w, t.w), z4[i].w));
-            int hi2;
-            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi2) : "r"(iw), "r"(iz));
-            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(word) : "r"(iy), "r"(ix), "r"(hi2));
-            acc = __dp4a(word, 0x01010101, acc);
-          } else {
-            const int ix = quant_code_i(t.x, s4[i].x, z4[i].x, p.qlo, p.qhi);
-            const int iy = quant_code_i(t.y, s4[i].y, z4[i].y, p.qlo, p.qhi);
-            const int iz = quant_code_i(t.z, s4[i].z, z4[i].z, p.qlo, p.qhi);
-            const int iw = quant_code_i(t.w, s4[i].w, z4[i].w, p.qlo, p.qhi);
-            acc += ix + iy + iz + iw;
-            word = (ix & 0xff) | ((iy & 0xff) << 8) | ((iz & 0xff) << 16) | (iw << 24);
-          }
-          *reinterpret_cast<int*>(crow + (long long)(w0 + k) * Cp + i * 128) = word;
-        }
-        sums[k] = acc;
-      }
-      int mine = 0;
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const int t = __reduce_add_sync(0xffffffffu, sums[k]);
-        if (lane == k) mine = t;
-      }
-      if (lane < R) p.rowsum[rbase + w0 + lane] = mine;
-    }
-    if (p.halo && w0 == 0) {
-      ring_row(rbase - 1);
-      ring_row(rbase + W);
-      if (h == 0)
-        for (int w = 0; w < Wp; ++w) ring_row(rbase - 1 - Wp + w);
-      if (h == p.H - 1)
-        for (int w = 0; w < Wp; ++w) ring_row(rbase - 1 + Wp + w);
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------
 // GroupNorm statistics
@@ -1302,6 +1113,15 @@ __global__ void weight_to_i8_kernel(const float* __restrict__ w_eff, int O, int 
   __syncthreads();
   const int shift = s_shift;
   if (shift == (1 << 20)) ok = false;
+  // The conv epilogue forms acc + zp*wsum + w_zp*cs in int32 (conv_common.cuh): |acc|, |zp*wsum| <= K*2^14 and
+  // |cs| <= K*2^8 for a_bit <= 8, so the channel's zero point must satisfy K*2^15 + |w_zp|*K*2^8 < 2^31.  A
+  // same-sign or narrow-range channel (w_zp = 2^(w-1) + round(s*lo), arbitrarily large) is declared off-grid
+  // and the layer takes the fp32 kernel instead of overflowing silently.
+  if (ok) {
+    const long long wz_final = (long long)z + shift;
+    const long long mag = wz_final < 0 ? -wz_final : wz_final;
+    if ((long long)K * 32768 + mag * (long long)K * 256 >= 2147483648LL) ok = false;
+  }
   int acc = 0;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     int tap = i / Cp, c = i - tap * Cp;
@@ -1348,81 +1168,6 @@ int attndm_act_quant(const float* x, int B, int H, int W, int C, const float* sc
   }
   return act_quant_impl(x, B, H, W, C, scale, zp, a_bit, pre_op, gn_stats, gn_gamma, gn_beta, gn_eps, codes,
                         rowsum, rows_layout, y_f32, true, (cudaStream_t)stream);
-}
-
-// cluster size for a sample of H x W x C fp32: the smallest power of two whose per-CTA share fits 128 KB
-static int gn_cluster_size(int H, int W, int C) {
-  static long long cta_bytes = -1;
-  if (cta_bytes < 0) {
-    const char* e = getenv("ATTNDM_GN_CLUSTER_CTA_KB");   // per-CTA share of a sample (KB); smaller = more CTAs per SM
-    cta_bytes = (e ? atoi(e) : 128) * 1024LL;
-    if (cta_bytes > 128 * 1024 || cta_bytes < 16 * 1024) cta_bytes = 128 * 1024;
-  }
-  const long long bytes = (long long)H * W * C * 4;
-  for (int cs = 1; cs <= kGnClusterMax; cs <<= 1)
-    if (H % cs == 0 && bytes / cs <= cta_bytes) return cs;
-  return 0;
-}
-// Off by default: measured on B200 (tools/gn_bench.py, batch 256, 32x32x128) the one-pass kernel takes as long
-// as the two passes it replaces (the CTAs of a cluster load, reduce, synchronise and quantize one after the
-// other, so HBM idles in between), and the sampling step got 5 % slower with it.  Kept as an opt-in:
-// ATTNDM_GN_CLUSTER_MIN_KB=512 in the environment, or attndm_set_gn_cluster_min_kb().
-static int g_gn_cluster_min_kb = -1;
-int attndm_set_gn_cluster_min_kb(int kb) {
-  const int old = g_gn_cluster_min_kb < 0 ? 0 : g_gn_cluster_min_kb;
-  g_gn_cluster_min_kb = kb < 0 ? 0 : kb;
-  return old;
-}
-int attndm_gn_quant_cluster_fits(int H, int W, int C) {
-  if (g_gn_cluster_min_kb < 0) {
-    const char* e = getenv("ATTNDM_GN_CLUSTER_MIN_KB");   // per-sample size (KB) from which the one-pass kernel is used; 0 = never
-    g_gn_cluster_min_kb = e ? atoi(e) : 0;
-  }
-  if (g_gn_cluster_min_kb == 0) return 0;
-  if (!(C == 128 || C == 256) || (W & 3) != 0) return 0;
-  if ((long long)H * W * C * 4 < (long long)g_gn_cluster_min_kb * 1024) return 0;
-  return gn_cluster_size(H, W, C) > 0 ? 1 : 0;
-}
-int attndm_gn_quant_cluster(const float* x, int B, int H, int W, int C, const float* gamma, const float* beta, float eps,
-                            const float* scale, const float* zp, int a_bit, int8_t* codes, int32_t* rowsum,
-                            int rows_layout, void* stream) {
-  ATTNDM_CHECK_ARG(x && gamma && beta && scale && zp && codes && rowsum && B > 0, "gn_quant_cluster: bad args");
-  ATTNDM_CHECK_ARG(a_bit >= 2 && a_bit <= 8, "gn_quant_cluster: 2 <= a_bit <= 8");
-  if (!attndm_gn_quant_cluster_fits(H, W, C)) {
-    set_error("gn_quant_cluster: shape %dx%dx%d is not supported", H, W, C);
-    return ATTNDM_ERR_UNSUPPORTED;
-  }
-  GnClusterParams p;
-  p.x = x; p.B = B; p.H = H; p.W = W; p.C = C; p.Cp = round_up(C, 16);
-  p.scale = scale; p.zp = zp;
-  p.qlo = -(float)(1 << (a_bit - 1));
-  p.qhi = (float)((1 << (a_bit - 1)) - 1);
-  p.gamma = gamma; p.beta = beta; p.eps = eps; p.codes = codes; p.rowsum = rowsum;
-  p.halo = rows_layout == ATTNDM_ROWS_HALO ? 1 : 0;
-  p.cs = gn_cluster_size(H, W, C);
-  p.rows_per_cta = H / p.cs;
-  const size_t smem = (size_t)p.rows_per_cta * W * C * sizeof(float);
-  void (*kern)(GnClusterParams) = nullptr;
-  if (C == 128) kern = a_bit == 8 ? gn_quant_cluster_kernel<1, true> : gn_quant_cluster_kernel<1, false>;
-  else kern = a_bit == 8 ? gn_quant_cluster_kernel<2, true> : gn_quant_cluster_kernel<2, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-  if (e != cudaSuccess) { set_error("gn_quant_cluster: smem attr: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(B * p.cs);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attrs[2] = {};
-  attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = p.cs; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attrs[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attrs;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  e = cudaLaunchKernelEx(&cfg, kern, p);
-  if (e != cudaSuccess) { set_error("gn_quant_cluster: launch failed: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
-  ATTNDM_CUDA_LAUNCH_CHECK("gn_quant_cluster");
-  return ATTNDM_OK;
 }
 
 int attndm_gn_act_quant_fits(int H, int W, int C) {

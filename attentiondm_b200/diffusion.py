@@ -29,11 +29,10 @@ def _need_quant(quantization, sequence):
 
 
 def _gn_args(norm: nn.GroupNorm, x):
-    """GroupNorm arguments for the consumer conv.  Small feature maps use the fused per-sample kernel and the
-    largest ones the one-pass cluster kernel (statistics computed in-kernel, stats=None -- ops.act_quant computes
-    them after all if the consumer turns out not to take the int8 path); the rest get a statistics pass."""
+    """GroupNorm arguments for the consumer conv.  Small feature maps use the fused per-sample kernel
+    (statistics computed in-kernel, stats=None); the rest get a statistics pass."""
     _, H, W, C = x.shape
-    stats = None if (ops.gn_fits_fused(H, W, C) or ops.gn_fits_cluster(H, W, C)) else ops.gn_stats(x)
+    stats = None if ops.gn_fits_fused(H, W, C) else ops.gn_stats(x)
     return ops.GnArgs(stats=stats, gamma=norm.weight.detach(), beta=norm.bias.detach(), eps=norm.eps)
 
 

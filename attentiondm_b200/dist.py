@@ -7,7 +7,9 @@ talk while sampling.  Calibration's per-channel activation min/max
 batch each QConv2d all-reduces [min_c || -max_c] with MIN before the init-range
 floor and the grouping.  MIN/MAX are order independent, so the result is
 bit-identical to single-process calibration on the concatenated batch
-(SURVEY.md section 8e).  Backend: NCCL over NVLink on the GPUs, gloo in the CPU tests.
+(SURVEY.md section 8e).  The first-calibrate search (utils/quant_util.py:237-254) scores nine candidate init
+ranges with a mean over the batch: the nine sums and the element count are all-reduced with SUM, so every rank
+chooses the same range (equal to the single-process choice up to fp64 summation order).  Backend: NCCL over NVLink on the GPUs, gloo in the CPU tests.
 """
 import os
 
@@ -47,13 +49,25 @@ def allreduce_minmax(min_c: torch.Tensor, max_c: torch.Tensor, group=None):
     return buf[:c].contiguous(), (-buf[c:]).contiguous()
 
 
+def allreduce_sum(v: torch.Tensor, group=None):
+    """SUM over ranks of a small vector (the nine first-calibrate lp sums and the element count)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return v
+    v = v.clone()
+    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+    return v
+
+
 def install(group=None):
-    """Make every QConv2d calibration call all-reduce its range statistics."""
+    """Make every QConv2d calibration call all-reduce its range statistics (MIN/MAX) and, in first-calibrate
+    mode, the scores of the nine candidate init ranges (SUM) -- every rank then holds identical tables."""
     quant_util.calib_allreduce = lambda mn, mx: allreduce_minmax(mn, mx, group)
+    quant_util.calib_allreduce_sum = lambda v: allreduce_sum(v, group)
 
 
 def uninstall():
     quant_util.calib_allreduce = None
+    quant_util.calib_allreduce_sum = None
 
 
 def gather_images(x_local: torch.Tensor, group=None):

@@ -9,8 +9,6 @@ counter -- so a single graph serves all steps with no host work in the loop.
 """
 from __future__ import annotations
 
-import os
-
 import torch
 
 from . import ops
@@ -84,21 +82,12 @@ class SamplerEngine:
         self.launches_per_step = 0
         # fused per-sample programs (time_mlp of every block; all blocks on 1x1 maps): graph mode only
         self.fused = None
-        # Experiment (ATTNDM_SPLIT=2): two half-batches on two streams of the same graph, so that one half's
-        # latency-bound layers (the fused trunk above all) overlap the other half's HBM-bound layers.  Samples are
-        # independent through every op, so the result is bit-identical -- but on B200 at batch 256 it measured
-        # SLOWER (679 vs 804 images/s): the half-size kernels lose more than the overlap wins.  Off by default.
-        self.nsplit = 1
-        if (use_graph and hasattr(model, "down_blocks") and self.B % 2 == 0 and self.B >= 64
-                and os.environ.get("ATTNDM_SPLIT", "1") == "2"):
-            self.nsplit = 2
-        self.side_stream = torch.cuda.Stream(device=dev) if self.nsplit == 2 else None
-        self.fused_parts = [None] * self.nsplit
+        self.fused_parts = [None]
         if use_graph and hasattr(model, "down_blocks"):
             if hasattr(model, "materialize_lazy_layers"):
                 model.materialize_lazy_layers()
             sl = {id(m): s_ for m, s_ in zip(self.layers, self.slices)}
-            self.fused_parts = [rowprog.build(model, self.B // self.nsplit, sl, dev) for _ in range(self.nsplit)]
+            self.fused_parts = [rowprog.build(model, self.B, sl, dev)]
             self.fused = self.fused_parts[0]
 
     def _versions(self):
@@ -118,32 +107,21 @@ class SamplerEngine:
         for b in self._blocks:
             b._temb_fused = fp.temb.get(id(b)) if fp is not None else None
 
-    def _forward_part(self, part):
-        """UNet forward + DDIM update of one slice of the batch, on the current stream."""
-        n = self.B // self.nsplit
-        lo, hi = part * n, (part + 1) * n
+    def _forward_part(self, part=0):
+        """UNet forward + DDIM update of the batch, on the current stream."""
         self._set_fused(self.fused_parts[part])
-        x = self.x_cur[lo:hi]
-        eps = self.model.forward_nhwc(x, self.cur[self.t_off + lo:self.t_off + hi])
-        noise = self.noise[lo:hi] if self.noise is not None else None
-        ops.ddim_step(x, eps, self.cur[self.coef_off:], noise, x_next=x, x0_out=self.x0[lo:hi])
+        x = self.x_cur
+        eps = self.model.forward_nhwc(x, self.cur[self.t_off:self.t_off + self.B])
+        ops.ddim_step(x, eps, self.cur[self.coef_off:], self.noise, x_next=x, x0_out=self.x0)
         return eps
 
     # ---- one denoising step on the current stream ----
     def _step_body(self):
+        # The noise buffer is refreshed OUTSIDE the captured body (run_loaded / run): a graph that baked in
+        # `normal_()` would overwrite a caller-supplied noise_fn's values, and one captured without it would
+        # replay stale noise -- the graph must not depend on who fills the buffer.
         ops.stage_tables(self.table, self.step, self.cur, advance=True)
-        if self.noise is not None and not self.ext_noise:
-            self.noise.normal_()
-        if self.nsplit == 1:
-            return self._forward_part(0)
-        main = torch.cuda.current_stream()
-        side = self.side_stream
-        side.wait_stream(main)                         # fork after the tables are staged
-        eps0 = self._forward_part(0)
-        with torch.cuda.stream(side):
-            eps1 = self._forward_part(1)
-        main.wait_stream(side)                         # join
-        return torch.cat([eps0, eps1], dim=0) if not torch.cuda.is_current_stream_capturing() else eps0
+        return self._forward_part(0)
 
     def _with_staged(self, fn):
         for m, (o, w) in zip(self.layers, self.slices):
@@ -197,13 +175,18 @@ class SamplerEngine:
         n = self.T if steps is None else steps
         if n <= 0:
             return
+        fresh_noise = self.noise is not None and not self.ext_noise      # eta > 0, engine-generated noise
         if self.use_graph:
             if self.graph is None:
                 self._capture()
             for _ in range(n):
+                if fresh_noise:
+                    self.noise.normal_()
                 self.graph.replay()
         else:
             for _ in range(n):
+                if fresh_noise:
+                    self.noise.normal_()
                 self._with_staged(self._step_body)
         # mirror the reference's per-module counter: wrap at the START of a call, +1 at its end
         self.done = getattr(self, "done", 0) + n

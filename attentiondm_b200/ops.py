@@ -66,11 +66,6 @@ def gn_fits_fused(H: int, W: int, Cc: int) -> bool:
     return bool(F_.lib().attndm_gn_act_quant_fits(H, W, Cc))
 
 
-def gn_fits_cluster(H: int, W: int, Cc: int) -> bool:
-    """Large maps: the one-pass cluster kernel (statistics + quantize from distributed shared memory)."""
-    return bool(F_.lib().attndm_gn_quant_cluster_fits(H, W, Cc))
-
-
 # One zero-filled [n, B, 32, 2] double buffer per UNet forward, handed out slice by slice, instead of
 # one memset per GroupNorm (97 of them on the CIFAR model).
 _gn_pool = None
@@ -134,11 +129,7 @@ def act_quant(x: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, a_bit: int
     if want_f32:
         y = torch.empty_like(x)
     if pre == PRE_GN_SILU and gn.stats is None and not gn_fits_fused(H, W, Cc):
-        # statistics were deferred (large map): one-pass cluster kernel for the int8 path, else compute them now
-        if want_codes and not want_f32 and gn_fits_cluster(H, W, Cc):
-            call("attndm_gn_quant_cluster", ptr(x), B, H, W, Cc, ptr(gn.gamma), ptr(gn.beta), float(gn.eps), ptr(scale),
-                 ptr(zp), int(a_bit), ptr(codes), ptr(rowsum), ROWS_HALO if halo else ROWS_PLAIN, stream())
-            return codes, rowsum, y
+        # statistics were deferred but this consumer cannot use the fused per-sample kernel: compute them now
         gn = GnArgs(stats=gn_stats(x), gamma=gn.gamma, beta=gn.beta, eps=gn.eps)
     if pre == PRE_GN_SILU and gn.stats is None:
         call("attndm_gn_act_quant", ptr(x), B, H, W, Cc, ptr(gn.gamma), ptr(gn.beta), float(gn.eps), ptr(scale),
@@ -182,7 +173,8 @@ def calib_mix(x: torch.Tensor, gr_t: torch.Tensor, sw: torch.Tensor, a_bit: int,
     G = gr_t.shape[0]
     y = torch.empty_like(x)
     lp = torch.zeros(1, dtype=torch.float64, device=x.device) if lp_p is not None else None
-    call("attndm_calib_mix", ptr(x), rows, Cc, G, ptr(gr_t.contiguous()), ptr(sw.contiguous()), int(a_bit), ptr(y),
+    gr_c, sw_c = gr_t.contiguous(), sw.contiguous()      # named: a temporary could be freed (and its block reused) before the call
+    call("attndm_calib_mix", ptr(x), rows, Cc, G, ptr(gr_c), ptr(sw_c), int(a_bit), ptr(y),
          ptr(lp), float(lp_p or 0.0), stream())
     return (y, lp) if lp_p is not None else y
 
@@ -201,8 +193,8 @@ def weight_clamp_pack(w: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor) -> to
     O, Cc, KH, KW = w.shape
     w = w.detach().float().contiguous()
     w_eff = torch.empty(O, KH * KW, Cc, dtype=torch.float32, device=w.device)
-    call("attndm_weight_clamp_pack", ptr(w), O, Cc, KH, KW, ptr(lo.float().contiguous()),
-         ptr(hi.float().contiguous()), ptr(w_eff), stream())
+    lo_f, hi_f = lo.float().contiguous(), hi.float().contiguous()     # keep both conversions alive across the call
+    call("attndm_weight_clamp_pack", ptr(w), O, Cc, KH, KW, ptr(lo_f), ptr(hi_f), ptr(w_eff), stream())
     return w_eff
 
 
@@ -236,7 +228,8 @@ def _weight_to_i8_on(w_eff, w_bit, grid) -> I8Pack:
     wsum = torch.empty(O, dtype=torch.int32, device=w_eff.device)
     flag = torch.empty(1, dtype=torch.int32, device=w_eff.device)
     wzp_i = torch.empty(O, dtype=torch.int32, device=w_eff.device)
-    call("attndm_weight_to_i8", ptr(w_eff), O, Cc, taps, ptr(w_scale.contiguous()), ptr(w_zp.contiguous()),
+    ws_c, wz_c = w_scale.float().contiguous(), w_zp.float().contiguous()
+    call("attndm_weight_to_i8", ptr(w_eff), O, Cc, taps, ptr(ws_c), ptr(wz_c),
          int(w_bit), ptr(qw), Cp, ptr(wsum), ptr(wzp_i), ptr(flag), stream())
     on_grid = bool(flag.item() == 1) and bool(torch.isfinite(w_scale).all().item())
     return I8Pack(qw=qw, wsum=wsum, w_zp=wzp_i, w_scale=w_scale, on_grid=on_grid)

@@ -25,6 +25,8 @@ from .quantization_utils import (AsymmetricQuantFunction, asymmetric_linear_quan
 # Optional hook: (min_c, max_c) -> (min_c, max_c) all-reduced over ranks
 # (attentiondm_b200.dist.install()).  SURVEY.md section 8(e).
 calib_allreduce = None
+# Optional hook: double tensor -> the same tensor summed over ranks (first-calibrate scores, :237-254).
+calib_allreduce_sum = None
 
 
 def lp_loss(pred, tgt, p=2.0, reduction='none'):
@@ -238,12 +240,11 @@ class QModule(nn.Module):
 
     def _tables(self):
         gr, al = self.groups_range, self.alpha_activ
+        w_eff, i8 = self._packed()           # first: an in-place weight update must invalidate the tables too
         key = (gr.data_ptr(), gr._version, al.data_ptr(), al._version, self._a_bit, self._state_version,
                self._pack_key)
         if self._tab is not None and self._tab_key == key:
             return self._tab
-        w_eff, i8 = self._packed()
-        key = key[:-1] + (self._pack_key,)
         T, G, Cc, O = self.len_seq, self.group_num, self.in_channels, self.out_channels
         with torch.no_grad():
             sw = F.softmax(al.detach().float(), dim=1)                   # [T,G,C]
@@ -287,13 +288,19 @@ class QModule(nn.Module):
         return (not self.force_f32) and all(self._tables()["i8_ok"])
 
     # ---- calibration branch (:186-224, :235-258) ----
-    def calibrate_quantization(self, x, init_min, init_max, want_lp=False):
-        """x: NHWC fp32 (already through any producer op). Returns the G-branch mix."""
-        t = self.index_seq
-        dev = x.device
+    def _calib_minmax(self, x):
+        """Per-channel (min, max) over (B, H, W) of the GLOBAL batch (:187-191): all-reduced over ranks when
+        attentiondm_b200.dist.install() is active."""
         min_c, max_c = ops.minmax_c(x)
         if calib_allreduce is not None:
             min_c, max_c = calib_allreduce(min_c, max_c)
+        return min_c, max_c
+
+    def calibrate_quantization(self, x, init_min, init_max, want_lp=False, minmax=None):
+        """x: NHWC fp32 (already through any producer op). Returns the G-branch mix."""
+        t = self.index_seq
+        dev = x.device
+        min_c, max_c = self._calib_minmax(x) if minmax is None else minmax
         gr_t = self.groups_range.data[t]
         xq_min, xq_max = ops.group_ranges(min_c, max_c, self.group_num, float(init_min), float(init_max), gr_t)
         self._state_version += 1
@@ -314,22 +321,33 @@ class QModule(nn.Module):
 
     def _calibrate_step(self, x):
         t = self.index_seq
+        minmax = self._calib_minmax(x)        # the statistics do not depend on the candidate range: reduce once
         if self._first_calibrate:
+            cand, lps = [], []
+            for aa in range(9):
+                new_max = self.init_range_max[t] * (1.0 - (aa * 0.1))
+                new_min = self.init_range_min[t] * (1.0 - (aa * 0.1))
+                _, lp = self.calibrate_quantization(x, new_min, new_max, want_lp=True, minmax=minmax)
+                cand.append((new_min, new_max))
+                lps.append(lp)
+            # lp_loss(p=0.5, reduction='all') is a mean over the GLOBAL batch: SUM the nine lp sums and the
+            # element count over ranks, so every replica scores -- and therefore chooses -- identically
+            # (SURVEY.md section 8e).  One host read for all nine candidates.
+            tot = torch.cat(lps + [torch.full((1,), float(x.numel()), dtype=torch.float64, device=x.device)])
+            if calib_allreduce_sum is not None:
+                tot = calib_allreduce_sum(tot)
+            tot = tot.cpu()
             best_score = 1e+10
             best_max = self.init_range_max[t]
             best_min = self.init_range_min[t]
             for aa in range(9):
-                new_max = self.init_range_max[t] * (1.0 - (aa * 0.1))
-                new_min = self.init_range_min[t] * (1.0 - (aa * 0.1))
-                _, lp = self.calibrate_quantization(x, new_min, new_max, want_lp=True)
-                score = float(lp.item() / x.numel())            # lp_loss(p=0.5, reduction='all')
-                score = float(np.float32(score))
+                score = float(np.float32(float(tot[aa]) / float(tot[9])))
                 if score < best_score:
-                    best_max, best_min, best_score = new_max, new_min, score
+                    (best_min, best_max), best_score = cand[aa], score
             if best_score < 0.2:
                 self.init_range_max[t] = best_max
                 self.init_range_min[t] = best_min
-        return self.calibrate_quantization(x, self.init_range_min[t], self.init_range_max[t])
+        return self.calibrate_quantization(x, self.init_range_min[t], self.init_range_max[t], minmax=minmax)
 
     def forward(self, *inputs):
         raise NotImplementedError

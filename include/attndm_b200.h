@@ -80,19 +80,6 @@ int attndm_act_quant(const float* x, int B, int H, int W, int C,
  * models/diffusion.py:36-37 (Normalize), 91,94 (GroupNorm eps 1e-6). */
 int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, void* stream);
 
-/* One-pass GroupNorm + SiLU + quantize for LARGE feature maps (a thread-block cluster per sample keeps the
- * sample in distributed shared memory, so the fp32 tensor is read from HBM once instead of twice).  Same
- * results as attndm_gn_stats followed by attndm_act_quant(pre_op = ATTNDM_PRE_GN_SILU) -- the reference's
- * nn.GroupNorm + SiLU + QConv2d input quantizer (models/diffusion.py:121-122, utils/quant_util.py:260-282).
- * Codes + row sums only; attndm_gn_quant_cluster_fits tells whether the shape is taken.  Opt-in (it measured no
- * faster than the two passes on B200): attndm_set_gn_cluster_min_kb(kb) enables it for samples of at least kb
- * KB of fp32 (0 = never, the default) and returns the previous setting. */
-int attndm_set_gn_cluster_min_kb(int kb);
-int attndm_gn_quant_cluster_fits(int H, int W, int C);
-int attndm_gn_quant_cluster(const float* x, int B, int H, int W, int C, const float* gamma, const float* beta,
-                            float eps, const float* scale, const float* zp, int a_bit, int8_t* codes,
-                            int32_t* rowsum, int rows_layout, void* stream);
-
 /* GroupNorm(32)+SiLU+quantize in ONE kernel (statistics computed in-kernel, one CTA per sample with
  * the sample's [H*W][C] tile resident in shared memory): same outputs as attndm_gn_stats followed by
  * attndm_act_quant(pre_op = ATTNDM_PRE_GN_SILU).  Only for tiles that fit (attndm_gn_act_quant_fits);
