@@ -322,27 +322,33 @@ def test_qconv_falls_back_to_f32_when_not_integer_exact():
     still match the reference arithmetic."""
     g = torch.Generator().manual_seed(4)
     for case in ("alpha", "weights", "one_sided_channel"):
-        q = make_qconv(32, 16, 1, 8, 4, 8)
+        Cin, k = (1024, 3) if case == "one_sided_channel" else (32, 1)
+        q = make_qconv(Cin, 16, k, 8, 4, 8)
         q.groups_range.data[..., 0] = -4.0 - torch.rand(4, 8, generator=g).to(DEV)
         q.groups_range.data[..., 1] = 6.0 + torch.rand(4, 8, generator=g).to(DEV)
         if case == "alpha":
             q.alpha_activ.data.copy_(torch.randn(4, 8, 32, generator=g))
             q.snap_weights_()
         elif case == "one_sided_channel":
-            # a same-sign, narrow-range out-channel: on the 8-bit grid, but its zero point
-            # 128 + round(255 * lo / (hi - lo)) ~ 2.5e6 would overflow the int32 epilogue bracket (ADVICE r1):
-            # weight_to_i8 must declare it off-grid so that the layer takes the fp32 kernel
-            q.weight.data[3] = 1.0 + 1e-4 * torch.rand(32, 1, 1, generator=g).to(DEV)
+            # a same-sign out-channel: exactly on the 8-bit grid, but with K = 9*1024 its zero point
+            # 128 + round(255 * lo / (hi - lo)) = 978 would overflow the int32 epilogue bracket
+            # acc + zp*wsum + w_zp*cs (ADVICE r1): weight_to_i8 must declare it off-grid -> fp32 kernel
+            q.weight.data[3] = 1.0 + 0.3 * torch.rand(Cin, 3, 3, generator=g).to(DEV)
             q.snap_weights_()
             assert not q._packed()[1].on_grid
+            q.weight.data[3] = -0.02 + 0.04 * torch.rand(Cin, 3, 3, generator=g).to(DEV)     # control: straddles 0
+            q.snap_weights_()
+            assert q._packed()[1].on_grid
+            q.weight.data[3] = 1.0 + 0.3 * torch.rand(Cin, 3, 3, generator=g).to(DEV)
+            q.snap_weights_()
         else:
             q.init_weight_range()
         q.invalidate_cache()
         assert not q.int8_ok_all_steps()
-        x = torch.randn(3, 32, 5, 5, generator=g) * 3
+        x = torch.randn(3, Cin, 5, 5, generator=g) * 3
         y = q(x.to(DEV))
         xq = R.act_fake_quant(x, q.groups_range.data[0].cpu(), q.alpha_activ.data[0].cpu(), 8)
-        want = F.conv2d(xq.double(), q.weight.data.cpu().double(), q.bias.data.cpu().double())
+        want = F.conv2d(xq.double(), q.weight.data.cpu().double(), q.bias.data.cpu().double(), padding=k // 2)
         assert rel_l2(y, want) < 1e-3, case      # device softmax -> ulp-different tables -> a few code flips
 
 
