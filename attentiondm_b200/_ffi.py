@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libattndm_b200.so")
+# ATTNDM_LIB selects an A/B build variant of the same library (attentiondm_b200.build.VARIANTS); never a fallback
+LIB_PATH = os.environ.get("ATTNDM_LIB") or os.path.join(_HERE, "libattndm_b200.so")
 
 ROWS_PLAIN, ROWS_HALO = 0, 1
 PRE_NONE, PRE_SILU, PRE_GN_SILU = 0, 1, 2

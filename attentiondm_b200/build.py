@@ -31,13 +31,30 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+# A/B variants of the library (same sources, extra defines), built next to the default one as
+# libattndm_b200_<name>.so and selected at run time with ATTNDM_LIB=<path> (see _ffi.py):
+VARIANTS = {"silu_sfu": ["-DATTNDM_SILU_SFU"]}
+
+
+def build(force=False, verbose=False, variant=None):
+    global NVCC_FLAGS
+    if variant is not None:
+        saved = NVCC_FLAGS
+        NVCC_FLAGS = NVCC_FLAGS + VARIANTS[variant]
+        try:
+            return _build(force, verbose, LIB.replace(".so", f"_{variant}.so"), "build_" + variant)
+        finally:
+            NVCC_FLAGS = saved
+    return _build(force, verbose, LIB, "build")
+
+
+def _build(force, verbose, LIB, objdir_name):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     stamp = LIB + ".stamp"
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -64,4 +81,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var[0] if var else None))

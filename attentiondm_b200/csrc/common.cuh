@@ -46,14 +46,44 @@ __device__ __forceinline__ float dequant(float code, float s, float zp) {
   return __fdiv_rn(__fadd_rn(code, zp), s);
 }
 
+// SiLU, x / (1 + exp(-x)) (models/diffusion.py:122, torch.nn.functional.silu).  Two builds of the ONE definition
+// every kernel shares (so fused and unfused paths agree bit for bit):
+//  * default: the exponential by range reduction + a degree-6 polynomial on the FMA pipe (<= 1 ulp, no
+//    special-function unit) and a correctly rounded quotient (rcp.approx seed + one Newton step + a residual
+//    correction).  ~22 FMA-pipe instructions and one MUFU per element -- about the issue cost of the two MUFU
+//    ops of the approximate form, since a MUFU op occupies the issue slot of ~8 FMAs.  torch's CPU kernel
+//    (Sleef expf, 1 ulp, + IEEE divide) and this agree to the last bit for most inputs, which keeps the number
+//    of activation codes that differ from the reference's to a minimum (profiles/parity_r02.json).
+//  * -DATTNDM_SILU_SFU: ex2.approx + rcp.approx (<= ~3 ulp), the round-1 form, kept for the A/B measurement.
+#ifdef ATTNDM_SILU_SFU
 __device__ __forceinline__ float silu_f(float v) {
-  // x * sigmoid(x) == x / (1 + exp(-x)) on the special-function unit: ex2.approx for the exponential and
-  // rcp.approx for the quotient (<= ~3 ulp in total, i.e. well inside what separates two fp32 SiLU
-  // implementations -- torch's CPU and CUDA kernels differ by as much).  The IEEE divide + accurate expf
-  // version cost ~40 instructions per element and made every GroupNorm+SiLU+quantize pass
-  // instruction-bound at a third of the HBM rate.  Every kernel shares this one definition.
   return __fdividef(v, __fadd_rn(1.0f, __expf(-v)));
 }
+#else
+__device__ __forceinline__ float silu_f(float v) {
+  // e = exp(a), a = -v clamped to [-87, 80]: beyond that the quotient is v (e -> 0) or |v| * 2e-35 (far below
+  // any quantization step), and every intermediate stays a normal number
+  const float a = fminf(fmaxf(-v, -87.0f), 80.0f);
+  const float n = rintf(a * 1.44269504088896341f);
+  float r = fmaf(n, -0.693359375f, a);                 // ln2 split hi/lo (Cody-Waite)
+  r = fmaf(n, 2.12194440e-4f, r);
+  float p = 1.9875691500e-4f;
+  p = fmaf(p, r, 1.3981999507e-3f);
+  p = fmaf(p, r, 8.3334519073e-3f);
+  p = fmaf(p, r, 4.1665795894e-2f);
+  p = fmaf(p, r, 1.6666665459e-1f);
+  p = fmaf(p, r, 5.0000001201e-1f);
+  p = fmaf(p, r * r, r);
+  p = __fadd_rn(p, 1.0f);
+  const float e = p * __int_as_float(((int)n + 127) << 23);      // n in [-126, 116]: a normal power of two
+  const float d = __fadd_rn(1.0f, e);
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d));
+  r0 = fmaf(fmaf(-d, r0, 1.0f), r0, r0);                         // Newton: |r0 - 1/d| < 1 ulp
+  const float q = v * r0;
+  return fmaf(fmaf(-q, d, v), r0, q);                            // residual correction -> correctly rounded v / d
+}
+#endif
 
 
 // GroupNorm(32) finalisation and application, shared by every kernel that normalises (so that the fused
