@@ -46,21 +46,29 @@ __device__ __forceinline__ float dequant(float code, float s, float zp) {
   return __fdiv_rn(__fadd_rn(code, zp), s);
 }
 
-// SiLU, x / (1 + exp(-x)) (models/diffusion.py:122, torch.nn.functional.silu).  Two builds of the ONE definition
-// every kernel shares (so fused and unfused paths agree bit for bit):
-//  * default: the exponential by range reduction + a degree-6 polynomial on the FMA pipe (<= 1 ulp, no
+// SiLU, x / (1 + exp(-x)) (models/diffusion.py:122, torch.nn.functional.silu).  ONE set of definitions shared by
+// every kernel, so fused and unfused paths agree bit for bit.
+//  * silu_acc: the exponential by range reduction + a degree-6 polynomial on the FMA pipe (<= 1 ulp, no
 //    special-function unit) and a correctly rounded quotient (rcp.approx seed + one Newton step + a residual
-//    correction).  ~22 FMA-pipe instructions and one MUFU per element -- about the issue cost of the two MUFU
-//    ops of the approximate form, since a MUFU op occupies the issue slot of ~8 FMAs.  torch's CPU kernel
-//    (Sleef expf, 1 ulp, + IEEE divide) and this agree to the last bit for most inputs, which keeps the number
-//    of activation codes that differ from the reference's to a minimum (profiles/parity_r02.json).
-//  * -DATTNDM_SILU_SFU: ex2.approx + rcp.approx (<= ~3 ulp), the round-1 form, kept for the A/B measurement.
-#ifdef ATTNDM_SILU_SFU
-__device__ __forceinline__ float silu_f(float v) {
+//    correction).  It agrees with torch's CPU kernel (Sleef expf, 1 ulp, + IEEE divide) to the last bit for
+//    99.6 % of inputs (mean |diff| 1e-10 on N(0, 1.3) inputs; the SFU form below: 46 %, 2.4e-8).  ~22 FMA-pipe
+//    instructions + one MUFU: used wherever the SiLU output is consumed as fp32 (calibration branch, time_embed).
+//  * silu_sfu: ex2.approx + rcp.approx, relative error <= ~5e-7, five instructions.
+//  * silu_quant_t: what the int8 hot path uses.  The consumer of SiLU there is always the activation quantizer,
+//    code = clamp(rne(s * y - zp)): only the SIDE of the rounding boundary matters.  Evaluate the SFU form first;
+//    if t = s * y - zp lands within kSiluGuard of a half-integer -- 0.05 % of the elements -- re-evaluate with
+//    silu_acc.  The codes are then exactly those of silu_acc everywhere (the guard is > 2x the worst-case SFU
+//    error of t for |s * y| < 400, beyond which the accurate form is always taken), at close to the SFU cost.
+//    Measured (profiles/parity_r02.json): activation codes that differ from the CPU reference's on identical layer
+//    inputs -- 3.7e-7 of the elements, against 9.0e-7 with the SFU form alone and 6.0e-7 for torch's own CUDA
+//    kernels against its CPU kernels.
+//  * -DATTNDM_SILU_SFU / -DATTNDM_SILU_ACCURATE: A/B builds that use one form everywhere.
+constexpr float kSiluGuard = 2.5e-4f;
+
+__device__ __forceinline__ float silu_sfu(float v) {
   return __fdividef(v, __fadd_rn(1.0f, __expf(-v)));
 }
-#else
-__device__ __forceinline__ float silu_f(float v) {
+__device__ __forceinline__ float silu_acc(float v) {
   // e = exp(a), a = -v clamped to [-87, 80]: beyond that the quotient is v (e -> 0) or |v| * 2e-35 (far below
   // any quantization step), and every intermediate stays a normal number
   const float a = fminf(fmaxf(-v, -87.0f), 80.0f);
@@ -83,7 +91,29 @@ __device__ __forceinline__ float silu_f(float v) {
   const float q = v * r0;
   return fmaf(fmaf(-q, d, v), r0, q);                            // residual correction -> correctly rounded v / d
 }
+#ifdef ATTNDM_SILU_SFU
+__device__ __forceinline__ float silu_f(float v) { return silu_sfu(v); }
+#else
+__device__ __forceinline__ float silu_f(float v) { return silu_acc(v); }
 #endif
+
+// t = s * silu(u) - zp, the argument of the quantizer's round (utils/quant_util.py:273), see above
+__device__ __forceinline__ float silu_quant_t(float u, float s, float zp) {
+#if defined(ATTNDM_SILU_SFU) || defined(ATTNDM_SILU_ACCURATE)
+  return __fsub_rn(__fmul_rn(s, silu_f(u)), zp);
+#else
+  const float sy = __fmul_rn(s, silu_sfu(u));
+  float t = __fsub_rn(sy, zp);
+  const float w = __fadd_rn(t, 12582912.0f);                      // 1.5 * 2^23: w - 1.5 * 2^23 == rne(t) for |t| < 2^22
+  const float d = fabsf(fabsf(__fsub_rn(t, __fsub_rn(w, 12582912.0f))) - 0.5f);
+  if (d < kSiluGuard || !(fabsf(sy) < 400.0f)) t = __fsub_rn(__fmul_rn(s, silu_acc(u)), zp);
+  return t;
+#endif
+}
+// the quantizer's round + clamp on t (same codes as quant_code)
+__device__ __forceinline__ float quant_code_t(float t, float lo, float hi) {
+  return fminf(fmaxf(rintf(t), lo), hi);
+}
 
 
 // GroupNorm(32) finalisation and application, shared by every kernel that normalises (so that the fused
@@ -99,9 +129,12 @@ __device__ __forceinline__ void gn_mean_rstd(double s, double ss, double inv_n, 
   rstd = __frsqrt_rn((float)__dadd_rn(var, (double)eps));
 }
 // silu(groupnorm(v)) with a = rstd*gamma, b = beta - mean*a  (models/diffusion.py:121-122)
-__device__ __forceinline__ float gn_silu_apply(float v, float mean, float rstd, float gamma, float beta) {
+__device__ __forceinline__ float gn_apply(float v, float mean, float rstd, float gamma, float beta) {
   const float a = __fmul_rn(rstd, gamma);
-  return silu_f(fmaf(v, a, fmaf(-mean, a, beta)));
+  return fmaf(v, a, fmaf(-mean, a, beta));
+}
+__device__ __forceinline__ float gn_silu_apply(float v, float mean, float rstd, float gamma, float beta) {
+  return silu_f(gn_apply(v, mean, rstd, gamma, beta));
 }
 
 // (c0, c1) = (a*b0 + c0, a*b1 + c1), each an IEEE fma, in one packed instruction

@@ -45,6 +45,14 @@ __device__ __forceinline__ float pre_op(float v, float a, float b) {
   if (PRE == ATTNDM_PRE_SILU) return silu_f(v);
   return v;
 }
+// t = s * pre_op(v) - zp, the argument of the quantizer's round; a SiLU producer goes through silu_quant_t
+// (SFU evaluation, refined next to a rounding boundary: same codes as the accurate form, common.cuh)
+template <int PRE>
+__device__ __forceinline__ float quant_t(float v, float a, float b, float s, float zp) {
+  if (PRE == ATTNDM_PRE_GN_SILU) return silu_quant_t(fmaf(v, a, b), s, zp);
+  if (PRE == ATTNDM_PRE_SILU) return silu_quant_t(v, s, zp);
+  return __fsub_rn(__fmul_rn(s, v), zp);
+}
 
 __device__ __forceinline__ void gn_refresh(const double* stats, int b, int lane, double inv_n,
                                            float eps, float& mean, float& rstd) {
@@ -116,15 +124,11 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActQuantParams p) {
             ga.z = r2_ * g4.z; gb.z = fmaf(-m2, ga.z, b4.z);
             ga.w = r3_ * g4.w; gb.w = fmaf(-m3, ga.w, b4.w);
           }
-          v.x = pre_op<PRE>(v.x, ga.x, gb.x);
-          v.y = pre_op<PRE>(v.y, ga.y, gb.y);
-          v.z = pre_op<PRE>(v.z, ga.z, gb.z);
-          v.w = pre_op<PRE>(v.w, ga.w, gb.w);
           if (QUANT) {
-            cd.x = quant_code(v.x, s4.x, z4.x, p.qlo, p.qhi);
-            cd.y = quant_code(v.y, s4.y, z4.y, p.qlo, p.qhi);
-            cd.z = quant_code(v.z, s4.z, z4.z, p.qlo, p.qhi);
-            cd.w = quant_code(v.w, s4.w, z4.w, p.qlo, p.qhi);
+            cd.x = quant_code_t(quant_t<PRE>(v.x, ga.x, gb.x, s4.x, z4.x), p.qlo, p.qhi);
+            cd.y = quant_code_t(quant_t<PRE>(v.y, ga.y, gb.y, s4.y, z4.y), p.qlo, p.qhi);
+            cd.z = quant_code_t(quant_t<PRE>(v.z, ga.z, gb.z, s4.z, z4.z), p.qlo, p.qhi);
+            cd.w = quant_code_t(quant_t<PRE>(v.w, ga.w, gb.w, s4.w, z4.w), p.qlo, p.qhi);
             if (p.y && act) {
               float4 o;
               o.x = dequant(cd.x, s4.x, z4.x);
@@ -134,6 +138,10 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActQuantParams p) {
               *reinterpret_cast<float4*>(p.y + pix * p.C + c) = o;
             }
           } else {
+            v.x = pre_op<PRE>(v.x, ga.x, gb.x);
+            v.y = pre_op<PRE>(v.y, ga.y, gb.y);
+            v.z = pre_op<PRE>(v.z, ga.z, gb.z);
+            v.w = pre_op<PRE>(v.w, ga.w, gb.w);
             if (p.y && act) *reinterpret_cast<float4*>(p.y + pix * p.C + c) = v;
             cd = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -159,12 +167,12 @@ __global__ void __launch_bounds__(256) act_quant_kernel(ActQuantParams p) {
           if (interior) {
             float v = p.x[pix * p.C + c];
             // C % 4 != 0 only occurs for the image latent, which has no GroupNorm (host-checked)
-            v = pre_op<PRE == ATTNDM_PRE_GN_SILU ? ATTNDM_PRE_NONE : PRE>(v, 0.f, 0.f);
+            constexpr int PS = PRE == ATTNDM_PRE_GN_SILU ? ATTNDM_PRE_NONE : PRE;
             if (QUANT) {
-              cd = quant_code(v, s, z, p.qlo, p.qhi);
+              cd = quant_code_t(quant_t<PS>(v, 0.f, 0.f, s, z), p.qlo, p.qhi);
               if (p.y) p.y[pix * p.C + c] = dequant(cd, s, z);
             } else if (p.y) {
-              p.y[pix * p.C + c] = v;
+              p.y[pix * p.C + c] = pre_op<PS>(v, 0.f, 0.f);
             }
           } else {
             cd = fminf(fmaxf(-z, p.qlo), p.qhi);
@@ -270,15 +278,11 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) act_quant_fast_kernel(Ac
           float4 cd;
           if (in[k]) {
             float4 t = v[k][i];
-            t.x = pre_op<PRE>(t.x, ga[i].x, gb[i].x);
-            t.y = pre_op<PRE>(t.y, ga[i].y, gb[i].y);
-            t.z = pre_op<PRE>(t.z, ga[i].z, gb[i].z);
-            t.w = pre_op<PRE>(t.w, ga[i].w, gb[i].w);
             if (QUANT) {
-              cd.x = quant_code(t.x, s4[i].x, z4[i].x, p.qlo, p.qhi);
-              cd.y = quant_code(t.y, s4[i].y, z4[i].y, p.qlo, p.qhi);
-              cd.z = quant_code(t.z, s4[i].z, z4[i].z, p.qlo, p.qhi);
-              cd.w = quant_code(t.w, s4[i].w, z4[i].w, p.qlo, p.qhi);
+              cd.x = quant_code_t(quant_t<PRE>(t.x, ga[i].x, gb[i].x, s4[i].x, z4[i].x), p.qlo, p.qhi);
+              cd.y = quant_code_t(quant_t<PRE>(t.y, ga[i].y, gb[i].y, s4[i].y, z4[i].y), p.qlo, p.qhi);
+              cd.z = quant_code_t(quant_t<PRE>(t.z, ga[i].z, gb[i].z, s4[i].z, z4[i].z), p.qlo, p.qhi);
+              cd.w = quant_code_t(quant_t<PRE>(t.w, ga[i].w, gb[i].w, s4[i].w, z4[i].w), p.qlo, p.qhi);
               if (p.y) {
                 float4 o;
                 o.x = dequant(cd.x, s4[i].x, z4[i].x);
@@ -288,6 +292,10 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) act_quant_fast_kernel(Ac
                 *reinterpret_cast<float4*>(p.y + pix[k] + c) = o;
               }
             } else {
+              t.x = pre_op<PRE>(t.x, ga[i].x, gb[i].x);
+              t.y = pre_op<PRE>(t.y, ga[i].y, gb[i].y);
+              t.z = pre_op<PRE>(t.z, ga[i].z, gb[i].z);
+              t.w = pre_op<PRE>(t.w, ga[i].w, gb[i].w);
               if (p.y) *reinterpret_cast<float4*>(p.y + pix[k] + c) = t;
               cd = make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -326,8 +334,7 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 3 : 2) act_quant_fast_kernel(Ac
 // Quantizer: clamp before round (bounds are integers, so it equals round-then-clamp, NaN -> lo as before)
 // and one F2I.RNI instead of rint + cvt.  ~15 instructions per element instead of ~25.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int quant_code_i(float v, float s, float zp, float lo, float hi) {
-  const float t = __fsub_rn(__fmul_rn(s, v), zp);
+__device__ __forceinline__ int quant_code_i(float t, float lo, float hi) {
   return __float2int_rn(fminf(fmaxf(t, lo), hi));
 }
 
@@ -401,28 +408,24 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_
         int acc = 0;
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
-          float4 t = v[k][i];
-          t.x = pre_op<PRE>(t.x, ga[i].x, gb[i].x);
-          t.y = pre_op<PRE>(t.y, ga[i].y, gb[i].y);
-          t.z = pre_op<PRE>(t.z, ga[i].z, gb[i].z);
-          t.w = pre_op<PRE>(t.w, ga[i].w, gb[i].w);
+          float4 t = v[k][i];                                  // -> the quantizer's pre-round values s * pre(x) - zp
+          t.x = quant_t<PRE>(t.x, ga[i].x, gb[i].x, s4[i].x, z4[i].x);
+          t.y = quant_t<PRE>(t.y, ga[i].y, gb[i].y, s4[i].y, z4[i].y);
+          t.z = quant_t<PRE>(t.z, ga[i].z, gb[i].z, s4[i].z, z4[i].z);
+          t.w = quant_t<PRE>(t.w, ga[i].w, gb[i].w, s4[i].w, z4[i].w);
           int word;
           if (A8) {
             // 8-bit codes: round to nearest even, then ONE saturating pack per two codes (cvt.pack.sat.s8.s32 clamps
             // to [-128, 127], which is the quantizer's clamp), and the code sum as one dp4a with a vector of ones
-            const int ix = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].x, t.x), z4[i].x));
-            const int iy = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].y, t.y), z4[i].y));
-            const int iz = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].z, t.z), z4[i].z));
-            const int iw = __float2int_rn(__fsub_rn(__fmul_rn(s4[i].w, t.w), z4[i].w));
+            const int ix = __float2int_rn(t.x), iy = __float2int_rn(t.y);
+            const int iz = __float2int_rn(t.z), iw = __float2int_rn(t.w);
             int hi2;
             asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi2) : "r"(iw), "r"(iz));
             asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(word) : "r"(iy), "r"(ix), "r"(hi2));
             acc = __dp4a(word, 0x01010101, acc);
           } else {
-            const int ix = quant_code_i(t.x, s4[i].x, z4[i].x, p.qlo, p.qhi);
-            const int iy = quant_code_i(t.y, s4[i].y, z4[i].y, p.qlo, p.qhi);
-            const int iz = quant_code_i(t.z, s4[i].z, z4[i].z, p.qlo, p.qhi);
-            const int iw = quant_code_i(t.w, s4[i].w, z4[i].w, p.qlo, p.qhi);
+            const int ix = quant_code_i(t.x, p.qlo, p.qhi), iy = quant_code_i(t.y, p.qlo, p.qhi);
+            const int iz = quant_code_i(t.z, p.qlo, p.qhi), iw = quant_code_i(t.w, p.qlo, p.qhi);
             acc += ix + iy + iz + iw;
             word = (ix & 0xff) | ((iy & 0xff) << 8) | ((iz & 0xff) << 16) | (iw << 24);
           }
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(256) act_quant_narrow_kernel(ActQuantParams p)
     q[c] = 0;
     if (c < p.C) {
       const float s = p.scale[c], z = p.zp[c];
-      q[c] = interior ? quant_code_i(xr[c], s, z, p.qlo, p.qhi) : (int)fminf(fmaxf(-z, p.qlo), p.qhi);
+      q[c] = interior ? quant_code_i(__fsub_rn(__fmul_rn(s, xr[c]), z), p.qlo, p.qhi) : (int)fminf(fmaxf(-z, p.qlo), p.qhi);
       acc += q[c];
     }
   }
@@ -655,16 +658,16 @@ __global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p)
         const float4 g4 = *reinterpret_cast<const float4*>(p.gamma + c);
         const float4 b4 = *reinterpret_cast<const float4*>(p.beta + c);
         const int g0 = c / cpg, g1 = (c + 1) / cpg, g2 = (c + 2) / cpg, g3 = (c + 3) / cpg;
-        v.x = gn_silu_apply(v.x, s_mean[g0], s_rstd[g0], g4.x, b4.x);
-        v.y = gn_silu_apply(v.y, s_mean[g1], s_rstd[g1], g4.y, b4.y);
-        v.z = gn_silu_apply(v.z, s_mean[g2], s_rstd[g2], g4.z, b4.z);
-        v.w = gn_silu_apply(v.w, s_mean[g3], s_rstd[g3], g4.w, b4.w);
+        v.x = gn_apply(v.x, s_mean[g0], s_rstd[g0], g4.x, b4.x);      // SiLU follows below
+        v.y = gn_apply(v.y, s_mean[g1], s_rstd[g1], g4.y, b4.y);
+        v.z = gn_apply(v.z, s_mean[g2], s_rstd[g2], g4.z, b4.z);
+        v.w = gn_apply(v.w, s_mean[g3], s_rstd[g3], g4.w, b4.w);
         const long long pix = (long long)b * HW + px;
         if (p.quant) {
-          cd.x = quant_code(v.x, s4.x, z4.x, p.qlo, p.qhi);
-          cd.y = quant_code(v.y, s4.y, z4.y, p.qlo, p.qhi);
-          cd.z = quant_code(v.z, s4.z, z4.z, p.qlo, p.qhi);
-          cd.w = quant_code(v.w, s4.w, z4.w, p.qlo, p.qhi);
+          cd.x = quant_code_t(silu_quant_t(v.x, s4.x, z4.x), p.qlo, p.qhi);
+          cd.y = quant_code_t(silu_quant_t(v.y, s4.y, z4.y), p.qlo, p.qhi);
+          cd.z = quant_code_t(silu_quant_t(v.z, s4.z, z4.z), p.qlo, p.qhi);
+          cd.w = quant_code_t(silu_quant_t(v.w, s4.w, z4.w), p.qlo, p.qhi);
           if (p.y) {
             float4 o;
             o.x = dequant(cd.x, s4.x, z4.x); o.y = dequant(cd.y, s4.y, z4.y);
@@ -672,6 +675,7 @@ __global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p)
             *reinterpret_cast<float4*>(p.y + pix * p.C + c) = o;
           }
         } else {
+          v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
           if (p.y) *reinterpret_cast<float4*>(p.y + pix * p.C + c) = v;
           cd = make_float4(0.f, 0.f, 0.f, 0.f);
         }

@@ -406,14 +406,15 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
               const float* mn = s_mean + n * kGnGroups;
               const float* rs = s_rstd + n * kGnGroups;
               const int g0 = c / cpg, g1 = (c + 1) / cpg;
-              v.x = gn_silu_apply(v.x, mn[g0], rs[g0], g2.x, b2.x);
-              v.y = gn_silu_apply(v.y, mn[g1], rs[g1], g2.y, b2.y);
-            } else if (pre == ATTNDM_PRE_SILU) {
-              v.x = silu_f(v.x); v.y = silu_f(v.y);
+              v.x = gn_apply(v.x, mn[g0], rs[g0], g2.x, b2.x);
+              v.y = gn_apply(v.y, mn[g1], rs[g1], g2.y, b2.y);
             }
             const float2 s2 = *reinterpret_cast<const float2*>(scale + c);
             const float2 z2 = *reinterpret_cast<const float2*>(zpv + c);
-            const int ix = (int)quant_code(v.x, s2.x, z2.x, qlo, qhi), iy = (int)quant_code(v.y, s2.y, z2.y, qlo, qhi);
+            // same pre-round values as the stand-alone quantizer kernels (quant_t in quant_kernels.cu)
+            const float tx = pre == ATTNDM_PRE_NONE ? __fsub_rn(__fmul_rn(s2.x, v.x), z2.x) : silu_quant_t(v.x, s2.x, z2.x);
+            const float ty = pre == ATTNDM_PRE_NONE ? __fsub_rn(__fmul_rn(s2.y, v.y), z2.y) : silu_quant_t(v.y, s2.y, z2.y);
+            const int ix = (int)quant_code_t(tx, qlo, qhi), iy = (int)quant_code_t(ty, qlo, qhi);
             *reinterpret_cast<char2*>(codes + n * crow_bytes + c) = make_char2((signed char)ix, (signed char)iy);
             int part = ix + iy;
             if (warp_rows) {

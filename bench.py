@@ -1,19 +1,25 @@
-"""Headline benchmark: CIFAR-10 UNet W8A8 (group-wise activation quant), DDIM-100,
-batch 256 per GPU -> images/sec/box (BASELINE.json configs[1]).
+"""Benchmark of the hot path: the fake-quantized DDIM sampler (BASELINE.json).
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
-    python bench.py --impl reference ...                     # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W                 # our arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --config {cifar10_w8a8,cifar10_w4_attn,celeba_w8a8,church_w8a8}   # BASELINE.json configs[1..4]
 
-One "step" = one full DDIM-100 sampling pass (100 UNet forwards + 100 DDIM updates)
-over one batch of 256 synthetic Gaussian latents per GPU, random-init weights
-snapped to the int8 grid (H1), calibrated once (untimed) on the same kind of
-latents.  `value` times the pass with the latents already in HBM; `e2e` times the
-public API call (attentiondm_b200.generalized_steps) with the latents in pinned
-host memory and the final images copied back, both inside the timed region.
+Default workload = BASELINE.json configs[1], the one the metric is quoted on: CIFAR-10 UNet W8A8 (group-wise
+activation quant), DDIM-100, batch 256 per GPU -> images/sec/box.  One "step" = one full DDIM-100 sampling pass
+(100 UNet forwards + 100 DDIM updates) over one batch of synthetic Gaussian latents per GPU, random-init weights
+snapped to the integer grid (H1), calibrated once (untimed) on the same kind of latents.
+  value  times the pass with the latents already in HBM (CUDA events, max over ranks);
+  e2e    times the public drop-in call attentiondm_b200.generalized_steps(x, seq, model, betas, eta=0) with the
+         latents in pinned host memory and -- as the reference API returns them -- every step's x_t and x0
+         prediction copied back to the host, all inside the timed region (e2e_keep_last: only the final images).
+Extra objects on the same line: roofline (dominant int8 conv kernel, live CUDA-event timing), roofline_hbm
+(the HBM-bound quantizer / collector kernels), int8_peak (torch._int_mm measured live), cuda_eager_baseline (the
+reference arithmetic in torch CUDA eager on the same B200), cpu_baseline.
 """
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -22,13 +28,35 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "CIFAR-10 W8A8 DDIM-100 images/sec/box"
 T_STEPS = 100
-BATCH = 256
-GFLOP_PER_IMG_STEP = 2.769          # SURVEY.md App. B (conv MACs x 2, CIFAR config)
+
+ns = argparse.Namespace
+CONFIGS = {
+    # name: (spec factory name, bitwidth, batch/GPU, conv GFLOP per image per step, description)
+    "cifar10_w8a8": dict(spec="cifar_spec", bitwidth=8, batch=256, gflop=2.769, layers=198, attn_mixed=False,
+                         alpha="uniform", ch_mult=[1, 2, 2, 2], size=32,
+                         text="CIFAR-10 32x32 UNet (configs/cifar10.yml, 198 QConv2d, random-init weights on the int8 "
+                              "grid) W8A8 group-wise fake-quant, DDIM 100 steps, batch 256/GPU"),
+    "cifar10_w4_attn": dict(spec="cifar_spec", bitwidth=4, batch=256, gflop=2.769, layers=198, attn_mixed=True,
+                            alpha="attn_random", ch_mult=[1, 2, 2, 2], size=32,
+                            text="CIFAR-10 32x32 UNet, bitwidth 4 (4-bit activation codes and weights on the 4-bit "
+                                 "grid), MixedPrecisionAttention on every attention site (4-bit logits, 3-bit "
+                                 "probabilities), trained-like attention alpha_activ ~ N(0,1) (those 1x1 convs take the "
+                                 "fp32 kernel, H2), calibration ranges all-reduced over ranks, DDIM 100, batch 256/GPU"),
+    "celeba_w8a8": dict(spec="celeba_spec", bitwidth=8, batch=64, gflop=10.963, layers=252, attn_mixed=False,
+                        alpha="uniform", ch_mult=[1, 2, 2, 2, 4], size=64,
+                        text="CelebA 64x64 UNet (configs/celeba.yml, 252 QConv2d) W8A8, DDIM 100 steps, batch 64/GPU"),
+    "church_w8a8": dict(spec="church_spec", bitwidth=8, batch=8, gflop=163.224, layers=305, attn_mixed=True,
+                        alpha="uniform", ch_mult=[1, 1, 2, 2, 4, 4], size=256,
+                        text="LSUN church 256x256 UNet (configs/church.yml, 305 QConv2d) W8A8 with quantized attention "
+                             "(MixedPrecisionAttention, 8-bit: attention-internal quantizers inactive above 6 bits), "
+                             "DDIM 100 steps, batch 8/GPU"),
+}
 
 
 def peaks():
-    p = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+    p = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
     f = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(f):
         try:
@@ -83,57 +111,90 @@ class ClockSampler:
                     samples=len(sm))
 
 
-def cifar_config():
-    ns = argparse.Namespace
-    return ns(data=ns(channels=3, image_size=32, dataset="CIFAR10", rescaled=True, logit_transform=False),
-              model=ns(ch=128, ch_mult=[1, 2, 2, 2], num_res_blocks=2, dropout=0.1, var_type="fixedlarge"),
+def model_config(c):
+    return ns(data=ns(channels=3, image_size=c["size"], dataset="synthetic", rescaled=True, logit_transform=False),
+              model=ns(ch=128, ch_mult=list(c["ch_mult"]), num_res_blocks=2, dropout=0.1, var_type="fixedlarge"),
               diffusion=ns(beta_schedule="linear", beta_start=0.0001, beta_end=0.02, num_diffusion_timesteps=1000))
 
 
 # ---------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's path on the host cores
+# CPU arm: the oracle port of the reference's path on the host cores (config 1)
 # ---------------------------------------------------------------------------
-def cpu_oracle_rate(forwards=2, batch=4, threads=None):
-    """images/sec of the reference's CPU path (oracle/restate.py), DDIM-100: a bounded sample of
-    `forwards` quantized UNet forwards at `batch`, extrapolated to 100 steps per image."""
-    import torch
-    from oracle import restate as R
-    from oracle import synth as S
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    spec = S.cifar_spec(T=T_STEPS, bitwidth=8)
-    sd = S.synth_state_dict(spec, seed=0)
-    for k in sd:
-        if k.endswith("groups_range"):
-            sd[k][..., 0] = -4.0
-            sd[k][..., 1] = 6.0
-    orc = R.Oracle(spec, sd)
-    x = torch.randn(batch, 3, 32, 32, generator=torch.Generator().manual_seed(1234))
-    t = torch.full((batch,), 990.0)
-    with torch.no_grad():
-        orc.forward(x, t)                      # warm-up
+class CpuConfig1:
+    """configs/cifar10.yml, random-init seed 0 on the int8 grid, W8A8, T = 10 (seq = range(0, 1000, 100)), eta 0,
+    x0 = randn(4, 3, 32, 32): one calibration pass, then quantized DDIM sampling passes."""
+
+    def __init__(self, threads=None):
+        import torch
+        from oracle import restate as R
+        from oracle import synth as S
+        self.torch, self.R = torch, R
+        self.threads = threads or os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        self.spec = S.cifar_spec(T=10, bitwidth=8)
+        self.orc = R.Oracle(self.spec, S.synth_state_dict(self.spec, seed=0))
+        self.betas = R.beta_schedule_linear()
+        self.x = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(1234))
+        self.calibration_s = None
+
+    def calibrate(self):
         t0 = time.perf_counter()
-        for _ in range(forwards):
-            orc.forward(x, t)
-        dt = (time.perf_counter() - t0) / forwards
-    return batch / (dt * T_STEPS), dt, threads
+        with self.torch.no_grad():
+            self.orc.set_calibrate(True)
+            self.R.ddim_sample(self.orc.forward, self.x, self.spec.seq, self.betas, eta=0.0)
+            self.orc.set_calibrate(False)
+            self.orc.reset_index()
+        self.calibration_s = time.perf_counter() - t0
+        return self.calibration_s
+
+    def sample_pass(self):
+        """One quantized DDIM-10 pass at batch 4 (seconds)."""
+        t0 = time.perf_counter()
+        with self.torch.no_grad():
+            self.orc.reset_index()
+            self.R.ddim_sample(self.orc.forward, self.x, self.spec.seq, self.betas, eta=0.0)
+        return time.perf_counter() - t0
+
+    @staticmethod
+    def images_per_s(pass_s):
+        """DDIM-100 images/s implied by a 10-step pass at batch 4: the per-step cost does not depend on T."""
+        return 4.0 / (pass_s * (T_STEPS / 10.0))
+
+
+def cpu_baseline(passes=2):
+    b = CpuConfig1()
+    cal = b.calibrate()
+    best = min(b.sample_pass() for _ in range(passes))
+    return {"value": CpuConfig1.images_per_s(best), "unit": "images/s", "cores": b.threads, "kind": "port",
+            "sample": f"BASELINE.md section 4 config 1 on the host cores: CIFAR-10 UNet W8A8, batch 4, DDIM T=10 "
+                      f"(oracle port of the reference): calibration pass {cal:.1f} s, quantized sampling best of "
+                      f"{passes} passes {best:.2f} s (= {4 / best:.2f} images/s at T=10), scaled to DDIM-100",
+            "calibration_s": cal, "sampling_s_T10_b4": best, "images_per_s_T10": 4.0 / best}
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path (the oracle port: the real reference is Python scripts
+    that cannot travel to the GPU box), all host threads, on config 1's shape; each step = one DDIM-10 pass at
+    batch 4, a bounded sample of the DDIM-100 batch-256 workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rates = []
-    for _ in range(max(1, args.warmup)):
-        pass
-    rate, dt, threads = cpu_oracle_rate(forwards=max(1, args.steps), batch=4)
-    sample = f"{max(1, args.steps)} quantized UNet forwards at batch 4 (oracle port of the reference, CPU), x100 steps/image"
+    b = CpuConfig1()
+    cal = b.calibrate()
+    for _ in range(max(1, min(args.warmup, 3))):
+        b.sample_pass()
+    times = [b.sample_pass() for _ in range(max(1, args.steps))]
+    mean = sum(times) / len(times)
+    rate = CpuConfig1.images_per_s(mean)
+    sample = (f"{len(times)} timed quantized DDIM-10 passes at batch 4 (config 1; oracle port of the reference, CPU, "
+              f"{b.threads} threads; calibration pass {cal:.1f} s untimed), mean {mean:.2f} s per pass, scaled to DDIM-100")
     line = {
-        "impl": "reference", "metric": "CIFAR-10 W8A8 DDIM-100 images/sec/box", "value": rate, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * T_STEPS * (BATCH / 4),
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CIFAR-10 32x32 UNet (198 QConv2d) W8A8 fake-quant, DDIM 100 steps, CPU host cores"},
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": CONFIGS["cifar10_w8a8"]["text"] + " -- timed on a bounded sample: batch 4, T=10, host cores"},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": b.threads, "kind": "port", "sample": sample,
+                         "calibration_s": cal, "sampling_s_T10_b4_best": min(times)},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -143,34 +204,84 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
-def build_model(dev, seed=0):
+def build_model(dev, c, seed=0):
     import torch
     import attentiondm_b200 as A
     torch.manual_seed(seed)
-    cfg = cifar_config()
-    args = argparse.Namespace(bitwidth=8, timesteps=T_STEPS, skip_type="uniform", eta=0.0)
+    args = ns(bitwidth=c["bitwidth"], timesteps=T_STEPS, skip_type="uniform", eta=0.0)
     seq = range(0, 1000, 1000 // T_STEPS)
-    m = A.Model(cfg, quantization=True, sequence=seq, args=args).to(dev).eval()
+    m = A.Model(model_config(c), quantization=True, sequence=seq, args=args).to(dev).eval()
     m.materialize_lazy_layers()
-    for mod in m.modules():                       # gamma = 0 makes attention a numerical no-op (H7)
+    for name, mod in m.named_modules():
         if isinstance(mod, A.EnhancedQSelfAttention):
-            mod.gamma.data.fill_(0.5)
-    m.snap_weights_()                             # H1: weights on the int8 grid, shared by every arm
+            mod.gamma.data.fill_(0.5)             # gamma = 0 makes attention a numerical no-op (H7)
+            if c["attn_mixed"]:
+                mod.enable_mixed_precision()
+                mod.attention_processor.update_quantization_params(-8.0, 8.0, 0.0, 1.0)
+            if c["alpha"] == "attn_random":       # emulates a post-calibrate_attention state
+                g = torch.Generator().manual_seed(7)
+                for conv in (mod.query_conv, mod.key_conv, mod.value_conv, mod.output_conv):
+                    conv.alpha_activ.data.copy_(torch.randn(conv.alpha_activ.shape, generator=g))
+    m.snap_weights_()                             # H1: weights on the integer grid, shared by every arm
     return m, seq
 
 
-def dominant_kernel_roofline(dev, pk):
-    """The 128->128 3x3 conv at 32x32, batch 256 (33 % of the step's FLOPs), timed
-    alone with CUDA events on the launching stream; operands (38 MB codes, 134 MB output) exceed L2."""
+def _time_kernel(fn, n=10, warm=3):
+    """Mean CUDA-event duration (ms) of fn() on the current stream; operands are sized beyond L2 by the callers."""
     import torch
+    for _ in range(warm):
+        fn()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record()
+    for i in range(n):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return sum(ev[i].elapsed_time(ev[i + 1]) for i in range(n)) / n
+
+
+def ncu_traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from a committed `ncu --set full` summary."""
+    try:
+        txt = open(os.path.join(ROOT, path)).read()
+        rd = re.search(r"dram__bytes_read\.sum \[(\w+)\] = ([0-9.]+)", txt)
+        wr = re.search(r"dram__bytes_write\.sum \[(\w+)\] = ([0-9.]+)", txt)
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        return float(rd.group(2)) * unit[rd.group(1)] + float(wr.group(2)) * unit[wr.group(1)]
+    except Exception:
+        return None
+
+
+def int8_peak(dev, pk):
+    """int8 tensor-core peaks: torch._int_mm 8192^3 measured live (a library kernel on this part), 2x the
+    driver-measured bf16 figure (tcgen05 kind::i8 issues at exactly twice the bf16 rate, tools/umma_rate_test.cu),
+    and the 4500 TOP/s dense datasheet figure."""
+    import torch
+    out = {"two_x_bf16_measured": 2.0 * pk["bf16_tflops"], "datasheet": 4500.0, "unit": "TOP/s",
+           "umma_rate_probe": "tools/umma_rate_test.cu: 8187 MAC/clk/SM = 4.76 POP/s at 1965 MHz (round 1, gpurun_out/umma_rate.log)"}
+    try:
+        n = 8192
+        a = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=dev)
+        b = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=dev)
+        ms = _time_kernel(lambda: torch._int_mm(a, b), n=10, warm=3)
+        out["int_mm_8192_measured"] = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
+    except Exception as e:
+        out["int_mm_8192_measured"] = None
+        out["int_mm_error"] = str(e)[:120]
+    return out
+
+
+def dominant_kernel_roofline(dev, pk, i8pk, batch=256):
+    """The 128->128 3x3 conv at 32x32, batch 256 (33 % of the step's FLOPs), timed alone with
+    CUDA events on the launching stream; operands (38 MB codes, 134 MB output) exceed L2."""
+    import torch
+    import attentiondm_b200 as A
     from attentiondm_b200 import ops
-    B, H, W, C, O = BATCH, 32, 32, 128, 128
+    B, H, W, C, O = batch, 32, 32, 128, 128
     g = torch.Generator().manual_seed(0)
     x = torch.randn(B, H, W, C, generator=g).to(dev)
     w = (torch.rand(O, C, 3, 3, generator=g) * 2 - 1).to(dev) / (C * 9) ** 0.5
     flat = w.reshape(O, -1)
-    w_eff = ops.weight_clamp_pack(w, flat.min(1)[0], flat.max(1)[0])
-    import attentiondm_b200 as A
     ws = A.AsymmetricQuantFunction.apply(w, 8, flat.min(1)[0], flat.max(1)[0])
     fl = ws.reshape(O, -1)
     pack = ops.weight_to_i8(ops.weight_clamp_pack(ws, fl.min(1)[0], fl.max(1)[0]), 8)
@@ -181,38 +292,116 @@ def dominant_kernel_roofline(dev, pk):
     azp = torch.tensor([26], dtype=torch.int32, device=dev)
     bias = torch.zeros(O, device=dev)
     out = torch.empty(B, H, W, O, device=dev)
-    res = {}
-    for name, impl in (("tcgen05", ops.CONV_TCGEN05),):
-        for _ in range(3):
-            ops.qconv_i8(codes, rowsum, B, H, W, C, pack, 9, mult, azp, bias, impl=impl, out=out)
-        n = 10
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
-        ev[0].record()
-        for i in range(n):
-            ops.qconv_i8(codes, rowsum, B, H, W, C, pack, 9, mult, azp, bias, impl=impl, out=out)
-            ev[i + 1].record()
-        torch.cuda.synchronize()
-        ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))
-        res[name] = sum(ms) / n
+    ms = _time_kernel(lambda: ops.qconv_i8(codes, rowsum, B, H, W, C, pack, 9, mult, azp, bias,
+                                           impl=ops.CONV_TCGEN05, out=out))
     flops = 2.0 * B * H * W * O * C * 9
-    ach = flops / (res["tcgen05"] * 1e-3) / 1e12
-    peak = 2.0 * pk["bf16_tflops"]
+    ach = flops / (ms * 1e-3) / 1e12
+    peak = i8pk["two_x_bf16_measured"]
     algo_bytes = codes.numel() + rowsum.numel() * 4 + out.numel() * 4 + pack.qw.numel()
-    hbm_s = algo_bytes / (pk["hbm_gbs"] * 1e9)               # what HBM alone would need for the algorithmic bytes
+    hbm_s = algo_bytes / (pk["hbm_gbs"] * 1e9)
+    traffic_file = "profiles/ncu_conv_r02.txt"
+    traffic = ncu_traffic(traffic_file)
     return {"bound": "tensor", "kernel": "qconv_i8_halo_kernel (128->128 3x3 @32x32, batch 256)", "achieved": ach,
             "peak": peak, "unit": "TOP/s", "frac": ach / peak,
-            "peak_source": f"2 x bf16_tflops of {pk['source']}: tcgen05 kind::i8 measured at exactly 2x the bf16 "
-                           "MMA rate on this part (tools/umma_rate_test.cu: 64 cycles per 128x128x32 MMA); "
-                           "MEASURED_PEAKS.json has no int8 entry",
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/ncu_conv_r01.txt)
-            "traffic": 119.57e6, "traffic_source": "profiles/ncu_conv_r01.txt (39.3 MB read + 80.3 MB written; "
-                                                   "the rest of the 134 MB output is still in L2 at kernel end)",
-            "ms_per_launch": res["tcgen05"], "algorithmic_bytes": algo_bytes,
-            "hbm_gbs_at_this_time": algo_bytes / (res["tcgen05"] * 1e-3) / 1e9,
-            "hbm_floor_ms": hbm_s * 1e3,
-            "note": "fp32 activations between layers make this layer HBM-co-bound: 173 MB at the measured "
-                    f"{pk['hbm_gbs']:.0f} GB/s is {hbm_s * 1e6:.0f} us, i.e. at most "
+            "peak_source": f"2 x bf16_tflops of {pk['source']} (burst figure, kernel timed alone): tcgen05 kind::i8 "
+                           "issues at exactly 2x the bf16 MMA rate on this part; MEASURED_PEAKS.json has no int8 entry",
+            "frac_vs": {"two_x_bf16_measured": ach / i8pk["two_x_bf16_measured"],
+                        "int_mm_8192_measured": (ach / i8pk["int_mm_8192_measured"]) if i8pk.get("int_mm_8192_measured") else None,
+                        "datasheet_4500": ach / 4500.0},
+            "traffic": traffic,
+            "traffic_source": (f"{traffic_file}: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full"
+                               if traffic is not None else "no committed ncu summary found"),
+            "ms_per_launch": ms, "algorithmic_bytes": algo_bytes, "algorithmic_flop": flops,
+            "hbm_gbs_at_this_time": algo_bytes / (ms * 1e-3) / 1e9, "hbm_floor_ms": hbm_s * 1e3,
+            "note": "fp32 activations between layers make this layer HBM-co-bound: its algorithmic bytes at the measured "
+                    f"{pk['hbm_gbs']:.0f} GB/s take {hbm_s * 1e6:.0f} us, i.e. at most "
                     f"{flops / hbm_s / 1e12 / peak:.2f} of the int8 peak is reachable without changing the layout"}
+
+
+def hbm_kernel_rooflines(dev, pk, batch=256):
+    """The HBM-bound kernels of the path, each timed alone (CUDA events) on a 128-channel 32x32 batch-256 map
+    (134 MB fp32 > L2).  Algorithmic bytes per element are SURVEY.md section 8(d)'s."""
+    import torch
+    from attentiondm_b200 import ops
+    B, H, W, C = batch, 32, 32, 128
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, H, W, C, generator=g).to(dev)
+    n = x.numel()
+    sv = torch.full((C,), 25.5, device=dev)
+    zv = torch.full((C,), 26.0, device=dev)
+    gamma = torch.ones(C, device=dev)
+    beta = torch.zeros(C, device=dev)
+    stats = ops.gn_stats(x)
+    gn = ops.GnArgs(stats, gamma, beta, 1e-6)
+    gr = torch.tensor([[-4.0, 6.0]] * 8, device=dev)
+    sw = torch.full((8, C), 0.125, device=dev)
+    eps = torch.randn_like(x)
+    coef = torch.tensor([0.6, 0.8, 0.81, 0.0, 0.59, 500.0, 0, 0], device=dev)
+    xo = torch.empty_like(x)
+    cases = [
+        ("act_quant_rows_kernel<GN+SiLU> (GroupNorm+SiLU+quantize -> int8 halo codes)", 5.0,
+         lambda: ops.act_quant(x, sv, zv, 8, ops.PRE_GN_SILU, gn, want_codes=True, halo=True)),
+        ("act_quant_rows_kernel<none> (quantize -> int8 codes)", 5.0,
+         lambda: ops.act_quant(x, sv, zv, 8, want_codes=True, halo=True)),
+        ("gn_stats_kernel (GroupNorm statistics)", 4.0, lambda: ops.gn_stats(x, out=stats)),
+        ("minmax_partial/final (per-channel calibration min/max)", 4.0, lambda: ops.minmax_c(x)),
+        ("calib_mix_kernel (G-branch calibration mix, fp32 -> fp32)", 8.0, lambda: ops.calib_mix(x, gr, sw, 8)),
+        ("ddim_step_kernel (x_t, eps -> x_next)", 12.0, lambda: ops.ddim_step(x, eps, coef, None, x_next=xo)),
+    ]
+    out = []
+    for name, bpe, fn in cases:
+        ms = _time_kernel(fn, n=10, warm=3)
+        gbs = bpe * n / (ms * 1e-3) / 1e9
+        out.append({"bound": "hbm", "kernel": name, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / pk["hbm_gbs"], "algorithmic_bytes_per_element": bpe, "elements": n,
+                    "ms_per_launch": ms,
+                    "note": "includes the output allocation of the Python wrapper" if "ops." in name else None})
+    for o in out:
+        if o["note"] is None:
+            del o["note"]
+    return out
+
+
+def cuda_eager_baseline(dev, c, batch, forwards=3):
+    """The reference arithmetic (oracle/restate.py, plain torch ops = what the reference executes) in CUDA eager on
+    this B200 at the bench batch: the same-box bar of BASELINE.md section 4 item 4.  Bounded sample: `forwards`
+    quantized UNet forwards, scaled to 100 steps per image."""
+    import torch
+    from oracle import restate as R
+    from oracle import synth as S
+    spec = getattr(S, c["spec"])(T=T_STEPS, bitwidth=c["bitwidth"])
+    sd = S.synth_state_dict(spec, seed=0)
+    for k in sd:
+        if k.endswith("groups_range"):             # in-range activations calibrate to the [-4, 6] floor (App. A.3)
+            sd[k][..., 0] = -4.0
+            sd[k][..., 1] = 6.0
+    orc = R.Oracle(spec, sd).to(dev)
+    x = torch.randn(batch, 3, spec.image_size, spec.image_size, generator=torch.Generator().manual_seed(5)).to(dev)
+    t = torch.full((batch,), 990.0, device=dev)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        with torch.no_grad():
+            res = {}
+            for tf32 in (False, True):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                orc.reset_index()
+                orc.forward(x, t)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(forwards):
+                    orc.forward(x, t)
+                torch.cuda.synchronize()
+                res[tf32] = (time.perf_counter() - t0) / forwards
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    del orc
+    torch.cuda.empty_cache()
+    return {"value": batch / (res[False] * T_STEPS), "unit": "images/s", "kind": "port (torch CUDA eager, fp32 convs)",
+            "value_tf32_convs": batch / (res[True] * T_STEPS),
+            "sample": f"{forwards} quantized UNet forwards at batch {batch} on one B200 (oracle/restate.py: the "
+                      f"reference's op chain through torch CUDA eager, {res[False] * 1e3:.0f} ms per forward with fp32 "
+                      f"convs, {res[True] * 1e3:.0f} ms with torch's default TF32 convs), x100 steps/image"}
 
 
 def run_ours(args):
@@ -224,21 +413,24 @@ def run_ours(args):
     from attentiondm_b200 import dist as adist
     from attentiondm_b200.engine import SamplerEngine
 
+    c = CONFIGS[args.config]
+    BATCH = args.batch or c["batch"]
     rank, world = adist.init_from_env()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     assert _ffi.lib().attndm_device_supported() == 1, "bench needs an sm_100 (B200) device"
     pk = peaks()
-    m, seq = build_model(dev, seed=0)             # same weights on every rank (replicated model)
+    m, seq = build_model(dev, c, seed=0)          # same weights on every rank (replicated model)
     betas = torch.from_numpy(A.get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02,
                                                  num_diffusion_timesteps=1000)).float().to(dev)
     gen = torch.Generator().manual_seed(1234 + rank)            # reference default seed 1234 (main.py:23)
-    x_host = torch.randn(BATCH, 3, 32, 32, generator=gen).pin_memory()
+    S_ = c["size"]
+    x_host = torch.randn(BATCH, 3, S_, S_, generator=gen).pin_memory()
     # ---- calibration (untimed): ranges all-reduced over ranks so every replica holds identical tables ----
     if world > 1:
         adist.install()
-    xc = x_host[:32].to(dev)
+    xc = x_host[:min(BATCH, 32 if S_ <= 64 else 4)].to(dev)
     with torch.no_grad():
         m.set_calibrate(True)
         A.generalized_steps(xc, seq, m, betas, eta=0.0, keep="last")
@@ -249,29 +441,26 @@ def run_ours(args):
             for nm, q in m.qconvs():
                 if not q.int8_ok_all_steps():
                     print(f"[bench] fp32 fallback layer {nm}: {q.int8_status()}", file=sys.stderr)
-        eng = SamplerEngine.for_model(m, seq, betas, 0.0, (BATCH, 3, 32, 32))
+        eng = SamplerEngine.for_model(m, seq, betas, 0.0, (BATCH, 3, S_, S_))
         x_dev = x_host.to(dev)
 
         def one_pass_resident():
             eng.load_input(x_dev)
             eng.run_loaded()
 
-        def one_pass_e2e():
-            xs, _ = A.generalized_steps(x_host_dev_view(), seq, m, betas, eta=0.0, keep="last")
-            return xs[-1]
-
-        def x_host_dev_view():
-            return x_host.to(dev, non_blocking=True)        # H2D inside the timed region
+        def one_pass_e2e(keep):
+            xs, x0s = A.generalized_steps(x_host.to(dev, non_blocking=True), seq, m, betas, eta=0.0, keep=keep)
+            return xs, x0s
 
         def barrier():
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
 
-        for _ in range(max(3, args.warmup)):
+        warm = max(3, args.warmup)
+        for _ in range(warm):
             one_pass_resident()
         torch.cuda.synchronize()
-        launches0 = _ffi.launches
         barrier()
         cs = ClockSampler(local)
         cs.start()
@@ -283,23 +472,36 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
         clocks = cs.stop()
-        # ---- end-to-end through the public API, host buffers, copies inside the timed region ----
-        m.reset_index_seq()
-        one_pass_e2e()
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for _ in range(args.steps):
-            img = one_pass_e2e()
-        t1.record()
-        barrier()
-        ms_e2e = t0.elapsed_time(t1)
+        # ---- end to end through the public API, host buffers, copies inside the timed region ----
+        e2e_ms = {}
+        d2h = {}
+        for keep in ("all", "last"):
+            m.reset_index_seq()
+            one_pass_e2e(keep)                     # warm-up (pinned result buffers come from torch's caching host allocator)
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(args.steps):
+                xs, x0s = one_pass_e2e(keep)
+            t1.record()
+            barrier()
+            e2e_ms[keep] = t0.elapsed_time(t1)
+            d2h[keep] = int(sum(t.numel() for t in xs[1:]) * 4 + sum(t.numel() for t in x0s) * 4)
+            del xs, x0s
         if world > 1:
-            tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+            tt = torch.tensor([ms, e2e_ms["all"], e2e_ms["last"]], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms, ms_e2e = float(tt[0]), float(tt[1])
-        roof = dominant_kernel_roofline(dev, pk) if rank == 0 else None
+            ms, e2e_ms["all"], e2e_ms["last"] = float(tt[0]), float(tt[1]), float(tt[2])
+        extras = rank == 0 and not args.no_extras
+        i8pk = int8_peak(dev, pk) if extras else None
+        roof = dominant_kernel_roofline(dev, pk, i8pk) if extras else None
+        roof_hbm = hbm_kernel_rooflines(dev, pk) if extras else None
+        eager = None
+        if extras:
+            try:
+                eager = cuda_eager_baseline(dev, c, BATCH if c["size"] <= 64 else min(BATCH, 4))
+            except Exception as e:
+                eager = {"value": None, "unit": "images/s", "sample": f"failed: {str(e)[:200]}"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -307,30 +509,38 @@ def run_ours(args):
         return
     ms_per_step = ms / args.steps
     value = world * BATCH / (ms_per_step * 1e-3)
-    e2e_v = world * BATCH / (ms_e2e / args.steps * 1e-3)
-    try:
-        cpu_rate, cpu_dt, cpu_threads = cpu_oracle_rate(forwards=2, batch=4)
-        cpu = {"value": cpu_rate, "unit": "images/s", "cores": cpu_threads, "kind": "port",
-               "sample": "2 quantized UNet forwards at batch 4 (oracle port, CPU), x100 steps/image"}
-    except Exception as e:                         # never lose the GPU line to a CPU hiccup
-        cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-    step_tops = GFLOP_PER_IMG_STEP * 1e9 * BATCH * T_STEPS / (ms_per_step * 1e-3) / 1e12
+    rate = lambda t: world * BATCH / (t / args.steps * 1e-3)
+    cpu = None
+    if not args.no_extras:
+        try:
+            cpu = cpu_baseline(passes=2)
+        except Exception as e:                     # never lose the GPU line to a CPU hiccup
+            cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    step_tops = c["gflop"] * 1e9 * BATCH * T_STEPS / (ms_per_step * 1e-3) / 1e12
+    headline = args.config == "cifar10_w8a8"
     line = {
-        "metric": "CIFAR-10 W8A8 DDIM-100 images/sec/box", "value": value, "unit": "images/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "metric": METRIC if headline else f"{args.config} DDIM-100 images/sec/box", "value": value, "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int8 x int8 -> s32 (fp32 activations between layers)",
         "data": "synthetic",
-        "config": {"workload": "CIFAR-10 32x32 UNet (configs/cifar10.yml, 198 QConv2d, random-init weights on the "
-                               "int8 grid) W8A8 group-wise fake-quant, DDIM 100 steps, batch 256/GPU",
-                   "batch_per_gpu": BATCH, "ddim_steps": T_STEPS, "parallelism": f"dp{world} (batch sharded)",
-                   "l2": "per-step working set (>= 134 MB fp32 activations per layer at 32x32) exceeds the 126 MB L2",
-                   "int8_layers": n_i8, "cuda_graph": True},
+        "config": {"workload": c["text"], "name": args.config, "batch_per_gpu": BATCH, "ddim_steps": T_STEPS,
+                   "parallelism": f"dp{world} (batch sharded, no data-path collective)",
+                   "l2": "inputs larger than L2: the per-step working set (fp32 activations of one layer at full "
+                         "resolution, >= 134 MB) exceeds the 126 MB L2, and 100 steps x ~170 layers run between repeats",
+                   "int8_layers": n_i8, "qconv_layers": len(m.qconvs()), "cuda_graph": True},
         "clocks": clocks,
-        "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
-                "d2h_bytes_per_step": int(img.numel() * 4)},
+        "e2e": {"value": rate(e2e_ms["all"]), "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
+                "d2h_bytes_per_step": d2h["all"],
+                "api": "attentiondm_b200.generalized_steps(x, seq, model, betas, eta=0): the reference-shaped call, "
+                       "every step's x_t and x0 prediction returned as host tensors"},
+        "e2e_keep_last": {"value": rate(e2e_ms["last"]), "unit": "images/s",
+                          "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": d2h["last"],
+                          "api": "same call with keep='last' (only the final images and x0 come back)"},
         "gpu_launches": int((eng.launches_per_step or 0) * T_STEPS * args.steps),
+        "launches_per_denoising_step": int(eng.launches_per_step or 0),
         "whole_step_conv_tops": step_tops,
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "roofline_hbm": roof_hbm, "int8_peak": i8pk,
+        "cuda_eager_baseline": eager, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
 
@@ -341,6 +551,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cifar10_w8a8", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="batch per GPU (default: the config's)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the per-kernel rooflines and the CUDA-eager / CPU baselines (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -417,6 +417,47 @@ def test_conv1x1_f32_tensor_core_3xtf32(B, H, W, C, O):
     assert torch.equal(y1, y_tc[1:2])
 
 
+def test_silu_quantizer_guard_equals_accurate_silu():
+    """The hot path evaluates SiLU on the special-function unit and re-evaluates it accurately only when
+    s * silu(u) - zp lands within kSiluGuard of a rounding boundary (csrc/common.cuh).  Its codes must be exactly
+    those of quantizing the accurate SiLU (the fp32 output of the same library), on random inputs and on inputs
+    constructed to sit right at the boundaries; and the accurate SiLU must agree with torch's to <= 2 ulp."""
+    from attentiondm_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    C = 128
+    for a_bit, lo, hi in ((8, -4.0, 6.0), (8, -0.5, 3.0), (6, -4.0, 6.0), (4, -4.0, 6.0), (8, -30.0, 50.0)):
+        s, z = R.asym_params(a_bit, torch.tensor(lo), torch.tensor(hi))
+        sv = torch.full((C,), float(s), device=DEV)
+        zv = torch.full((C,), float(z), device=DEV)
+        # random pre-activations + adversarial ones: u with s * silu(u) - zp = k + 0.5 +- delta
+        u_rand = torch.randn(64, 32, 32, C, generator=g) * 2.5
+        k = torch.randint(-2 ** (a_bit - 1), 2 ** (a_bit - 1), (8, 32, 32, C), generator=g).double()
+        delta = (torch.rand(8, 32, 32, C, generator=g).double() - 0.5) * 4e-4
+        y_t = (k + 0.5 + delta + float(z)) / float(s)                      # target silu value
+        y_t = y_t.clamp_min(-0.27)                                         # silu >= -0.2785
+        u = y_t.clone().clamp_min(0.1)
+        for _ in range(60):                                                # Newton on silu(u) = y_t, u > -1.2785 branch
+            sg = torch.sigmoid(u)
+            f = u * sg - y_t
+            u = u - f / (sg * (1 + u * (1 - sg))).clamp_min(1e-3)
+        x = torch.cat([u_rand, u.float()]).to(DEV)
+        y_acc = ops.silu(x)                                                # accurate fp32 SiLU of the library
+        want, _, _ = ops.act_quant(y_acc, sv, zv, a_bit, ops.PRE_NONE, want_codes=True, halo=False)
+        got, rs, _ = ops.act_quant(x, sv, zv, a_bit, ops.PRE_SILU, want_codes=True, halo=False)
+        assert torch.equal(got, want), (a_bit, lo, hi, int((got != want).sum()))
+        got_h, _, _ = ops.act_quant(x, sv, zv, a_bit, ops.PRE_SILU, want_codes=True, halo=True)   # rows kernel
+        B, H, W, _ = x.shape
+        inner = got_h.view(B, H + 2, W + 2, -1)[:, 1:-1, 1:-1].reshape(-1, got_h.shape[-1])
+        assert torch.equal(inner, want)
+        # how many of the adversarial elements really are boundary cases (sanity of the construction)
+        t = float(s) * F.silu(u.double()) - float(z)
+        near = ((t - t.floor() - 0.5).abs() < 3e-4).float().mean()
+        assert near > 0.5 or a_bit < 8 or lo < -10, float(near)
+    ref = F.silu(x.cpu())
+    ulp = (y_acc.cpu().view(torch.int32).long() - ref.view(torch.int32).long()).abs()
+    assert int(ulp.max()) <= 2 and float((ulp > 0).float().mean()) < 0.02, (int(ulp.max()), float((ulp > 0).float().mean()))
+
+
 def test_attention_core():
     from attentiondm_b200 import ops
     g = torch.Generator().manual_seed(6)
