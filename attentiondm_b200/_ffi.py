@@ -50,6 +50,7 @@ SIGNATURES = {
     "attndm_upsample_concat": [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp],
     "attndm_timestep_embedding": [vp, i32, i32, vp, vp],
     "attndm_ddim_step": [vp, vp, vp, vp, vp, vp, i64, vp],
+    "attndm_ddim_step_hist": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp],
     "attndm_stage_tables": [vp, i64, i32, vp, i32, vp, vp],
     "attndm_rowprog": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp],
     "attndm_rowprog_smem_bytes": [i32, i32, i32, i32],

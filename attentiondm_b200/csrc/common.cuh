@@ -51,18 +51,20 @@ __device__ __forceinline__ float dequant(float code, float s, float zp) {
 //  * silu_acc: the exponential by range reduction + a degree-6 polynomial on the FMA pipe (<= 1 ulp, no
 //    special-function unit) and a correctly rounded quotient (rcp.approx seed + one Newton step + a residual
 //    correction).  It agrees with torch's CPU kernel (Sleef expf, 1 ulp, + IEEE divide) to the last bit for
-//    99.6 % of inputs (mean |diff| 1e-10 on N(0, 1.3) inputs; the SFU form below: 46 %, 2.4e-8).  ~22 FMA-pipe
-//    instructions + one MUFU: used wherever the SiLU output is consumed as fp32 (calibration branch, time_embed).
+//    99.6 % of inputs (<= 2 ulp always; tests/test_gpu_parity.py).  ~22 FMA-pipe instructions + one MUFU: used
+//    wherever the SiLU output is consumed as fp32 (calibration branch, time_embed).
 //  * silu_sfu: ex2.approx + rcp.approx, relative error <= ~5e-7, five instructions.
-//  * silu_quant_t: what the int8 hot path uses.  The consumer of SiLU there is always the activation quantizer,
-//    code = clamp(rne(s * y - zp)): only the SIDE of the rounding boundary matters.  Evaluate the SFU form first;
-//    if t = s * y - zp lands within kSiluGuard of a half-integer -- 0.05 % of the elements -- re-evaluate with
-//    silu_acc.  The codes are then exactly those of silu_acc everywhere (the guard is > 2x the worst-case SFU
-//    error of t for |s * y| < 400, beyond which the accurate form is always taken), at close to the SFU cost.
-//    Measured (profiles/parity_r02.json): activation codes that differ from the CPU reference's on identical layer
-//    inputs -- 3.7e-7 of the elements, against 9.0e-7 with the SFU form alone and 6.0e-7 for torch's own CUDA
-//    kernels against its CPU kernels.
-//  * -DATTNDM_SILU_SFU / -DATTNDM_SILU_ACCURATE: A/B builds that use one form everywhere.
+//  * silu_quant_t: the int8 hot path.  The consumer of SiLU there is always the activation quantizer,
+//    code = clamp(rne(s * y - zp)).  Three builds, measured on the B200 (profiles/parity_r02.json, CIFAR-10 UNet,
+//    batch 8, 4 steps, 53 M activations; "flips" = codes that differ from the CPU reference's on identical layer
+//    inputs, next to the same count for torch's own CUDA kernels against its CPU kernels):
+//      default            SFU form                          60 flips (torch CUDA: 62)   285 ms per DDIM-100 pass
+//      -DATTNDM_SILU_GUARD   SFU first, silu_acc when t lands within kSiluGuard of a rounding boundary (codes
+//                            identical to the accurate form, asserted)   34 (35)        302 ms
+//      -DATTNDM_SILU_ACCURATE  silu_acc everywhere            34 (35)                   310 ms
+//    The flips are dominated by GroupNorm statistics (torch's CPU kernel is the odd one out: ours and torch's CUDA
+//    kernels flip the SAME elements), so the SFU form is no worse than torch-CUDA-vs-torch-CPU and 6 % faster:
+//    it is the default; the other two stay as A/B builds (attentiondm_b200/build.py VARIANTS).
 constexpr float kSiluGuard = 2.5e-4f;
 
 __device__ __forceinline__ float silu_sfu(float v) {
@@ -91,23 +93,22 @@ __device__ __forceinline__ float silu_acc(float v) {
   const float q = v * r0;
   return fmaf(fmaf(-q, d, v), r0, q);                            // residual correction -> correctly rounded v / d
 }
-#ifdef ATTNDM_SILU_SFU
-__device__ __forceinline__ float silu_f(float v) { return silu_sfu(v); }
-#else
 __device__ __forceinline__ float silu_f(float v) { return silu_acc(v); }
-#endif
 
 // t = s * silu(u) - zp, the argument of the quantizer's round (utils/quant_util.py:273), see above
 __device__ __forceinline__ float silu_quant_t(float u, float s, float zp) {
-#if defined(ATTNDM_SILU_SFU) || defined(ATTNDM_SILU_ACCURATE)
-  return __fsub_rn(__fmul_rn(s, silu_f(u)), zp);
-#else
+#if defined(ATTNDM_SILU_ACCURATE)
+  return __fsub_rn(__fmul_rn(s, silu_acc(u)), zp);
+#elif defined(ATTNDM_SILU_GUARD)
   const float sy = __fmul_rn(s, silu_sfu(u));
   float t = __fsub_rn(sy, zp);
   const float w = __fadd_rn(t, 12582912.0f);                      // 1.5 * 2^23: w - 1.5 * 2^23 == rne(t) for |t| < 2^22
   const float d = fabsf(fabsf(__fsub_rn(t, __fsub_rn(w, 12582912.0f))) - 0.5f);
+  // the guard is > 2x the worst-case SFU error of t for |s * y| < 400; beyond that always the accurate form
   if (d < kSiluGuard || !(fabsf(sy) < 400.0f)) t = __fsub_rn(__fmul_rn(s, silu_acc(u)), zp);
   return t;
+#else
+  return __fsub_rn(__fmul_rn(s, silu_sfu(u)), zp);
 #endif
 }
 // the quantizer's round + clamp on t (same codes as quant_code)

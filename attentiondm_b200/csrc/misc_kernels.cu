@@ -158,9 +158,16 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
 // ---------------------------------------------------------------------------
 __global__ void ddim_step_kernel(const float* __restrict__ xt, const float* __restrict__ eps,
                                  const float* __restrict__ coef, const float* __restrict__ noise,
-                                 float* __restrict__ x_next, float* __restrict__ x0_out, long long n) {
+                                 float* __restrict__ x_next, float* __restrict__ x0_out, long long n,
+                                 float* __restrict__ hist_x, float* __restrict__ hist_x0,
+                                 const int* __restrict__ step_after, int T) {
   pdl_enter();
   const float s1mat = coef[0], sat = coef[1], satn = coef[2], c1 = coef[3], c2 = coef[4];
+  if (hist_x != nullptr) {                       // history slot of this step (the counter was advanced already)
+    const int k = (*step_after + T - 1) % T;
+    hist_x += (long long)k * n;
+    hist_x0 += (long long)k * n;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float x = xt[i], e = eps[i];
     // x0_t = (xt - et * (1 - at).sqrt()) / at.sqrt()
@@ -171,6 +178,10 @@ __global__ void ddim_step_kernel(const float* __restrict__ xt, const float* __re
     r = __fadd_rn(r, __fmul_rn(c2, e));
     x_next[i] = r;
     if (x0_out) x0_out[i] = x0;
+    if (hist_x != nullptr) {
+      hist_x[i] = r;
+      hist_x0[i] = x0;
+    }
   }
 }
 
@@ -258,8 +269,20 @@ int attndm_timestep_embedding(const float* t, int B, int dim, float* emb, void* 
 int attndm_ddim_step(const float* xt, const float* eps, const float* coef, const float* noise, float* x_next,
                      float* x0_out, long long n, void* stream) {
   ATTNDM_CHECK_ARG(xt && eps && coef && x_next && n > 0, "ddim_step: bad args");
-  launch_pdl(ddim_step_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, xt, eps, coef, noise, x_next, x0_out, n);
+  launch_pdl(ddim_step_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, xt, eps, coef, noise, x_next, x0_out, n,
+             (float*)nullptr, (float*)nullptr, (const int*)nullptr, 1);
   ATTNDM_CUDA_LAUNCH_CHECK("ddim_step");
+  return ATTNDM_OK;
+}
+
+int attndm_ddim_step_hist(const float* xt, const float* eps, const float* coef, const float* noise, float* x_next,
+                          float* x0_out, long long n, float* hist_x, float* hist_x0, const int* step_after, int T,
+                          void* stream) {
+  ATTNDM_CHECK_ARG(xt && eps && coef && x_next && n > 0, "ddim_step_hist: bad args");
+  ATTNDM_CHECK_ARG(hist_x && hist_x0 && step_after && T > 0, "ddim_step_hist: history rings, step counter and T are required");
+  launch_pdl(ddim_step_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, xt, eps, coef, noise, x_next, x0_out, n,
+             hist_x, hist_x0, step_after, T);
+  ATTNDM_CUDA_LAUNCH_CHECK("ddim_step_hist");
   return ATTNDM_OK;
 }
 

@@ -75,6 +75,12 @@ class SamplerEngine:
         self.versions = self._versions()
         self.x_cur = torch.zeros(self.B, self.H, self.W, self.C, device=dev)
         self.x0 = torch.zeros_like(self.x_cur)
+        # device-side history rings: every step's x_t and x0 prediction, which generalized_steps returns as lists
+        # (functions/denoising.py:34,40).  The DDIM kernel fills slot `step`; run() copies whole chunks to the host
+        # on a side stream while later steps compute.
+        self.hist_x = torch.empty(self.T, self.B, self.H, self.W, self.C, device=dev)
+        self.hist_x0 = torch.empty_like(self.hist_x)
+        self.copy_stream = torch.cuda.Stream(device=dev)
         self.noise = torch.zeros_like(self.x_cur) if self.eta != 0 else None
         self.ext_noise = False
         self.graph = None
@@ -112,7 +118,8 @@ class SamplerEngine:
         self._set_fused(self.fused_parts[part])
         x = self.x_cur
         eps = self.model.forward_nhwc(x, self.cur[self.t_off:self.t_off + self.B])
-        ops.ddim_step(x, eps, self.cur[self.coef_off:], self.noise, x_next=x, x0_out=self.x0)
+        ops.ddim_step(x, eps, self.cur[self.coef_off:], self.noise, x_next=x, x0_out=self.x0,
+                      hist=(self.hist_x, self.hist_x0, self.step))
         return eps
 
     # ---- one denoising step on the current stream ----
@@ -202,26 +209,44 @@ class SamplerEngine:
         if self.ext_noise and self.noise is None:
             self.noise = torch.zeros_like(self.x_cur)
             self.graph = None
+        main = torch.cuda.current_stream()
+        main.wait_stream(self.copy_stream)                 # a previous run's history copies have left the rings
         if self.use_graph and self.graph is None:
             self.load_input(x)
             self._capture()
         self.load_input(x)
-        host_x, host_x0 = [], []
-        if keep == "last" and not self.ext_noise:
-            self.run_loaded()
-            host_x.append(_pinned_copy(self.x_cur))
-            host_x0.append(_pinned_copy(self.x0))
-        else:
-            for k in range(self.T):
-                if self.ext_noise:
+        T = self.T
+        if keep == "last":
+            if self.ext_noise:
+                for k in range(T):
                     self.noise.copy_(noise_fn(k, ops.to_nchw(self.x_cur)).permute(0, 2, 3, 1))
-                self.run_loaded(1)
-                if keep == "all" or k == self.T - 1:
-                    host_x.append(_pinned_copy(self.x_cur))
-                    host_x0.append(_pinned_copy(self.x0))
-        torch.cuda.current_stream().synchronize()
-        xs = [x] + [ops.to_nchw(h) for h in host_x]
-        return xs, [ops.to_nchw(h) for h in host_x0]
+                    self.run_loaded(1)
+            else:
+                self.run_loaded()
+            hx, hx0 = _pinned_copy(self.x_cur), _pinned_copy(self.x0)
+            main.synchronize()
+            return [x, ops.to_nchw(hx)], [ops.to_nchw(hx0)]
+        # keep == "all": ONE pinned block per call (fresh tensors for the caller, like the reference's .to('cpu')),
+        # filled chunk by chunk from the history rings on the copy stream, overlapped with the following steps
+        host = torch.empty((2,) + tuple(self.hist_x.shape), dtype=torch.float32, device="cpu", pin_memory=True)
+        chunk = 1 if self.ext_noise else max(1, min(16, T // 6))
+        k0 = 0
+        while k0 < T:
+            n = min(chunk, T - k0)
+            if self.ext_noise:
+                self.noise.copy_(noise_fn(k0, ops.to_nchw(self.x_cur)).permute(0, 2, 3, 1))
+            self.run_loaded(n)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.copy_stream.wait_event(ev)
+            with torch.cuda.stream(self.copy_stream):
+                host[0, k0:k0 + n].copy_(self.hist_x[k0:k0 + n], non_blocking=True)
+                host[1, k0:k0 + n].copy_(self.hist_x0[k0:k0 + n], non_blocking=True)
+            k0 += n
+        self.copy_stream.synchronize()
+        main.synchronize()
+        xs = [x] + [ops.to_nchw(host[0, k]) for k in range(T)]
+        return xs, [ops.to_nchw(host[1, k]) for k in range(T)]
 
 
 def _pinned_copy(t):

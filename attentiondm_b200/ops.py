@@ -363,11 +363,18 @@ def timestep_embedding(t: torch.Tensor, dim: int):
     return emb
 
 
-def ddim_step(xt, eps, coef, noise=None, x_next=None, x0_out=None, want_x0=False):
+def ddim_step(xt, eps, coef, noise=None, x_next=None, x0_out=None, want_x0=False, hist=None):
+    """hist = (hist_x [T, ...], hist_x0 [T, ...], step_after int32[1]): also record this step's x_next / x0 in
+    slot (step_after - 1) mod T of the device-side history rings (attndm_ddim_step_hist)."""
     if x_next is None:
         x_next = torch.empty_like(xt)
     x0 = x0_out if x0_out is not None else (torch.empty_like(xt) if want_x0 else None)
-    call("attndm_ddim_step", ptr(xt), ptr(eps), ptr(coef), ptr(noise), ptr(x_next), ptr(x0), xt.numel(), stream())
+    if hist is not None:
+        hx, hx0, step_after = hist
+        call("attndm_ddim_step_hist", ptr(xt), ptr(eps), ptr(coef), ptr(noise), ptr(x_next), ptr(x0), xt.numel(),
+             ptr(hx), ptr(hx0), ptr(step_after), hx.shape[0], stream())
+    else:
+        call("attndm_ddim_step", ptr(xt), ptr(eps), ptr(coef), ptr(noise), ptr(x_next), ptr(x0), xt.numel(), stream())
     return x_next, x0
 
 

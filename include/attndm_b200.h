@@ -228,6 +228,15 @@ int attndm_timestep_embedding(const float* t, int B, int dim, float* emb, void* 
 int attndm_ddim_step(const float* xt, const float* eps, const float* coef, const float* noise,
                      float* x_next, float* x0_out, long long n, void* stream);
 
+/* The same update that ALSO records x_next and x0 of this step in device-side history rings
+ * hist_x / hist_x0 [T][n] -- what generalized_steps returns as its per-step lists (functions/denoising.py:34,40
+ * appends x0_t.to('cpu') and xt_next.to('cpu') every step).  The slot is (*step_after - 1) mod T, where
+ * step_after is the device counter attndm_stage_tables has already advanced for this step, so that one captured
+ * CUDA graph fills a different slot at every replay; the host then copies whole chunks of the rings. */
+int attndm_ddim_step_hist(const float* xt, const float* eps, const float* coef, const float* noise,
+                          float* x_next, float* x0_out, long long n, float* hist_x, float* hist_x0,
+                          const int* step_after, int T, void* stream);
+
 /* Copy row `*step` of a [T][n] table into `dst` and (if advance) increment *step
  * modulo T: lets one captured CUDA graph serve every denoising step, mirroring
  * the per-module index_seq counter (utils/quant_util.py:228-229,281). */

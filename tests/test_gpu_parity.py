@@ -417,12 +417,15 @@ def test_conv1x1_f32_tensor_core_3xtf32(B, H, W, C, O):
     assert torch.equal(y1, y_tc[1:2])
 
 
-def test_silu_quantizer_guard_equals_accurate_silu():
-    """The hot path evaluates SiLU on the special-function unit and re-evaluates it accurately only when
-    s * silu(u) - zp lands within kSiluGuard of a rounding boundary (csrc/common.cuh).  Its codes must be exactly
-    those of quantizing the accurate SiLU (the fp32 output of the same library), on random inputs and on inputs
-    constructed to sit right at the boundaries; and the accurate SiLU must agree with torch's to <= 2 ulp."""
-    from attentiondm_b200 import ops
+def test_silu_quantizer_forms():
+    """SiLU in front of the quantizer (csrc/common.cuh).  The default build evaluates it on the special-function
+    unit: on random pre-activations fewer than 5e-6 of the codes may differ from quantizing the library's accurate
+    fp32 SiLU.  The A/B builds (ATTNDM_LIB=..._silu_guard.so: SFU first, accurate next to a rounding boundary;
+    ..._silu_accurate.so) must give EXACTLY the accurate codes, also on inputs constructed to sit right at the
+    boundaries.  In every build the accurate SiLU agrees with torch's to <= 2 ulp."""
+    import os
+    from attentiondm_b200 import ops, _ffi
+    exact = any(v in os.path.basename(_ffi.LIB_PATH) for v in ("silu_guard", "silu_accurate"))
     g = torch.Generator().manual_seed(12)
     C = 128
     for a_bit, lo, hi in ((8, -4.0, 6.0), (8, -0.5, 3.0), (6, -4.0, 6.0), (4, -4.0, 6.0), (8, -30.0, 50.0)):
@@ -444,11 +447,16 @@ def test_silu_quantizer_guard_equals_accurate_silu():
         y_acc = ops.silu(x)                                                # accurate fp32 SiLU of the library
         want, _, _ = ops.act_quant(y_acc, sv, zv, a_bit, ops.PRE_NONE, want_codes=True, halo=False)
         got, rs, _ = ops.act_quant(x, sv, zv, a_bit, ops.PRE_SILU, want_codes=True, halo=False)
-        assert torch.equal(got, want), (a_bit, lo, hi, int((got != want).sum()))
         got_h, _, _ = ops.act_quant(x, sv, zv, a_bit, ops.PRE_SILU, want_codes=True, halo=True)   # rows kernel
         B, H, W, _ = x.shape
         inner = got_h.view(B, H + 2, W + 2, -1)[:, 1:-1, 1:-1].reshape(-1, got_h.shape[-1])
-        assert torch.equal(inner, want)
+        assert torch.equal(inner, got)                                     # every quantizer kernel shares the form
+        if exact:
+            assert torch.equal(got, want), (a_bit, lo, hi, int((got != want).sum()))
+        else:
+            nr = u_rand.shape[0] * H * W
+            d = (got[:nr].int() - want[:nr].int()).abs()
+            assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 5e-6, (a_bit, lo, hi, float((d > 0).float().mean()))
         # how many of the adversarial elements really are boundary cases (sanity of the construction)
         t = float(s) * F.silu(u.double()) - float(z)
         near = ((t - t.floor() - 0.5).abs() < 3e-4).float().mean()
