@@ -42,10 +42,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// bounded wait: a lost arrival traps (fails the launch) instead of hanging the GPU
+// bounded wait: a lost arrival traps (fails the launch) instead of hanging the GPU.  mbarrier.try_wait suspends the
+// thread in hardware until the phase completes or a system time limit passes, so the loop around it issues only a
+// few instructions per poll; the bound is a poll count (reading the clock in the loop costs more issue slots than
+// the poll itself).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
-  long long t0 = clock64();
+  uint32_t polls = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -54,16 +57,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!done && clock64() - t0 > 4000000000LL) __trap();
+    if (!done && ++polls > (1u << 24)) __trap();
   } while (!done);
 }
-// Waits of the warps that are NOT on the critical path (epilogue, geometry, producers): back off between polls.
-// A spinning warp issues try_wait / clock / branch instructions back to back and takes issue slots away from
-// the MMA-issuing warp that shares its SM sub-partition -- measured: with eleven warps spinning the MMA warp
-// sustained one tcgen05.mma per ~130 cycles instead of the 64 the tensor pipe needs.
+// Waits of the warps that are NOT on the critical path (epilogue, geometry, producers).  They used to back off with
+// nanosleep between polls; the sleeps (up to 2x the requested time each) chained through the producer -> MMA ->
+// epilogue handshakes and set the tile rate of the whole kernel (30 us with neither MMAs nor epilogue work), so
+// they now rely on try_wait's own hardware suspend like the critical waits.
+#ifndef ATTNDM_TC_RELAX_NS
+#define ATTNDM_TC_RELAX_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (ATTNDM_TC_RELAX_NS == 0) { mbar_wait(bar, parity); return; }
   uint32_t done;
-  long long t0 = clock64();
+  uint32_t polls = 0;
   for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -73,8 +80,8 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(128);
-    if (clock64() - t0 > 4000000000LL) __trap();
+    __nanosleep(ATTNDM_TC_RELAX_NS);
+    if (++polls > (1u << 24)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -187,6 +194,46 @@ __device__ __forceinline__ void umma_i8_x4_if(uint32_t leader, uint32_t tmem_d, 
       "}"
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(leader), "r"(nk), "r"(0x40004040u)
       : "memory");
+}
+// One MMA from the two descriptor low words (high word 0x40004040: SBO = 1024 B, version 1, SWIZZLE_128B), for code
+// that runs inside `if (elect_one())`: under a branch on elect.sync ptxas keeps every operand in uniform registers
+// and emits a bare UTCIMMA with ~3 uniform-datapath instructions around it.  The predicated forms above cost ~20
+// instructions per MMA (VOTEU.ANY / R2UR / UMOV under predicates): the issuing warp, not the tensor pipe, then sets
+// the MMA rate (measured 75-87 cycles per MMA instead of 64).
+__device__ __forceinline__ void umma_i8_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 ad, {%1, %5};\n\t"
+      "mov.b64 bd, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], ad, bd, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+      : "memory");
+}
+// All MMAs of one output tile with resident weights (called by the elected lane only).  a_lo0 / b_lo0: descriptor low
+// words of the halo buffer and of the weight block; tap (kh, kw) slides A by (kh*Wp + kw) rows of 128 B = 8 units.
+__device__ __forceinline__ void umma_tile_resident(uint32_t tmem_d, uint32_t a_lo0, uint32_t b_lo0, uint32_t idesc, int kdim,
+                                                   int wp8, int ncb, uint32_t a_step, uint32_t b_step, int ksteps_last) {
+  uint32_t b_lo = b_lo0, accumulate = 0;
+#pragma unroll 1
+  for (int kh = 0; kh < kdim; ++kh) {
+    const uint32_t a_row = a_lo0 + (uint32_t)(kh * wp8);
+#pragma unroll 1
+    for (int kw = 0; kw < kdim; ++kw) {
+      uint32_t a_lo = a_row + (uint32_t)(kw * 8);
+#pragma unroll 1
+      for (int cb = 0; cb < ncb; ++cb) {
+        const int nk = (cb == ncb - 1) ? ksteps_last : 4;      // warp-uniform: cheap uniform predicates
+        umma_i8_lo(tmem_d, a_lo, b_lo, idesc, accumulate);
+        if (nk > 1) umma_i8_lo(tmem_d, a_lo + 2, b_lo + 2, idesc, 1u);
+        if (nk > 2) umma_i8_lo(tmem_d, a_lo + 4, b_lo + 4, idesc, 1u);
+        if (nk > 3) umma_i8_lo(tmem_d, a_lo + 6, b_lo + 6, idesc, 1u);
+        accumulate = 1;
+        a_lo += a_step;
+        b_lo += b_step;
+      }
+    }
+  }
 }
 __device__ __forceinline__ void tcgen05_commit_if(uint32_t leader, uint32_t bar) {
   asm volatile(
@@ -508,32 +555,36 @@ qconv_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   }
 }
 
-// ---- optional timeline trace (debug): CTA 0 records globaltimer at pipeline events ----------------
-__device__ unsigned long long* g_tc_trace = nullptr;    // [role 0..11][it 0..31][event 0..3], [1536] = CTA, [1540+it] = clock64
-__device__ __forceinline__ void tc_trace(int role, int it, int ev) {
-#ifndef ATTNDM_TC_TRACE
-  return;       // the hooks cost a global load each: compiled in only with -DATTNDM_TC_TRACE (tools/conv_trace.py)
+// ---- optional timeline trace (debug, -DATTNDM_TC_TRACE): one CTA records globaltimer at pipeline events ----------
+// The buffer and the CTA to record travel in the kernel parameters (TcGeomH::trace / trace_cta): a hook is a
+// timer read and one store.  (The first version fetched them with two global LOADS per hook; those queue behind
+// the epilogue's stores in the SM's memory pipeline, so every stamp was taken ~1 us late and the hooks themselves
+// serialised the warps they were meant to observe.)
+// layout: [role 0..15][it 0..31][event 0..3]; [2048 + it] = clock64 at each tile start; [2100 + 4*cta + ev] = per-CTA
+// spans; [4096 + 32*cta + it] = MMA issue-complete time of every tile of every CTA
+#ifdef ATTNDM_TC_TRACE
+#define TC_TRACE(role, it, ev)                                                                        \
+  do {                                                                                                \
+    if (g.trace != nullptr && blockIdx.x == (unsigned)g.trace_cta && (it) < 32) {                     \
+      unsigned long long now_;                                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_)::"memory");                              \
+      g.trace[((role) * 32 + (it)) * 4 + (ev)] = now_;                                                \
+      if ((role) == 1 && (ev) == 0) g.trace[2048 + (it)] = (unsigned long long)clock64();             \
+    }                                                                                                 \
+  } while (0)
+#define TC_SPAN(ev)                                                                                   \
+  do {                                                                                                \
+    if (g.trace != nullptr) {                                                                         \
+      unsigned long long now_;                                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_)::"memory");                              \
+      g.trace[2100 + 4 * blockIdx.x + (ev)] = now_;                                                   \
+    }                                                                                                 \
+  } while (0)
+#else
+#define TC_TRACE(role, it, ev) do { } while (0)
+#define TC_SPAN(ev) do { } while (0)
 #endif
-  unsigned long long* t = g_tc_trace;
-  if (t != nullptr && blockIdx.x == (unsigned)t[1536] && it < 32) {        // t[1536]: which CTA to record
-    unsigned long long now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory");
-    t[(role * 32 + it) * 4 + ev] = now;
-    if (role == 1 && ev == 0) t[1540 + it] = (unsigned long long)clock64();   // SM clock at each tile start
-  }
-}
-
-__device__ __forceinline__ void tc_span(int ev) {          // per-CTA kernel-level timestamps (all CTAs)
-#ifndef ATTNDM_TC_TRACE
-  return;
-#endif
-  unsigned long long* t = g_tc_trace;
-  if (t != nullptr) {
-    unsigned long long now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory");
-    t[1600 + 4 * blockIdx.x + ev] = now;
-  }
-}
+static unsigned long long* g_tc_trace_host = nullptr;     // set by attndm_debug_set_tc_trace
 
 // ---- halo-reuse variant ------------------------------------------------------------------
 // Measured on B200 (tools/umma_shift_test.cu): a K-major SWIZZLE_128B matrix descriptor may start at ANY
@@ -548,9 +599,20 @@ __device__ __forceinline__ void tc_span(int ev) {          // per-CTA kernel-lev
 // (a warp may only read the TMEM lane quarter warp % 4).  As warp 1 it lost the issue slot to them whenever they
 // had ALU work and the tensor pipe idled between MMAs (85-96 cycles per MMA instead of 64, tools/umma_contend_test.cu).
 constexpr int TC_H_EPI0 = 0;                           // first epilogue warp (multiple of 4: quarter = warp % 4)
-constexpr int TC_H_EPI_WARPS = 8;                      // 2 per TMEM lane quarter (16 measured slower: register spills, LSU contention)
+#ifndef ATTNDM_TC_EPI_WARPS
+#define ATTNDM_TC_EPI_WARPS 12
+#endif
+// Epilogue warps, a multiple of four (one per TMEM lane quarter and group).  The epilogue is latency bound: with two
+// epilogue warps per SM sub-partition the schedulers issued 0.3 instructions per cycle (ncu), i.e. ~3 us for the
+// ~9000 warp instructions of a tile against 1.3 us of MMAs.  Twelve warps (three groups taking every third tile in
+// split mode) leave 128 registers per thread; sixteen (96 registers) spill.
+constexpr int TC_H_EPI_WARPS = ATTNDM_TC_EPI_WARPS;
 constexpr int TC_H_R0 = TC_H_EPI0 + TC_H_EPI_WARPS;    // first role warp
-constexpr int TC_H_NGEO = 4;                           // row-geometry buffers (the geometry warp runs this far ahead)
+// Row-geometry buffers: the geometry warp runs this many tiles ahead of the epilogue.  Sixteen on purpose: its
+// row-sum gathers are global loads that queue behind the epilogue's stores in the SM's memory pipeline (ncu: the
+// epilogue warps' top stall was the wait for this warp), so it takes its lead while the weights are still loading
+// and the memory system is idle, and keeps it.
+constexpr int TC_H_NGEO = 16;
 // The TMA output path (per-warp staging slot + tensor stores) is compiled out: it measured 76 us against 59 us
 // for direct stores (see launch_qconv_i8_halo) and its four epilogue instantiations cost instruction cache.
 // Build with -DATTNDM_TC_TMA_STORE (ATTNDM_NVCC_EXTRA) and set ATTNDM_TC_TMA_STORE=1 to experiment with it.
@@ -561,6 +623,7 @@ constexpr bool TC_H_TMA_STORE = false;
 #endif
 // (measured without effect on the plain conv: reading both accumulator blocks of a warp up front, 62.5 us vs
 // 58.8 us, and reading the next block while the current one is processed, 57.1 us vs 56.9 us)
+constexpr int TC_H_NRS = 4;                            // row-sum tiles in flight (bulk copies issued by the geometry warp)
 constexpr int TC_H_NBOX = 5;                           // output tensor maps: boxes of 32, 31, 30, 29, 28 pixels
 constexpr int TC_H_EPI_GROUPS = TC_H_EPI_WARPS / 4;    // warps sharing a quarter split the 32-column chunks
 constexpr int TC_THREADS_H = 32 * (TC_H_R0 + 4);
@@ -580,8 +643,14 @@ __device__ __forceinline__ void tile_geometry(const ConvI8Params& p, long long r
   }
 }
 
+// n / d for n < 2^31 with a precomputed multiplier: q = umulhi(n, m) >> sh, m = ceil(2^(31+s) / d), s = ceil(log2 d), sh = s - 1
+struct FastDiv { unsigned m, sh, d; };
+__device__ __forceinline__ unsigned fdiv(unsigned n, const FastDiv& f) { return f.d == 1 ? n : (__umulhi(n, f.m) >> f.sh); }
+
 struct TcGeomH {
   int BN, ncb, tmem_cols, acc_stride, ntn;
+  int split;              // 1: the two groups of four epilogue warps take ALTERNATE tiles (all chunks of their quarter)
+  int nacc, nacc_shift;   // accumulators in TMEM (4 when they fit in the 512 columns, else 2) and log2 of that
   long long ntiles;
   int hr;             // halo rows per tile (128 for a 1x1 conv)
   int hr_stride;      // bytes per (halo, channel block) in smem, multiple of 1024
@@ -589,10 +658,14 @@ struct TcGeomH {
   int b_resident;     // 1: weights loaded once; 0: streamed
   int nb;             // weight ring depth (streamed)
   int a_off, b_off, stg_off;   // byte offsets inside the 1024-aligned dynamic smem
+  int rs_off, rs_stride;       // row-sum ring of the geometry warp (TC_H_NRS slots of rs_stride bytes); rs_stride = 0: gather by loads
   int tma_store;      // 1: full 16-column pieces leave through per-warp staging + TMA tensor stores
+  unsigned long long* trace;   // debug timeline buffer (trace builds), else nullptr
+  int trace_cta;               // which CTA records it (ATTNDM_TRACE_CTA)
+  FastDiv d_per, d_wp, d_hw;   // divisions by Hp*Wp, Wp and H*W in the geometry warp
   int dbg;            // debug experiments (ATTNDM_TC_DBG, bit mask): low two bits 1 = epilogue skips the math/stores,
-                      // 2 = skips the TMEM loads too; 4 = A descriptor not shifted per tap; 8 = B descriptor fixed;
-                      // 16 = no halo loads; 32 = epilogue arithmetic without loads/stores; 128 / 256 = the MMA warp
+                      // 2 = skips the TMEM loads too;
+                      // 16 = no halo loads; 32 = epilogue arithmetic without loads/stores; 64 = no MMAs; 512 = geometry warp without row-sum loads; 128 / 256 = the MMA warp
                       // skips the halo-full / accumulator-free waits (results are garbage: timing only)
 };
 
@@ -730,6 +803,12 @@ __device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const
 
 // ADDS: the epilogue adds a residual and/or a time embedding.  Two instantiations so that each carries only its
 // own epilogue code (the kernel's size is felt in the instruction cache).
+// Tile index arithmetic in 32 bits (the launcher checks ntiles < 2^31): the role warps run these once per tile on
+// their serial path, where a 64-bit division is a ~150-instruction dependent chain (the geometry warp alone spent
+// ~1.2 us per tile in them).
+__device__ __forceinline__ unsigned tile_mt(const TcGeomH& g, unsigned tile) { return g.ntn == 1 ? tile : tile / (unsigned)g.ntn; }
+__device__ __forceinline__ unsigned tile_nt(const TcGeomH& g, unsigned tile) { return g.ntn == 1 ? 0u : tile % (unsigned)g.ntn; }
+
 template <bool ADDS>
 __global__ void __launch_bounds__(TC_THREADS_H, 1)
 qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -741,21 +820,22 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __shared__ __align__(8) uint64_t a_full[4], a_empty[4];
   __shared__ __align__(8) uint64_t b_full[TC_H_MAXB], b_empty[TC_H_MAXB];
   __shared__ __align__(8) uint64_t b_res_bar;
-  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t tmem_full_bar[4], tmem_empty_bar[4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ ColConst colc[256];
-  __shared__ __align__(8) uint64_t geo_full[TC_H_NGEO], geo_empty[TC_H_NGEO];
+  __shared__ __align__(8) uint64_t geo_full[TC_H_NGEO], geo_empty[TC_H_NGEO], rs_bar[TC_H_NRS];
   __shared__ int geo_pix[TC_H_NGEO][TC_BM];        // output pixel of each tile row (-1: not an output)
-  __shared__ int geo_b[TC_H_NGEO][TC_BM], geo_cs[TC_H_NGEO][TC_BM];  // sample index, window row-sum + zp*K
+  __shared__ int geo_cs[TC_H_NGEO][TC_BM];         // window row-sum + zp*K (the sample index is pixel / (H*W))
   // tensor-store segments of each 32-row quarter: {first-row x coordinate, image row, sample, valid}
   // tensor store of each 32-row quarter: {first pixel inside its sample, sample, first pixel (global), box index or -1}
-  __shared__ int4 geo_seg[TC_H_NGEO][4];
+  __shared__ int4 geo_seg[TC_H_TMA_STORE ? TC_H_NGEO : 1][4];
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nkb = p.taps * g.ncb;
   const int b_tile_bytes = g.BN * TC_BK;
+  const unsigned ntiles = (unsigned)g.ntiles;
 
   if (warp == TC_H_R0) {
     if (lane == 0) {
@@ -770,13 +850,14 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int i = 0; i < g.na; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
     for (int i = 0; i < g.nb; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
     mbar_init(smem_u32(&b_res_bar), 1);
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < g.nacc; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), TC_H_EPI_WARPS);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), g.split ? 4 : TC_H_EPI_WARPS);
     }
+    for (int a = 0; a < TC_H_NRS; ++a) mbar_init(smem_u32(&rs_bar[a]), 1);
     for (int a = 0; a < TC_H_NGEO; ++a) {
       mbar_init(smem_u32(&geo_full[a]), 1);
-      mbar_init(smem_u32(&geo_empty[a]), TC_H_EPI_WARPS);
+      mbar_init(smem_u32(&geo_empty[a]), g.split ? 4 : TC_H_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -784,7 +865,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  if (threadIdx.x == 0) tc_span(0);
+  if (threadIdx.x == 0) TC_SPAN(0);
 
   if (warp == TC_H_R0 + 2) {
     {
@@ -798,20 +879,20 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tma_load_2d_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK, 0);
         }
 #ifdef ATTNDM_TC_TRACE
-        if (g_tc_trace != nullptr && blockIdx.x == (unsigned)g_tc_trace[1536]) {
+        if (g.trace != nullptr && blockIdx.x == (unsigned)g.trace_cta) {
           // trace only: this otherwise idle warp timestamps the true completion of every tile's MMAs
           int it = 0;
-          for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
-            mbar_wait(smem_u32(&tmem_full_bar[it & 1]), (uint32_t)((it >> 1) & 1));
-            if (lane == 0) tc_trace(2, it, 0);
+          for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            mbar_wait(smem_u32(&tmem_full_bar[it & (g.nacc - 1)]), (uint32_t)((it >> g.nacc_shift) & 1));
+            if (lane == 0) TC_TRACE(2, it, 0);
           }
         }
 #endif
       } else {
         int s = 0;
         uint32_t ph = 0;
-        for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
-          const int n0 = (int)(tile % g.ntn) * g.BN;
+        for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+          const int n0 = (int)tile_nt(g, tile) * g.BN;
           for (int kb = 0; kb < nkb; ++kb) {
             const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
             mbar_wait_relaxed(smem_u32(&b_empty[s]), ph ^ 1);
@@ -829,12 +910,12 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int hr1 = g.hr > 256 ? 256 : g.hr;          // a TMA box holds at most 256 rows
       const int hr2 = g.hr - hr1;
       int it = 0;
-      for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
-        const long long m0 = (tile / g.ntn) * TC_BM;
-        const int buf = it % g.na;
-        if (lane == 0) tc_trace(0, it, 0);
-        mbar_wait_relaxed(smem_u32(&a_empty[buf]), (uint32_t)(((it / g.na) & 1) ^ 1));
-        if (lane == 0) tc_trace(0, it, 1);
+      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const unsigned m0 = tile_mt(g, tile) * TC_BM;
+        const int buf = g.na == 2 ? (it & 1) : 0;
+        if (lane == 0) TC_TRACE(0, it, 0);
+        mbar_wait_relaxed(smem_u32(&a_empty[buf]), (uint32_t)((((g.na == 2 ? it >> 1 : it)) & 1) ^ 1));
+        if (lane == 0) TC_TRACE(0, it, 1);
         const uint32_t bar = smem_u32(&a_full[buf]);
         if (g.dbg & 16) { mbar_expect_tx_elect(bar, 0u); continue; }       // experiment: no halo loads at all
         mbar_expect_tx_elect(bar, (uint32_t)(g.ncb * g.hr * TC_BK));
@@ -845,9 +926,9 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         // pull the halos of the tiles 2 and 3 iterations ahead into L2
         for (int ahead = (it == 0 ? 1 : 3); ahead <= 3; ++ahead) {
-          const long long tf = tile + (long long)ahead * gridDim.x;
-          if (tf < g.ntiles) {
-            const long long mf = (tf / g.ntn) * TC_BM;
+          const unsigned tf = tile + (unsigned)ahead * gridDim.x;
+          if (tf < ntiles) {
+            const unsigned mf = tile_mt(g, tf) * TC_BM;
             for (int cb = 0; cb < g.ncb; ++cb) {
               tma_prefetch_2d_elect(&tmA, cb * TC_BK, (int)mf);
               if (hr2 > 0) tma_prefetch_2d_elect(&tmA2, cb * TC_BK, (int)mf + 256);
@@ -872,43 +953,54 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int ksteps_last = ((p.Cp - (g.ncb - 1) * TC_BK) + TC_UMMA_K - 1) / TC_UMMA_K;   // 1..4
       const uint32_t leader = elect_one();
 #ifdef ATTNDM_TC_TRACE
-      unsigned long long* const tr_all = g_tc_trace;     // debug: per-tile issue-complete timestamps of every CTA
+      unsigned long long* const tr_all = g.trace;        // debug: per-tile issue-complete timestamps of every CTA
 #else
       unsigned long long* const tr_all = nullptr;
 #endif
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1, buf = it % g.na;
-        if (lane == 0) tc_trace(1, it, 0);
-        if (!(g.dbg & 256)) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((it >> 1) & 1) ^ 1));
-        if (lane == 0) tc_trace(1, it, 1);
-        if (!(g.dbg & 128)) mbar_wait(smem_u32(&a_full[buf]), (uint32_t)((it / g.na) & 1));
-        if (g.b_resident && it == 0) { mbar_wait(smem_u32(&b_res_bar), 0); if (lane == 0) tc_span(1); }
+      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int acc = it & (g.nacc - 1), buf = g.na == 2 ? (it & 1) : 0;
+        if (lane == 0) TC_TRACE(1, it, 0);
+        if (!(g.dbg & 256)) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((it >> g.nacc_shift) & 1) ^ 1));
+        if (lane == 0) TC_TRACE(1, it, 1);
+        if (!(g.dbg & 128)) mbar_wait(smem_u32(&a_full[buf]), (uint32_t)((g.na == 2 ? it >> 1 : it) & 1));
+        if (g.b_resident && it == 0) { mbar_wait(smem_u32(&b_res_bar), 0); if (lane == 0) TC_SPAN(1); }
         tcgen05_fence_after();
-        if (lane == 0) tc_trace(1, it, 2);
+        if (lane == 0) TC_TRACE(1, it, 2);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
         const uint32_t a_buf0 = base + g.a_off + (uint32_t)(buf * g.ncb) * g.hr_stride;
         uint32_t b_res = base + g.b_off;               // resident mode: walks through the whole weight block
         uint32_t accumulate = 0;
-        if (g.b_resident) {
-          // no waits inside a tile: descriptor low words advance additively, four MMAs per asm block
+        if (g.dbg & 64) {
+          // experiment: no MMAs at all (the commits below arrive at once): the epilogue's own tile rate
+        } else if (g.b_resident) {
+          // no waits inside a tile: the elected lane issues the whole tile from a branch (see umma_i8_lo)
           const uint32_t a_lo0 = ((a_buf0 >> 4) & 0x3FFF) | 0x10000u;
-          uint32_t b_lo = ((b_res >> 4) & 0x3FFF) | 0x10000u;
+          const uint32_t b_lo0 = ((b_res >> 4) & 0x3FFF) | 0x10000u;
           const uint32_t a_step = (uint32_t)g.hr_stride >> 4, b_step = (uint32_t)b_tile_bytes >> 4;
+#ifdef ATTNDM_TC_OLD_ISSUE
+          uint32_t b_lo = b_lo0;
           for (int kh = 0; kh < kdim; ++kh) {
             for (int kw = 0; kw < kdim; ++kw) {
-              uint32_t a_lo = a_lo0 + ((g.dbg & 4) ? 0u : (uint32_t)(kh * p.Wp + kw) * (TC_BK >> 4));
+              uint32_t a_lo = a_lo0 + (uint32_t)(kh * p.Wp + kw) * (TC_BK >> 4);
               for (int cb = 0; cb < g.ncb; ++cb) {
                 umma_i8_x4_if(leader, d_tmem, a_lo, b_lo, idesc, accumulate,
                               (cb == g.ncb - 1) ? ksteps_last : TC_BK / TC_UMMA_K);
                 accumulate = 1;
                 a_lo += a_step;
-                if (!(g.dbg & 8)) b_lo += b_step;
+                b_lo += b_step;
               }
             }
           }
+#else
+          if (leader) {
+            umma_tile_resident(d_tmem, a_lo0, b_lo0, idesc, kdim, p.Wp * (TC_BK >> 4), g.ncb, a_step, b_step, ksteps_last);
+          }
+          __syncwarp();
+          accumulate = 1;
+#endif
         } else
         for (int kh = 0; kh < kdim; ++kh) {
           for (int kw = 0; kw < kdim; ++kw) {
@@ -942,7 +1034,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         tcgen05_commit_if(leader, smem_u32(&a_empty[buf]));
         tcgen05_commit_if(leader, smem_u32(&tmem_full_bar[acc]));
-        if (lane == 0) tc_trace(1, it, 3);
+        if (lane == 0) TC_TRACE(1, it, 3);
         if (tr_all != nullptr && lane == 0 && it < 32) {
           unsigned long long now;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory");
@@ -960,68 +1052,129 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int zp = *p.act_zp;
     const unsigned rows_u = (unsigned)p.rows, per = (unsigned)(p.Hp * p.Wp), hw = (unsigned)(p.H * p.W);
     const int zk = zp * (p.taps * p.C);
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
-      const int buf = it % TC_H_NGEO;
-      const unsigned m0 = (unsigned)(tile / g.ntn) * TC_BM;
-      int px[4], bb[4], cc[4];
+    if (g.rs_stride > 0) {
+      // Row sums through the TMA unit: the halo tile's row sums are hr consecutive int32 of p.rowsum, so ONE 1-D bulk
+      // copy per tile brings them into a small shared-memory ring (this warp issues the copies TC_H_NRS - 1 tiles
+      // ahead and is their only reader: no empty barrier).  Gathered with ordinary loads they queued behind the
+      // epilogue's stores in the SM's load/store pipeline -- measured ~2.9 us per tile for this warp, which paced
+      // the whole kernel (ncu: the epilogue warps' top stall was the wait for this warp's buffer).
+      const uint32_t rs_base = base + (uint32_t)g.rs_off;
+      const int* rs_gen = reinterpret_cast<const int*>(smem_raw + (base - smem_u32(smem_raw)) + g.rs_off);
+      auto rs_issue = [&](unsigned tile, int it) {
+        const int slot = it % TC_H_NRS;
+        const unsigned m0 = tile_mt(g, tile) * TC_BM;
+        int n_ent = (int)rows_u - (int)m0;
+        if (n_ent > g.hr) n_ent = g.hr;
+        if (n_ent < 0) n_ent = 0;
+        const uint32_t n4 = (uint32_t)n_ent & ~3u;         // bulk copies move multiples of 16 bytes
+        const uint32_t bar = smem_u32(&rs_bar[slot]);
+        const uint32_t dst = rs_base + (uint32_t)(slot * g.rs_stride);
+        asm volatile(
+            "{\n\t.reg .pred q, c;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.and.b32 c, %3, 0, q;\n\t"
+            "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %3;\n\t"
+            "@c cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2], %3, [%0];\n\t}"
+            ::"r"(bar), "r"(dst), "l"(p.rowsum + m0), "r"(n4 * 4u)
+            : "memory");
+        if ((uint32_t)n_ent != n4) {                       // last tile of a row count that is no multiple of 4
+          int* gen = const_cast<int*>(rs_gen) + slot * (g.rs_stride >> 2);
+          if ((uint32_t)lane < (uint32_t)n_ent - n4) gen[n4 + lane] = __ldg(p.rowsum + m0 + n4 + lane);
+          fence_proxy_async_smem();                        // a later bulk copy overwrites these generic-proxy writes
+          __syncwarp();
+        }
+      };
+      unsigned tile_i = blockIdx.x;                        // issue cursor, TC_H_NRS - 1 tiles ahead
+      int it_i = 0;
+      for (; it_i < TC_H_NRS - 1 && tile_i < ntiles; ++it_i, tile_i += gridDim.x) rs_issue(tile_i, it_i);
+      int it = 0;
+      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        if (tile_i < ntiles) { rs_issue(tile_i, it_i); ++it_i; tile_i += gridDim.x; }
+        const int slot = it % TC_H_NRS;
+        const unsigned m0 = tile_mt(g, tile) * TC_BM;
+        int px[4], off[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned row = m0 + lane + 32 * j;
-        px[j] = -1;
-        bb[j] = 0;
-        cc[j] = 0;
-        if (row < rows_u) {
-          if (p.taps == 1) {
-            px[j] = (int)row;
-            bb[j] = (int)(row / hw);
-            cc[j] = __ldg(p.rowsum + row) + zk;
-          } else {
-            const unsigned b = row / per, rem = row - b * per;
-            const unsigned hp = rem / (unsigned)p.Wp, wp = rem - hp * (unsigned)p.Wp;
-            if (hp < (unsigned)p.H && wp < (unsigned)p.W) {
-              px[j] = (int)((b * (unsigned)p.H + hp) * (unsigned)p.W + wp);
-              bb[j] = (int)b;
-              const int32_t* rs = p.rowsum + row;
-              int s0 = __ldg(rs) + __ldg(rs + 1) + __ldg(rs + 2);
-              int s1 = __ldg(rs + p.Wp) + __ldg(rs + p.Wp + 1) + __ldg(rs + p.Wp + 2);
-              int s2 = __ldg(rs + 2 * p.Wp) + __ldg(rs + 2 * p.Wp + 1) + __ldg(rs + 2 * p.Wp + 2);
-              cc[j] = s0 + s1 + s2 + zk;
+        for (int j = 0; j < 4; ++j) {                      // index arithmetic before the wait
+          const unsigned row = m0 + lane + 32 * j;
+          px[j] = -1;
+          off[j] = lane + 32 * j;
+          if (row < rows_u) {
+            if (p.taps == 1) {
+              px[j] = (int)row;
+            } else {
+              const unsigned b = fdiv(row, g.d_per), rem = row - b * per;
+              const unsigned hp = fdiv(rem, g.d_wp), wp = rem - hp * (unsigned)p.Wp;
+              if (hp < (unsigned)p.H && wp < (unsigned)p.W) px[j] = (int)((b * (unsigned)p.H + hp) * (unsigned)p.W + wp);
             }
           }
         }
-      }
-      mbar_wait_relaxed(smem_u32(&geo_empty[buf]), (uint32_t)(((it / TC_H_NGEO) & 1) ^ 1));
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        geo_pix[buf][lane + 32 * j] = px[j];
-        geo_b[buf][lane + 32 * j] = bb[j];
-        geo_cs[buf][lane + 32 * j] = cc[j];
-      }
-      if (TC_H_TMA_STORE && g.tma_store) {
-        // The output pixels of a quarter (lane l holds row 32 j + l of quarter j) are consecutive in memory:
-        // the ring positions between two image rows are skipped in the padded row order, not in the output.
-        // One tensor store per 16-column piece covers them when they sit in one sample and either fill one
-        // of the box heights or run up to the end of the sample (the rest of the box is clipped).
+        if (lane == 0) TC_TRACE(3, it, 0);
+        mbar_wait(smem_u32(&rs_bar[slot]), (uint32_t)((it / TC_H_NRS) & 1));
+        const int* rs = rs_gen + slot * (g.rs_stride >> 2);
+        int cs[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const unsigned okm = __ballot_sync(0xffffffffu, px[j] >= 0);
-          const unsigned pmin = __reduce_min_sync(0xffffffffu, px[j] >= 0 ? (unsigned)px[j] : 0xffffffffu);
-          const unsigned bmin = __reduce_min_sync(0xffffffffu, px[j] >= 0 ? (unsigned)bb[j] : 0xffffffffu);
-          const unsigned bmax = __reduce_max_sync(0xffffffffu, px[j] >= 0 ? (unsigned)bb[j] : 0u);
-          const int n = __popc(okm);
-          int4 sgm = make_int4(0, 0, 0, -1);
-          if (n > 0 && bmin == bmax) {
-            const unsigned in_sample = pmin - bmin * hw;
-            const bool to_end = in_sample + (unsigned)n == hw;
-            const int box = to_end ? 0 : 32 - n;               // box 0 = 32 pixels (clipped at the sample end)
-            if (box < TC_H_NBOX) sgm = make_int4((int)in_sample, (int)bmin, (int)pmin, box);
+          cs[j] = 0;
+          if (px[j] >= 0) {
+            const int* w0 = rs + off[j];
+            if (p.taps == 1) {
+              cs[j] = w0[0] + zk;
+            } else {
+              const int* w1 = w0 + p.Wp;
+              const int* w2 = w1 + p.Wp;
+              cs[j] = w0[0] + w0[1] + w0[2] + w1[0] + w1[1] + w1[2] + w2[0] + w2[1] + w2[2] + zk;
+            }
           }
-          if (lane == 0) geo_seg[buf][j] = sgm;
         }
+        const int buf = it % TC_H_NGEO;
+        mbar_wait_relaxed(smem_u32(&geo_empty[buf]), (uint32_t)(((it / TC_H_NGEO) & 1) ^ 1));
+        if (lane == 0) TC_TRACE(3, it, 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          geo_pix[buf][lane + 32 * j] = px[j];
+          geo_cs[buf][lane + 32 * j] = cs[j];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&geo_full[buf]));
+        if (lane == 0) TC_TRACE(3, it, 2);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&geo_full[buf]));
+    } else {
+      // fallback (row sums not 16-byte aligned): gather with ordinary loads, one tile at a time
+      int it = 0;
+      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const unsigned m0 = tile_mt(g, tile) * TC_BM;
+        int px[4], cs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned row = m0 + lane + 32 * j;
+          px[j] = -1;
+          cs[j] = 0;
+          if (row < rows_u) {
+            if (p.taps == 1) {
+              px[j] = (int)row;
+              cs[j] = __ldg(p.rowsum + row) + zk;
+            } else {
+              const unsigned b = row / per, rem = row - b * per;
+              const unsigned hp = rem / (unsigned)p.Wp, wp = rem - hp * (unsigned)p.Wp;
+              if (hp < (unsigned)p.H && wp < (unsigned)p.W) {
+                px[j] = (int)((b * (unsigned)p.H + hp) * (unsigned)p.W + wp);
+                const int32_t* rs = p.rowsum + row;
+                cs[j] = __ldg(rs) + __ldg(rs + 1) + __ldg(rs + 2) + __ldg(rs + p.Wp) + __ldg(rs + p.Wp + 1) + __ldg(rs + p.Wp + 2) +
+                        __ldg(rs + 2 * p.Wp) + __ldg(rs + 2 * p.Wp + 1) + __ldg(rs + 2 * p.Wp + 2) + zk;
+              }
+            }
+          }
+        }
+        const int buf = it % TC_H_NGEO;
+        mbar_wait_relaxed(smem_u32(&geo_empty[buf]), (uint32_t)(((it / TC_H_NGEO) & 1) ^ 1));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          geo_pix[buf][lane + 32 * j] = px[j];
+          geo_cs[buf][lane + 32 * j] = cs[j];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&geo_full[buf]));
+      }
     }
   } else if (warp >= TC_H_EPI0 && warp < TC_H_R0) {
     // ===== epilogue warps (8): quarter = warp % 4, the two warps of a quarter take 32-column chunks round robin.
@@ -1035,10 +1188,17 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int zp = *p.act_zp;
     const int tq = lane & 3, tr = lane >> 2;           // fragment coordinates of this thread
     int last_nt = -1;
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const int nt = (int)(tile % g.ntn);
+    // Split mode (one N tile, four accumulators): group j of four warps (warps 4j .. 4j+3) takes the tiles j, j + G,
+    // j + 2G, ... of this CTA, each warp all column chunks of its lane quarter.  The two groups then sit in different phases (one
+    // waits / loads TMEM while the other stores), which keeps the SM's store path -- the resource that bounds
+    // this kernel -- busy; with all eight warps on one tile they stored and idled in lock step.
+    const int tile_step = g.split ? TC_H_EPI_GROUPS : 1;
+    const int ci0 = g.split ? 0 : half, ci_step = g.split ? 1 : TC_H_EPI_GROUPS;
+    int it = g.split ? half : 0;
+    for (unsigned tile = blockIdx.x + (unsigned)it * gridDim.x; tile < ntiles || last_nt < 0;
+         tile += (unsigned)tile_step * gridDim.x, it += tile_step) {
+      const int acc = it & (g.nacc - 1);
+      const int nt = (int)tile_nt(g, tile);
       const int n0 = nt * g.BN;
       if (nt != last_nt) {
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_H_EPI_WARPS) : "memory");
@@ -1055,6 +1215,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_H_EPI_WARPS) : "memory");
         last_nt = nt;
+        if (tile >= ntiles) break;                   // (split mode, a CTA with a single tile: the odd group only helped with the constants)
       }
       // row geometry of this thread's four fragment rows (tr, tr+8, tr+16, tr+24 of the quarter), prepared
       // by the geometry warp
@@ -1068,7 +1229,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int pix = geo_pix[gb][r];
         rows.ok |= (pix >= 0 ? 1u : 0u) << k;
         rows.off[k] = (uint32_t)(pix < 0 ? 0 : pix) * (uint32_t)p.O + (uint32_t)(n0 + 2 * tq);
-        rows.te_off[k] = (uint32_t)geo_b[gb][r] * (uint32_t)p.O + (uint32_t)(n0 + 2 * tq);
+        rows.te_off[k] = (ADDS && p.temb != nullptr && pix >= 0 ? fdiv((uint32_t)pix, g.d_hw) : 0u) * (uint32_t)p.O + (uint32_t)(n0 + 2 * tq);
         rows.cs[k] = geo_cs[gb][r];
       }
       if (g.dbg & 32) rows.ok = 0;                           // experiment: the epilogue math without loads/stores
@@ -1084,19 +1245,19 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const bool vec4 = (p.O & 3) == 0;                      // 128-bit path for full 32-column blocks
       constexpr bool adds = ADDS;
       float4 rs4[2][4];
-      if (ADDS && p.residual != nullptr && half < nchunks) {   // first block's residual: issued before the wait below
-        const int cf = half << 5;
+      if (ADDS && p.residual != nullptr && ci0 < nchunks) {   // first block's residual: issued before the wait below
+        const int cf = ci0 << 5;
         if (vec4 && cf + 32 <= g.BN && n0 + cf + 32 <= p.O) epi_load_residual_v4(rs4, p.residual, rows, cf, tq);
       }
-      mbar_wait_relaxed(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> 1) & 1));
+      mbar_wait_relaxed(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> g.nacc_shift) & 1));
       tcgen05_fence_after();
-      if (lane == 0) tc_trace(4 + (ew & 7), it, 0);
+      if (lane == 0) TC_TRACE(4 + ew, it, 0);
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(quarter * 32) << 16);
-      if (half >= nchunks) {
+      if (ci0 >= nchunks) {
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
       }
-      for (int ci = half; ci < nchunks; ci += TC_H_EPI_GROUPS) {
+      for (int ci = ci0; ci < nchunks; ci += ci_step) {
         const int c0 = ci << 5;
         uint32_t v0[16], v1[16];
         __syncwarp();
@@ -1104,19 +1265,19 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tmem_ld_16x256b_x4(t_acc + (uint32_t)c0, v0);                      // tile rows 32q + 0..15
           tmem_ld_16x256b_x4(t_acc + (16u << 16) + (uint32_t)c0, v1);        // tile rows 32q + 16..31
           tmem_ld_wait();
-          if (lane == 0 && ci == half) tc_trace(4 + (ew & 7), it, 1);
+          if (lane == 0 && ci == ci0) TC_TRACE(4 + ew, it, 1);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) { v0[j] = 0; v1[j] = 0; }
         }
-        if (ci + TC_H_EPI_GROUPS >= nchunks) {
+        if (ci + ci_step >= nchunks) {
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
         }
         if ((g.dbg & 3) >= 1) continue;
         const bool use4 = vec4 && c0 + 32 <= g.BN && n0 + c0 + 32 <= p.O;
-        if (use4 && p.residual != nullptr && ci != half) epi_load_residual_v4(rs4, p.residual, rows, c0, tq);
+        if (use4 && p.residual != nullptr && ci != ci0) epi_load_residual_v4(rs4, p.residual, rows, c0, tq);
         if (TC_H_TMA_STORE && use4 && seg.w >= 0) {
           // results -> this warp's staging slot -> tensor store.  The warp never waits for the SM's store port
           // (32 B/clk, and every SM bursts at the same time): the TMA unit drains the slot while the warp is
@@ -1157,14 +1318,14 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           // ragged last block or O % 4 != 0 (the 3-channel output): scalar, per-column checks
           epi_block_scalar(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, p.residual, p.temb);
         }
-        if (lane == 0) tc_trace(4 + (ew & 7), it, ci == half ? 2 : 3);
+        if (lane == 0) TC_TRACE(4 + ew, it, ci == ci0 ? 2 : 3);
       }
     }
   }
   if (TC_H_TMA_STORE && g.tma_store && warp >= TC_H_EPI0 && warp < TC_H_R0 && lane == 0) bulk_wait0();
   tcgen05_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) tc_span(2);
+  if (threadIdx.x == 0) TC_SPAN(2);
   if (warp == TC_H_R0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
                  : "memory");
@@ -1245,10 +1406,24 @@ static int launch_qconv_i8_tc_persistent(const ConvI8Params& p, cudaStream_t st)
 
 }  // namespace attndm
 extern "C" int attndm_debug_set_tc_trace(unsigned long long* buf) {
-  cudaError_t e = cudaMemcpyToSymbol(attndm::g_tc_trace, &buf, sizeof(buf));
-  return e == cudaSuccess ? 0 : -2;
+  attndm::g_tc_trace_host = buf;
+  return 0;
 }
 namespace attndm {
+
+static FastDiv make_fastdiv(unsigned d) {
+  FastDiv f;
+  f.d = d < 1 ? 1 : d;
+  f.m = 0;
+  f.sh = 0;
+  if (f.d > 1) {
+    unsigned sft = 0;
+    while ((1ull << sft) < f.d) ++sft;                       // ceil(log2 d) >= 1
+    f.m = (unsigned)(((1ull << (31 + sft)) + f.d - 1) / f.d); // ceil(2^(31+s) / d) < 2^32
+    f.sh = sft - 1;
+  }
+  return f;
+}
 
 static bool tc_halo_enabled() {
   static int v = -1;
@@ -1261,7 +1436,6 @@ static bool tc_halo_enabled() {
 
 // returns 1 if the halo kernel was launched, 0 if the shape does not fit it, <0 on error
 static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
-  constexpr int kBudget = 213 * 1024;                   // dynamic smem we allow ourselves (227 KB - static - slack)
   TcGeomH g;
   g.BN = p.O <= 256 ? round_up(p.O, 16) : 256;
   const long long mtiles = (p.rows + TC_BM - 1) / TC_BM;
@@ -1272,8 +1446,13 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   g.hr = p.taps == 9 ? TC_BM + 2 * p.Wp + 2 : TC_BM;
   if (g.hr > 512) return 0;
   if ((long long)p.B * p.H * p.W * p.O >= (1LL << 31)) return 0;      // the epilogue keeps 32-bit output offsets
-  if (p.rows + TC_BM >= (1LL << 31)) return 0;                        // the geometry warp keeps 32-bit row indices
+  if (p.rows + TC_BM >= (1LL << 31) || g.ntiles >= (1LL << 31)) return 0;   // 32-bit row and tile indices in the kernel
   g.hr_stride = round_up(g.hr * TC_BK, 1024);
+  // row-sum ring of the geometry warp (bulk copies need a 16-byte aligned source; else it gathers with loads)
+  static const bool rs_bulk_on = [] { const char* e = getenv("ATTNDM_TC_RS_BULK"); return !(e && e[0] == '0'); }();
+  const int rs_bytes = (rs_bulk_on && ((uintptr_t)p.rowsum & 15) == 0) ? TC_H_NRS * round_up(g.hr * 4, 16) : 0;
+  // dynamic smem we allow ourselves: 227 KB - 20.5 KB static - alignment slack - the row-sum ring
+  const int kBudget = 205 * 1024 - rs_bytes;
   const int nkb = p.taps * g.ncb;
   const int b_tile = g.BN * TC_BK;
   // output path: per-warp 2 KB staging slots + TMA tensor stores when the 128-bit path applies (O % 4 == 0)
@@ -1309,11 +1488,23 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   g.a_off = 0;
   g.b_off = g.na * a_buf;
   g.stg_off = g.b_off + (g.b_resident ? nkb : g.nb) * b_tile;
+  g.rs_off = g.stg_off + stg_bytes;
+  g.rs_stride = rs_bytes / TC_H_NRS;
   { const char* e = getenv("ATTNDM_TC_DBG"); g.dbg = e ? atoi(e) : 0; }
+  g.trace = g_tc_trace_host;
+  g.d_per = make_fastdiv((unsigned)(p.Hp * p.Wp));
+  g.d_wp = make_fastdiv((unsigned)p.Wp);
+  g.d_hw = make_fastdiv((unsigned)(p.H * p.W));
+  { const char* e = getenv("ATTNDM_TRACE_CTA"); g.trace_cta = e ? atoi(e) : 0; }
   g.acc_stride = round_up(g.BN, 32);
+  // Four accumulators when they fit: the MMA warp may then run up to three tiles ahead of the epilogue, so the
+  // latency of the epilogue -> MMA hand-back (and every other per-tile handshake) hides behind queued work.
+  { const char* e = getenv("ATTNDM_TC_NACC"); g.nacc = (4 * g.acc_stride <= 512 && !(e && e[0] == '2')) ? 4 : 2; }
+  g.nacc_shift = g.nacc == 4 ? 2 : 1;
+  { const char* e = getenv("ATTNDM_TC_SPLIT"); g.split = (g.ntn == 1 && g.nacc == 4 && !(e && e[0] == '0')) ? 1 : 0; }
   g.tmem_cols = 32;
-  while (g.tmem_cols < 2 * g.acc_stride) g.tmem_cols <<= 1;
-  const int smem = g.stg_off + stg_bytes + 1024;
+  while (g.tmem_cols < g.nacc * g.acc_stride) g.tmem_cols <<= 1;
+  const int smem = g.stg_off + stg_bytes + rs_bytes + 1024;
   CUtensorMap tmA, tmA2, tmB;
   const int hr1 = g.hr > 256 ? 256 : g.hr;
   int rc = make_map_2d(&tmA, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, (uint32_t)hr1);
@@ -1328,9 +1519,9 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024);
+    attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
     if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024);
+      attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("qconv_i8_halo: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
   CUtensorMap tmO[TC_H_NBOX];

@@ -31,32 +31,32 @@ bias = torch.zeros(O, device=dev); out = torch.empty(B, H, W, O, device=dev)
 for _ in range(3):
     ops.qconv_i8(codes, rowsum, B, H, W, C, pack, k * k, mult, azp, bias, out=out)
 tr = torch.zeros(4096 + 148 * 32, dtype=torch.int64, device=dev)
-tr[1536] = int(os.environ.get('TRACE_CTA', '0'))
+os.environ['ATTNDM_TRACE_CTA'] = os.environ.get('TRACE_CTA', '0')
 L = _ffi.lib(); L.attndm_debug_set_tc_trace.argtypes = [ctypes.c_void_p]
 L.attndm_debug_set_tc_trace(ctypes.c_void_p(tr.data_ptr()))
 ops.qconv_i8(codes, rowsum, B, H, W, C, pack, k * k, mult, azp, bias, out=out)
 torch.cuda.synchronize()
 L.attndm_debug_set_tc_trace(None)
 full = tr.cpu()
-t = full[:1536].view(12, 32, 4)
+t = full[:2048].view(16, 32, 4)
 t0 = int(t[t > 0].min())
-names = ["Aprod", "MMA", "MMAdone", "-"] + [f"epi{i}" for i in range(8)]
-evn = [["wait_empty", "got_empty", "-", "-"], ["start", "tmem_free", "a_full", "issued"], ["mma_done", "-", "-", "-"], []] + [["tmem_full", "c0_loaded", "c0_done", "c1_done"]] * 8
+names = ["Aprod", "MMA", "MMAdone", "geo"] + [f"epi{i}" for i in range(12)]
+evn = [["wait_empty", "got_empty", "-", "-"], ["start", "tmem_free", "a_full", "issued"], ["mma_done", "-", "-", "-"], ["finish_top", "got_empty", "arrived", "-"]] + [["tmem_full", "c0_loaded", "c0_done", "last_done"]] * 12
 for it in range(int(os.environ.get('TRACE_ITS', '8'))):
-    for r in (1, 2, 4, 5, 6, 7, 8, 9, 10, 11):
+    for r in (1, 2, 3, 4, 8, 12):
         row = [(int(v) - t0) / 1000.0 if v > 0 else float('nan') for v in t[r, it]]
         print(f"it={it} {names[r]:6s} " + "  ".join(f"{evn[r][e]}={row[e]:8.2f}us" for e in range(4)))
 
 v = t[t > 0]
-print(f"CTA {int(tr[1536])}: span first..last event {(int(v.max()) - int(v.min())) / 1000.0:.2f} us")
+print(f"CTA {os.environ['ATTNDM_TRACE_CTA']}: span first..last event {(int(v.max()) - int(v.min())) / 1000.0:.2f} us")
 
-ck = full[1540:1540 + 16]
+ck = full[2048:2048 + 16]
 st = t[1, :16, 0]
 for i in range(1, 14):
     if ck[i] > 0 and ck[i - 1] > 0:
         print(f"tile {i}: {(int(ck[i]) - int(ck[i-1])) / max(1, int(st[i]) - int(st[i-1])) * 1000:.0f} MHz")
 
-sp = full[1600:1600 + 4 * 148].view(148, 4)
+sp = full[2100:2100 + 4 * 148].view(148, 4)
 ok = sp[:, 0] > 0
 k0 = int(sp[ok, 0].min())
 import statistics
