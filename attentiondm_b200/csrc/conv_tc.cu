@@ -823,7 +823,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __shared__ __align__(8) uint64_t tmem_full_bar[4], tmem_empty_bar[4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ ColConst colc[256];
-  __shared__ __align__(8) uint64_t geo_full[TC_H_NGEO], geo_empty[TC_H_NGEO], rs_bar[TC_H_NRS];
+  __shared__ __align__(8) uint64_t geo_full[TC_H_NGEO], geo_empty[TC_H_NGEO], rs_bar[2][TC_H_NRS];
   __shared__ int geo_pix[TC_H_NGEO][TC_BM];        // output pixel of each tile row (-1: not an output)
   __shared__ int geo_cs[TC_H_NGEO][TC_BM];         // window row-sum + zp*K (the sample index is pixel / (H*W))
   // tensor-store segments of each 32-row quarter: {first-row x coordinate, image row, sample, valid}
@@ -854,7 +854,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[a]), g.split ? 4 : TC_H_EPI_WARPS);
     }
-    for (int a = 0; a < TC_H_NRS; ++a) mbar_init(smem_u32(&rs_bar[a]), 1);
+    for (int a = 0; a < TC_H_NRS; ++a) { mbar_init(smem_u32(&rs_bar[0][a]), 1); mbar_init(smem_u32(&rs_bar[1][a]), 1); }
     for (int a = 0; a < TC_H_NGEO; ++a) {
       mbar_init(smem_u32(&geo_full[a]), 1);
       mbar_init(smem_u32(&geo_empty[a]), g.split ? 4 : TC_H_EPI_WARPS);
@@ -867,6 +867,145 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tmem_base = tmem_base_slot;
   if (threadIdx.x == 0) TC_SPAN(0);
 
+  // ===== geometry: per-row output pixel and window row-sum of a tile, prepared ahead of the epilogue.  Run by the
+  // geometry warp and, with resident weights, also by the weight producer once its loads are issued (gw = 1 of 2) =====
+  auto geometry_role = [&](const int gw, const int ngw) {
+    // ===== geometry warp: per-row output pixel / sample / window row-sum for the NEXT tiles, so the
+    // epilogue never waits on the nine dependent-latency row-sum loads or the index divisions =====
+    // One warp has to keep up with the tile rate, so: 32-bit index arithmetic (the launcher guarantees
+    // rows < 2^31), all 36 row-sum loads of a tile in flight together, and the wait for a free buffer only
+    // AFTER they were issued -- with four buffers the warp runs up to four tiles ahead of the epilogue.
+    pdl_wait();
+    const int zp = *p.act_zp;
+    const unsigned rows_u = (unsigned)p.rows, per = (unsigned)(p.Hp * p.Wp), hw = (unsigned)(p.H * p.W);
+    const int zk = zp * (p.taps * p.C);
+    if (g.rs_stride > 0) {
+      // Row sums through the TMA unit: the halo tile's row sums are hr consecutive int32 of p.rowsum, so ONE 1-D bulk
+      // copy per tile brings them into a small shared-memory ring (this warp issues the copies TC_H_NRS - 1 tiles
+      // ahead and is their only reader: no empty barrier).  Gathered with ordinary loads they queued behind the
+      // epilogue's stores in the SM's load/store pipeline -- measured ~2.9 us per tile for this warp, which paced
+      // the whole kernel (ncu: the epilogue warps' top stall was the wait for this warp's buffer).
+      const uint32_t rs_base = base + (uint32_t)(g.rs_off + gw * TC_H_NRS * g.rs_stride);
+      const int* rs_gen = reinterpret_cast<const int*>(smem_raw + (base - smem_u32(smem_raw)) + g.rs_off + gw * TC_H_NRS * g.rs_stride);
+      auto rs_issue = [&](unsigned tile, int seq) {
+        const int slot = seq % TC_H_NRS;
+        const unsigned m0 = tile_mt(g, tile) * TC_BM;
+        int n_ent = (int)rows_u - (int)m0;
+        if (n_ent > g.hr) n_ent = g.hr;
+        if (n_ent < 0) n_ent = 0;
+        const uint32_t n4 = (uint32_t)n_ent & ~3u;         // bulk copies move multiples of 16 bytes
+        const uint32_t bar = smem_u32(&rs_bar[gw][slot]);
+        const uint32_t dst = rs_base + (uint32_t)(slot * g.rs_stride);
+        asm volatile(
+            "{\n\t.reg .pred q, c;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.and.b32 c, %3, 0, q;\n\t"
+            "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %3;\n\t"
+            "@c cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2], %3, [%0];\n\t}"
+            ::"r"(bar), "r"(dst), "l"(p.rowsum + m0), "r"(n4 * 4u)
+            : "memory");
+        if ((uint32_t)n_ent != n4) {                       // last tile of a row count that is no multiple of 4
+          int* gen = const_cast<int*>(rs_gen) + slot * (g.rs_stride >> 2);
+          if ((uint32_t)lane < (uint32_t)n_ent - n4) gen[n4 + lane] = __ldg(p.rowsum + m0 + n4 + lane);
+          fence_proxy_async_smem();                        // a later bulk copy overwrites these generic-proxy writes
+          __syncwarp();
+        }
+      };
+      const unsigned tstride = (unsigned)ngw * gridDim.x;  // this warp takes the tiles gw, gw + ngw, ... of the CTA
+      unsigned tile_i = blockIdx.x + (unsigned)gw * gridDim.x;   // issue cursor, TC_H_NRS - 1 of its tiles ahead
+      int seq_i = 0;
+      for (; seq_i < TC_H_NRS - 1 && tile_i < ntiles; ++seq_i, tile_i += tstride) rs_issue(tile_i, seq_i);
+      int it = gw, seq = 0;
+      for (unsigned tile = blockIdx.x + (unsigned)gw * gridDim.x; tile < ntiles; tile += tstride, it += ngw, ++seq) {
+        if (tile_i < ntiles) { rs_issue(tile_i, seq_i); ++seq_i; tile_i += tstride; }
+        const int slot = seq % TC_H_NRS;
+        const unsigned m0 = tile_mt(g, tile) * TC_BM;
+        int px[4], off[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                      // index arithmetic before the wait
+          const unsigned row = m0 + lane + 32 * j;
+          px[j] = -1;
+          off[j] = lane + 32 * j;
+          if (row < rows_u) {
+            if (p.taps == 1) {
+              px[j] = (int)row;
+            } else {
+              const unsigned b = fdiv(row, g.d_per), rem = row - b * per;
+              const unsigned hp = fdiv(rem, g.d_wp), wp = rem - hp * (unsigned)p.Wp;
+              if (hp < (unsigned)p.H && wp < (unsigned)p.W) px[j] = (int)((b * (unsigned)p.H + hp) * (unsigned)p.W + wp);
+            }
+          }
+        }
+        if (lane == 0) TC_TRACE(2 + (gw ^ 1), it, 0);
+        mbar_wait(smem_u32(&rs_bar[gw][slot]), (uint32_t)((seq / TC_H_NRS) & 1));
+        const int* rs = rs_gen + slot * (g.rs_stride >> 2);
+        int cs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cs[j] = 0;
+          if (px[j] >= 0) {
+            const int* w0 = rs + off[j];
+            if (p.taps == 1) {
+              cs[j] = w0[0] + zk;
+            } else {
+              const int* w1 = w0 + p.Wp;
+              const int* w2 = w1 + p.Wp;
+              cs[j] = w0[0] + w0[1] + w0[2] + w1[0] + w1[1] + w1[2] + w2[0] + w2[1] + w2[2] + zk;
+            }
+          }
+        }
+        const int buf = it % TC_H_NGEO;
+        mbar_wait_relaxed(smem_u32(&geo_empty[buf]), (uint32_t)(((it / TC_H_NGEO) & 1) ^ 1));
+        if (lane == 0) TC_TRACE(2 + (gw ^ 1), it, 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          geo_pix[buf][lane + 32 * j] = px[j];
+          geo_cs[buf][lane + 32 * j] = cs[j];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&geo_full[buf]));
+        if (lane == 0) TC_TRACE(2 + (gw ^ 1), it, 2);
+      }
+    } else {
+      // fallback (row sums not 16-byte aligned): gather with ordinary loads, one tile at a time
+      int it = gw;
+      for (unsigned tile = blockIdx.x + (unsigned)gw * gridDim.x; tile < ntiles; tile += (unsigned)ngw * gridDim.x, it += ngw) {
+        const unsigned m0 = tile_mt(g, tile) * TC_BM;
+        int px[4], cs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned row = m0 + lane + 32 * j;
+          px[j] = -1;
+          cs[j] = 0;
+          if (row < rows_u) {
+            if (p.taps == 1) {
+              px[j] = (int)row;
+              cs[j] = __ldg(p.rowsum + row) + zk;
+            } else {
+              const unsigned b = row / per, rem = row - b * per;
+              const unsigned hp = rem / (unsigned)p.Wp, wp = rem - hp * (unsigned)p.Wp;
+              if (hp < (unsigned)p.H && wp < (unsigned)p.W) {
+                px[j] = (int)((b * (unsigned)p.H + hp) * (unsigned)p.W + wp);
+                const int32_t* rs = p.rowsum + row;
+                cs[j] = __ldg(rs) + __ldg(rs + 1) + __ldg(rs + 2) + __ldg(rs + p.Wp) + __ldg(rs + p.Wp + 1) + __ldg(rs + p.Wp + 2) +
+                        __ldg(rs + 2 * p.Wp) + __ldg(rs + 2 * p.Wp + 1) + __ldg(rs + 2 * p.Wp + 2) + zk;
+              }
+            }
+          }
+        }
+        const int buf = it % TC_H_NGEO;
+        mbar_wait_relaxed(smem_u32(&geo_empty[buf]), (uint32_t)(((it / TC_H_NGEO) & 1) ^ 1));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          geo_pix[buf][lane + 32 * j] = px[j];
+          geo_cs[buf][lane + 32 * j] = cs[j];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&geo_full[buf]));
+      }
+    }
+  };
+
   if (warp == TC_H_R0 + 2) {
     {
       // ===== weight producer (weights are static: no need to wait for the previous kernel) =====
@@ -878,16 +1017,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
           tma_load_2d_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK, 0);
         }
-#ifdef ATTNDM_TC_TRACE
-        if (g.trace != nullptr && blockIdx.x == (unsigned)g.trace_cta) {
-          // trace only: this otherwise idle warp timestamps the true completion of every tile's MMAs
-          int it = 0;
-          for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            mbar_wait(smem_u32(&tmem_full_bar[it & (g.nacc - 1)]), (uint32_t)((it >> g.nacc_shift) & 1));
-            if (lane == 0) TC_TRACE(2, it, 0);
-          }
-        }
-#endif
+        geometry_role(1, 2);
       } else {
         int s = 0;
         uint32_t ph = 0;
@@ -1043,139 +1173,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp == TC_H_R0 + 3) {
-    // ===== geometry warp: per-row output pixel / sample / window row-sum for the NEXT tiles, so the
-    // epilogue never waits on the nine dependent-latency row-sum loads or the index divisions =====
-    // One warp has to keep up with the tile rate, so: 32-bit index arithmetic (the launcher guarantees
-    // rows < 2^31), all 36 row-sum loads of a tile in flight together, and the wait for a free buffer only
-    // AFTER they were issued -- with four buffers the warp runs up to four tiles ahead of the epilogue.
-    pdl_wait();
-    const int zp = *p.act_zp;
-    const unsigned rows_u = (unsigned)p.rows, per = (unsigned)(p.Hp * p.Wp), hw = (unsigned)(p.H * p.W);
-    const int zk = zp * (p.taps * p.C);
-    if (g.rs_stride > 0) {
-      // Row sums through the TMA unit: the halo tile's row sums are hr consecutive int32 of p.rowsum, so ONE 1-D bulk
-      // copy per tile brings them into a small shared-memory ring (this warp issues the copies TC_H_NRS - 1 tiles
-      // ahead and is their only reader: no empty barrier).  Gathered with ordinary loads they queued behind the
-      // epilogue's stores in the SM's load/store pipeline -- measured ~2.9 us per tile for this warp, which paced
-      // the whole kernel (ncu: the epilogue warps' top stall was the wait for this warp's buffer).
-      const uint32_t rs_base = base + (uint32_t)g.rs_off;
-      const int* rs_gen = reinterpret_cast<const int*>(smem_raw + (base - smem_u32(smem_raw)) + g.rs_off);
-      auto rs_issue = [&](unsigned tile, int it) {
-        const int slot = it % TC_H_NRS;
-        const unsigned m0 = tile_mt(g, tile) * TC_BM;
-        int n_ent = (int)rows_u - (int)m0;
-        if (n_ent > g.hr) n_ent = g.hr;
-        if (n_ent < 0) n_ent = 0;
-        const uint32_t n4 = (uint32_t)n_ent & ~3u;         // bulk copies move multiples of 16 bytes
-        const uint32_t bar = smem_u32(&rs_bar[slot]);
-        const uint32_t dst = rs_base + (uint32_t)(slot * g.rs_stride);
-        asm volatile(
-            "{\n\t.reg .pred q, c;\n\t"
-            "elect.sync _|q, 0xffffffff;\n\t"
-            "setp.ne.and.b32 c, %3, 0, q;\n\t"
-            "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %3;\n\t"
-            "@c cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2], %3, [%0];\n\t}"
-            ::"r"(bar), "r"(dst), "l"(p.rowsum + m0), "r"(n4 * 4u)
-            : "memory");
-        if ((uint32_t)n_ent != n4) {                       // last tile of a row count that is no multiple of 4
-          int* gen = const_cast<int*>(rs_gen) + slot * (g.rs_stride >> 2);
-          if ((uint32_t)lane < (uint32_t)n_ent - n4) gen[n4 + lane] = __ldg(p.rowsum + m0 + n4 + lane);
-          fence_proxy_async_smem();                        // a later bulk copy overwrites these generic-proxy writes
-          __syncwarp();
-        }
-      };
-      unsigned tile_i = blockIdx.x;                        // issue cursor, TC_H_NRS - 1 tiles ahead
-      int it_i = 0;
-      for (; it_i < TC_H_NRS - 1 && tile_i < ntiles; ++it_i, tile_i += gridDim.x) rs_issue(tile_i, it_i);
-      int it = 0;
-      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        if (tile_i < ntiles) { rs_issue(tile_i, it_i); ++it_i; tile_i += gridDim.x; }
-        const int slot = it % TC_H_NRS;
-        const unsigned m0 = tile_mt(g, tile) * TC_BM;
-        int px[4], off[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {                      // index arithmetic before the wait
-          const unsigned row = m0 + lane + 32 * j;
-          px[j] = -1;
-          off[j] = lane + 32 * j;
-          if (row < rows_u) {
-            if (p.taps == 1) {
-              px[j] = (int)row;
-            } else {
-              const unsigned b = fdiv(row, g.d_per), rem = row - b * per;
-              const unsigned hp = fdiv(rem, g.d_wp), wp = rem - hp * (unsigned)p.Wp;
-              if (hp < (unsigned)p.H && wp < (unsigned)p.W) px[j] = (int)((b * (unsigned)p.H + hp) * (unsigned)p.W + wp);
-            }
-          }
-        }
-        if (lane == 0) TC_TRACE(3, it, 0);
-        mbar_wait(smem_u32(&rs_bar[slot]), (uint32_t)((it / TC_H_NRS) & 1));
-        const int* rs = rs_gen + slot * (g.rs_stride >> 2);
-        int cs[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          cs[j] = 0;
-          if (px[j] >= 0) {
-            const int* w0 = rs + off[j];
-            if (p.taps == 1) {
-              cs[j] = w0[0] + zk;
-            } else {
-              const int* w1 = w0 + p.Wp;
-              const int* w2 = w1 + p.Wp;
-              cs[j] = w0[0] + w0[1] + w0[2] + w1[0] + w1[1] + w1[2] + w2[0] + w2[1] + w2[2] + zk;
-            }
-          }
-        }
-        const int buf = it % TC_H_NGEO;
-        mbar_wait_relaxed(smem_u32(&geo_empty[buf]), (uint32_t)(((it / TC_H_NGEO) & 1) ^ 1));
-        if (lane == 0) TC_TRACE(3, it, 1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          geo_pix[buf][lane + 32 * j] = px[j];
-          geo_cs[buf][lane + 32 * j] = cs[j];
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&geo_full[buf]));
-        if (lane == 0) TC_TRACE(3, it, 2);
-      }
-    } else {
-      // fallback (row sums not 16-byte aligned): gather with ordinary loads, one tile at a time
-      int it = 0;
-      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const unsigned m0 = tile_mt(g, tile) * TC_BM;
-        int px[4], cs[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const unsigned row = m0 + lane + 32 * j;
-          px[j] = -1;
-          cs[j] = 0;
-          if (row < rows_u) {
-            if (p.taps == 1) {
-              px[j] = (int)row;
-              cs[j] = __ldg(p.rowsum + row) + zk;
-            } else {
-              const unsigned b = row / per, rem = row - b * per;
-              const unsigned hp = rem / (unsigned)p.Wp, wp = rem - hp * (unsigned)p.Wp;
-              if (hp < (unsigned)p.H && wp < (unsigned)p.W) {
-                px[j] = (int)((b * (unsigned)p.H + hp) * (unsigned)p.W + wp);
-                const int32_t* rs = p.rowsum + row;
-                cs[j] = __ldg(rs) + __ldg(rs + 1) + __ldg(rs + 2) + __ldg(rs + p.Wp) + __ldg(rs + p.Wp + 1) + __ldg(rs + p.Wp + 2) +
-                        __ldg(rs + 2 * p.Wp) + __ldg(rs + 2 * p.Wp + 1) + __ldg(rs + 2 * p.Wp + 2) + zk;
-              }
-            }
-          }
-        }
-        const int buf = it % TC_H_NGEO;
-        mbar_wait_relaxed(smem_u32(&geo_empty[buf]), (uint32_t)(((it / TC_H_NGEO) & 1) ^ 1));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          geo_pix[buf][lane + 32 * j] = px[j];
-          geo_cs[buf][lane + 32 * j] = cs[j];
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&geo_full[buf]));
-      }
-    }
+    geometry_role(0, g.b_resident ? 2 : 1);
   } else if (warp >= TC_H_EPI0 && warp < TC_H_R0) {
     // ===== epilogue warps (8): quarter = warp % 4, the two warps of a quarter take 32-column chunks round robin.
     // No shared-memory staging: the 16x256b TMEM load shape already hands four consecutive threads 32
@@ -1450,7 +1448,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   g.hr_stride = round_up(g.hr * TC_BK, 1024);
   // row-sum ring of the geometry warp (bulk copies need a 16-byte aligned source; else it gathers with loads)
   static const bool rs_bulk_on = [] { const char* e = getenv("ATTNDM_TC_RS_BULK"); return !(e && e[0] == '0'); }();
-  const int rs_bytes = (rs_bulk_on && ((uintptr_t)p.rowsum & 15) == 0) ? TC_H_NRS * round_up(g.hr * 4, 16) : 0;
+  const int rs_bytes = (rs_bulk_on && ((uintptr_t)p.rowsum & 15) == 0) ? 2 * TC_H_NRS * round_up(g.hr * 4, 16) : 0;   // two geometry warps
   // dynamic smem we allow ourselves: 227 KB - 20.5 KB static - alignment slack - the row-sum ring
   const int kBudget = 205 * 1024 - rs_bytes;
   const int nkb = p.taps * g.ncb;
@@ -1489,7 +1487,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   g.b_off = g.na * a_buf;
   g.stg_off = g.b_off + (g.b_resident ? nkb : g.nb) * b_tile;
   g.rs_off = g.stg_off + stg_bytes;
-  g.rs_stride = rs_bytes / TC_H_NRS;
+  g.rs_stride = rs_bytes / (2 * TC_H_NRS);
   { const char* e = getenv("ATTNDM_TC_DBG"); g.dbg = e ? atoi(e) : 0; }
   g.trace = g_tc_trace_host;
   g.d_per = make_fastdiv((unsigned)(p.Hp * p.Wp));

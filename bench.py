@@ -226,11 +226,30 @@ def build_model(dev, c, seed=0):
     return m, seq
 
 
-def _time_kernel(fn, n=10, warm=3):
-    """Mean CUDA-event duration (ms) of fn() on the current stream; operands are sized beyond L2 by the callers."""
+def _time_kernel(fn, n=10, warm=3, graph=False):
+    """Mean CUDA-event duration (ms) of fn(); operands are sized beyond L2 by the callers.  graph=True: the n launches are
+    captured into ONE CUDA graph and the events bracket a replay on the replaying stream -- the way the sampler
+    engine launches these kernels; eager launches of a < 50 us kernel through ctypes (tensor-map encodes included)
+    are paced by the host, not by the GPU (tools/conv_bench.py: 54 us eager, 47 us replayed, same kernel)."""
     import torch
     for _ in range(warm):
         fn()
+    if graph:
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=st):
+                for _ in range(n):
+                    fn()
+            gr.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            gr.replay()
+            e1.record(st)
+        torch.cuda.synchronize()
+        torch.cuda.current_stream().wait_stream(st)
+        return e0.elapsed_time(e1) / n
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
     ev[0].record()
     for i in range(n):
@@ -292,8 +311,9 @@ def dominant_kernel_roofline(dev, pk, i8pk, batch=256):
     azp = torch.tensor([26], dtype=torch.int32, device=dev)
     bias = torch.zeros(O, device=dev)
     out = torch.empty(B, H, W, O, device=dev)
-    ms = _time_kernel(lambda: ops.qconv_i8(codes, rowsum, B, H, W, C, pack, 9, mult, azp, bias,
-                                           impl=ops.CONV_TCGEN05, out=out))
+    launch = lambda: ops.qconv_i8(codes, rowsum, B, H, W, C, pack, 9, mult, azp, bias, impl=ops.CONV_TCGEN05, out=out)
+    ms_eager = _time_kernel(launch)
+    ms = _time_kernel(launch, graph=True)
     flops = 2.0 * B * H * W * O * C * 9
     ach = flops / (ms * 1e-3) / 1e12
     peak = i8pk["two_x_bf16_measured"]
@@ -311,7 +331,10 @@ def dominant_kernel_roofline(dev, pk, i8pk, batch=256):
             "traffic": traffic,
             "traffic_source": (f"{traffic_file}: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full"
                                if traffic is not None else "no committed ncu summary found"),
-            "ms_per_launch": ms, "algorithmic_bytes": algo_bytes, "algorithmic_flop": flops,
+            "ms_per_launch": ms, "ms_per_launch_eager": ms_eager,
+            "timing": "CUDA events around a replay of 10 launches captured in one CUDA graph (the way the engine launches "
+                      "it), /10; ms_per_launch_eager = the same launches issued eagerly through ctypes (host-paced)",
+            "algorithmic_bytes": algo_bytes, "algorithmic_flop": flops,
             "hbm_gbs_at_this_time": algo_bytes / (ms * 1e-3) / 1e9, "hbm_floor_ms": hbm_s * 1e3,
             "note": "fp32 activations between layers make this layer HBM-co-bound: its algorithmic bytes at the measured "
                     f"{pk['hbm_gbs']:.0f} GB/s take {hbm_s * 1e6:.0f} us, i.e. at most "
@@ -350,7 +373,11 @@ def hbm_kernel_rooflines(dev, pk, batch=256):
     ]
     out = []
     for name, bpe, fn in cases:
-        ms = _time_kernel(fn, n=10, warm=3)
+        try:
+            ms = _time_kernel(fn, n=10, warm=3, graph=True)
+        except Exception:                                  # a wrapper that cannot be captured: eager launches
+            torch.cuda.synchronize()
+            ms = _time_kernel(fn, n=10, warm=3)
         gbs = bpe * n / (ms * 1e-3) / 1e9
         out.append({"bound": "hbm", "kernel": name, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": gbs / pk["hbm_gbs"], "algorithmic_bytes_per_element": bpe, "elements": n,

@@ -40,8 +40,8 @@ L.attndm_debug_set_tc_trace(None)
 full = tr.cpu()
 t = full[:2048].view(16, 32, 4)
 t0 = int(t[t > 0].min())
-names = ["Aprod", "MMA", "MMAdone", "geo"] + [f"epi{i}" for i in range(12)]
-evn = [["wait_empty", "got_empty", "-", "-"], ["start", "tmem_free", "a_full", "issued"], ["mma_done", "-", "-", "-"], ["finish_top", "got_empty", "arrived", "-"]] + [["tmem_full", "c0_loaded", "c0_done", "last_done"]] * 12
+names = ["Aprod", "MMA", "geo1", "geo"] + [f"epi{i}" for i in range(12)]
+evn = [["wait_empty", "got_empty", "-", "-"], ["start", "tmem_free", "a_full", "issued"], ["finish_top", "got_empty", "arrived", "-"], ["finish_top", "got_empty", "arrived", "-"]] + [["tmem_full", "c0_loaded", "c0_done", "last_done"]] * 12
 for it in range(int(os.environ.get('TRACE_ITS', '8'))):
     for r in (1, 2, 3, 4, 8, 12):
         row = [(int(v) - t0) / 1000.0 if v > 0 else float('nan') for v in t[r, it]]
