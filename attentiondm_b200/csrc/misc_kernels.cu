@@ -198,6 +198,90 @@ __global__ void stage_advance_kernel(int* step, int T) {
   *step = s >= T ? 0 : s;
 }
 
+
+// ---- the callers either side of the sampler -------------------------------------------------
+// ddpm_steps, functions/denoising.py:119-151.  coef (device float[6]) = {(1/at).sqrt(), (1/at - 1).sqrt(),
+// atm1.sqrt() * beta_t, (1 - beta_t).sqrt() * (1 - atm1), 1 - at, mask * exp(0.5 * log(beta_t))} in the reference's fp32
+// op order (host side); every elementwise operation below is rounded separately like the eager ops it replaces.
+__global__ void ddpm_step_kernel(const float* __restrict__ xt, const float* __restrict__ eps, const float* __restrict__ coef,
+                                 const float* __restrict__ noise, float* __restrict__ x_next, float* __restrict__ x0_out,
+                                 long long n) {
+  pdl_enter();
+  const float ca = coef[0], cb = coef[1], cc = coef[2], cd = coef[3], ce = coef[4], cf = coef[5];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = xt[i], e = eps[i];
+    float x0 = __fsub_rn(__fmul_rn(ca, x), __fmul_rn(cb, e));            // x0_from_e (:137)
+    x0 = fminf(fmaxf(x0, -1.f), 1.f);                                    // torch.clamp(-1, 1) (:138)
+    const float mean = __fdiv_rn(__fadd_rn(__fmul_rn(cc, x0), __fmul_rn(cd, x)), ce);   // (:140-142)
+    x_next[i] = __fadd_rn(mean, __fmul_rn(cf, noise[i]));                // mean + mask * exp(0.5 logvar) * noise (:149)
+    if (x0_out) x0_out[i] = x0;
+  }
+}
+
+// noise_estimation_loss, functions/denoising.py:52-54: x = x0 * a.sqrt() + e * (1.0 - a).sqrt(), coef = {a.sqrt(), (1 - a).sqrt()}
+__global__ void noise_mix_kernel(const float* __restrict__ x0, const float* __restrict__ e, const float* __restrict__ coef,
+                                 float* __restrict__ x, long long n) {
+  pdl_enter();
+  const float sa = coef[0], s1a = coef[1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = __fadd_rn(__fmul_rn(x0[i], sa), __fmul_rn(e[i], s1a));
+}
+
+// (e - output).square().sum(dim=(1,2,3)) per sample (:58-60), accumulated in double: out[b]
+__global__ void sq_err_kernel(const float* __restrict__ a, const float* __restrict__ b, long long per, double* __restrict__ out) {
+  pdl_enter();
+  __shared__ double part[8];
+  const float* pa = a + (long long)blockIdx.x * per;
+  const float* pb = b + (long long)blockIdx.x * per;
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+    const float d = __fsub_rn(pa[i], pb[i]);
+    acc += (double)__fmul_rn(d, d);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    out[blockIdx.x] = t;
+  }
+}
+
+// The entropy regulariser of generalized_steps_loss (functions/denoising.py:83-100) for ONE layer and timestep:
+//   s = softmax(alpha_t, dim over the G groups), H = cal_entropy(s) = -(1/G) sum_g sum_c s log s, term = H / (G*C);
+// writes grad[g][c] = weight * d term / d alpha_t[g][c]
+//        = -(weight / (G*G*C)) * s[g][c] * ((log s[g][c] + 1) - sum_g' s[g'][c] (log s[g'][c] + 1))
+// and adds weight * term to *value (double).  One thread per channel; G <= 32.
+__global__ void alpha_entropy_grad_kernel(const float* __restrict__ alpha_t, int G, int C, float weight, float* __restrict__ grad,
+                                          double* __restrict__ value) {
+  pdl_enter();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double h = 0.0;
+  if (c < C) {
+    double mx = -1e300;
+    for (int g = 0; g < G; ++g) mx = fmax(mx, (double)alpha_t[(long long)g * C + c]);
+    double den = 0.0;
+    for (int g = 0; g < G; ++g) den += exp((double)alpha_t[(long long)g * C + c] - mx);
+    const double lden = log(den);
+    double m1 = 0.0;                                   // sum_g s (log s + 1)
+    for (int g = 0; g < G; ++g) {
+      const double ls = (double)alpha_t[(long long)g * C + c] - mx - lden, sg = exp(ls);
+      m1 += sg * (ls + 1.0);
+      h -= sg * ls;
+    }
+    const double k = -(double)weight / ((double)G * G * C);
+    for (int g = 0; g < G; ++g) {
+      const double ls = (double)alpha_t[(long long)g * C + c] - mx - lden, sg = exp(ls);
+      grad[(long long)g * C + c] = (float)(k * sg * ((ls + 1.0) - m1));
+    }
+  }
+  if (value != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0 && h != 0.0) atomicAdd(value, (double)weight * h / ((double)G * G * C));
+  }
+}
+
 static inline int ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   long long cap = (long long)kNumSMs * 32;
@@ -283,6 +367,35 @@ int attndm_ddim_step_hist(const float* xt, const float* eps, const float* coef, 
   launch_pdl(ddim_step_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, xt, eps, coef, noise, x_next, x0_out, n,
              hist_x, hist_x0, step_after, T);
   ATTNDM_CUDA_LAUNCH_CHECK("ddim_step_hist");
+  return ATTNDM_OK;
+}
+
+int attndm_ddpm_step(const float* xt, const float* eps, const float* coef, const float* noise, float* x_next, float* x0_out,
+                     long long n, void* stream) {
+  ATTNDM_CHECK_ARG(xt && eps && coef && noise && x_next && n > 0, "ddpm_step: bad args");
+  launch_pdl(ddpm_step_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, xt, eps, coef, noise, x_next, x0_out, n);
+  ATTNDM_CUDA_LAUNCH_CHECK("ddpm_step");
+  return ATTNDM_OK;
+}
+
+int attndm_noise_mix(const float* x0, const float* e, const float* coef, float* x, long long n, void* stream) {
+  ATTNDM_CHECK_ARG(x0 && e && coef && x && n > 0, "noise_mix: bad args");
+  launch_pdl(noise_mix_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, x0, e, coef, x, n);
+  ATTNDM_CUDA_LAUNCH_CHECK("noise_mix");
+  return ATTNDM_OK;
+}
+
+int attndm_sq_err(const float* a, const float* b, int B, long long per, double* out, void* stream) {
+  ATTNDM_CHECK_ARG(a && b && out && B > 0 && per > 0, "sq_err: bad args");
+  launch_pdl(sq_err_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, a, b, per, out);
+  ATTNDM_CUDA_LAUNCH_CHECK("sq_err");
+  return ATTNDM_OK;
+}
+
+int attndm_alpha_entropy_grad(const float* alpha_t, int G, int C, float weight, float* grad, double* value, void* stream) {
+  ATTNDM_CHECK_ARG(alpha_t && grad && G > 0 && G <= 32 && C > 0, "alpha_entropy_grad: bad args (1 <= G <= 32)");
+  launch_pdl(alpha_entropy_grad_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, alpha_t, G, C, weight, grad, value);
+  ATTNDM_CUDA_LAUNCH_CHECK("alpha_entropy_grad");
   return ATTNDM_OK;
 }
 

@@ -11,7 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .quant_util import QConv2d
+from .quant_util import FConv2d, QConv2d
 from .self_attention import EnhancedQSelfAttention
 
 
@@ -21,11 +21,14 @@ def get_timestep_embedding(timesteps, embedding_dim):
     return ops.timestep_embedding(timesteps, embedding_dim)
 
 
-def _need_quant(quantization, sequence):
-    if not (quantization and sequence is not None):
-        raise NotImplementedError(
-            "attentiondm_b200 implements the fake-quantized path (quantization=True, sequence given); "
-            "the FP model of the reference is outside the hot path")
+def _conv(quantization, sequence, args, cin, cout, k):
+    """A QConv2d when `quantization and sequence is not None`, else the FP model's plain conv
+    (models/diffusion.py:90-116 and every other such switch in that file)."""
+    pad = 1 if k == 3 else 0
+    if quantization and sequence is not None:
+        return QConv2d(cin, cout, kernel_size=k, stride=1, padding=pad, w_bit=args.bitwidth, a_bit=args.bitwidth,
+                       sequence=sequence, args=args)
+    return FConv2d(cin, cout, kernel_size=k, stride=1, padding=pad)
 
 
 def _gn_args(norm: nn.GroupNorm, x):
@@ -42,22 +45,21 @@ class ResidualBlock(nn.Module):
     def __init__(self, in_channels, out_channels=None, conv_shortcut=False, dropout=0.1, quantization=False,
                  sequence=None, args=None):
         super().__init__()
-        _need_quant(quantization, sequence)
         self.in_channels = in_channels
         self.out_channels = in_channels if out_channels is None else out_channels
         out_channels = self.out_channels
         self.use_conv_shortcut = conv_shortcut
-        q = dict(w_bit=args.bitwidth, a_bit=args.bitwidth, sequence=sequence, args=args)
+        mk = lambda cin, cout, k: _conv(quantization, sequence, args, cin, cout, k)
         self.norm1 = nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6)
-        self.conv1 = QConv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1, **q)
+        self.conv1 = mk(in_channels, out_channels, 3)
         self.norm2 = nn.GroupNorm(num_groups=32, num_channels=out_channels, eps=1e-6)
         self.dropout = nn.Dropout(dropout)
-        self.conv2 = QConv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1, **q)
+        self.conv2 = mk(out_channels, out_channels, 3)
         if self.in_channels != self.out_channels:
             if self.use_conv_shortcut:
-                self.conv_shortcut = QConv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1, **q)
+                self.conv_shortcut = mk(in_channels, out_channels, 3)
             else:
-                self.nin_shortcut = QConv2d(in_channels, out_channels, kernel_size=1, stride=1, padding=0, **q)
+                self.nin_shortcut = mk(in_channels, out_channels, 1)
 
     def forward_fused(self, x, temb=None):
         """x NHWC.  temb [B, out_channels] (optional) is the block's `x + time_mlp(t_emb)`
@@ -76,11 +78,8 @@ class ResidualBlock(nn.Module):
         return ops.to_nchw(self.forward_fused(ops.to_nhwc(x)))
 
 
-def _time_mlp(time_emb_dim, out_channels, sequence, args):
-    return nn.Sequential(
-        nn.SiLU(),
-        QConv2d(time_emb_dim, out_channels, kernel_size=1, stride=1, padding=0, w_bit=args.bitwidth,
-                a_bit=args.bitwidth, sequence=sequence, args=args))
+def _time_mlp(time_emb_dim, out_channels, quantization, sequence, args):
+    return nn.Sequential(nn.SiLU(), _conv(quantization, sequence, args, time_emb_dim, out_channels, 1))
 
 
 class _TimeBlock(nn.Module):
@@ -108,14 +107,13 @@ class DownBlock(_TimeBlock):
     def __init__(self, in_channels, out_channels, time_emb_dim=None, dropout=0.1, quantization=False, sequence=None,
                  args=None, use_attention=True):
         super().__init__()
-        _need_quant(quantization, sequence)
         self.maxpool = nn.MaxPool2d(2)
         kw = dict(dropout=dropout, quantization=quantization, sequence=sequence, args=args)
         self.res1 = ResidualBlock(in_channels, out_channels, **kw)
         self.res2 = ResidualBlock(out_channels, out_channels, **kw)
         self.attn = (EnhancedQSelfAttention(out_channels, quantization=quantization, sequence=sequence, args=args)
                      if use_attention else nn.Identity())
-        self.time_mlp = _time_mlp(time_emb_dim, out_channels, sequence, args) if time_emb_dim is not None else None
+        self.time_mlp = _time_mlp(time_emb_dim, out_channels, quantization, sequence, args) if time_emb_dim is not None else None
 
     def forward_fused(self, x, time_emb=None):
         if not (x.shape[1] <= 1 or x.shape[2] <= 1):       # :172 (NHWC: dims 1,2 are H,W)
@@ -133,14 +131,13 @@ class UpBlock(_TimeBlock):
     def __init__(self, in_channels, out_channels, time_emb_dim=None, dropout=0.1, quantization=False, sequence=None,
                  args=None, use_attention=True):
         super().__init__()
-        _need_quant(quantization, sequence)
         self.upsample = nn.Upsample(scale_factor=2, mode='nearest')
         kw = dict(dropout=dropout, quantization=quantization, sequence=sequence, args=args)
         self.res1 = ResidualBlock(in_channels + out_channels, out_channels, **kw)
         self.res2 = ResidualBlock(out_channels, out_channels, **kw)
         self.attn = (EnhancedQSelfAttention(out_channels, quantization=quantization, sequence=sequence, args=args)
                      if use_attention else nn.Identity())
-        self.time_mlp = _time_mlp(time_emb_dim, out_channels, sequence, args) if time_emb_dim is not None else None
+        self.time_mlp = _time_mlp(time_emb_dim, out_channels, quantization, sequence, args) if time_emb_dim is not None else None
 
     def forward_fused(self, x, skip_x, time_emb=None):
         combined = ops.upsample_concat(x, skip_x)            # :225-229 + cat
@@ -178,7 +175,6 @@ class Model(nn.Module):
 
     def __init__(self, config, quantization=False, sequence=None, args=None):
         super().__init__()
-        _need_quant(quantization, sequence)
         self.config = config
         self.quantization = quantization
         self.sequence = sequence
@@ -190,8 +186,7 @@ class Model(nn.Module):
         ted = config.model.time_embed_dim
         self.time_embed = nn.Sequential(nn.Linear(ted, ted * 4), nn.SiLU(), nn.Linear(ted * 4, ted * 4))
         ch = config.model.ch
-        q = dict(w_bit=args.bitwidth, a_bit=args.bitwidth, sequence=sequence, args=args)
-        self.init_conv = QConv2d(config.data.channels, ch, kernel_size=3, stride=1, padding=1, **q)
+        self.init_conv = _conv(quantization, sequence, args, config.data.channels, ch, 3)
         kw = dict(time_emb_dim=ted * 4, dropout=config.model.dropout, quantization=quantization, sequence=sequence,
                   args=args)
         self.down_blocks = nn.ModuleList()
@@ -216,7 +211,7 @@ class Model(nn.Module):
                 self.up_blocks.append(UpBlock(blk_in, out_ch, use_attention=(i >= config.model.attention_resolutions), **kw))
                 now_ch = out_ch
         self.norm_out = nn.GroupNorm(num_groups=32, num_channels=now_ch, eps=1e-6)
-        self.conv_out = QConv2d(now_ch, config.data.channels, kernel_size=3, stride=1, padding=1, **q)
+        self.conv_out = _conv(quantization, sequence, args, now_ch, config.data.channels, 3)
 
     # ---- helpers over all quantized layers ----
     def qconvs(self):

@@ -381,3 +381,33 @@ def ddim_step(xt, eps, coef, noise=None, x_next=None, x0_out=None, want_x0=False
 def stage_tables(table: torch.Tensor, step: torch.Tensor, dst: torch.Tensor, advance: bool = True):
     T, n = table.shape
     call("attndm_stage_tables", ptr(table), n, T, ptr(step), 1 if advance else 0, ptr(dst), stream())
+
+
+def ddpm_step(xt, eps, coef, noise, want_x0=True):
+    """One ddpm_steps update (functions/denoising.py:137-149); coef: device float[6] (denoising.ddpm_coefficients)."""
+    x_next = torch.empty_like(xt)
+    x0 = torch.empty_like(xt) if want_x0 else None
+    call("attndm_ddpm_step", ptr(xt), ptr(eps), ptr(coef), ptr(noise), ptr(x_next), ptr(x0), xt.numel(), stream())
+    return x_next, x0
+
+
+def noise_mix(x0, e, coef):
+    """x0 * a.sqrt() + e * (1 - a).sqrt(); coef: device float[2]."""
+    x = torch.empty_like(x0)
+    call("attndm_noise_mix", ptr(x0), ptr(e), ptr(coef), ptr(x), x0.numel(), stream())
+    return x
+
+
+def sq_err(a, b):
+    """Per-sample sum of squared differences, double [B]."""
+    B = a.shape[0]
+    out = torch.empty(B, dtype=torch.float64, device=a.device)
+    call("attndm_sq_err", ptr(a), ptr(b), B, a.numel() // B, ptr(out), stream())
+    return out
+
+
+def alpha_entropy_grad(alpha_t, weight, grad_out, value=None):
+    """grad_out[G,C] = weight * d(cal_entropy(softmax(alpha_t, 0)) / (G*C)) / d alpha_t; value (double[1]) += weight * term."""
+    G, Cc = alpha_t.shape
+    call("attndm_alpha_entropy_grad", ptr(alpha_t), int(G), int(Cc), float(weight), ptr(grad_out), ptr(value), stream())
+    return grad_out

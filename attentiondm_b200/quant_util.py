@@ -468,3 +468,48 @@ class QConv2d(QModule):
     def extra_repr(self):
         return (f'{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, '
                 f'padding={self.padding}, w_bit={self.w_bit}, a_bit={self.a_bit}')
+
+
+class FConv2d(nn.Conv2d):
+    """The un-quantized conv of the reference's FP model (`quantization=False`: every QConv2d site is a plain
+    nn.Conv2d, models/diffusion.py:106-116,166-169,281-285,341-345; models/self_attention.py:56-59), which
+    `Diffusion.generate_calibrate_set` samples from (runners/diffusion.py:198-216).  Same parameters / state_dict keys
+    as nn.Conv2d; the arithmetic runs through the fp32 conv kernel behind the C-ABI (batch-invariant summation
+    order), with the same fused producer (GroupNorm+SiLU / SiLU) and consumer adds as QConv2d.forward_fused."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, **kw):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding, **kw)
+        k = self.kernel_size
+        ok = (k == (3, 3) and self.padding == (1, 1)) or (k == (1, 1) and self.padding == (0, 0))
+        if not ok or self.stride != (1, 1) or self.dilation != (1, 1) or self.groups != 1:
+            raise NotImplementedError("attentiondm_b200.FConv2d: 3x3/s1/p1 and 1x1/s1/p0, groups=1 only")
+        self._wp = None
+        self._wp_key = None
+
+    def _w_pack(self):
+        """weight [O,C,kh,kw] -> [O, taps, C] (the fp32 kernel's layout) and the centre tap for 1x1 maps."""
+        w = self.weight
+        key = (w.data_ptr(), w._version)
+        if self._wp is None or self._wp_key != key:
+            O, Cc, KH, KW = w.shape
+            full = w.detach().float().permute(0, 2, 3, 1).reshape(O, KH * KW, Cc).contiguous()
+            centre = full[:, 4:5, :].contiguous() if KH * KW == 9 else None
+            self._wp, self._wp_key = (full, centre), key
+        return self._wp
+
+    def forward_fused(self, x, pre=ops.PRE_NONE, gn: Optional[ops.GnArgs] = None, residual=None, temb=None):
+        B, H, W, Cc = x.shape
+        if Cc != self.in_channels:
+            raise RuntimeError(f"FConv2d: expected {self.in_channels} input channels, got {Cc}")
+        full, centre = self._w_pack()
+        w = centre if (centre is not None and H == 1 and W == 1) else full
+        if pre == ops.PRE_GN_SILU:
+            xa = ops.gn_silu(x, gn)
+        elif pre == ops.PRE_SILU:
+            xa = ops.silu(x)
+        else:
+            xa = x
+        return ops.conv_f32(xa, w, self.bias.detach() if self.bias is not None else None, residual, temb)
+
+    def forward(self, inputs):
+        return ops.to_nchw(self.forward_fused(ops.to_nhwc(inputs)))

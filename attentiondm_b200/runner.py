@@ -12,7 +12,7 @@ import os
 import numpy as np
 import torch
 
-from .denoising import generalized_steps
+from .denoising import generalized_steps, generalized_steps_loss
 from .diffusion import Model
 
 
@@ -162,6 +162,139 @@ class Diffusion(object):
         model.eval()
         self.model = model
         return model
+
+    def build_fp_model(self, states=None):
+        """The un-quantized twin (Model(quantization=False), models/diffusion.py:281-345) whose trajectories
+        generate_calibrate_set samples; same checkpoint loader as the quantized model."""
+        if self.seq is None:
+            self.seq = make_seq(self.args, self.num_timesteps)
+        fp = Model(self.config, quantization=False, sequence=self.seq, args=self.args).to(self.device)
+        if states is not None:
+            load_by_shape_match(fp, states)
+        fp.eval()
+        self.fpmodel = fp
+        return fp
+
+    # ---- active timestep selection (runners/diffusion.py:195-264) ----
+    def cal_entropy(self, attn):
+        """:195-196."""
+        return -1 * torch.sum((attn * torch.log(attn)), dim=-1).mean()
+
+    def timestep_uncertainty(self, model):
+        """The `diff` branch's score (:232-241): sum over QConv2d of the entropy of softmax(alpha_activ, dim=1)[t] / C_in,
+        minus sample_weight * sample_count; one [T] vector (tiny host-side math on [T,G,C] tables)."""
+        Tn = self.args.timesteps
+        unc = torch.zeros(Tn, device=self.device)
+        for _, layer in model.qconvs():
+            alpha = torch.softmax(layer.alpha_activ.detach().float(), dim=1)            # [T,G,C]
+            dim = alpha.shape[2]
+            ent = (-1 * torch.sum(alpha * torch.log(alpha), dim=-1)).mean(dim=-1)        # cal_entropy(alpha[t]) for every t
+            unc += ent.to(self.device) / dim
+        if not hasattr(self, "sample_count"):
+            self.sample_count = torch.zeros(Tn)
+        unc -= float(self.args.sample_weight) * self.sample_count.to(self.device)
+        return unc
+
+    def generate_calibrate_set(self, fpmodel, model, t_mode, num_calibrate_set, x=None, t_random=None):
+        """:198-264.  Samples n <= 16 latents through the FP model and picks, per t_mode, which point of each
+        trajectory calibration sees.  `x` / `t_random` (tests) replace the two random draws (:202-208, :225-227).
+        Returns the calibration images on the device."""
+        with torch.no_grad():
+            n = min(num_calibrate_set, 16)
+            if x is None:
+                x = torch.randn(n, self.config.data.channels, self.config.data.image_size, self.config.data.image_size,
+                                device=self.device)
+            x = x.to(self.device).clone()
+            xs = generalized_steps(x, self.seq, fpmodel, self.betas, eta=self.args.eta)[0]
+            if t_mode == "real":
+                x = xs[-1].to(self.device)
+            elif t_mode == "range":
+                for s_ in range(n):
+                    x[s_] = (xs[-1][s_] if s_ >= 100 else xs[s_][s_]).to(self.device)
+            elif t_mode == "random":
+                if t_random is None:
+                    normal_val = torch.nn.init.normal_(torch.Tensor(n), mean=0.4, std=0.4) * self.args.timesteps
+                    t_random = normal_val.clone().type(torch.int).clamp(0, self.args.timesteps - 1)
+                for s_ in range(n):
+                    x[s_] = xs[int(t_random[s_])][s_].to(self.device)
+            elif t_mode == "diff":
+                unc = self.timestep_uncertainty(model)
+                mark = torch.arange(0, self.args.timesteps, device=self.device)
+                unc, mark = unc[30:], mark[30:]                       # (:242-243)
+                t_sel = int(mark[unc == torch.max(unc)][-1])
+                self.sample_count[t_sel] += 1
+                x = xs[t_sel].to(self.device)
+                self.timestep_select = t_sel
+            else:
+                raise NotImplementedError(t_mode)
+            return inverse_data_transform(self.config, x)
+
+    # ---- attention calibration with the entropy regulariser (runners/diffusion.py:266-306) ----
+    def attention_qconvs(self, model):
+        from .quant_util import QConv2d
+        from .self_attention import EnhancedQSelfAttention
+        out = []
+        for _, module in model.named_modules():
+            if isinstance(module, EnhancedQSelfAttention):
+                out += [sub for _, sub in module.named_modules() if isinstance(sub, QConv2d)]
+        return out
+
+    def calibrate_attention(self, model, image, device=None, batchsize=None, **kw):
+        """:266-306: the attention projections' QConv2d go to calibration mode, their alpha_activ is optimised with AdamW
+        (lr 0.05, weight decay 0.05) along one generalized_steps_loss trajectory, then they return to inference mode."""
+        device = self.device if device is None else device
+        convs = self.attention_qconvs(model)
+        for q in convs:
+            q.set_calibrate(calibrate=True)
+            q.first_calibrate(calibrate=getattr(self, "first_flag", False))
+        image = image.to(device)
+        attention_params = []
+        for name, param in model.named_parameters():
+            if "alpha_activ" in name and any(a in name for a in ["query_conv", "key_conv", "value_conv", "output_conv"]):
+                param.requires_grad = True
+                attention_params += [param]
+        try:
+            if attention_params:
+                optimizer = torch.optim.AdamW(attention_params, 0.05, weight_decay=0.05)
+                self.last_calibration = generalized_steps_loss(
+                    image, self.seq, model, self.betas, optimizer, eta=getattr(self.args, "eta", 0.0),
+                    t_mode=getattr(self, "t_mode", None), timestep_select=getattr(self, "timestep_select", None),
+                    args=self.args, attention_focus=True, **kw)
+        finally:
+            for q in convs:
+                q.set_calibrate(calibrate=False)
+        return model
+
+    def calibrate_general(self, model, data, device=None, batchsize=None, first=False):
+        """Stage 1 of calibrate_model (:461-467); the reference calls it but never defines it.  One calibration pass of
+        every QConv2d along the sample trajectory of `data`."""
+        model.reset_index_seq()
+        model.set_calibrate(True, first=first)
+        try:
+            generalized_steps(data.to(self.device), self.seq, model, self.betas, eta=getattr(self.args, "eta", 0.0), keep="last")
+        finally:
+            model.set_calibrate(False)
+        model.reset_index_seq()
+        return model
+
+    def calibrate_pipeline(self, model, data, device=None):
+        """calibrate_model of the reference (:461-478): general calibration, attention calibration with the entropy
+        regulariser, and -- with args.mixed_precision_attention -- the attention-internal quantizers."""
+        self.calibrate_general(model, data, device, getattr(self.args, "batchsize", None))
+        self.calibrate_attention(model, data, device, getattr(self.args, "batchsize", None))
+        model.reset_index_seq()
+        if getattr(self.args, "mixed_precision_attention", False):
+            self.calibrate_mixed_precision_attention(model, data, device)
+        return model
+
+    def calibrate_mixed_precision_attention(self, model, image, device=None):
+        """:480-513."""
+        from .attention_quant_utils import AttentionCalibrator
+        mods = [m for _, m in model.named_modules()
+                if getattr(m, "mixed_precision", False) and getattr(m, "quantization", False)]
+        if not mods:
+            return
+        AttentionCalibrator(model, self.device if device is None else device).calibrate(image.to(self.device), [0, 250, 500, 750, 999])
 
     def calibrate_model(self, x, first=False):
         """One calibration pass over the sample trajectory (what calibrate_general was meant to

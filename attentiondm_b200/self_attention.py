@@ -10,15 +10,13 @@ import torch.nn as nn
 
 from . import ops
 from .attention_quant_utils import MixedPrecisionAttention
-from .quant_util import QConv2d
+from .quant_util import FConv2d, QConv2d
 
 
 class EnhancedQSelfAttention(nn.Module):
     def __init__(self, in_channels, quantization=False, sequence=None, args=None, mixed_precision=False,
                  bit_config=None):
         super().__init__()
-        if not (quantization and sequence is not None):
-            raise NotImplementedError("attentiondm_b200 implements the quantized path (quantization=True) only")
         self.quantization = quantization
         self.in_channels = in_channels
         self.key_channels = in_channels // 8
@@ -35,12 +33,16 @@ class EnhancedQSelfAttention(nn.Module):
             }
         else:
             self.bit_config = bit_config
-        mk = lambda cin, cout, b: QConv2d(cin, cout, kernel_size=1, w_bit=b, a_bit=b, sequence=sequence, args=args)
+        if quantization and sequence is not None:
+            mk = lambda cin, cout, b: QConv2d(cin, cout, kernel_size=1, w_bit=b, a_bit=b, sequence=sequence, args=args)
+        else:                                                    # the FP model (:56-59)
+            mk = lambda cin, cout, b: FConv2d(cin, cout, kernel_size=1)
         self.query_conv = mk(in_channels, self.key_channels, self.bit_config["query"])
         self.key_conv = mk(in_channels, self.key_channels, self.bit_config["key"])
         self.value_conv = mk(in_channels, self.value_channels, self.bit_config["value"])
         self.output_conv = mk(self.value_channels, in_channels, self.bit_config["output"])
-        self.configure_group_quantization()
+        if quantization and sequence is not None:
+            self.configure_group_quantization()
         self.gamma = nn.Parameter(torch.zeros(1))
         if mixed_precision and quantization:
             self.enable_mixed_precision()

@@ -237,6 +237,32 @@ int attndm_ddim_step_hist(const float* xt, const float* eps, const float* coef, 
                           float* x_next, float* x0_out, long long n, float* hist_x, float* hist_x0,
                           const int* step_after, int T, void* stream);
 
+/* ---- the callers either side of the sampler ---------- */
+
+/* One ancestral (DDPM) update, functions/denoising.py:137-149 (ddpm_steps; the ablation driver's sampler,
+ * ablation_study_attention_quantization.py:300-340).  coef (device float[6]) = {(1/at).sqrt(), (1/at - 1).sqrt(),
+ * atm1.sqrt() * beta_t, (1 - beta_t).sqrt() * (1 - atm1), 1 - at, mask * exp(0.5 * log(beta_t))}; x0_out (the
+ * clamped x0 prediction) may be NULL. */
+int attndm_ddpm_step(const float* xt, const float* eps, const float* coef, const float* noise,
+                     float* x_next, float* x0_out, long long n, void* stream);
+
+/* x = x0 * a.sqrt() + e * (1 - a).sqrt(), the forward-noised input of noise_estimation_loss
+ * (functions/denoising.py:52-54); coef (device float[2]) = {a.sqrt(), (1 - a).sqrt()}. */
+int attndm_noise_mix(const float* x0, const float* e, const float* coef, float* x, long long n, void* stream);
+
+/* out[b] = sum over a sample of (a - b)^2 (double), the per-sample term of noise_estimation_loss
+ * (functions/denoising.py:58-60); a, b: [B][per]. */
+int attndm_sq_err(const float* a, const float* b, int B, long long per, double* out, void* stream);
+
+/* Gradient of the entropy regulariser of generalized_steps_loss (functions/denoising.py:83-100) for one layer and
+ * timestep: term = cal_entropy(softmax(alpha_t, over the G groups)) / (G*C), alpha_t [G][C];
+ * grad[g][c] = weight * d term / d alpha_t[g][c]; *value (device double, may be NULL) += weight * term.
+ * It is the ONLY non-zero gradient the attention alphas receive: torch.round in every downstream quantizer
+ * (utils/quant_util.py:271) has derivative zero and conv_out is itself a QConv2d, so the noise-estimation loss
+ * contributes exactly 0 (measured on the reference: oracle/make_golden_calib.py, tests/golden/tiny_calib.npz). */
+int attndm_alpha_entropy_grad(const float* alpha_t, int G, int C, float weight, float* grad, double* value,
+                              void* stream);
+
 /* Copy row `*step` of a [T][n] table into `dst` and (if advance) increment *step
  * modulo T: lets one captured CUDA graph serve every denoising step, mirroring
  * the per-module index_seq counter (utils/quant_util.py:228-229,281). */

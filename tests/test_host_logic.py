@@ -60,8 +60,9 @@ def test_no_cpu_fallback():
         m(torch.randn(1, 3, 8, 8), torch.zeros(1))
     with pytest.raises(RuntimeError, match="CUDA"):
         A.generalized_steps(torch.randn(1, 3, 8, 8), spec.seq, m, R.beta_schedule_linear())
-    with pytest.raises(NotImplementedError):
-        A.Model(config_for(spec), quantization=False, sequence=spec.seq, args=args_for(spec))
+    fp = A.Model(config_for(spec), quantization=False, sequence=spec.seq, args=args_for(spec))     # the FP model builds ...
+    with pytest.raises(RuntimeError, match="no CPU fallback"):                                     # ... and has no CPU path either
+        fp(torch.randn(1, 3, 8, 8), torch.zeros(1))
 
 
 def test_ddim_coefficients_match_oracle():

@@ -15,7 +15,7 @@ ap.add_argument("--events", type=int, default=1)
 a = ap.parse_args()
 dev = torch.device("cuda")
 bench.T_STEPS = 100
-m, seq = bench.build_model(dev)
+m, seq = bench.build_model(dev, bench.CONFIGS[os.environ.get("ATTNDM_CONFIG", "cifar10_w8a8")])
 for n, q in m.qconvs():          # skip calibration: every activation range = the reference floor [-4, 6]
     q.groups_range.data[..., 0] = -4.0
     q.groups_range.data[..., 1] = 6.0

@@ -7,7 +7,7 @@ from attentiondm_b200 import _ffi
 from attentiondm_b200.engine import SamplerEngine
 dev = torch.device("cuda")
 bench.T_STEPS = 100
-m, seq = bench.build_model(dev)
+m, seq = bench.build_model(dev, bench.CONFIGS[os.environ.get("ATTNDM_CONFIG", "cifar10_w8a8")])
 for n, q in m.qconvs():
     q.groups_range.data[..., 0] = -4.0
     q.groups_range.data[..., 1] = 6.0
