@@ -156,6 +156,19 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
 // ---------------------------------------------------------------------------
 // sampler
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void ddim_update_1(float x, float e, float nz, bool has_noise, float s1mat, float sat, float satn,
+                                              float c1, float c2, float& r, float& x0) {
+  // x0_t = (xt - et * (1 - at).sqrt()) / at.sqrt()
+  x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(e, s1mat)), sat);
+  // xt_next = at_next.sqrt() * x0_t + c1 * randn + c2 * et
+  r = __fmul_rn(satn, x0);
+  if (has_noise) r = __fadd_rn(r, __fmul_rn(c1, nz));
+  r = __fadd_rn(r, __fmul_rn(c2, e));
+}
+
+// VEC = 4: 128-bit accesses (n % 4 == 0, 16-byte aligned operands); VEC = 1: scalar.  12 B/element of traffic
+// (x_t, eps in; x_next out) + the optional x0 / history outputs.
+template <int VEC>
 __global__ void ddim_step_kernel(const float* __restrict__ xt, const float* __restrict__ eps,
                                  const float* __restrict__ coef, const float* __restrict__ noise,
                                  float* __restrict__ x_next, float* __restrict__ x0_out, long long n,
@@ -168,14 +181,29 @@ __global__ void ddim_step_kernel(const float* __restrict__ xt, const float* __re
     hist_x += (long long)k * n;
     hist_x0 += (long long)k * n;
   }
+  const bool has_noise = noise != nullptr;
+  if (VEC == 4) {
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 x = reinterpret_cast<const float4*>(xt)[i], e = reinterpret_cast<const float4*>(eps)[i];
+      const float4 z = has_noise ? reinterpret_cast<const float4*>(noise)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 r, x0;
+      ddim_update_1(x.x, e.x, z.x, has_noise, s1mat, sat, satn, c1, c2, r.x, x0.x);
+      ddim_update_1(x.y, e.y, z.y, has_noise, s1mat, sat, satn, c1, c2, r.y, x0.y);
+      ddim_update_1(x.z, e.z, z.z, has_noise, s1mat, sat, satn, c1, c2, r.z, x0.z);
+      ddim_update_1(x.w, e.w, z.w, has_noise, s1mat, sat, satn, c1, c2, r.w, x0.w);
+      reinterpret_cast<float4*>(x_next)[i] = r;
+      if (x0_out) reinterpret_cast<float4*>(x0_out)[i] = x0;
+      if (hist_x != nullptr) {
+        reinterpret_cast<float4*>(hist_x)[i] = r;
+        reinterpret_cast<float4*>(hist_x0)[i] = x0;
+      }
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float x = xt[i], e = eps[i];
-    // x0_t = (xt - et * (1 - at).sqrt()) / at.sqrt()
-    const float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(e, s1mat)), sat);
-    // xt_next = at_next.sqrt() * x0_t + c1 * randn + c2 * et
-    float r = __fmul_rn(satn, x0);
-    if (noise) r = __fadd_rn(r, __fmul_rn(c1, noise[i]));
-    r = __fadd_rn(r, __fmul_rn(c2, e));
+    float r, x0;
+    ddim_update_1(xt[i], eps[i], has_noise ? noise[i] : 0.f, has_noise, s1mat, sat, satn, c1, c2, r, x0);
     x_next[i] = r;
     if (x0_out) x0_out[i] = x0;
     if (hist_x != nullptr) {
@@ -292,6 +320,18 @@ static inline int ew_blocks(long long n) {
 
 using namespace attndm;
 
+static void launch_ddim(const float* xt, const float* eps, const float* coef, const float* noise, float* x_next, float* x0_out,
+                        long long n, float* hist_x, float* hist_x0, const int* step_after, int T, cudaStream_t st) {
+  auto al = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
+  const bool v4 = (n & 3) == 0 && al(xt) && al(eps) && al(noise) && al(x_next) && al(x0_out) && al(hist_x) && al(hist_x0);
+  if (v4)
+    launch_pdl(ddim_step_kernel<4>, dim3(ew_blocks(n >> 2)), dim3(256), 0, st, xt, eps, coef, noise, x_next, x0_out, n, hist_x,
+               hist_x0, step_after, T);
+  else
+    launch_pdl(ddim_step_kernel<1>, dim3(ew_blocks(n)), dim3(256), 0, st, xt, eps, coef, noise, x_next, x0_out, n, hist_x,
+               hist_x0, step_after, T);
+}
+
 extern "C" {
 
 int attndm_attention(const float* q, const float* k, const float* v, float* out, int B, int N, int d, int dv,
@@ -353,8 +393,7 @@ int attndm_timestep_embedding(const float* t, int B, int dim, float* emb, void* 
 int attndm_ddim_step(const float* xt, const float* eps, const float* coef, const float* noise, float* x_next,
                      float* x0_out, long long n, void* stream) {
   ATTNDM_CHECK_ARG(xt && eps && coef && x_next && n > 0, "ddim_step: bad args");
-  launch_pdl(ddim_step_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, xt, eps, coef, noise, x_next, x0_out, n,
-             (float*)nullptr, (float*)nullptr, (const int*)nullptr, 1);
+  launch_ddim(xt, eps, coef, noise, x_next, x0_out, n, nullptr, nullptr, nullptr, 1, (cudaStream_t)stream);
   ATTNDM_CUDA_LAUNCH_CHECK("ddim_step");
   return ATTNDM_OK;
 }
@@ -364,8 +403,7 @@ int attndm_ddim_step_hist(const float* xt, const float* eps, const float* coef, 
                           void* stream) {
   ATTNDM_CHECK_ARG(xt && eps && coef && x_next && n > 0, "ddim_step_hist: bad args");
   ATTNDM_CHECK_ARG(hist_x && hist_x0 && step_after && T > 0, "ddim_step_hist: history rings, step counter and T are required");
-  launch_pdl(ddim_step_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, xt, eps, coef, noise, x_next, x0_out, n,
-             hist_x, hist_x0, step_after, T);
+  launch_ddim(xt, eps, coef, noise, x_next, x0_out, n, hist_x, hist_x0, step_after, T, (cudaStream_t)stream);
   ATTNDM_CUDA_LAUNCH_CHECK("ddim_step_hist");
   return ATTNDM_OK;
 }

@@ -704,27 +704,32 @@ __global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p)
 // GroupNorm statistics
 // ---------------------------------------------------------------------------
 // block = (C/4 channel quads) x P pixel lanes, fixed quad per thread; grid = (splits, B)
+// reverse != 0: blocks walk the tensor from its END.  The producer (a conv epilogue) wrote it front to back and it is
+// larger than L2 at the big maps, so the back is what L2 still holds; the consumer of the statistics
+// (GroupNorm+SiLU+quantize) then walks front to back again and meets what THIS kernel touched last.
+template <int UNROLL>
 __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int P, int rows_per_block,
-                                double* __restrict__ stats) {
+                                double* __restrict__ stats, int reverse) {
   pdl_enter();
   __shared__ double s_sum[kGnGroups], s_sq[kGnGroups];
-  const int b = blockIdx.y;
+  const int b = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int bx = reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int Q = C >> 2;
   const int cpg = C / kGnGroups;
   if (threadIdx.x < kGnGroups) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
   __syncthreads();
   const int q = threadIdx.x % Q, pl = threadIdx.x / Q;
-  int r0 = blockIdx.x * rows_per_block, r1 = min(HW, r0 + rows_per_block);
+  int r0 = bx * rows_per_block, r1 = min(HW, r0 + rows_per_block);
   double a0 = 0, a1 = 0, a2 = 0, a3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
   if (pl < P) {
     const float* base = x + ((long long)b * HW) * C + (q << 2);
     int r = r0 + pl;
-    for (; r + 3 * P < r1; r += 4 * P) {          // four independent loads in flight, accumulated in row order
-      float4 v[4];
+    for (; r + (UNROLL - 1) * P < r1; r += UNROLL * P) {   // UNROLL independent loads in flight, accumulated in row order
+      float4 v[UNROLL];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ldg_stream(reinterpret_cast<const float4*>(base + (long long)(r + u * P) * C));
+      for (int u = 0; u < UNROLL; ++u) v[u] = ldg_stream(reinterpret_cast<const float4*>(base + (long long)(r + u * P) * C));
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         a0 += v[u].x; q0 += (double)v[u].x * v[u].x;
         a1 += v[u].y; q1 += (double)v[u].y * v[u].y;
         a2 += v[u].z; q2 += (double)v[u].z * v[u].z;
@@ -921,6 +926,7 @@ __global__ void __launch_bounds__(256) calib_mix_kernel(const float* __restrict_
                                                         int a_bit, float* __restrict__ y, double* lp_sum, float lp_p,
                                                         long long rows_per_warp) {
   __shared__ float s_s[kMaxGroups], s_z[kMaxGroups];
+  __shared__ int s_same[kMaxGroups];      // group g has the same (scale, zero point) as group g - 1: its branch output is reused
   __shared__ double s_lp[8];
   if (threadIdx.x < G) {
     float lo = gr[threadIdx.x * 2], hi = gr[threadIdx.x * 2 + 1];
@@ -929,6 +935,12 @@ __global__ void __launch_bounds__(256) calib_mix_kernel(const float* __restrict_
     s_s[threadIdx.x] = s;
     s_z[threadIdx.x] = __fadd_rn(rintf(__fmul_rn(s, lo)), (float)(1 << (a_bit - 1)));
   }
+  __syncthreads();
+  // With the [-4, 6] floor most (often all) groups share one range: the G branches are then the
+  // SAME fake-quant of x and differ only in their mixing weight -- one quantize/de-quantize (an IEEE divide) per
+  // distinct range instead of G.  Bit-identical: the reused value is the value the branch would recompute.
+  if (threadIdx.x < G)
+    s_same[threadIdx.x] = threadIdx.x > 0 && s_s[threadIdx.x] == s_s[threadIdx.x - 1] && s_z[threadIdx.x] == s_z[threadIdx.x - 1];
   __syncthreads();
   const float qlo = -(float)(1 << (a_bit - 1)), qhi = (float)((1 << (a_bit - 1)) - 1);
   const int lane = threadIdx.x & 31;
@@ -943,13 +955,20 @@ __global__ void __launch_bounds__(256) calib_mix_kernel(const float* __restrict_
         const int c = q << 2;
         float4 v = ldg_stream(reinterpret_cast<const float4*>(x + r * C + c));
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
         for (int g = 0; g < G; ++g) {
           float4 w4 = *reinterpret_cast<const float4*>(sw + (long long)g * C + c);
-          float s = s_s[g], z = s_z[g];
-          float t0 = __fmul_rn(dequant(quant_code(v.x, s, z, qlo, qhi), s, z), w4.x);
-          float t1 = __fmul_rn(dequant(quant_code(v.y, s, z, qlo, qhi), s, z), w4.y);
-          float t2 = __fmul_rn(dequant(quant_code(v.z, s, z, qlo, qhi), s, z), w4.z);
-          float t3 = __fmul_rn(dequant(quant_code(v.w, s, z, qlo, qhi), s, z), w4.w);
+          if (!s_same[g]) {
+            const float s = s_s[g], z = s_z[g];
+            d0 = dequant(quant_code(v.x, s, z, qlo, qhi), s, z);
+            d1 = dequant(quant_code(v.y, s, z, qlo, qhi), s, z);
+            d2 = dequant(quant_code(v.z, s, z, qlo, qhi), s, z);
+            d3 = dequant(quant_code(v.w, s, z, qlo, qhi), s, z);
+          }
+          float t0 = __fmul_rn(d0, w4.x);
+          float t1 = __fmul_rn(d1, w4.y);
+          float t2 = __fmul_rn(d2, w4.z);
+          float t3 = __fmul_rn(d3, w4.w);
           if (g == 0) { acc.x = t0; acc.y = t1; acc.z = t2; acc.w = t3; }
           else {
             acc.x = __fadd_rn(acc.x, t0); acc.y = __fadd_rn(acc.y, t1);
@@ -965,10 +984,10 @@ __global__ void __launch_bounds__(256) calib_mix_kernel(const float* __restrict_
     } else {
       for (int c = lane; c < C; c += 32) {
         float v = x[r * C + c];
-        float acc = 0.f;
+        float acc = 0.f, d = 0.f;
         for (int g = 0; g < G; ++g) {
-          float s = s_s[g], z = s_z[g];
-          float t = __fmul_rn(dequant(quant_code(v, s, z, qlo, qhi), s, z), sw[(long long)g * C + c]);
+          if (!s_same[g]) d = dequant(quant_code(v, s_s[g], s_z[g], qlo, qhi), s_s[g], s_z[g]);
+          float t = __fmul_rn(d, sw[(long long)g * C + c]);
           acc = (g == 0) ? t : __fadd_rn(acc, t);
         }
         y[r * C + c] = acc;
@@ -1229,14 +1248,22 @@ int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, v
   int P = Q >= 256 ? 1 : 256 / Q;
   if (P > HW) P = HW;
   int threads = round_up(Q * P, 32);
-  int splits = cdiv(4 * kNumSMs, B);
+  static const int tune_ctas = [] { const char* e = getenv("ATTNDM_GN_CTAS_PER_SM"); return e ? atoi(e) : 8; }();
+  static const int tune_unroll = [] { const char* e = getenv("ATTNDM_GN_UNROLL"); return e ? atoi(e) : 4; }();
+  static const int reverse = [] { const char* e = getenv("ATTNDM_GN_REVERSE"); return e ? atoi(e) : 1; }();
+  int splits = cdiv(tune_ctas * kNumSMs, B);
   int max_splits = cdiv(HW, P * 16);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int rows_per_block = cdiv(HW, splits);
   splits = cdiv(HW, rows_per_block);
   dim3 grid(splits, B);
-  launch_pdl(gn_stats_kernel, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, x, HW, C, P, rows_per_block, stats);
+  // (the partial sums of a sample's `splits` blocks meet in double-precision atomics: their order can change the last
+  // bit of a double, far below the fp32 mean / rstd the consumers form from them)
+  if (tune_unroll >= 8)
+    launch_pdl(gn_stats_kernel<8>, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, x, HW, C, P, rows_per_block, stats, reverse);
+  else
+    launch_pdl(gn_stats_kernel<4>, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, x, HW, C, P, rows_per_block, stats, reverse);
   ATTNDM_CUDA_LAUNCH_CHECK("gn_stats");
   return ATTNDM_OK;
 }

@@ -17,8 +17,10 @@ SHAPES = {
     "c128_32": (256, 32, 32, 128, 128, 3), "c256_32": (256, 32, 32, 256, 128, 3), "c128_16": (256, 16, 16, 128, 128, 3),
     "c128_8": (256, 8, 8, 128, 128, 3), "n256_32": (256, 32, 32, 256, 128, 1), "t256_1": (256, 1, 1, 256, 256, 1),
     "t1024_1": (256, 1, 1, 1024, 256, 1), "out_32": (256, 32, 32, 128, 3, 3), "in_32": (256, 32, 32, 3, 128, 3),
+    # LSUN church (batch 8): the 256x256 and 128x128 layers; CelebA (batch 64): 64x64
+    "c128_256": (8, 256, 256, 128, 128, 3), "c128_128": (8, 128, 128, 128, 128, 3), "c128_64": (64, 64, 64, 128, 128, 3),
 }
-names = list(SHAPES) if a.shapes == "all" else a.shapes.split(",")
+names = [n for n in SHAPES if not n.startswith("c128_") or n in ("c128_32", "c128_16", "c128_8")] if a.shapes == "all" else a.shapes.split(",")
 impl = ops.CONV_TCGEN05 if a.impl == "tc" else ops.CONV_SIMT
 for name in names:
     B, H, W, C, O, k = SHAPES[name]
