@@ -198,6 +198,34 @@ inline cudaError_t launch_pdl(void (*kernel)(ExpTypes...), dim3 grid, dim3 block
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<ExpTypes>(args)...);
 }
 
+// the same with a thread-block cluster of `cluster` CTAs along x (1: no cluster attribute)
+template <typename... ExpTypes, typename... ActTypes>
+inline cudaError_t launch_pdl_cluster(void (*kernel)(ExpTypes...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      int cluster, ActTypes&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2] = {};
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<ExpTypes>(args)...);
+}
+
 // streaming 128-bit global accesses (activations are touched once per kernel)
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 r;

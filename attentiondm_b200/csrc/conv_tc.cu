@@ -195,6 +195,58 @@ __device__ __forceinline__ void umma_i8_x4_if(uint32_t leader, uint32_t tmem_d, 
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(leader), "r"(nk), "r"(0x40004040u)
       : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster, i.e. the two SMs of a TPC, execute ONE M = 256 MMA.  Each CTA holds
+// its own 128 rows of A and HALF of B (N/2 weight rows); the leader CTA (cluster rank 0) issues the MMAs for both and
+// the accumulator rows of a CTA land in its own TMEM.  Per SM the operand fetch drops from 8 KB to 6 KB per MMA (the
+// single-CTA N = 128 MMA saturates the 128 B/clk shared-memory port: measured 75-80 cycles per MMA instead of 64 next to
+// the epilogue's traffic) and the resident weights from 144 KB to 72 KB, which buys more halo buffers.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address: rank 0's copy
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of the pair into ITS OWN shared memory; the transaction bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the barrier at the same offset in the leader CTA (from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+// commit of the pair's MMAs: one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tcgen05_commit_pair_if(uint32_t leader, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(bar), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_lo_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 ad, {%1, %5};\n\t"
+      "mov.b64 bd, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], ad, bd, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+      : "memory");
+}
 // One MMA from the two descriptor low words (high word 0x40004040: SBO = 1024 B, version 1, SWIZZLE_128B), for code
 // that runs inside `if (elect_one())`: under a branch on elect.sync ptxas keeps every operand in uniform registers
 // and emits a bare UTCIMMA with ~3 uniform-datapath instructions around it.  The predicated forms above cost ~20
@@ -212,6 +264,7 @@ __device__ __forceinline__ void umma_i8_lo(uint32_t tmem_d, uint32_t a_lo, uint3
 }
 // All MMAs of one output tile with resident weights (called by the elected lane only).  a_lo0 / b_lo0: descriptor low
 // words of the halo buffer and of the weight block; tap (kh, kw) slides A by (kh*Wp + kw) rows of 128 B = 8 units.
+template <bool PAIR>
 __device__ __forceinline__ void umma_tile_resident(uint32_t tmem_d, uint32_t a_lo0, uint32_t b_lo0, uint32_t idesc, int kdim,
                                                    int wp8, int ncb, uint32_t a_step, uint32_t b_step, int ksteps_last) {
   uint32_t b_lo = b_lo0, accumulate = 0;
@@ -224,10 +277,17 @@ __device__ __forceinline__ void umma_tile_resident(uint32_t tmem_d, uint32_t a_l
 #pragma unroll 1
       for (int cb = 0; cb < ncb; ++cb) {
         const int nk = (cb == ncb - 1) ? ksteps_last : 4;      // warp-uniform: cheap uniform predicates
-        umma_i8_lo(tmem_d, a_lo, b_lo, idesc, accumulate);
-        if (nk > 1) umma_i8_lo(tmem_d, a_lo + 2, b_lo + 2, idesc, 1u);
-        if (nk > 2) umma_i8_lo(tmem_d, a_lo + 4, b_lo + 4, idesc, 1u);
-        if (nk > 3) umma_i8_lo(tmem_d, a_lo + 6, b_lo + 6, idesc, 1u);
+        if (PAIR) {
+          umma_i8_lo_pair(tmem_d, a_lo, b_lo, idesc, accumulate);
+          if (nk > 1) umma_i8_lo_pair(tmem_d, a_lo + 2, b_lo + 2, idesc, 1u);
+          if (nk > 2) umma_i8_lo_pair(tmem_d, a_lo + 4, b_lo + 4, idesc, 1u);
+          if (nk > 3) umma_i8_lo_pair(tmem_d, a_lo + 6, b_lo + 6, idesc, 1u);
+        } else {
+          umma_i8_lo(tmem_d, a_lo, b_lo, idesc, accumulate);
+          if (nk > 1) umma_i8_lo(tmem_d, a_lo + 2, b_lo + 2, idesc, 1u);
+          if (nk > 2) umma_i8_lo(tmem_d, a_lo + 4, b_lo + 4, idesc, 1u);
+          if (nk > 3) umma_i8_lo(tmem_d, a_lo + 6, b_lo + 6, idesc, 1u);
+        }
         accumulate = 1;
         a_lo += a_step;
         b_lo += b_step;
@@ -649,6 +709,8 @@ __device__ __forceinline__ unsigned fdiv(unsigned n, const FastDiv& f) { return 
 
 struct TcGeomH {
   int BN, ncb, tmem_cols, acc_stride, ntn;
+  int pair;               // 1: CTA pairs (cluster of 2, cta_group::2 MMAs: M = 256 per pair, each CTA holds half of B)
+  int na_shift;           // log2(na): na is 1, 2 or 4
   int split;              // 1: the two groups of four epilogue warps take ALTERNATE tiles (all chunks of their quarter)
   int nacc, nacc_shift;   // accumulators in TMEM (4 when they fit in the 512 columns, else 2) and log2 of that
   long long ntiles;
@@ -809,7 +871,9 @@ __device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const
 __device__ __forceinline__ unsigned tile_mt(const TcGeomH& g, unsigned tile) { return g.ntn == 1 ? tile : tile / (unsigned)g.ntn; }
 __device__ __forceinline__ unsigned tile_nt(const TcGeomH& g, unsigned tile) { return g.ntn == 1 ? 0u : tile % (unsigned)g.ntn; }
 
-template <bool ADDS>
+// PAIR: the CTA-pair (cta_group::2) build of the kernel; it must be launched as clusters of two CTAs, and the single-CTA
+// build must not contain cta_group::2 code (the driver rejects its launch without a matching cluster shape).
+template <bool ADDS, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS_H, 1)
 qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
@@ -834,25 +898,37 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nkb = p.taps * g.ncb;
-  const int b_tile_bytes = g.BN * TC_BK;
+  const int b_tile_bytes = (PAIR ? g.BN / 2 : g.BN) * TC_BK;      // pair: each CTA holds half of the weight rows
   const unsigned ntiles = (unsigned)g.ntiles;
+  // Tile sequence of this CTA: tile0, tile0 + gridDim.x, ...  A CTA pair takes two adjacent tiles per step (rank r the
+  // tile 2*(pair index + it*pairs) + r), so both CTAs run the same number of iterations; the odd CTA's last tile may lie
+  // past the end (all its rows are then invalid: TMA zero-fills, the epilogue stores nothing).
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const unsigned tile0 = PAIR ? 2u * (blockIdx.x >> 1) + rank : blockIdx.x;
 
   if (warp == TC_H_R0) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"((uint32_t)g.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                   "r"((uint32_t)g.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                   "r"((uint32_t)g.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   } else if (warp == TC_H_R0 + 1 && lane == 0) {
     for (int i = 0; i < g.na; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
     for (int i = 0; i < g.nb; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
     mbar_init(smem_u32(&b_res_bar), 1);
     for (int a = 0; a < g.nacc; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), g.split ? 4 : TC_H_EPI_WARPS);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), (g.split ? 4 : TC_H_EPI_WARPS) * (PAIR ? 2 : 1));   // pair: both CTAs' warps arrive at the leader's
     }
     for (int a = 0; a < TC_H_NRS; ++a) { mbar_init(smem_u32(&rs_bar[0][a]), 1); mbar_init(smem_u32(&rs_bar[1][a]), 1); }
     for (int a = 0; a < TC_H_NGEO; ++a) {
@@ -863,6 +939,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                       // the peer's barriers exist before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   if (threadIdx.x == 0) TC_SPAN(0);
@@ -912,12 +989,12 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       };
       const unsigned tstride = (unsigned)ngw * gridDim.x;  // this warp takes the tiles gw, gw + ngw, ... of the CTA
-      unsigned tile_i = blockIdx.x + (unsigned)gw * gridDim.x;   // issue cursor, TC_H_NRS - 1 of its tiles ahead
+      unsigned tile_i = tile0 + (unsigned)gw * gridDim.x;        // issue cursor, TC_H_NRS - 1 of its tiles ahead
       int seq_i = 0;
-      for (; seq_i < TC_H_NRS - 1 && tile_i < ntiles; ++seq_i, tile_i += tstride) rs_issue(tile_i, seq_i);
+      for (; seq_i < TC_H_NRS - 1 && tile_i - rank < ntiles; ++seq_i, tile_i += tstride) rs_issue(tile_i, seq_i);
       int it = gw, seq = 0;
-      for (unsigned tile = blockIdx.x + (unsigned)gw * gridDim.x; tile < ntiles; tile += tstride, it += ngw, ++seq) {
-        if (tile_i < ntiles) { rs_issue(tile_i, seq_i); ++seq_i; tile_i += tstride; }
+      for (unsigned tile = tile0 + (unsigned)gw * gridDim.x; tile - rank < ntiles; tile += tstride, it += ngw, ++seq) {
+        if (tile_i - rank < ntiles) { rs_issue(tile_i, seq_i); ++seq_i; tile_i += tstride; }
         const int slot = seq % TC_H_NRS;
         const unsigned m0 = tile_mt(g, tile) * TC_BM;
         int px[4], off[4];
@@ -969,7 +1046,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
       // fallback (row sums not 16-byte aligned): gather with ordinary loads, one tile at a time
       int it = gw;
-      for (unsigned tile = blockIdx.x + (unsigned)gw * gridDim.x; tile < ntiles; tile += (unsigned)ngw * gridDim.x, it += ngw) {
+      for (unsigned tile = tile0 + (unsigned)gw * gridDim.x; tile - rank < ntiles; tile += (unsigned)ngw * gridDim.x, it += ngw) {
         const unsigned m0 = tile_mt(g, tile) * TC_BM;
         int px[4], cs[4];
 #pragma unroll
@@ -1012,16 +1089,26 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (g.b_resident) {
         const int ntn_tiles_here = 1;   // resident mode is only chosen when ntn == 1
         (void)ntn_tiles_here;
-        mbar_expect_tx_elect(smem_u32(&b_res_bar), (uint32_t)(nkb * b_tile_bytes));
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
-          tma_load_2d_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK, 0);
+        if (PAIR) {
+          // each CTA loads ITS half of the output channels (rows rank*BN/2 ...); both halves count on the leader's barrier
+          if (rank == 0) mbar_expect_tx_elect(smem_u32(&b_res_bar), (uint32_t)(2 * nkb * b_tile_bytes));
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
+            tma_load_2d_pair_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK,
+                                   (int)rank * (g.BN >> 1));
+          }
+        } else {
+          mbar_expect_tx_elect(smem_u32(&b_res_bar), (uint32_t)(nkb * b_tile_bytes));
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
+            tma_load_2d_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK, 0);
+          }
         }
         geometry_role(1, 2);
       } else {
         int s = 0;
         uint32_t ph = 0;
-        for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (unsigned tile = tile0; tile - rank < ntiles; tile += gridDim.x) {
           const int n0 = (int)tile_nt(g, tile) * g.BN;
           for (int kb = 0; kb < nkb; ++kb) {
             const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
@@ -1037,31 +1124,41 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     pdl_wait();                                        // the codes come from the previous kernel
     {
       // ===== activation (halo) producer: one halo per (tile, channel block) =====
-      const int hr1 = g.hr > 256 ? 256 : g.hr;          // a TMA box holds at most 256 rows
-      const int hr2 = g.hr - hr1;
+      const int nfull = g.hr >= 256 ? g.hr / 256 : 1;    // a TMA box holds at most 256 rows: nfull boxes of tmA ...
+      const int hr2 = g.hr >= 256 ? g.hr - 256 * nfull : 0;   // ... and the remainder through tmA2
       int it = 0;
-      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (unsigned tile = tile0; tile - rank < ntiles; tile += gridDim.x, ++it) {
         const unsigned m0 = tile_mt(g, tile) * TC_BM;
-        const int buf = g.na == 2 ? (it & 1) : 0;
+        const int buf = it & (g.na - 1);
         if (lane == 0) TC_TRACE(0, it, 0);
-        mbar_wait_relaxed(smem_u32(&a_empty[buf]), (uint32_t)((((g.na == 2 ? it >> 1 : it)) & 1) ^ 1));
+        mbar_wait_relaxed(smem_u32(&a_empty[buf]), (uint32_t)(((it >> g.na_shift) & 1) ^ 1));
         if (lane == 0) TC_TRACE(0, it, 1);
         const uint32_t bar = smem_u32(&a_full[buf]);
-        if (g.dbg & 16) { mbar_expect_tx_elect(bar, 0u); continue; }       // experiment: no halo loads at all
-        mbar_expect_tx_elect(bar, (uint32_t)(g.ncb * g.hr * TC_BK));
-        for (int cb = 0; cb < g.ncb; ++cb) {
-          const uint32_t dst = base + g.a_off + (uint32_t)(buf * g.ncb + cb) * g.hr_stride;
-          tma_load_2d_elect(dst, &tmA, bar, cb * TC_BK, (int)m0);
-          if (hr2 > 0) tma_load_2d_elect(dst + 256 * TC_BK, &tmA2, bar, cb * TC_BK, (int)m0 + 256);
+        if ((g.dbg & 16) && !PAIR) { mbar_expect_tx_elect(bar, 0u); continue; }       // experiment: no halo loads at all
+        if (PAIR) {
+          // both CTAs' halos count on the LEADER's barrier (its MMA warp issues for the pair)
+          if (rank == 0) mbar_expect_tx_elect(bar, (uint32_t)(2 * g.ncb * g.hr * TC_BK));
+          for (int cb = 0; cb < g.ncb; ++cb) {
+            const uint32_t dst = base + g.a_off + (uint32_t)(buf * g.ncb + cb) * g.hr_stride;
+            for (int bx = 0; bx < nfull; ++bx) tma_load_2d_pair_elect(dst + bx * 256 * TC_BK, &tmA, bar, cb * TC_BK, (int)m0 + 256 * bx);
+            if (hr2 > 0) tma_load_2d_pair_elect(dst + nfull * 256 * TC_BK, &tmA2, bar, cb * TC_BK, (int)m0 + 256 * nfull);
+          }
+        } else {
+          mbar_expect_tx_elect(bar, (uint32_t)(g.ncb * g.hr * TC_BK));
+          for (int cb = 0; cb < g.ncb; ++cb) {
+            const uint32_t dst = base + g.a_off + (uint32_t)(buf * g.ncb + cb) * g.hr_stride;
+            for (int bx = 0; bx < nfull; ++bx) tma_load_2d_elect(dst + bx * 256 * TC_BK, &tmA, bar, cb * TC_BK, (int)m0 + 256 * bx);
+            if (hr2 > 0) tma_load_2d_elect(dst + nfull * 256 * TC_BK, &tmA2, bar, cb * TC_BK, (int)m0 + 256 * nfull);
+          }
         }
         // pull the halos of the tiles 2 and 3 iterations ahead into L2
         for (int ahead = (it == 0 ? 1 : 3); ahead <= 3; ++ahead) {
           const unsigned tf = tile + (unsigned)ahead * gridDim.x;
-          if (tf < ntiles) {
+          if (tf - rank < ntiles) {
             const unsigned mf = tile_mt(g, tf) * TC_BM;
             for (int cb = 0; cb < g.ncb; ++cb) {
-              tma_prefetch_2d_elect(&tmA, cb * TC_BK, (int)mf);
-              if (hr2 > 0) tma_prefetch_2d_elect(&tmA2, cb * TC_BK, (int)mf + 256);
+              for (int bx = 0; bx < nfull; ++bx) tma_prefetch_2d_elect(&tmA, cb * TC_BK, (int)mf + 256 * bx);
+              if (hr2 > 0) tma_prefetch_2d_elect(&tmA2, cb * TC_BK, (int)mf + 256 * nfull);
             }
           }
         }
@@ -1069,14 +1166,14 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp == TC_H_R0 + 1) {
     pdl_wait();
-    {
+    if (rank == 0) {                                   // pair mode: the leader CTA issues for both
       // ===== MMA issuer =====
       // The issue loop is scalar code on one warp: anything slow between two tcgen05.mma shows up as idle
       // tensor-pipe time (an integer division per k-block cost ~200 cycles per MMA).  So: nested loops with
       // additive address updates only, and descriptors assembled from a constant high word plus a 14-bit
       // (address >> 4) low field that is simply incremented (+2 per 32-byte K step).
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
-                             ((uint32_t)(TC_BM >> 4) << 24);
+                             ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
       const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
                                ((uint64_t)2 << 61);
       const int kdim = p.taps == 9 ? 3 : 1;
@@ -1090,12 +1187,12 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int acc = it & (g.nacc - 1), buf = g.na == 2 ? (it & 1) : 0;
+      for (unsigned tile = tile0; tile - rank < ntiles; tile += gridDim.x, ++it) {
+        const int acc = it & (g.nacc - 1), buf = it & (g.na - 1);
         if (lane == 0) TC_TRACE(1, it, 0);
         if (!(g.dbg & 256)) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((it >> g.nacc_shift) & 1) ^ 1));
         if (lane == 0) TC_TRACE(1, it, 1);
-        if (!(g.dbg & 128)) mbar_wait(smem_u32(&a_full[buf]), (uint32_t)((g.na == 2 ? it >> 1 : it) & 1));
+        if (!(g.dbg & 128)) mbar_wait(smem_u32(&a_full[buf]), (uint32_t)((it >> g.na_shift) & 1));
         if (g.b_resident && it == 0) { mbar_wait(smem_u32(&b_res_bar), 0); if (lane == 0) TC_SPAN(1); }
         tcgen05_fence_after();
         if (lane == 0) TC_TRACE(1, it, 2);
@@ -1126,7 +1223,8 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
 #else
           if (leader) {
-            umma_tile_resident(d_tmem, a_lo0, b_lo0, idesc, kdim, p.Wp * (TC_BK >> 4), g.ncb, a_step, b_step, ksteps_last);
+            if (PAIR) umma_tile_resident<true>(d_tmem, a_lo0, b_lo0, idesc, kdim, p.Wp * (TC_BK >> 4), g.ncb, a_step, b_step, ksteps_last);
+            else        umma_tile_resident<false>(d_tmem, a_lo0, b_lo0, idesc, kdim, p.Wp * (TC_BK >> 4), g.ncb, a_step, b_step, ksteps_last);
           }
           __syncwarp();
           accumulate = 1;
@@ -1162,8 +1260,13 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
         }
-        tcgen05_commit_if(leader, smem_u32(&a_empty[buf]));
-        tcgen05_commit_if(leader, smem_u32(&tmem_full_bar[acc]));
+        if (PAIR) {
+          tcgen05_commit_pair_if(leader, smem_u32(&a_empty[buf]));
+          tcgen05_commit_pair_if(leader, smem_u32(&tmem_full_bar[acc]));
+        } else {
+          tcgen05_commit_if(leader, smem_u32(&a_empty[buf]));
+          tcgen05_commit_if(leader, smem_u32(&tmem_full_bar[acc]));
+        }
         if (lane == 0) TC_TRACE(1, it, 3);
         if (tr_all != nullptr && lane == 0 && it < 32) {
           unsigned long long now;
@@ -1193,7 +1296,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int tile_step = g.split ? TC_H_EPI_GROUPS : 1;
     const int ci0 = g.split ? 0 : half, ci_step = g.split ? 1 : TC_H_EPI_GROUPS;
     int it = g.split ? half : 0;
-    for (unsigned tile = blockIdx.x + (unsigned)it * gridDim.x; tile < ntiles || last_nt < 0;
+    for (unsigned tile = tile0 + (unsigned)it * gridDim.x; tile - rank < ntiles || last_nt < 0;
          tile += (unsigned)tile_step * gridDim.x, it += tile_step) {
       const int acc = it & (g.nacc - 1);
       const int nt = (int)tile_nt(g, tile);
@@ -1213,7 +1316,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_H_EPI_WARPS) : "memory");
         last_nt = nt;
-        if (tile >= ntiles) break;                   // (split mode, a CTA with a single tile: the odd group only helped with the constants)
+        if (tile - rank >= ntiles) break;                   // (split mode, a CTA with a single tile: the odd group only helped with the constants)
       }
       // row geometry of this thread's four fragment rows (tr, tr+8, tr+16, tr+24 of the quarter), prepared
       // by the geometry warp
@@ -1253,7 +1356,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * g.acc_stride) + ((uint32_t)(quarter * 32) << 16);
       if (ci0 >= nchunks) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(smem_u32(&tmem_empty_bar[acc])); else mbar_arrive(smem_u32(&tmem_empty_bar[acc])); }
       }
       for (int ci = ci0; ci < nchunks; ci += ci_step) {
         const int c0 = ci << 5;
@@ -1271,7 +1374,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (ci + ci_step >= nchunks) {
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(smem_u32(&tmem_empty_bar[acc])); else mbar_arrive(smem_u32(&tmem_empty_bar[acc])); }
         }
         if ((g.dbg & 3) >= 1) continue;
         const bool use4 = vec4 && c0 + 32 <= g.BN && n0 + c0 + 32 <= p.O;
@@ -1323,10 +1426,13 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (TC_H_TMA_STORE && g.tma_store && warp >= TC_H_EPI0 && warp < TC_H_R0 && lane == 0) bulk_wait0();
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                       // neither CTA leaves (or frees TMEM) while the pair still works
   if (threadIdx.x == 0) TC_SPAN(2);
   if (warp == TC_H_R0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
   }
 }
 
@@ -1442,7 +1548,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   g.ntiles = mtiles * g.ntn;
   g.ncb = cdiv(p.Cp, TC_BK);
   g.hr = p.taps == 9 ? TC_BM + 2 * p.Wp + 2 : TC_BM;
-  if (g.hr > 512) return 0;
+  if (g.hr > 1024) return 0;                                          // W <= 446 (the halo is moved in 256-row TMA boxes)
   if ((long long)p.B * p.H * p.W * p.O >= (1LL << 31)) return 0;      // the epilogue keeps 32-bit output offsets
   if (p.rows + TC_BM >= (1LL << 31) || g.ntiles >= (1LL << 31)) return 0;   // 32-bit row and tile indices in the kernel
   g.hr_stride = round_up(g.hr * TC_BK, 1024);
@@ -1452,7 +1558,6 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   // dynamic smem we allow ourselves: 227 KB - 20.5 KB static - alignment slack - the row-sum ring
   const int kBudget = 205 * 1024 - rs_bytes;
   const int nkb = p.taps * g.ncb;
-  const int b_tile = g.BN * TC_BK;
   // output path: per-warp 2 KB staging slots + TMA tensor stores when the 128-bit path applies (O % 4 == 0)
   // and a quarter's 32 rows meet at most TC_H_NSEG image rows
   // Off by default: with one 2 KB slot per warp (all the shared memory left beside resident weights) the warp
@@ -1462,9 +1567,29 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   g.tma_store = (TC_H_TMA_STORE && tma_store_on && (p.O & 3) == 0 && g.BN % 32 == 0 && ((uintptr_t)p.out & 15) == 0) ? 1 : 0;
   int stg_bytes = g.tma_store ? TC_H_EPI_WARPS * 32 * 16 * 4 : 0;
   const int a_buf = g.ncb * g.hr_stride;
-  const int grid = (int)(g.ntiles < kNumSMs ? g.ntiles : kNumSMs);
+  int grid = (int)(g.ntiles < kNumSMs ? g.ntiles : kNumSMs);
   const long long tiles_per_cta = (g.ntiles + grid - 1) / grid;
   g.na = tiles_per_cta > 1 ? 2 : 1;
+  int b_tile = g.BN * TC_BK;
+  // CTA pairs (cta_group::2): one N tile whose two halves go to the two CTAs of a cluster; the weights then take half
+  // the shared memory per CTA and stay resident next to up to four halo buffers.  ATTNDM_TC_PAIR=0 turns it off.
+  static const bool pair_on = [] { const char* e = getenv("ATTNDM_TC_PAIR"); return !(e && e[0] == '0'); }();
+  g.pair = 0;
+  // Chosen where the single-CTA kernel cannot keep the weights resident next to two halo buffers (W >= 64 at 128 -> 128:
+  // 63.9 -> 40.8 us at 64x64, 35.9 -> 22.7 us at 128x128); where it can (the CIFAR shapes) the two measure the same and
+  // the single-CTA kernel has the shorter prologue.  ATTNDM_TC_PAIR=2 forces pairs wherever they fit.
+  static const int pair_mode = [] { const char* e = getenv("ATTNDM_TC_PAIR"); return e ? atoi(e) : 1; }();
+  const bool single_resident = g.ntn == 1 && (long long)nkb * b_tile + (long long)g.na * a_buf <= kBudget;
+  if (pair_on && !g.tma_store && g.ntn == 1 && g.BN % 32 == 0 && mtiles >= 2 && (kNumSMs % 2) == 0 &&
+      (long long)nkb * (b_tile / 2) + (long long)a_buf <= kBudget && (pair_mode == 2 || !single_resident)) {
+    g.pair = 1;
+    b_tile /= 2;                                        // each CTA holds BN/2 weight rows
+    const long long pairs = (mtiles + 1) / 2;
+    grid = (int)(2 * (pairs < kNumSMs / 2 ? pairs : kNumSMs / 2));
+    const long long its = (pairs + grid / 2 - 1) / (grid / 2);
+    const long long wb = (long long)nkb * b_tile;
+    g.na = (wb + 4LL * a_buf <= kBudget && its >= 4) ? 4 : ((wb + 2LL * a_buf <= kBudget && its >= 2) ? 2 : 1);
+  }
   // weights resident when they fit next to two halo buffers (and there is a single N tile)
   if (g.tma_store && g.ntn == 1 && (long long)nkb * b_tile + (long long)g.na * a_buf <= kBudget &&
       (long long)nkb * b_tile + (long long)g.na * a_buf + stg_bytes > kBudget) {
@@ -1483,6 +1608,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
     if (g.nb > nkb * 2) g.nb = nkb * 2;
     if (g.nb < 2) g.nb = 2;
   }
+  g.na_shift = g.na == 4 ? 2 : (g.na == 2 ? 1 : 0);
   g.a_off = 0;
   g.b_off = g.na * a_buf;
   g.stg_off = g.b_off + (g.b_resident ? nkb : g.nb) * b_tile;
@@ -1508,18 +1634,22 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   int rc = make_map_2d(&tmA, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, (uint32_t)hr1);
   if (rc) return rc;
   tmA2 = tmA;
-  if (g.hr > 256) {
-    rc = make_map_2d(&tmA2, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, (uint32_t)(g.hr - 256));
+  if (g.hr > 256 && g.hr % 256 != 0) {
+    rc = make_map_2d(&tmA2, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, (uint32_t)(g.hr % 256));
     if (rc) return rc;
   }
-  rc = make_map_2d(&tmB, p.qw, (uint64_t)p.taps * p.Cp, (uint64_t)p.O, TC_BK, (uint32_t)g.BN);
+  rc = make_map_2d(&tmB, p.qw, (uint64_t)p.taps * p.Cp, (uint64_t)p.O, TC_BK, (uint32_t)(g.pair ? g.BN / 2 : g.BN));
   if (rc) return rc;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
     if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+      attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("qconv_i8_halo: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
   CUtensorMap tmO[TC_H_NBOX];
@@ -1538,10 +1668,18 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
       if (r != CUDA_SUCCESS) { set_error("qconv_i8_halo: output tensor map failed (%d)", (int)r); return ATTNDM_ERR_CUDA; }
     }
   }
-  if (p.residual != nullptr || p.temb != nullptr)
-    launch_pdl(qconv_i8_halo_kernel<true>, dim3(grid), dim3(TC_THREADS_H), smem, st, tmA, tmA2, tmB, tmO[0], tmO[1], tmO[2], tmO[3], tmO[4], p, g);
-  else
-    launch_pdl(qconv_i8_halo_kernel<false>, dim3(grid), dim3(TC_THREADS_H), smem, st, tmA, tmA2, tmB, tmO[0], tmO[1], tmO[2], tmO[3], tmO[4], p, g);
+  const bool adds = p.residual != nullptr || p.temb != nullptr;
+#define ATTNDM_HALO_ARGS dim3(grid), dim3(TC_THREADS_H), smem, st
+#define ATTNDM_HALO_PARAMS tmA, tmA2, tmB, tmO[0], tmO[1], tmO[2], tmO[3], tmO[4], p, g
+  if (g.pair) {
+    if (adds) launch_pdl_cluster(qconv_i8_halo_kernel<true, true>, ATTNDM_HALO_ARGS, 2, ATTNDM_HALO_PARAMS);
+    else      launch_pdl_cluster(qconv_i8_halo_kernel<false, true>, ATTNDM_HALO_ARGS, 2, ATTNDM_HALO_PARAMS);
+  } else {
+    if (adds) launch_pdl(qconv_i8_halo_kernel<true, false>, ATTNDM_HALO_ARGS, ATTNDM_HALO_PARAMS);
+    else      launch_pdl(qconv_i8_halo_kernel<false, false>, ATTNDM_HALO_ARGS, ATTNDM_HALO_PARAMS);
+  }
+#undef ATTNDM_HALO_ARGS
+#undef ATTNDM_HALO_PARAMS
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("qconv_i8_halo: launch failed: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
   return 1;
