@@ -44,14 +44,14 @@ CONFIGS = {
                                  "grid), MixedPrecisionAttention on every attention site (4-bit logits, 3-bit "
                                  "probabilities), trained-like attention alpha_activ ~ N(0,1) (those 1x1 convs take the "
                                  "fp32 kernel, H2), calibration ranges all-reduced over ranks, DDIM 100, batch 256/GPU"),
-    "celeba_w8a8": dict(spec="celeba_spec", bitwidth=8, batch=64, gflop=10.963, layers=252, attn_mixed=False,
+    "celeba_w8a8": dict(spec="celeba_spec", bitwidth=8, batch=256, gflop=10.963, layers=252, attn_mixed=False,
                         alpha="uniform", ch_mult=[1, 2, 2, 2, 4], size=64,
-                        text="CelebA 64x64 UNet (configs/celeba.yml, 252 QConv2d) W8A8, DDIM 100 steps, batch 64/GPU"),
-    "church_w8a8": dict(spec="church_spec", bitwidth=8, batch=8, gflop=163.224, layers=305, attn_mixed=True,
+                        text="CelebA 64x64 UNet (configs/celeba.yml, 252 QConv2d) W8A8, DDIM 100 steps, batch 256/GPU"),
+    "church_w8a8": dict(spec="church_spec", bitwidth=8, batch=32, gflop=163.224, layers=305, attn_mixed=True,
                         alpha="uniform", ch_mult=[1, 1, 2, 2, 4, 4], size=256,
                         text="LSUN church 256x256 UNet (configs/church.yml, 305 QConv2d) W8A8 with quantized attention "
                              "(MixedPrecisionAttention, 8-bit: attention-internal quantizers inactive above 6 bits), "
-                             "DDIM 100 steps, batch 8/GPU"),
+                             "DDIM 100 steps, batch 32/GPU"),
 }
 
 

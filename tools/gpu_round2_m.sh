@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+for c in church_w8a8 celeba_w8a8; do
+export ATTNDM_CONFIG=$c
+timeout 600 python tools/profile_engine.py --steps 1 --events 0 > gpurun_out/ncu_plain_$c.log 2>&1 &&
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --profile-from-start off -c 2500 --csv \
+   --log-file gpurun_out/launches_r02_$c.csv python tools/profile_engine.py --steps 1 --events 0 > gpurun_out/ncu_run_$c.log 2>&1
+echo "ncu $c rc=$?"
+python tools/parse_launches.py gpurun_out/launches_r02_$c.csv > gpurun_out/launches_r02_$c.txt
+head -28 gpurun_out/launches_r02_$c.txt
+done

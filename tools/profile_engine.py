@@ -10,25 +10,29 @@ from attentiondm_b200 import _ffi, ops, rowprog
 from attentiondm_b200.engine import SamplerEngine
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--batch", type=int, default=0)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--events", type=int, default=1)
 a = ap.parse_args()
 dev = torch.device("cuda")
 bench.T_STEPS = 100
-m, seq = bench.build_model(dev, bench.CONFIGS[os.environ.get("ATTNDM_CONFIG", "cifar10_w8a8")])
+CFG = bench.CONFIGS[os.environ.get("ATTNDM_CONFIG", "cifar10_w8a8")]
+SIZE = CFG["size"]
+if a.batch <= 0:
+    a.batch = CFG["batch"]
+m, seq = bench.build_model(dev, CFG)
 for n, q in m.qconvs():          # skip calibration: every activation range = the reference floor [-4, 6]
     q.groups_range.data[..., 0] = -4.0
     q.groups_range.data[..., 1] = 6.0
     q.invalidate_cache(weights=False)
 betas = torch.linspace(1e-4, 0.02, 1000, dtype=torch.float64).float().to(dev)
-eng = SamplerEngine(m, seq, betas, 0.0, (a.batch, 3, 32, 32))
+eng = SamplerEngine(m, seq, betas, 0.0, (a.batch, 3, SIZE, SIZE))
 print("fused:", eng.fused is not None, "trunk:", eng.fused is not None and eng.fused.trunk_plan is not None)
 if eng.fused is not None and eng.fused.trunk_plan is not None:
     tp = eng.fused.trunk_plan
     print(f"trunk: ns={tp.ns} ops={tp.n_ops} arena={tp.arena_floats*4} B cp_max={tp.cp_max} first_down={eng.fused.first_down} n_up={eng.fused.n_up}")
     print(f"time_mlp: ns={eng.fused.time_plan.ns} programs={len(eng.fused.time_plan.programs)}")
-x = torch.randn(a.batch, 3, 32, 32, device=dev)
+x = torch.randn(a.batch, 3, SIZE, SIZE, device=dev)
 eng.load_input(x)
 with torch.no_grad():
     for _ in range(2):
