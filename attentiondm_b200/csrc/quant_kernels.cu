@@ -37,6 +37,8 @@ struct ActQuantParams {
   float* y;
   long long rows;          // rows of the code layout (halo or plain)
   long long rows_per_warp;
+  const float* x2;         // CAT kernels: x = [B][H/2][W/2][C1] (read through a nearest x2 upsample), x2 = [B][H][W][C - C1]
+  int C1;
 };
 
 template <int PRE>
@@ -338,7 +340,10 @@ __device__ __forceinline__ int quant_code_i(float t, float lo, float hi) {
   return __float2int_rn(fminf(fmaxf(t, lo), hi));
 }
 
-template <int PRE, int NQ, bool A8>
+// CAT: the input is the never-materialised concat of an UpBlock (models/diffusion.py:225-229 + torch.cat): channels
+// [0, C1) are p.x [B][H/2][W/2][C1] seen through a nearest-neighbour x2 upsample, channels [C1, C) are p.x2
+// [B][H][W][C - C1].  C1 % 128 == 0, so each of a lane's NQ float4 slots lies entirely in one part.
+template <int PRE, int NQ, bool A8, bool CAT>
 __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_rows_kernel(ActQuantParams p) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
@@ -393,6 +398,9 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_
       }
     }
     const float* xrow = p.x + (long long)ir * W * C + (lane << 2);
+    const int C2 = C - p.C1, Wa = W >> 1;
+    const float* arow = CAT ? p.x + ((long long)(b * (p.H >> 1) + (h >> 1)) * Wa) * p.C1 + (lane << 2) : nullptr;
+    const float* brow = CAT ? p.x2 + (long long)ir * W * C2 + (lane << 2) - p.C1 : nullptr;
     const long long rbase = p.halo ? ((long long)b * Hp + h + 1) * Wp + 1 : (long long)ir * W;   // code row of pixel w = 0
     int8_t* crow = p.codes + rbase * Cp + (lane << 2);
     for (int w0 = 0; w0 < W; w0 += R) {
@@ -401,7 +409,14 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_
       for (int k = 0; k < R; ++k)
 #pragma unroll
         for (int i = 0; i < NQ; ++i)
-          v[k][i] = ldg_stream(reinterpret_cast<const float4*>(xrow + (long long)(w0 + k) * C + i * 128));
+          if (!CAT) {
+            v[k][i] = ldg_stream(reinterpret_cast<const float4*>(xrow + (long long)(w0 + k) * C + i * 128));
+          } else if (i * 128 < p.C1) {                          // upsampled part: pixels 2j and 2j + 1 read the same element
+            if ((k & 1) == 0) v[k][i] = __ldg(reinterpret_cast<const float4*>(arow + (long long)((w0 + k) >> 1) * p.C1 + i * 128));
+            else v[k][i] = v[k - 1][i];
+          } else {
+            v[k][i] = ldg_stream(reinterpret_cast<const float4*>(brow + (long long)(w0 + k) * C2 + i * 128));
+          }
       int sums[R];
 #pragma unroll
       for (int k = 0; k < R; ++k) {
@@ -523,6 +538,7 @@ static int act_quant_impl(const float* x, int B, int H, int W, int C, const floa
   p.gn_stats = gn_stats; p.gamma = gamma; p.beta = beta; p.eps = eps;
   p.codes = codes; p.rowsum = rowsum; p.halo = (rows_layout == ATTNDM_ROWS_HALO && codes) ? 1 : 0;
   p.y = y;
+  p.x2 = nullptr; p.C1 = 0;
   p.rows = p.halo ? (long long)B * (H + 2) * (W + 2) : (long long)B * H * W;
   // ~8 warps per block; aim at <= 16 resident blocks per SM worth of warps, rows contiguous per warp
   // one wave: the fast kernels keep 3 (C = 128) or 2 (C = 256) blocks of 8 warps resident per SM
@@ -548,8 +564,8 @@ static int act_quant_impl(const float* x, int B, int H, int W, int C, const floa
     const int nb = cdiv(w2, 8);
 #define ATTNDM_AQ_ROWS_N(PREV, NQV)                                                                                 \
     do {                                                                                                              \
-      if (a_bit == 8) launch_pdl(act_quant_rows_kernel<PREV, NQV, true>, dim3(nb), dim3(256), 0, st, p);             \
-      else launch_pdl(act_quant_rows_kernel<PREV, NQV, false>, dim3(nb), dim3(256), 0, st, p);                       \
+      if (a_bit == 8) launch_pdl(act_quant_rows_kernel<PREV, NQV, true, false>, dim3(nb), dim3(256), 0, st, p);      \
+      else launch_pdl(act_quant_rows_kernel<PREV, NQV, false, false>, dim3(nb), dim3(256), 0, st, p);                \
     } while (0)
 #define ATTNDM_AQ_ROWS(PREV)                                                                                         \
     do {                                                                                                              \
@@ -707,15 +723,17 @@ __global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p)
 // reverse != 0: blocks walk the tensor from its END.  The producer (a conv epilogue) wrote it front to back and it is
 // larger than L2 at the big maps, so the back is what L2 still holds; the consumer of the statistics
 // (GroupNorm+SiLU+quantize) then walks front to back again and meets what THIS kernel touched last.
+// cpg / g0 / mult: the tensor may be one PART of a GroupNorm input (the upsampled half or the skip half of an
+// UpBlock's concat, which is never materialised): its channels fall into groups of cpg channels starting at group g0
+// of the stats row, and every sum is scaled by mult (4 for the half that nearest-neighbour upsampling repeats 2x2).
 template <int UNROLL>
 __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int P, int rows_per_block,
-                                double* __restrict__ stats, int reverse) {
+                                double* __restrict__ stats, int reverse, int cpg, int g0, double mult) {
   pdl_enter();
   __shared__ double s_sum[kGnGroups], s_sq[kGnGroups];
   const int b = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int bx = reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int Q = C >> 2;
-  const int cpg = C / kGnGroups;
   if (threadIdx.x < kGnGroups) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
   __syncthreads();
   const int q = threadIdx.x % Q, pl = threadIdx.x / Q;
@@ -756,9 +774,9 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int 
     }
   }
   __syncthreads();
-  if (threadIdx.x < kGnGroups) {
-    atomicAdd(&stats[((long long)b * kGnGroups + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
-    atomicAdd(&stats[((long long)b * kGnGroups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+  if (threadIdx.x < C / cpg) {                  // scaling by a power of two is exact
+    atomicAdd(&stats[((long long)b * kGnGroups + g0 + threadIdx.x) * 2 + 0], mult * s_sum[threadIdx.x]);
+    atomicAdd(&stats[((long long)b * kGnGroups + g0 + threadIdx.x) * 2 + 1], mult * s_sq[threadIdx.x]);
   }
 }
 
@@ -1193,6 +1211,64 @@ int attndm_act_quant(const float* x, int B, int H, int W, int C, const float* sc
                         rowsum, rows_layout, y_f32, true, (cudaStream_t)stream);
 }
 
+int attndm_act_quant_cat_fits(int H, int W, int C1, int C2) {
+  const int C = C1 + C2;
+  return (C1 > 0 && C2 > 0 && C1 % 128 == 0 && (C == 256 || C == 384 || C == 512) && (W & 3) == 0 && (H & 1) == 0 &&
+          (C / kGnGroups) % 4 == 0 && C1 % (C / kGnGroups) == 0) ? 1 : 0;
+}
+
+int attndm_act_quant_cat(const float* xa, int C1, const float* xb, int C2, int B, int H, int W, const float* scale,
+                         const float* zp, int a_bit, int pre_op, const double* gn_stats, const float* gn_gamma,
+                         const float* gn_beta, float gn_eps, int8_t* codes, int32_t* rowsum, int rows_layout,
+                         void* stream) {
+  ATTNDM_CHECK_ARG(xa && xb && B > 0 && H > 0 && W > 0 && scale && zp && codes && rowsum && a_bit >= 2 && a_bit <= 8,
+                   "act_quant_cat: bad args");
+  ATTNDM_CHECK_ARG(rows_layout == ATTNDM_ROWS_PLAIN || rows_layout == ATTNDM_ROWS_HALO, "act_quant_cat: bad layout");
+  ATTNDM_CHECK_ARG(pre_op == ATTNDM_PRE_NONE || pre_op == ATTNDM_PRE_SILU || (pre_op == ATTNDM_PRE_GN_SILU && gn_stats && gn_gamma && gn_beta),
+                   "act_quant_cat: bad pre-op");
+  const int C = C1 + C2;
+  if (!attndm_act_quant_cat_fits(H, W, C1, C2) || (long long)B * H * W * C >= (1LL << 31) ||
+      ((((uintptr_t)xa | (uintptr_t)xb | (uintptr_t)codes | (uintptr_t)scale | (uintptr_t)zp) & 15) != 0)) {
+    set_error("act_quant_cat: shape %dx%dx(%d+%d) not supported (see attndm_act_quant_cat_fits)", H, W, C1, C2);
+    return ATTNDM_ERR_UNSUPPORTED;
+  }
+  ActQuantParams p;
+  p.x = xa; p.x2 = xb; p.C1 = C1;
+  p.B = B; p.H = H; p.W = W; p.C = C; p.Cp = round_up(C, 16);
+  p.scale = scale; p.zp = zp;
+  p.qlo = -(float)(1 << (a_bit - 1));
+  p.qhi = (float)((1 << (a_bit - 1)) - 1);
+  p.gn_stats = gn_stats; p.gamma = gn_gamma; p.beta = gn_beta; p.eps = gn_eps;
+  p.codes = codes; p.rowsum = rowsum; p.halo = rows_layout == ATTNDM_ROWS_HALO ? 1 : 0;
+  p.y = nullptr;
+  p.rows = p.halo ? (long long)B * (H + 2) * (W + 2) : (long long)B * H * W;
+  const int nimg = B * H;
+  int w2 = kNumSMs * 8 * (C == 256 ? 3 : 2);
+  if (w2 > nimg) w2 = nimg;
+  p.rows_per_warp = (nimg + w2 - 1) / w2;
+  w2 = (nimg + (int)p.rows_per_warp - 1) / (int)p.rows_per_warp;
+  const int nb = cdiv(w2, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define ATTNDM_AQ_CAT_N(PREV, NQV)                                                                                  \
+  do {                                                                                                              \
+    if (a_bit == 8) launch_pdl(act_quant_rows_kernel<PREV, NQV, true, true>, dim3(nb), dim3(256), 0, st, p);        \
+    else launch_pdl(act_quant_rows_kernel<PREV, NQV, false, true>, dim3(nb), dim3(256), 0, st, p);                  \
+  } while (0)
+#define ATTNDM_AQ_CAT(PREV)                                                                                         \
+  do {                                                                                                              \
+    if (C == 256) ATTNDM_AQ_CAT_N(PREV, 2);                                                                         \
+    else if (C == 384) ATTNDM_AQ_CAT_N(PREV, 3);                                                                    \
+    else ATTNDM_AQ_CAT_N(PREV, 4);                                                                                  \
+  } while (0)
+  if (pre_op == ATTNDM_PRE_GN_SILU) ATTNDM_AQ_CAT(ATTNDM_PRE_GN_SILU);
+  else if (pre_op == ATTNDM_PRE_SILU) ATTNDM_AQ_CAT(ATTNDM_PRE_SILU);
+  else ATTNDM_AQ_CAT(ATTNDM_PRE_NONE);
+#undef ATTNDM_AQ_CAT_N
+#undef ATTNDM_AQ_CAT
+  ATTNDM_CUDA_LAUNCH_CHECK("act_quant_cat");
+  return ATTNDM_OK;
+}
+
 int attndm_gn_act_quant_fits(int H, int W, int C) {
   static int max_hw = -1;
   if (max_hw < 0) {
@@ -1241,10 +1317,8 @@ int attndm_gn_silu(const float* x, int B, int H, int W, int C, const double* gn_
                         nullptr, nullptr, ATTNDM_ROWS_PLAIN, y, false, (cudaStream_t)stream);
 }
 
-int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, void* stream) {
-  ATTNDM_CHECK_ARG(x && stats && B > 0 && H > 0 && W > 0, "gn_stats: bad args");
-  ATTNDM_CHECK_ARG(C % kGnGroups == 0 && C % 4 == 0 && C <= 4096, "gn_stats: C must be a multiple of 32, <= 4096");
-  const int Q = C / 4, HW = H * W;
+static int gn_stats_impl(const float* x, int B, int HW, int C, int cpg, int g0, double mult, double* stats, cudaStream_t st) {
+  const int Q = C / 4;
   int P = Q >= 256 ? 1 : 256 / Q;
   if (P > HW) P = HW;
   int threads = round_up(Q * P, 32);
@@ -1261,11 +1335,31 @@ int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, v
   // (the partial sums of a sample's `splits` blocks meet in double-precision atomics: their order can change the last
   // bit of a double, far below the fp32 mean / rstd the consumers form from them)
   if (tune_unroll >= 8)
-    launch_pdl(gn_stats_kernel<8>, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, x, HW, C, P, rows_per_block, stats, reverse);
+    launch_pdl(gn_stats_kernel<8>, dim3(grid), dim3(threads), 0, st, x, HW, C, P, rows_per_block, stats, reverse, cpg, g0, mult);
   else
-    launch_pdl(gn_stats_kernel<4>, dim3(grid), dim3(threads), 0, (cudaStream_t)stream, x, HW, C, P, rows_per_block, stats, reverse);
+    launch_pdl(gn_stats_kernel<4>, dim3(grid), dim3(threads), 0, st, x, HW, C, P, rows_per_block, stats, reverse, cpg, g0, mult);
   ATTNDM_CUDA_LAUNCH_CHECK("gn_stats");
   return ATTNDM_OK;
+}
+
+int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, void* stream) {
+  ATTNDM_CHECK_ARG(x && stats && B > 0 && H > 0 && W > 0, "gn_stats: bad args");
+  ATTNDM_CHECK_ARG(C % kGnGroups == 0 && C % 4 == 0 && C <= 4096, "gn_stats: C must be a multiple of 32, <= 4096");
+  return gn_stats_impl(x, B, H * W, C, C / kGnGroups, 0, 1.0, stats, (cudaStream_t)stream);
+}
+
+int attndm_gn_stats_cat(const float* xa, int Ha, int Wa, int C1, const float* xb, int H, int W, int C2, int B,
+                        double* stats, void* stream) {
+  ATTNDM_CHECK_ARG(xa && xb && stats && B > 0 && Ha > 0 && Wa > 0 && H == 2 * Ha && W == 2 * Wa,
+                   "gn_stats_cat: the first part must be half the size of the second");
+  const int C = C1 + C2;
+  ATTNDM_CHECK_ARG(C1 > 0 && C2 > 0 && C % kGnGroups == 0 && C <= 4096, "gn_stats_cat: C1 + C2 must be a multiple of 32, <= 4096");
+  const int cpg = C / kGnGroups;
+  ATTNDM_CHECK_ARG(cpg % 4 == 0 && C1 % cpg == 0, "gn_stats_cat: the parts must meet on a group boundary (groups of a multiple of 4 channels)");
+  // nearest-neighbour x2 repeats every element of the first part 2x2 times: its sums are 4x the low-resolution sums
+  int rc = gn_stats_impl(xa, B, Ha * Wa, C1, cpg, 0, 4.0, stats, (cudaStream_t)stream);
+  if (rc) return rc;
+  return gn_stats_impl(xb, B, H * W, C2, cpg, C1 / cpg, 1.0, stats, (cudaStream_t)stream);
 }
 
 int attndm_minmax_workspace_blocks(void) { return kMinMaxBlocks; }

@@ -71,7 +71,7 @@ class ResidualBlock(nn.Module):
         if self.in_channels != self.out_channels:
             sc = (self.conv_shortcut if self.use_conv_shortcut else self.nin_shortcut).forward_fused(x)
         else:
-            sc = x
+            sc = x.materialize() if isinstance(x, ops.CatView) else x
         return self.conv2.forward_fused(h, ops.PRE_GN_SILU, gn2, residual=sc, temb=temb)
 
     def forward(self, x):
@@ -140,8 +140,11 @@ class UpBlock(_TimeBlock):
         self.time_mlp = _time_mlp(time_emb_dim, out_channels, quantization, sequence, args) if time_emb_dim is not None else None
 
     def forward_fused(self, x, skip_x, time_emb=None):
-        combined = ops.upsample_concat(x, skip_x)            # :225-229 + cat
         expected = self.res1.in_channels
+        if x.shape[-1] + skip_x.shape[-1] == expected and ops.CatView.fits(x, skip_x):
+            # the concat feeds only res1's GroupNorm statistics and its two quantizers: they read x and skip_x in place
+            return self._tail(ops.CatView(x, skip_x), time_emb)
+        combined = ops.upsample_concat(x, skip_x)            # :225-229 + cat
         actual = combined.shape[-1]
         if actual != expected:
             if not hasattr(self, 'channel_proj'):             # lazily created, fresh RNG (:238-241)

@@ -62,6 +62,39 @@ class GnArgs:
     eps: float
 
 
+class CatView:
+    """The input of UpBlock.res1 -- cat([upsample_x2(x), skip], channel) (models/diffusion.py:225-229,244) -- WITHOUT the
+    copy: `lo` is x [B, H/2, W/2, C1], `skip` is [B, H, W, C2].  gn_stats / act_quant read the two parts in place
+    (attndm_gn_stats_cat, attndm_act_quant_cat); anything else calls materialize(), which runs the concat kernel once."""
+
+    def __init__(self, lo: torch.Tensor, skip: torch.Tensor):
+        _chk(lo, "CatView x")
+        _chk(skip, "CatView skip")
+        self.lo, self.skip = lo, skip
+        B, H, W, C2 = skip.shape
+        self.shape = torch.Size((B, H, W, lo.shape[-1] + C2))
+        self.device = skip.device
+        self._full = None
+
+    @staticmethod
+    def fits(lo: torch.Tensor, skip: torch.Tensor) -> bool:
+        """The shapes the in-place kernels take, and only where the per-sample fused GroupNorm kernel is not used."""
+        if os.environ.get("ATTNDM_CAT", "1") == "0":
+            return False
+        B, H, W, C1 = lo.shape
+        Bs, Hs, Ws, C2 = skip.shape
+        return (B == Bs and Hs == 2 * H and Ws == 2 * W and not gn_fits_fused(Hs, Ws, C1 + C2)
+                and bool(F_.lib().attndm_act_quant_cat_fits(Hs, Ws, C1, C2)) and B * Hs * Ws * (C1 + C2) < 2 ** 31)
+
+    def materialize(self) -> torch.Tensor:
+        if self._full is None:
+            self._full = upsample_concat(self.lo, self.skip)
+        return self._full
+
+    def cpu(self):
+        return self.materialize().cpu()
+
+
 def gn_fits_fused(H: int, W: int, Cc: int) -> bool:
     return bool(F_.lib().attndm_gn_act_quant_fits(H, W, Cc))
 
@@ -83,9 +116,11 @@ def gn_pool_end():
     _gn_pool = None
 
 
-def gn_stats(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def gn_stats(x, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     global _gn_pool_next
-    _chk(x, "gn_stats input")
+    cat = x if isinstance(x, CatView) else None
+    if cat is None:
+        _chk(x, "gn_stats input")
     B, H, W, Cc = x.shape
     if out is None:
         if _gn_pool is not None and _gn_pool_next < _gn_pool.shape[0] and _gn_pool.shape[1] == B:
@@ -95,11 +130,17 @@ def gn_stats(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tenso
             out = torch.zeros(B, GN_GROUPS, 2, dtype=torch.float64, device=x.device)
     else:
         out.zero_()
+    if cat is not None:
+        call("attndm_gn_stats_cat", ptr(cat.lo), H // 2, W // 2, cat.lo.shape[-1], ptr(cat.skip), H, W,
+             cat.skip.shape[-1], B, ptr(out), stream())
+        return out
     call("attndm_gn_stats", ptr(x), B, H, W, Cc, ptr(out), stream())
     return out
 
 
-def gn_silu(x: torch.Tensor, gn: GnArgs) -> torch.Tensor:
+def gn_silu(x, gn: GnArgs) -> torch.Tensor:
+    if isinstance(x, CatView):
+        x = x.materialize()
     _chk(x, "gn_silu input")
     B, H, W, Cc = x.shape
     y = torch.empty_like(x)
@@ -117,6 +158,18 @@ def gn_silu(x: torch.Tensor, gn: GnArgs) -> torch.Tensor:
 def act_quant(x: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, a_bit: int, pre: int = PRE_NONE,
               gn: Optional[GnArgs] = None, want_codes: bool = True, halo: bool = False, want_f32: bool = False):
     """Returns (codes int8 [rows, Cp] | None, rowsum int32 [rows] | None, y fp32 NHWC | None)."""
+    if isinstance(x, CatView):
+        if want_codes and not want_f32 and (pre != PRE_GN_SILU or gn.stats is not None):
+            B, H, W, Cc = x.shape
+            rows = B * (H + 2) * (W + 2) if halo else B * H * W
+            codes = torch.empty(rows, cp_of(Cc), dtype=torch.int8, device=x.device)
+            rowsum = torch.empty(rows, dtype=torch.int32, device=x.device)
+            call("attndm_act_quant_cat", ptr(x.lo), x.lo.shape[-1], ptr(x.skip), x.skip.shape[-1], B, H, W, ptr(scale),
+                 ptr(zp), int(a_bit), int(pre), ptr(gn.stats) if gn else None, ptr(gn.gamma) if gn else None,
+                 ptr(gn.beta) if gn else None, float(gn.eps) if gn else 0.0, ptr(codes), ptr(rowsum),
+                 ROWS_HALO if halo else ROWS_PLAIN, stream())
+            return codes, rowsum, None
+        x = x.materialize()
     _chk(x, "act_quant input")
     B, H, W, Cc = x.shape
     Cp = cp_of(Cc)

@@ -418,6 +418,8 @@ class QConv2d(QModule):
             taps = 1
         bias = self.bias.detach() if self.bias is not None else None
         if self._calibrate:
+            if isinstance(x, ops.CatView):
+                x = x.materialize()
             if pre == ops.PRE_GN_SILU:
                 xa = ops.gn_silu(x, gn)
             elif pre == ops.PRE_SILU:
@@ -498,6 +500,8 @@ class FConv2d(nn.Conv2d):
         return self._wp
 
     def forward_fused(self, x, pre=ops.PRE_NONE, gn: Optional[ops.GnArgs] = None, residual=None, temb=None):
+        if isinstance(x, ops.CatView):
+            x = x.materialize()
         B, H, W, Cc = x.shape
         if Cc != self.in_channels:
             raise RuntimeError(f"FConv2d: expected {self.in_channels} input channels, got {Cc}")

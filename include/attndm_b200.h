@@ -80,6 +80,22 @@ int attndm_act_quant(const float* x, int B, int H, int W, int C,
  * models/diffusion.py:36-37 (Normalize), 91,94 (GroupNorm eps 1e-6). */
 int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, void* stream);
 
+/* The input of UpBlock.res1 is cat([upsample_x2(x), skip], dim=1) (models/diffusion.py:225-229,244); that concat
+ * is pure data movement, so the hot path never materialises it: its GroupNorm statistics and its two quantizers
+ * (res1.conv1 behind GroupNorm+SiLU, models/diffusion.py:119-122, and res1.nin_shortcut, :131-134) read the two parts
+ * in place.  xa: [B][H/2][W/2][C1] (seen through the nearest-neighbour x2 upsample), xb: [B][H][W][C2].
+ * attndm_gn_stats_cat accumulates the statistics of the (C1 + C2)-channel concat into stats (caller-zeroed): the sums
+ * of the upsampled part are exactly 4x its low-resolution sums.  attndm_act_quant_cat = attndm_act_quant on the concat
+ * (codes + row sums only); shapes outside attndm_act_quant_cat_fits return ATTNDM_ERR_UNSUPPORTED (the caller then
+ * materialises the concat with attndm_upsample_concat). */
+int attndm_gn_stats_cat(const float* xa, int Ha, int Wa, int C1, const float* xb, int H, int W, int C2, int B,
+                        double* stats, void* stream);
+int attndm_act_quant_cat_fits(int H, int W, int C1, int C2);
+int attndm_act_quant_cat(const float* xa, int C1, const float* xb, int C2, int B, int H, int W,
+                         const float* scale, const float* zp, int a_bit, int pre_op, const double* gn_stats,
+                         const float* gn_gamma, const float* gn_beta, float gn_eps, int8_t* codes,
+                         int32_t* rowsum, int rows_layout, void* stream);
+
 /* GroupNorm(32)+SiLU+quantize in ONE kernel (statistics computed in-kernel, one CTA per sample with
  * the sample's [H*W][C] tile resident in shared memory): same outputs as attndm_gn_stats followed by
  * attndm_act_quant(pre_op = ATTNDM_PRE_GN_SILU).  Only for tiles that fit (attndm_gn_act_quant_fits);

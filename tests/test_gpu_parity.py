@@ -390,6 +390,44 @@ def test_groupnorm_silu_quant_fused():
             assert torch.equal(r3.long() - rowsum.long(), (c3.long() - codes.long()).sum(1))
             assert rel_l2(ops.gn_silu(xn, gl), ops.gn_silu(xn, gn)) < 1e-6
 
+@pytest.mark.parametrize("B,H,W,C1,C2,a_bit", [(3, 16, 16, 128, 128, 8), (2, 8, 12, 384, 128, 8), (2, 16, 8, 128, 256, 4),
+                                               (2, 32, 32, 256, 256, 8), (5, 4, 4, 128, 128, 6)])
+def test_upblock_concat_read_in_place(B, H, W, C1, C2, a_bit):
+    """UpBlock.res1's input cat([upsample_x2(x), skip]) (models/diffusion.py:225-229,244) is never written: GroupNorm
+    statistics and both quantizers read x and skip in place.  Codes and row sums are bit-identical to the same kernels
+    run on the materialised concat (which test_unet_glue_ops pins to torch), plain and halo layouts, with and without
+    the GroupNorm+SiLU producer; the statistics agree to the last bits of a double."""
+    from attentiondm_b200 import ops
+    g = torch.Generator().manual_seed(11 + C1 + H)
+    lo = (torch.randn(B, H // 2, W // 2, C1, generator=g) * 1.5 + 0.3).to(DEV)
+    skip = (torch.randn(B, H, W, C2, generator=g) * 0.8 - 0.2).to(DEV)
+    C = C1 + C2
+    assert ops.CatView.fits(lo, skip) == (not ops.gn_fits_fused(H, W, C))
+    if not ops.CatView.fits(lo, skip):
+        return
+    view = ops.CatView(lo, skip)
+    full = ops.upsample_concat(lo, skip)
+    want = torch.cat([lo.repeat_interleave(2, 1).repeat_interleave(2, 2), skip], -1)
+    assert torch.equal(full, want) and torch.equal(view.materialize(), want)
+    st_v, st_f = ops.gn_stats(view), ops.gn_stats(full)
+    assert torch.allclose(st_v, st_f, rtol=1e-13, atol=1e-9)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(C, generator=g)).to(DEV)
+    s, z = R.asym_params(a_bit, torch.tensor(-4.0), torch.tensor(6.0))
+    sv, zv = torch.full((C,), float(s), device=DEV), torch.full((C,), float(z), device=DEV)
+    for halo in (False, True):
+        for pre in (ops.PRE_NONE, ops.PRE_GN_SILU, ops.PRE_SILU):
+            gn = ops.GnArgs(st_f, gamma, beta, 1e-6) if pre == ops.PRE_GN_SILU else None
+            c_v, r_v, _ = ops.act_quant(ops.CatView(lo, skip), sv, zv, a_bit, pre, gn, want_codes=True, halo=halo)
+            c_f, r_f, _ = ops.act_quant(full, sv, zv, a_bit, pre, gn, want_codes=True, halo=halo)
+            assert torch.equal(c_v, c_f) and torch.equal(r_v, r_f), (halo, pre)
+    # with its own (in-place) statistics: at most a last-bit difference of the fp32 mean / rstd
+    gn_v = ops.GnArgs(st_v, gamma, beta, 1e-6)
+    c_v, _, _ = ops.act_quant(view, sv, zv, a_bit, ops.PRE_GN_SILU, gn_v, want_codes=True, halo=True)
+    c_f, _, _ = ops.act_quant(full, sv, zv, a_bit, ops.PRE_GN_SILU, ops.GnArgs(st_f, gamma, beta, 1e-6), want_codes=True, halo=True)
+    assert ((c_v.int() - c_f.int()).abs() > 0).float().mean() < 1e-6
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,H,W,C,O", [(4, 8, 8, 768, 512), (3, 5, 7, 320, 128), (2, 4, 4, 100, 256), (300, 2, 2, 64, 128)])
 def test_conv1x1_f32_tensor_core_3xtf32(B, H, W, C, O):
