@@ -21,6 +21,7 @@ struct ConvI8Params {
   const float* residual;   // [B*H*W][O] or NULL
   const float* temb;       // [B][O] or NULL
   float* out;              // [B*H*W][O]
+  double* gn_out;          // [B][32][2] or NULL: GroupNorm {sum, sumsq} of `out`, accumulated (tile-tree order, below)
 };
 
 // code-row index -> output pixel.  For 3x3 the GEMM row r is the halo-layout row of
@@ -71,8 +72,24 @@ __device__ __forceinline__ float conv_epilogue_add(const float* residual, const 
   return v;
 }
 
+// ---- GroupNorm statistics of a conv output in "tile-tree" order -------------------------------------------------
+// The tcgen05 epilogue holds the output as 128-row tiles of GEMM rows (code-layout rows), a 32-row quarter per warp,
+// thread (tr = lane / 4, tq = lane % 4) owning rows tr + 8k (k = 0..3) x four consecutive channels of every
+// 16-channel unit.  The statistics are DEFINED by that shape so that any kernel can reproduce them bit for bit:
+//   per thread, fp32:   s = sum_k (x0 + x1) + (x2 + x3),  q = sum_k fma(x3,x3, fma(x2,x2, fma(x1,x1, x0*x0)))   (k ascending)
+//   per warp, fp32:     butterfly over tr (lane xor 4, 8, 16)
+//   per (sample, group): the warp partials meet in double-precision atomics (their order can move the last bit of a
+//                        double, far below the fp32 mean / rstd formed from them -- as in attndm_gn_stats).
+// A quarter that straddles two samples keeps two partials (rows of the first sample / rows of the second).
+// Supported when O % 128 == 0 (a thread's four channels share a group) and a sample has >= 32 GEMM rows.
+inline bool conv_gn_tiletree_ok(const ConvI8Params& p) {
+  return p.O % 128 == 0 && (long long)p.Hp * p.Wp >= 32 && p.rows + 128 < (1LL << 31);
+}
+int launch_gn_stats_tiletree(const ConvI8Params& p, cudaStream_t st);     // from p.out (the twin of the fused epilogue)
+
 int launch_qconv_i8_simt(const ConvI8Params& p, cudaStream_t st);
-int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st);
+// *stats_fused = true when the kernel that ran also accumulated p.gn_out in its epilogue
+int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st, bool* stats_fused);
 int conv_f32_tc_fits(long long rows, int C, int O);
 int launch_split_tf32(const float* x, long long n, float* big, float* small, cudaStream_t st);
 int launch_gemm_tf32x3(const float* a_big, const float* a_small, long long rows, int C, const float* w_big,

@@ -352,17 +352,6 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) 
       : "r"(taddr)
       : "memory");
 }
-// ---- asynchronous output stores: shared -> global through the TMA unit ------------------------------
-// (measured, tools/tma_store_4d_test.cu: a tensor store clips coordinates beyond the tensor, but a NEGATIVE
-// start coordinate raises an illegal-instruction fault -- so every store below starts inside the tensor)
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -673,18 +662,12 @@ constexpr int TC_H_R0 = TC_H_EPI0 + TC_H_EPI_WARPS;    // first role warp
 // epilogue warps' top stall was the wait for this warp), so it takes its lead while the weights are still loading
 // and the memory system is idle, and keeps it.
 constexpr int TC_H_NGEO = 16;
-// The TMA output path (per-warp staging slot + tensor stores) is compiled out: it measured 76 us against 59 us
-// for direct stores (see launch_qconv_i8_halo) and its four epilogue instantiations cost instruction cache.
-// Build with -DATTNDM_TC_TMA_STORE (ATTNDM_NVCC_EXTRA) and set ATTNDM_TC_TMA_STORE=1 to experiment with it.
-#ifdef ATTNDM_TC_TMA_STORE
-constexpr bool TC_H_TMA_STORE = true;
-#else
-constexpr bool TC_H_TMA_STORE = false;
-#endif
+// (An asynchronous TMA-store epilogue -- per-warp 2 KB staging slots + tensor stores -- was built and measured in round 1/2:
+// 76 us against 59 us for direct 128-bit stores on the 128->128 3x3 layer, because one slot per warp is all the shared memory
+// left beside resident weights and the warp waits for the TMA unit before every piece.  The code was removed.)
 // (measured without effect on the plain conv: reading both accumulator blocks of a warp up front, 62.5 us vs
 // 58.8 us, and reading the next block while the current one is processed, 57.1 us vs 56.9 us)
 constexpr int TC_H_NRS = 4;                            // row-sum tiles in flight (bulk copies issued by the geometry warp)
-constexpr int TC_H_NBOX = 5;                           // output tensor maps: boxes of 32, 31, 30, 29, 28 pixels
 constexpr int TC_H_EPI_GROUPS = TC_H_EPI_WARPS / 4;    // warps sharing a quarter split the 32-column chunks
 constexpr int TC_THREADS_H = 32 * (TC_H_R0 + 4);
 constexpr int TC_H_MAXB = 8;                           // weight ring depth (streamed mode)
@@ -719,12 +702,13 @@ struct TcGeomH {
   int na;             // halo buffers (ring)
   int b_resident;     // 1: weights loaded once; 0: streamed
   int nb;             // weight ring depth (streamed)
-  int a_off, b_off, stg_off;   // byte offsets inside the 1024-aligned dynamic smem
+  int a_off, b_off, end_off;   // byte offsets inside the 1024-aligned dynamic smem (end_off: first byte after the weights)
   int rs_off, rs_stride;       // row-sum ring of the geometry warp (TC_H_NRS slots of rs_stride bytes); rs_stride = 0: gather by loads
-  int tma_store;      // 1: full 16-column pieces leave through per-warp staging + TMA tensor stores
   unsigned long long* trace;   // debug timeline buffer (trace builds), else nullptr
   int trace_cta;               // which CTA records it (ATTNDM_TRACE_CTA)
   FastDiv d_per, d_wp, d_hw;   // divisions by Hp*Wp, Wp and H*W in the geometry warp
+  FastDiv d_cpg;               // division by the channels per GroupNorm group, O / 32 (STATS builds)
+  int res_prefetch;            // 1: the halo producer pulls each tile's residual rows into L2 (one bulk prefetch per tile)
   int dbg;            // debug experiments (ATTNDM_TC_DBG, bit mask): low two bits 1 = epilogue skips the math/stores,
                       // 2 = skips the TMEM loads too;
                       // 16 = no halo loads; 32 = epilogue arithmetic without loads/stores; 64 = no MMAs; 512 = geometry warp without row-sum loads; 128 / 256 = the MMA warp
@@ -752,20 +736,31 @@ struct EpiRows {
 // with the neighbouring lane (xor 1) gives every lane FOUR consecutive columns of its rows: even lanes keep
 // their pair of column group i and receive the neighbour's, odd lanes keep group i+1 -- then stores (and the
 // residual / time-embedding loads) are 128-bit, 8 rows x 64 B per instruction: half the line-cycles.
-__device__ __forceinline__ void epi_load_residual_v4(float4 (&rs)[2][4], const float* res, const EpiRows& r, int c0, int tq) {
+// One residual element group: the four channels this lane stores for row k of column half h of the block at c0.
+// The epilogue keeps a rolling window of FOUR of them (one per row k): as soon as rs[k] has been added for (c0, h) it is
+// re-loaded for the next use of that slot -- (c0, h + 1), or (next block, 0) -- so each load is in flight for half a
+// block of arithmetic, with 16 registers instead of the 32 a whole block would pin.
+__device__ __forceinline__ float4 epi_res_load(const float* res, const EpiRows& r, int k, int c0, int h, int tq) {
   const int col4 = (tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq;        // first of this lane's four columns inside a group pair
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      rs[h][k] = ((r.ok >> k) & 1) ? __ldg(reinterpret_cast<const float4*>(res + (r.off[k] - 2 * tq) + c0 + 16 * h + col4))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+  return ((r.ok >> k) & 1) ? __ldg(reinterpret_cast<const float4*>(res + (r.off[k] - 2 * tq) + c0 + 16 * h + col4))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-template <bool ADD>
+// STATS: also accumulate the GroupNorm statistics of the values stored, in tile-tree order (conv_common.cuh).  st_m1: bit k
+// = row k belongs to the SECOND sample of this quarter (st_two, warp-uniform: the quarter straddles two samples);
+// st_dst: &gn_out[(first sample * 32) * 2].
+struct EpiStats {
+  double* dst;
+  uint32_t m1;
+  bool two;
+};
+
+template <bool ADD, bool STATS>
 __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
-                                             int c0, int tq, const EpiRows& r, float* out, const float4 (&rs)[2][4],
-                                             bool has_res, const float* temb) {
+                                             int c0, int tq, const EpiRows& r, float* out, float4 (&rs)[4], const float* res,
+                                             int c0_next, const float* temb, const EpiStats& st, int n0, const FastDiv& d_cpg) {
+  // res: residual tensor or nullptr; rs[k] holds its elements for (c0, h = 0) on entry and for (c0_next, 0) on exit
+  // (c0_next < 0: no further 128-bit block in this tile)
   const bool odd = tq & 1;
   const int col4 = odd ? 8 + 2 * (tq - 1) : 2 * tq;
 #pragma unroll
@@ -773,6 +768,7 @@ __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uin
     const int i0 = 2 * h, i1 = 2 * h + 1;
     const int cl0 = c0 + 8 * i0 + 2 * tq, cl1 = c0 + 8 * i1 + 2 * tq;
     const ColConst a0c = colc[cl0 & 255], a1c = colc[(cl0 + 1) & 255], b0c = colc[cl1 & 255], b1c = colc[(cl1 + 1) & 255];
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j0 = (i0 << 2) | ((k & 1) << 1), j1 = (i1 << 2) | ((k & 1) << 1);
@@ -781,14 +777,16 @@ __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uin
       const float hi0 = conv_i8_value((int)(k < 2 ? v0[j1] : v1[j1]), b0c.A, b0c.B, r.cs[k], b0c.m, b0c.bias);
       const float hi1 = conv_i8_value((int)(k < 2 ? v0[j1 | 1] : v1[j1 | 1]), b1c.A, b1c.B, r.cs[k], b1c.m, b1c.bias);
       // even lanes send their group-i1 pair, odd lanes their group-i0 pair
-      const float s0 = odd ? lo0 : hi0, s1 = odd ? lo1 : hi1;
-      const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+      const float sa = odd ? lo0 : hi0, sb = odd ? lo1 : hi1;
+      const float g0 = __shfl_xor_sync(0xffffffffu, sa, 1), g1 = __shfl_xor_sync(0xffffffffu, sb, 1);
       float4 o = odd ? make_float4(g0, g1, hi0, hi1) : make_float4(lo0, lo1, g0, g1);
       const bool ok = (r.ok >> k) & 1;
       if (ADD) {
-        if (has_res) {
-          o.x = __fadd_rn(o.x, rs[h][k].x); o.y = __fadd_rn(o.y, rs[h][k].y);
-          o.z = __fadd_rn(o.z, rs[h][k].z); o.w = __fadd_rn(o.w, rs[h][k].w);
+        if (res != nullptr) {
+          o.x = __fadd_rn(o.x, rs[k].x); o.y = __fadd_rn(o.y, rs[k].y);
+          o.z = __fadd_rn(o.z, rs[k].z); o.w = __fadd_rn(o.w, rs[k].w);
+          if (h == 0) rs[k] = epi_res_load(res, r, k, c0, 1, tq);
+          else if (c0_next >= 0) rs[k] = epi_res_load(res, r, k, c0_next, 0, tq);
         }
         if (temb != nullptr) {
           const float4 te = ok ? __ldg(reinterpret_cast<const float4*>(temb + (r.te_off[k] - 2 * tq) + c0 + 16 * h + col4))
@@ -797,43 +795,37 @@ __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uin
         }
       }
       if (ok) *reinterpret_cast<float4*>(out + (r.off[k] - 2 * tq) + c0 + 16 * h + col4) = o;
+      if (STATS) {
+        const float rsum = __fadd_rn(__fadd_rn(o.x, o.y), __fadd_rn(o.z, o.w));
+        const float rsq = fmaf(o.w, o.w, fmaf(o.z, o.z, fmaf(o.y, o.y, __fmul_rn(o.x, o.x))));
+        const bool in1 = (st.m1 >> k) & 1;
+        if (ok && !in1) { s0 = __fadd_rn(s0, rsum); q0 = __fadd_rn(q0, rsq); }
+        if (st.two && ok && in1) { s1 = __fadd_rn(s1, rsum); q1 = __fadd_rn(q1, rsq); }
+      }
     }
-  }
-}
-
-// 32 rows x 16 columns of results into this warp's staging slot ([32][16] fp32, dense: a warp-wide 128-bit
-// store writes 512 contiguous bytes, conflict free).  Rows that are not output pixels are staged as they are --
-// the tensor store clips them.
-template <bool ADD>
-__device__ __forceinline__ void epi_piece_compute(const uint32_t (&v0)[16], const uint32_t (&v1)[16], int h, const ColConst* colc,
-                                                  int c0, int tq, const EpiRows& r, float4 (&res)[4],
-                                                  const float4 (&rs)[2][4], bool has_res, const float* temb) {
-  const bool odd = tq & 1;
-  const int col4 = odd ? 8 + 2 * (tq - 1) : 2 * tq;
-  const int i0 = 2 * h, i1 = 2 * h + 1;
-  const int cl0 = c0 + 8 * i0 + 2 * tq, cl1 = c0 + 8 * i1 + 2 * tq;
-  const ColConst a0c = colc[cl0 & 255], a1c = colc[(cl0 + 1) & 255], b0c = colc[cl1 & 255], b1c = colc[(cl1 + 1) & 255];
+    if (STATS) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int j0 = (i0 << 2) | ((k & 1) << 1), j1 = (i1 << 2) | ((k & 1) << 1);
-    const float lo0 = conv_i8_value((int)(k < 2 ? v0[j0] : v1[j0]), a0c.A, a0c.B, r.cs[k], a0c.m, a0c.bias);
-    const float lo1 = conv_i8_value((int)(k < 2 ? v0[j0 | 1] : v1[j0 | 1]), a1c.A, a1c.B, r.cs[k], a1c.m, a1c.bias);
-    const float hi0 = conv_i8_value((int)(k < 2 ? v0[j1] : v1[j1]), b0c.A, b0c.B, r.cs[k], b0c.m, b0c.bias);
-    const float hi1 = conv_i8_value((int)(k < 2 ? v0[j1 | 1] : v1[j1 | 1]), b1c.A, b1c.B, r.cs[k], b1c.m, b1c.bias);
-    const float s0 = odd ? lo0 : hi0, s1 = odd ? lo1 : hi1;
-    const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-    float4 o = odd ? make_float4(g0, g1, hi0, hi1) : make_float4(lo0, lo1, g0, g1);
-    const bool ok = (r.ok >> k) & 1;
-    if (ADD && has_res) {
-      o.x = __fadd_rn(o.x, rs[h][k].x); o.y = __fadd_rn(o.y, rs[h][k].y);
-      o.z = __fadd_rn(o.z, rs[h][k].z); o.w = __fadd_rn(o.w, rs[h][k].w);
+      for (int m = 4; m <= 16; m <<= 1) {
+        s0 = __fadd_rn(s0, __shfl_xor_sync(0xffffffffu, s0, m));
+        q0 = __fadd_rn(q0, __shfl_xor_sync(0xffffffffu, q0, m));
+      }
+      if (st.two) {
+#pragma unroll
+        for (int m = 4; m <= 16; m <<= 1) {
+          s1 = __fadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, m));
+          q1 = __fadd_rn(q1, __shfl_xor_sync(0xffffffffu, q1, m));
+        }
+      }
+      if (tq == (int)(threadIdx.x & 31)) {                 // lanes 0..3 (tr == 0) hold the warp's partials of their four channels
+        double* d = st.dst + 2 * fdiv((unsigned)(n0 + c0 + 16 * h + col4), d_cpg);
+        atomicAdd(d, (double)s0);
+        atomicAdd(d + 1, (double)q0);
+        if (st.two) {
+          atomicAdd(d + 2 * kGnGroups, (double)s1);
+          atomicAdd(d + 2 * kGnGroups + 1, (double)q1);
+        }
+      }
     }
-    if (ADD && temb != nullptr) {
-      const float4 te = ok ? __ldg(reinterpret_cast<const float4*>(temb + (r.te_off[k] - 2 * tq) + c0 + 16 * h + col4))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      o.x = __fadd_rn(o.x, te.x); o.y = __fadd_rn(o.y, te.y); o.z = __fadd_rn(o.z, te.z); o.w = __fadd_rn(o.w, te.w);
-    }
-    res[k] = o;
   }
 }
 
@@ -863,6 +855,19 @@ __device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const
   }
 }
 
+// First output pixel at or after GEMM row `row` (the output pixels of consecutive GEMM rows are consecutive: ring rows
+// and ring columns of the halo layout are simply skipped), so the residual elements of a tile are ONE contiguous block.
+__device__ __forceinline__ unsigned first_pixel_from_row(const ConvI8Params& p, const TcGeomH& g, unsigned row) {
+  const unsigned total = (unsigned)(p.B * p.H * p.W);
+  if (row >= (unsigned)p.rows) return total;
+  if (p.taps == 1) return row;
+  const unsigned b = fdiv(row, g.d_per), rem = row - b * (unsigned)(p.Hp * p.Wp);
+  const unsigned hp = fdiv(rem, g.d_wp), wp = rem - hp * (unsigned)p.Wp;
+  if (hp >= (unsigned)p.H) return (b + 1) * (unsigned)(p.H * p.W);
+  if (wp >= (unsigned)p.W) return (b * (unsigned)p.H + hp + 1) * (unsigned)p.W;
+  return (b * (unsigned)p.H + hp) * (unsigned)p.W + wp;
+}
+
 // ADDS: the epilogue adds a residual and/or a time embedding.  Two instantiations so that each carries only its
 // own epilogue code (the kernel's size is felt in the instruction cache).
 // Tile index arithmetic in 32 bits (the launcher checks ntiles < 2^31): the role warps run these once per tile on
@@ -873,13 +878,10 @@ __device__ __forceinline__ unsigned tile_nt(const TcGeomH& g, unsigned tile) { r
 
 // PAIR: the CTA-pair (cta_group::2) build of the kernel; it must be launched as clusters of two CTAs, and the single-CTA
 // build must not contain cta_group::2 code (the driver rejects its launch without a matching cluster shape).
-template <bool ADDS, bool PAIR>
+template <bool ADDS, bool PAIR, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS_H, 1)
 qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
-                     const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
-                     const __grid_constant__ CUtensorMap tmO3, const __grid_constant__ CUtensorMap tmO4,
-                     const ConvI8Params p, const TcGeomH g) {
+                     const __grid_constant__ CUtensorMap tmB, const ConvI8Params p, const TcGeomH g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[4], a_empty[4];
   __shared__ __align__(8) uint64_t b_full[TC_H_MAXB], b_empty[TC_H_MAXB];
@@ -890,9 +892,6 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __shared__ __align__(8) uint64_t geo_full[TC_H_NGEO], geo_empty[TC_H_NGEO], rs_bar[2][TC_H_NRS];
   __shared__ int geo_pix[TC_H_NGEO][TC_BM];        // output pixel of each tile row (-1: not an output)
   __shared__ int geo_cs[TC_H_NGEO][TC_BM];         // window row-sum + zp*K (the sample index is pixel / (H*W))
-  // tensor-store segments of each 32-row quarter: {first-row x coordinate, image row, sample, valid}
-  // tensor store of each 32-row quarter: {first pixel inside its sample, sample, first pixel (global), box index or -1}
-  __shared__ int4 geo_seg[TC_H_TMA_STORE ? TC_H_NGEO : 1][4];
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1151,6 +1150,20 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (hr2 > 0) tma_load_2d_elect(dst + nfull * 256 * TC_BK, &tmA2, bar, cb * TC_BK, (int)m0 + 256 * nfull);
           }
         }
+        if (ADDS && g.res_prefetch) {
+          // this tile's residual rows -> L2, now (the epilogue reaches the tile a few iterations from here): its
+          // 128-bit loads then pay L2 latency, and DRAM streams the block instead of answering scattered requests
+          const unsigned px0 = first_pixel_from_row(p, g, m0), px1 = first_pixel_from_row(p, g, m0 + TC_BM);
+          const uint32_t bytes = (px1 - px0) * (uint32_t)p.O * 4u;
+          if (bytes != 0) {
+            asm volatile(
+                "{\n\t.reg .pred q;\n\t"
+                "elect.sync _|q, 0xffffffff;\n\t"
+                "@q cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}"
+                ::"l"(p.residual + (size_t)px0 * p.O), "r"(bytes)
+                : "memory");
+          }
+        }
         // pull the halos of the tiles 2 and 3 iterations ahead into L2
         for (int ahead = (it == 0 ? 1 : 3); ahead <= 3; ++ahead) {
           const unsigned tf = tile + (unsigned)ahead * gridDim.x;
@@ -1334,21 +1347,35 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         rows.cs[k] = geo_cs[gb][r];
       }
       if (g.dbg & 32) rows.ok = 0;                           // experiment: the epilogue math without loads/stores
-      int4 seg = make_int4(0, 0, 0, -1);
-      if (TC_H_TMA_STORE && g.tma_store) seg = geo_seg[gb][quarter];
-      // staging row of each of this thread's rows: its rank among the quarter's output pixels
-      uint32_t srow = 0;
+      EpiStats est = {nullptr, 0u, false};
+      if (STATS) {
+        // samples of this quarter's output rows: all rows of the first one go to partial 0, the rest (the next sample:
+        // a sample has >= 32 GEMM rows) to partial 1
+        int bk[4], mn = 0x7fffffff, mx = -1;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) srow |= (uint32_t)((geo_pix[gb][quarter * 32 + tr + 8 * k] - seg.z) & 31) << (8 * k);
+        for (int k = 0; k < 4; ++k) {
+          const int pix = geo_pix[gb][quarter * 32 + tr + 8 * k];
+          bk[k] = pix >= 0 ? (int)fdiv((uint32_t)pix, g.d_hw) : -1;
+          if (pix >= 0) { mn = min(mn, bk[k]); mx = max(mx, bk[k]); }
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        est.two = mx > mn;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) est.m1 |= (bk[k] > mn ? 1u : 0u) << k;
+        est.dst = p.gn_out + (long long)(mx >= 0 ? mn : 0) * (2 * kGnGroups);
+        if (mx < 0) est.m1 = 0;                              // no output row in this quarter: every `ok` bit is clear too
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&geo_empty[gb]));
       const int nchunks = (g.BN + 31) >> 5;
       const bool vec4 = (p.O & 3) == 0;                      // 128-bit path for full 32-column blocks
       constexpr bool adds = ADDS;
-      float4 rs4[2][4];
-      if (ADDS && p.residual != nullptr && ci0 < nchunks) {   // first block's residual: issued before the wait below
-        const int cf = ci0 << 5;
-        if (vec4 && cf + 32 <= g.BN && n0 + cf + 32 <= p.O) epi_load_residual_v4(rs4, p.residual, rows, cf, tq);
+      auto use4_at = [&](int ci) { return vec4 && ci < nchunks && (ci << 5) + 32 <= g.BN && n0 + (ci << 5) + 32 <= p.O; };
+      float4 rs4[4];                                         // rolling residual window (epi_res_load)
+      if (ADDS && p.residual != nullptr && use4_at(ci0)) {   // first block's residual: issued before the wait below
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rs4[k] = epi_res_load(p.residual, rows, k, ci0 << 5, 0, tq);
       }
       mbar_wait_relaxed(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> g.nacc_shift) & 1));
       tcgen05_fence_after();
@@ -1377,44 +1404,13 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (lane == 0) { if (PAIR) mbar_arrive_leader(smem_u32(&tmem_empty_bar[acc])); else mbar_arrive(smem_u32(&tmem_empty_bar[acc])); }
         }
         if ((g.dbg & 3) >= 1) continue;
-        const bool use4 = vec4 && c0 + 32 <= g.BN && n0 + c0 + 32 <= p.O;
-        if (use4 && p.residual != nullptr && ci != ci0) epi_load_residual_v4(rs4, p.residual, rows, c0, tq);
-        if (TC_H_TMA_STORE && use4 && seg.w >= 0) {
-          // results -> this warp's staging slot -> tensor store.  The warp never waits for the SM's store port
-          // (32 B/clk, and every SM bursts at the same time): the TMA unit drains the slot while the warp is
-          // already doing the arithmetic of the next piece.
-          float* const stage = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + g.stg_off) + ew * (32 * 16);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float4 o[4];
-            if (adds) epi_piece_compute<true>(v0, v1, h, colc, c0, tq, rows, o, rs4, p.residual != nullptr, p.temb);
-            else      epi_piece_compute<false>(v0, v1, h, colc, c0, tq, rows, o, rs4, false, nullptr);
-            if (lane == 0) bulk_wait_read0();                // the previous piece has left the slot
-            __syncwarp();
-            const int col4 = (tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if ((rows.ok >> k) & 1) *reinterpret_cast<float4*>(stage + ((srow >> (8 * k)) & 31) * 16 + col4) = o[k];
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {                                 // one thread: the tensor store takes uniform operands
-              const uint32_t src = smem_u32(stage);
-              const int col = n0 + c0 + 16 * h;
-              switch (seg.w) {
-                case 0: tma_store_3d(&tmO0, src, col, seg.x, seg.y); break;
-                case 1: tma_store_3d(&tmO1, src, col, seg.x, seg.y); break;
-                case 2: tma_store_3d(&tmO2, src, col, seg.x, seg.y); break;
-                case 3: tma_store_3d(&tmO3, src, col, seg.x, seg.y); break;
-                default: tma_store_3d(&tmO4, src, col, seg.x, seg.y); break;
-              }
-              bulk_commit();
-            }
-          }
-        } else if (use4) {
+        const bool use4 = use4_at(ci);
+        if (use4) {
           // two instantiations only (the kernel's code size is felt in the instruction cache): the plain
           // conv, and one variant that checks the residual / time-embedding pointers at run time
-          if (adds) epi_block_v4<true>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.residual != nullptr, p.temb);
-          else      epi_block_v4<false>(v0, v1, colc, c0, tq, rows, p.out, rs4, false, nullptr);
+          const int c0_next = use4_at(ci + ci_step) ? (ci + ci_step) << 5 : -1;
+          if (adds) epi_block_v4<true, STATS>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.residual, c0_next, p.temb, est, n0, g.d_cpg);
+          else      epi_block_v4<false, STATS>(v0, v1, colc, c0, tq, rows, p.out, rs4, nullptr, -1, nullptr, est, n0, g.d_cpg);
         } else {
           // ragged last block or O % 4 != 0 (the 3-channel output): scalar, per-column checks
           epi_block_scalar(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, p.residual, p.temb);
@@ -1423,7 +1419,6 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   }
-  if (TC_H_TMA_STORE && g.tma_store && warp >= TC_H_EPI0 && warp < TC_H_R0 && lane == 0) bulk_wait0();
   tcgen05_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();                       // neither CTA leaves (or frees TMEM) while the pair still works
@@ -1539,7 +1534,7 @@ static bool tc_halo_enabled() {
 }
 
 // returns 1 if the halo kernel was launched, 0 if the shape does not fit it, <0 on error
-static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
+static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st, bool* stats_fused) {
   TcGeomH g;
   g.BN = p.O <= 256 ? round_up(p.O, 16) : 256;
   const long long mtiles = (p.rows + TC_BM - 1) / TC_BM;
@@ -1558,14 +1553,6 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   // dynamic smem we allow ourselves: 227 KB - 20.5 KB static - alignment slack - the row-sum ring
   const int kBudget = 205 * 1024 - rs_bytes;
   const int nkb = p.taps * g.ncb;
-  // output path: per-warp 2 KB staging slots + TMA tensor stores when the 128-bit path applies (O % 4 == 0)
-  // and a quarter's 32 rows meet at most TC_H_NSEG image rows
-  // Off by default: with one 2 KB slot per warp (all the shared memory left beside resident weights) the warp
-  // waits for the TMA unit to read the slot before every piece, and the 128->128 3x3 layer measured 76 us
-  // against 59 us for direct 128-bit stores.  ATTNDM_TC_TMA_STORE=1 enables it for experiments.
-  static const bool tma_store_on = [] { const char* e = getenv("ATTNDM_TC_TMA_STORE"); return e && e[0] == '1'; }();
-  g.tma_store = (TC_H_TMA_STORE && tma_store_on && (p.O & 3) == 0 && g.BN % 32 == 0 && ((uintptr_t)p.out & 15) == 0) ? 1 : 0;
-  int stg_bytes = g.tma_store ? TC_H_EPI_WARPS * 32 * 16 * 4 : 0;
   const int a_buf = g.ncb * g.hr_stride;
   int grid = (int)(g.ntiles < kNumSMs ? g.ntiles : kNumSMs);
   const long long tiles_per_cta = (g.ntiles + grid - 1) / grid;
@@ -1580,7 +1567,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   // the single-CTA kernel has the shorter prologue.  ATTNDM_TC_PAIR=2 forces pairs wherever they fit.
   static const int pair_mode = [] { const char* e = getenv("ATTNDM_TC_PAIR"); return e ? atoi(e) : 1; }();
   const bool single_resident = g.ntn == 1 && (long long)nkb * b_tile + (long long)g.na * a_buf <= kBudget;
-  if (pair_on && !g.tma_store && g.ntn == 1 && g.BN % 32 == 0 && mtiles >= 2 && (kNumSMs % 2) == 0 &&
+  if (pair_on && g.ntn == 1 && g.BN % 32 == 0 && mtiles >= 2 && (kNumSMs % 2) == 0 &&
       (long long)nkb * (b_tile / 2) + (long long)a_buf <= kBudget && (pair_mode == 2 || !single_resident)) {
     g.pair = 1;
     b_tile /= 2;                                        // each CTA holds BN/2 weight rows
@@ -1590,17 +1577,12 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
     const long long wb = (long long)nkb * b_tile;
     g.na = (wb + 4LL * a_buf <= kBudget && its >= 4) ? 4 : ((wb + 2LL * a_buf <= kBudget && its >= 2) ? 2 : 1);
   }
-  // weights resident when they fit next to two halo buffers (and there is a single N tile)
-  if (g.tma_store && g.ntn == 1 && (long long)nkb * b_tile + (long long)g.na * a_buf <= kBudget &&
-      (long long)nkb * b_tile + (long long)g.na * a_buf + stg_bytes > kBudget) {
-    g.tma_store = 0;                                    // resident weights are worth more than the staging slots
-    stg_bytes = 0;
-  }
-  g.b_resident = (g.ntn == 1 && (long long)nkb * b_tile + (long long)g.na * a_buf + stg_bytes <= kBudget) ? 1 : 0;
+  // weights resident when they fit next to the halo buffers (and there is a single N tile)
+  g.b_resident = (g.ntn == 1 && (long long)nkb * b_tile + (long long)g.na * a_buf <= kBudget) ? 1 : 0;
   if (g.b_resident) {
     g.nb = 1;
   } else {
-    long long left = (long long)kBudget - (long long)g.na * a_buf - stg_bytes;
+    long long left = (long long)kBudget - (long long)g.na * a_buf;
     if (left < 2LL * b_tile && g.na == 2) { g.na = 1; left += a_buf; }
     if (left < 2LL * b_tile) return 0;
     g.nb = (int)(left / b_tile);
@@ -1611,14 +1593,17 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   g.na_shift = g.na == 4 ? 2 : (g.na == 2 ? 1 : 0);
   g.a_off = 0;
   g.b_off = g.na * a_buf;
-  g.stg_off = g.b_off + (g.b_resident ? nkb : g.nb) * b_tile;
-  g.rs_off = g.stg_off + stg_bytes;
+  g.end_off = g.b_off + (g.b_resident ? nkb : g.nb) * b_tile;
+  g.rs_off = g.end_off;
   g.rs_stride = rs_bytes / (2 * TC_H_NRS);
   { const char* e = getenv("ATTNDM_TC_DBG"); g.dbg = e ? atoi(e) : 0; }
   g.trace = g_tc_trace_host;
   g.d_per = make_fastdiv((unsigned)(p.Hp * p.Wp));
   g.d_wp = make_fastdiv((unsigned)p.Wp);
   g.d_hw = make_fastdiv((unsigned)(p.H * p.W));
+  g.d_cpg = make_fastdiv((unsigned)(p.O >= kGnGroups ? p.O / kGnGroups : 1));
+  static const bool res_pf_on = [] { const char* e = getenv("ATTNDM_TC_RES_PREFETCH"); return !(e && e[0] == '0'); }();
+  g.res_prefetch = (res_pf_on && p.residual != nullptr && g.ntn == 1 && (p.O & 3) == 0 && ((uintptr_t)p.residual & 15) == 0) ? 1 : 0;
   { const char* e = getenv("ATTNDM_TRACE_CTA"); g.trace_cta = e ? atoi(e) : 0; }
   g.acc_stride = round_up(g.BN, 32);
   // Four accumulators when they fit: the MMA warp may then run up to three tiles ahead of the epilogue, so the
@@ -1628,7 +1613,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   { const char* e = getenv("ATTNDM_TC_SPLIT"); g.split = (g.ntn == 1 && g.nacc == 4 && !(e && e[0] == '0')) ? 1 : 0; }
   g.tmem_cols = 32;
   while (g.tmem_cols < g.nacc * g.acc_stride) g.tmem_cols <<= 1;
-  const int smem = g.stg_off + stg_bytes + rs_bytes + 1024;
+  const int smem = g.end_off + rs_bytes + 1024;
   CUtensorMap tmA, tmA2, tmB;
   const int hr1 = g.hr > 256 ? 256 : g.hr;
   int rc = make_map_2d(&tmA, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, (uint32_t)hr1);
@@ -1643,41 +1628,39 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(qconv_i8_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    auto raise = [](const void* fn) {
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    };
+    raise((const void*)qconv_i8_halo_kernel<false, false, false>);
+    raise((const void*)qconv_i8_halo_kernel<false, true, false>);
+    raise((const void*)qconv_i8_halo_kernel<true, true, false>);
+    raise((const void*)qconv_i8_halo_kernel<true, false, false>);
+    raise((const void*)qconv_i8_halo_kernel<false, false, true>);
+    raise((const void*)qconv_i8_halo_kernel<false, true, true>);
+    raise((const void*)qconv_i8_halo_kernel<true, true, true>);
+    raise((const void*)qconv_i8_halo_kernel<true, false, true>);
   });
   if (attr_err != cudaSuccess) { set_error("qconv_i8_halo: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
-  CUtensorMap tmO[TC_H_NBOX];
-  for (int i = 0; i < TC_H_NBOX; ++i) tmO[i] = tmA;
-  if (g.tma_store) {
-    // the output as [sample][pixel][channel]; one map per box height (32 - i pixels x 16 channels)
-    EncodeTiledFn enc = get_encode_fn();
-    const uint64_t hw = (uint64_t)p.H * p.W;
-    cuuint64_t dims[3] = {(cuuint64_t)p.O, hw, (cuuint64_t)p.B};
-    cuuint64_t strides[2] = {(cuuint64_t)p.O * 4, hw * p.O * 4};
-    cuuint32_t estr[3] = {1, 1, 1};
-    for (int i = 0; i < TC_H_NBOX; ++i) {
-      cuuint32_t box[3] = {16, (cuuint32_t)(32 - i), 1};
-      CUresult r = enc(&tmO[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) { set_error("qconv_i8_halo: output tensor map failed (%d)", (int)r); return ATTNDM_ERR_CUDA; }
-    }
-  }
   const bool adds = p.residual != nullptr || p.temb != nullptr;
+  // GroupNorm statistics of the output from the epilogue (tile-tree order): every chunk must take the 128-bit path
+  static const bool stats_on = [] { const char* e = getenv("ATTNDM_TC_STATS"); return !(e && e[0] == '0'); }();
+  const bool stats = stats_on && p.gn_out != nullptr && conv_gn_tiletree_ok(p) && g.BN % 32 == 0;
 #define ATTNDM_HALO_ARGS dim3(grid), dim3(TC_THREADS_H), smem, st
-#define ATTNDM_HALO_PARAMS tmA, tmA2, tmB, tmO[0], tmO[1], tmO[2], tmO[3], tmO[4], p, g
-  if (g.pair) {
-    if (adds) launch_pdl_cluster(qconv_i8_halo_kernel<true, true>, ATTNDM_HALO_ARGS, 2, ATTNDM_HALO_PARAMS);
-    else      launch_pdl_cluster(qconv_i8_halo_kernel<false, true>, ATTNDM_HALO_ARGS, 2, ATTNDM_HALO_PARAMS);
-  } else {
-    if (adds) launch_pdl(qconv_i8_halo_kernel<true, false>, ATTNDM_HALO_ARGS, ATTNDM_HALO_PARAMS);
-    else      launch_pdl(qconv_i8_halo_kernel<false, false>, ATTNDM_HALO_ARGS, ATTNDM_HALO_PARAMS);
-  }
+#define ATTNDM_HALO_PARAMS tmA, tmA2, tmB, p, g
+#define ATTNDM_HALO_LAUNCH(STATSV)                                                                                  \
+  do {                                                                                                              \
+    if (g.pair) {                                                                                                   \
+      if (adds) launch_pdl_cluster(qconv_i8_halo_kernel<true, true, STATSV>, ATTNDM_HALO_ARGS, 2, ATTNDM_HALO_PARAMS);   \
+      else      launch_pdl_cluster(qconv_i8_halo_kernel<false, true, STATSV>, ATTNDM_HALO_ARGS, 2, ATTNDM_HALO_PARAMS);  \
+    } else {                                                                                                        \
+      if (adds) launch_pdl(qconv_i8_halo_kernel<true, false, STATSV>, ATTNDM_HALO_ARGS, ATTNDM_HALO_PARAMS);        \
+      else      launch_pdl(qconv_i8_halo_kernel<false, false, STATSV>, ATTNDM_HALO_ARGS, ATTNDM_HALO_PARAMS);       \
+    }                                                                                                               \
+  } while (0)
+  if (stats) ATTNDM_HALO_LAUNCH(true);
+  else ATTNDM_HALO_LAUNCH(false);
+  if (stats_fused) *stats_fused = stats;
+#undef ATTNDM_HALO_LAUNCH
 #undef ATTNDM_HALO_ARGS
 #undef ATTNDM_HALO_PARAMS
   cudaError_t e = cudaGetLastError();
@@ -1685,17 +1668,89 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st) {
   return 1;
 }
 
-int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st) {
+int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st, bool* stats_fused) {
+  if (stats_fused) *stats_fused = false;
   ATTNDM_CHECK_ARG(((uintptr_t)p.codes & 15) == 0 && ((uintptr_t)p.qw & 15) == 0, "qconv_i8_tc: operands must be 16-byte aligned");
   ATTNDM_CHECK_ARG(p.rows + 2LL * p.Wp + 2 + TC_BM < 0x7fffffffLL, "qconv_i8_tc: too many rows for 32-bit TMA coordinates");
   if (tc_halo_enabled()) {
-    int rc = launch_qconv_i8_halo(p, st);
+    int rc = launch_qconv_i8_halo(p, st, stats_fused);
     if (rc < 0) return rc;
     if (rc == 1) return ATTNDM_OK;
   }
   return launch_qconv_i8_tc_persistent(p, st);     // shapes the halo kernel does not take (halo > 512 rows, >= 2^31 outputs)
 }
 
+
+// ---- GroupNorm statistics of a conv output in tile-tree order, from the output tensor -------------------------
+// The twin of the STATS epilogue above (conv_common.cuh states the order): one warp per 32-row quarter of a 128-row
+// tile of GEMM rows, thread (tr, tq) sums rows tr + 8k of its four channels of every 16-channel unit with the same
+// fp32 operations in the same order, the same butterfly, the same double atomics.  Runs after the dp4a conv kernel and
+// after the ring-fed tcgen05 kernel, so that the statistics of a layer do not depend on which kernel computed it.
+__global__ void __launch_bounds__(256) gn_stats_tiletree_kernel(const ConvI8Params p, long long nquarters) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31, tq = lane & 3, tr = lane >> 2;
+  const long long wq = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wq >= nquarters) return;
+  const long long row0 = wq * 32;
+  const int col4 = (tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq;
+  const int cpg = p.O / kGnGroups;
+  long long pix[4];
+  int bk[4], mn = 0x7fffffff, mx = -1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    pix[k] = -1;
+    bk[k] = -1;
+    long long px = 0;
+    int b = 0;
+    if (conv_row_to_pixel(p, row0 + tr + 8 * k, px, b)) {
+      pix[k] = px;
+      bk[k] = (int)(px / ((long long)p.H * p.W));
+      mn = min(mn, bk[k]);
+      mx = max(mx, bk[k]);
+    }
+  }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (mx < 0) return;
+  const bool two = mx > mn;
+  double* dst = p.gn_out + (long long)mn * (2 * kGnGroups);
+  for (int u = 0; u < p.O; u += 16) {
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (pix[k] < 0) continue;
+      const float4 o = __ldg(reinterpret_cast<const float4*>(p.out + pix[k] * p.O + u + col4));
+      const float rsum = __fadd_rn(__fadd_rn(o.x, o.y), __fadd_rn(o.z, o.w));
+      const float rsq = fmaf(o.w, o.w, fmaf(o.z, o.z, fmaf(o.y, o.y, __fmul_rn(o.x, o.x))));
+      if (bk[k] == mn) { s0 = __fadd_rn(s0, rsum); q0 = __fadd_rn(q0, rsq); }
+      else { s1 = __fadd_rn(s1, rsum); q1 = __fadd_rn(q1, rsq); }
+    }
+#pragma unroll
+    for (int m = 4; m <= 16; m <<= 1) {
+      s0 = __fadd_rn(s0, __shfl_xor_sync(0xffffffffu, s0, m));
+      q0 = __fadd_rn(q0, __shfl_xor_sync(0xffffffffu, q0, m));
+      s1 = __fadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, m));
+      q1 = __fadd_rn(q1, __shfl_xor_sync(0xffffffffu, q1, m));
+    }
+    if (lane < 4) {
+      double* d = dst + 2 * ((u + col4) / cpg);
+      atomicAdd(d, (double)s0);
+      atomicAdd(d + 1, (double)q0);
+      if (two) {
+        atomicAdd(d + 2 * kGnGroups, (double)s1);
+        atomicAdd(d + 2 * kGnGroups + 1, (double)q1);
+      }
+    }
+  }
+}
+
+int launch_gn_stats_tiletree(const ConvI8Params& p, cudaStream_t st) {
+  ATTNDM_CHECK_ARG(p.gn_out && p.out && conv_gn_tiletree_ok(p), "gn_stats_tiletree: shape not supported");
+  const long long nquarters = (p.rows + 31) / 32;
+  launch_pdl(gn_stats_tiletree_kernel, dim3((unsigned)cdiv(nquarters, 8)), dim3(256), 0, st, p, nquarters);
+  ATTNDM_CUDA_LAUNCH_CHECK("gn_stats_tiletree");
+  return ATTNDM_OK;
+}
 
 // =====================================================================================================
 // fp32 GEMM on the tensor cores with fp32-level accuracy ("3xTF32"): out[M][N] = x[M][K] . w[N][K]^T + bias

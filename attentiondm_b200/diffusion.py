@@ -35,7 +35,12 @@ def _gn_args(norm: nn.GroupNorm, x):
     """GroupNorm arguments for the consumer conv.  Small feature maps use the fused per-sample kernel
     (statistics computed in-kernel, stats=None); the rest get a statistics pass."""
     _, H, W, C = x.shape
-    stats = None if ops.gn_fits_fused(H, W, C) else ops.gn_stats(x)
+    if ops.gn_fits_fused(H, W, C):
+        stats = None
+    else:
+        stats = getattr(x, "_gn_stats", None)                # left by the conv that produced x (QConv2d.forward_fused)
+        if stats is None:
+            stats = ops.gn_stats(x)
     return ops.GnArgs(stats=stats, gamma=norm.weight.detach(), beta=norm.bias.detach(), eps=norm.eps)
 
 
@@ -61,18 +66,19 @@ class ResidualBlock(nn.Module):
             else:
                 self.nin_shortcut = mk(in_channels, out_channels, 1)
 
-    def forward_fused(self, x, temb=None):
+    def forward_fused(self, x, temb=None, out_stats=False):
         """x NHWC.  temb [B, out_channels] (optional) is the block's `x + time_mlp(t_emb)`
-        (models/diffusion.py:175-177), applied after the residual add, fused in conv2's epilogue."""
+        (models/diffusion.py:175-177), applied after the residual add, fused in conv2's epilogue.
+        out_stats: the block's output goes straight into a GroupNorm (conv2 then also emits its statistics)."""
         if self.training and self.dropout.p > 0:
             raise NotImplementedError("attentiondm_b200 runs the eval-mode path (model.eval()); dropout is identity")
-        h = self.conv1.forward_fused(x, ops.PRE_GN_SILU, _gn_args(self.norm1, x))
+        h = self.conv1.forward_fused(x, ops.PRE_GN_SILU, _gn_args(self.norm1, x), want_stats=True)
         gn2 = _gn_args(self.norm2, h)
         if self.in_channels != self.out_channels:
             sc = (self.conv_shortcut if self.use_conv_shortcut else self.nin_shortcut).forward_fused(x)
         else:
             sc = x.materialize() if isinstance(x, ops.CatView) else x
-        return self.conv2.forward_fused(h, ops.PRE_GN_SILU, gn2, residual=sc, temb=temb)
+        return self.conv2.forward_fused(h, ops.PRE_GN_SILU, gn2, residual=sc, temb=temb, want_stats=out_stats)
 
     def forward(self, x):
         return ops.to_nchw(self.forward_fused(ops.to_nhwc(x)))
@@ -94,8 +100,8 @@ class _TimeBlock(nn.Module):
         return y.view(y.shape[0], -1)
 
     def _tail(self, x, time_emb):
-        x = self.res1.forward_fused(x, self._temb(time_emb))
-        x = self.res2.forward_fused(x)
+        x = self.res1.forward_fused(x, self._temb(time_emb), out_stats=True)     # res2.norm1 follows
+        x = self.res2.forward_fused(x, out_stats=getattr(self, "_out_feeds_gn", False))
         if isinstance(self.attn, EnhancedQSelfAttention):
             x = self.attn.forward_fused(x)
         return x
@@ -215,6 +221,8 @@ class Model(nn.Module):
                 now_ch = out_ch
         self.norm_out = nn.GroupNorm(num_groups=32, num_channels=now_ch, eps=1e-6)
         self.conv_out = _conv(quantization, sequence, args, now_ch, config.data.channels, 3)
+        if not isinstance(self.up_blocks[-1].attn, EnhancedQSelfAttention):
+            self.up_blocks[-1]._out_feeds_gn = True            # its output goes straight into norm_out
 
     # ---- helpers over all quantized layers ----
     def qconvs(self):

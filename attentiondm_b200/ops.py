@@ -116,18 +116,28 @@ def gn_pool_end():
     _gn_pool = None
 
 
-def gn_stats(x, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def gn_stats_buffer(B: int, device) -> torch.Tensor:
+    """A zeroed [B, 32, 2] double accumulation target (a slice of the per-forward pool when one is open)."""
     global _gn_pool_next
+    if _gn_pool is not None and _gn_pool_next < _gn_pool.shape[0] and _gn_pool.shape[1] == B:
+        out = _gn_pool[_gn_pool_next]
+        _gn_pool_next += 1
+        return out
+    return torch.zeros(B, GN_GROUPS, 2, dtype=torch.float64, device=device)
+
+
+def conv_stats_enabled() -> bool:
+    """GroupNorm statistics of a conv output from the conv's own epilogue (ATTNDM_CONV_STATS=0: separate pass)."""
+    return os.environ.get("ATTNDM_CONV_STATS", "1") != "0"
+
+
+def gn_stats(x, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     cat = x if isinstance(x, CatView) else None
     if cat is None:
         _chk(x, "gn_stats input")
     B, H, W, Cc = x.shape
     if out is None:
-        if _gn_pool is not None and _gn_pool_next < _gn_pool.shape[0] and _gn_pool.shape[1] == B:
-            out = _gn_pool[_gn_pool_next]
-            _gn_pool_next += 1
-        else:
-            out = torch.zeros(B, GN_GROUPS, 2, dtype=torch.float64, device=x.device)
+        out = gn_stats_buffer(B, x.device)
     else:
         out.zero_()
     if cat is not None:
@@ -315,12 +325,15 @@ def weight_to_i8(w_eff: torch.Tensor, w_bit: int, grid=None) -> I8Pack:
 
 
 def qconv_i8(codes, rowsum, B: int, H: int, W: int, Cc: int, pack: I8Pack, taps: int, mult, act_zp, bias,
-             residual=None, temb=None, impl: Optional[int] = None, out: Optional[torch.Tensor] = None):
+             residual=None, temb=None, impl: Optional[int] = None, out: Optional[torch.Tensor] = None,
+             gn_stats_out: Optional[torch.Tensor] = None):
+    """gn_stats_out: zeroed double [B, 32, 2]; receives the GroupNorm {sum, sumsq} of the output (from the conv's own
+    epilogue where the kernel supports it, include/attndm_b200.h)."""
     O = pack.qw.shape[0]
     if out is None:
         out = torch.empty(B, H, W, O, dtype=torch.float32, device=codes.device)
     call("attndm_qconv_i8", ptr(codes), ptr(rowsum), B, H, W, Cc, ptr(pack.qw), ptr(pack.wsum), ptr(pack.w_zp), O,
-         taps, ptr(mult), ptr(act_zp), ptr(bias), ptr(residual), ptr(temb), ptr(out), None,
+         taps, ptr(mult), ptr(act_zp), ptr(bias), ptr(residual), ptr(temb), ptr(out), ptr(gn_stats_out),
          DEFAULT_CONV_IMPL if impl is None else impl, stream())
     return out
 

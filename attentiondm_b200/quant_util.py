@@ -403,8 +403,11 @@ class QConv2d(QModule):
         """Engine hook: `row` is this layer's slice of the staged current-step table."""
         self._staged = row
 
-    def forward_fused(self, x, pre=ops.PRE_NONE, gn: Optional[ops.GnArgs] = None, residual=None, temb=None):
-        """x: NHWC fp32 CUDA.  residual: NHWC like the output.  temb: [B, O]."""
+    def forward_fused(self, x, pre=ops.PRE_NONE, gn: Optional[ops.GnArgs] = None, residual=None, temb=None,
+                      want_stats=False):
+        """x: NHWC fp32 CUDA.  residual: NHWC like the output.  temb: [B, O].  want_stats: the output feeds a
+        GroupNorm -- on the integer path its statistics come out of the conv's epilogue, attached to the result as
+        `out._gn_stats` (double [B, 32, 2]) for diffusion._gn_args."""
         if self.index_seq >= self.args.timesteps:          # :228-229
             self.index_seq = 0
         t = self.index_seq
@@ -442,8 +445,14 @@ class QConv2d(QModule):
         zp = row[lay["zp"]:]
         if use_i8:
             codes, rowsum, _ = ops.act_quant(x, scale, zp, self._a_bit, pre, gn, want_codes=True, halo=(taps == 9))
+            stats = None
+            if (want_stats and ops.conv_stats_enabled() and self.out_channels % ops.GN_GROUPS == 0
+                    and not ops.gn_fits_fused(H, W, self.out_channels)):
+                stats = ops.gn_stats_buffer(B, x.device)
             out = ops.qconv_i8(codes, rowsum, B, H, W, Cc, i8, taps, row[lay["mult"]:], row[lay["act_zp"]:],
-                               bias, residual, temb)
+                               bias, residual, temb, gn_stats_out=stats)
+            if stats is not None:
+                out._gn_stats = stats
         else:
             _, _, y = ops.act_quant(x, scale, zp, self._a_bit, pre, gn, want_codes=False, want_f32=True)
             out = ops.conv_f32(y, w_eff, bias, residual, temb)
@@ -499,7 +508,8 @@ class FConv2d(nn.Conv2d):
             self._wp, self._wp_key = (full, centre), key
         return self._wp
 
-    def forward_fused(self, x, pre=ops.PRE_NONE, gn: Optional[ops.GnArgs] = None, residual=None, temb=None):
+    def forward_fused(self, x, pre=ops.PRE_NONE, gn: Optional[ops.GnArgs] = None, residual=None, temb=None,
+                      want_stats=False):
         if isinstance(x, ops.CatView):
             x = x.materialize()
         B, H, W, Cc = x.shape

@@ -17,9 +17,9 @@ def record_layers(model):
     for n, q in model.qconvs():
         orig = q.forward_fused
 
-        def wrap(x, pre=PRE_NONE, gn=None, residual=None, temb=None, _o=orig, _n=n, _q=q):
+        def wrap(x, pre=PRE_NONE, gn=None, residual=None, temb=None, want_stats=False, _o=orig, _n=n, _q=q):
             t = 0 if _q.index_seq >= _q.args.timesteps else _q.index_seq
-            y = _o(x, pre, gn, residual, temb)
+            y = _o(x, pre, gn, residual, temb, want_stats)
             rec.append(dict(name=_n, t=t, x=x.cpu(), pre=pre,
                             gn=(gn.gamma.cpu(), gn.beta.cpu(), gn.eps) if gn is not None else None,
                             residual=None if residual is None else residual.cpu(),

@@ -274,6 +274,49 @@ def test_qconv_i8_simt_and_tcgen05_vs_oracle(shape):
     assert rel_l2(ops.to_nchw(of), want) < 1e-5
 
 
+@pytest.mark.parametrize("shape,adds", [((3, 16, 16, 128, 128, 3), False), ((3, 16, 16, 128, 128, 3), True),
+                                        ((2, 32, 32, 256, 128, 3), True), ((5, 8, 8, 128, 256, 3), False),
+                                        ((2, 64, 64, 128, 128, 3), True), ((3, 8, 12, 256, 384, 1), False),
+                                        ((7, 4, 4, 256, 256, 3), True), ((2, 16, 16, 128, 64, 3), False)])
+def test_qconv_epilogue_groupnorm_statistics(shape, adds):
+    """GroupNorm {sum, sumsq} of the conv output from the tcgen05 epilogue (models/diffusion.py:119-127: every conv of a
+    ResidualBlock feeds a GroupNorm): equal to the statistics pass over the stored output up to fp32 summation order
+    (the fp32 mean / rstd the consumers form agree to ~1 ulp), and IDENTICAL -- up to the order of the final double
+    atomics -- to the dp4a path's twin kernel, which walks the output in the same tile-tree order."""
+    from attentiondm_b200 import ops
+    B, H, W, C, O, k = shape
+    x, w, bias, s, z = _conv_case(B, H, W, C, O, k, seed=3)
+    taps = k * k
+    xn = ops.to_nhwc(x.to(DEV))
+    sv, zv = torch.full((C,), float(s), device=DEV), torch.full((C,), float(z), device=DEV)
+    codes, rowsum, _ = ops.act_quant(xn, sv, zv, 8, want_codes=True, halo=(k == 3))
+    flat = w.reshape(O, -1)
+    w_eff = ops.weight_clamp_pack(w.to(DEV), flat.min(1)[0].to(DEV), flat.max(1)[0].to(DEV))
+    pack = ops.weight_to_i8(w_eff, 8)
+    mult = (1.0 / (float(s) * pack.w_scale.double())).float().contiguous()
+    azp = torch.tensor([int(z)], dtype=torch.int32, device=DEV)
+    g = torch.Generator().manual_seed(1)
+    res = torch.randn(B, H, W, O, generator=g).to(DEV) if adds else None
+    temb = torch.randn(B, O, generator=g).to(DEV) if adds else None
+    st, outs = {}, {}
+    for impl in (ops.CONV_SIMT, ops.CONV_TCGEN05):
+        st[impl] = torch.zeros(B, 32, 2, dtype=torch.float64, device=DEV)
+        outs[impl] = ops.qconv_i8(codes, rowsum, B, H, W, C, pack, taps, mult, azp, bias.to(DEV), res, temb, impl=impl,
+                                  gn_stats_out=st[impl])
+    plain = ops.qconv_i8(codes, rowsum, B, H, W, C, pack, taps, mult, azp, bias.to(DEV), res, temb)
+    assert torch.equal(outs[ops.CONV_TCGEN05], plain) and torch.equal(outs[ops.CONV_SIMT], plain)
+    a, b = st[ops.CONV_TCGEN05], st[ops.CONV_SIMT]
+    assert torch.allclose(a, b, rtol=1e-13, atol=1e-10), (a - b).abs().max()
+    ref = plain.double().reshape(B, H * W, 32, O // 32)
+    want = torch.stack([ref.sum((1, 3)), (ref * ref).sum((1, 3))], -1)
+    n = H * W * (O // 32)
+    mean_a, mean_w = a[..., 0] / n, want[..., 0] / n
+    var_a, var_w = a[..., 1] / n - mean_a ** 2, want[..., 1] / n - mean_w ** 2
+    assert (mean_a - mean_w).abs().max() < 2e-7 * ref.abs().max()
+    assert ((var_a - var_w).abs() / var_w).max() < 1e-6
+    assert torch.allclose(ops.gn_stats(plain), want, rtol=1e-12, atol=1e-9)
+
+
 @pytest.mark.parametrize("bits", [(4, 4), (6, 8), (8, 4)])
 def test_qconv_low_bit(bits):
     from attentiondm_b200 import ops
@@ -390,7 +433,7 @@ def test_groupnorm_silu_quant_fused():
             assert torch.equal(r3.long() - rowsum.long(), (c3.long() - codes.long()).sum(1))
             assert rel_l2(ops.gn_silu(xn, gl), ops.gn_silu(xn, gn)) < 1e-6
 
-@pytest.mark.parametrize("B,H,W,C1,C2,a_bit", [(3, 16, 16, 128, 128, 8), (2, 8, 12, 384, 128, 8), (2, 16, 8, 128, 256, 4),
+@pytest.mark.parametrize("B,H,W,C1,C2,a_bit", [(3, 16, 16, 128, 128, 8), (2, 8, 12, 384, 128, 8), (2, 16, 8, 128, 128, 4),
                                                (2, 32, 32, 256, 256, 8), (5, 4, 4, 128, 128, 6)])
 def test_upblock_concat_read_in_place(B, H, W, C1, C2, a_bit):
     """UpBlock.res1's input cat([upsample_x2(x), skip]) (models/diffusion.py:225-229,244) is never written: GroupNorm

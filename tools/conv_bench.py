@@ -11,6 +11,7 @@ ap.add_argument("--shapes", default="all")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--impl", default="tc")
 ap.add_argument("--graph", type=int, default=1)
+ap.add_argument("--stats", type=int, default=0, help="1: the conv also emits the GroupNorm statistics of its output")
 a = ap.parse_args()
 dev = torch.device("cuda")
 SHAPES = {
@@ -39,9 +40,10 @@ for name in names:
     bias = torch.zeros(O, device=dev)
     out = torch.empty(B, H, W, O, device=dev)
     res = torch.randn(B, H, W, O, device=dev)
+    gst = torch.zeros(B, 32, 2, dtype=torch.float64, device=dev) if a.stats and O % 32 == 0 else None
     for use_res in (False, True):
         for _ in range(3):
-            ops.qconv_i8(codes, rowsum, B, H, W, C, pack, k * k, mult, azp, bias, res if use_res else None, impl=impl, out=out)
+            ops.qconv_i8(codes, rowsum, B, H, W, C, pack, k * k, mult, azp, bias, res if use_res else None, impl=impl, out=out, gn_stats_out=gst)
         if a.graph:
             # the launches are replayed from a CUDA graph: for kernels shorter than ~35 us the host-side launch path
             # (tensor-map encodes + ctypes) is slower than the kernel and event timing of eager launches measures IT
@@ -51,7 +53,7 @@ for name in names:
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr, stream=st):
                     for i in range(a.iters):
-                        ops.qconv_i8(codes, rowsum, B, H, W, C, pack, k * k, mult, azp, bias, res if use_res else None, impl=impl, out=out)
+                        ops.qconv_i8(codes, rowsum, B, H, W, C, pack, k * k, mult, azp, bias, res if use_res else None, impl=impl, out=out, gn_stats_out=gst)
                 gr.replay()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(st)
@@ -63,10 +65,10 @@ for name in names:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
             ev[0].record()
             for i in range(a.iters):
-                ops.qconv_i8(codes, rowsum, B, H, W, C, pack, k * k, mult, azp, bias, res if use_res else None, impl=impl, out=out)
+                ops.qconv_i8(codes, rowsum, B, H, W, C, pack, k * k, mult, azp, bias, res if use_res else None, impl=impl, out=out, gn_stats_out=gst)
                 ev[i + 1].record()
             torch.cuda.synchronize()
             ms = sum(ev[i].elapsed_time(ev[i + 1]) for i in range(a.iters)) / a.iters
         flops = 2.0 * B * H * W * O * C * k * k
         by = codes.numel() + out.numel() * 4 * (2 if use_res else 1) + pack.qw.numel()
-        print(f"{name:8s} res={int(use_res)} {ms*1e3:8.1f} us  {flops/ms/1e9:8.1f} TOP/s  {by/ms/1e6:7.0f} GB/s (algorithmic)")
+        print(f"{name:8s} res={int(use_res)} {ms*1e3:8.1f} us  {flops/ms/1e9:8.1f} TOP/s  {by/ms/1e6:7.0f} GB/s (algorithmic){' +stats' if gst is not None else ''}")
