@@ -218,6 +218,23 @@ __device__ __forceinline__ void tma_load_2d_pair_elect(uint32_t dst, const CUten
       ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same two loads through a 5-D view of the weight matrix (make_map_b_perm): coordinates {k, 0, 0, 0, unit of 16 rows}
+__device__ __forceinline__ void tma_load_5d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c4) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %5, %5, %5, %4}], [%2];\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c4), "r"(0)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c4) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %5, %5, %5, %4}], [%2];\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c4), "r"(0)
+      : "memory");
+}
 // arrive on the barrier at the same offset in the leader CTA (from either CTA)
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile(
@@ -708,6 +725,7 @@ struct TcGeomH {
   int trace_cta;               // which CTA records it (ATTNDM_TRACE_CTA)
   FastDiv d_per, d_wp, d_hw;   // divisions by Hp*Wp, Wp and H*W in the geometry warp
   FastDiv d_cpg;               // division by the channels per GroupNorm group, O / 32 (STATS builds)
+  int perm;                    // 1: weight rows arrive channel-permuted inside each unit of 16 (make_map_b_perm): 128-bit epilogue
   int res_prefetch;            // 1: the halo producer pulls each tile's residual rows into L2 (one bulk prefetch per tile)
   int dbg;            // debug experiments (ATTNDM_TC_DBG, bit mask): low two bits 1 = epilogue skips the math/stores,
                       // 2 = skips the TMEM loads too;
@@ -730,63 +748,90 @@ struct EpiRows {
   uint32_t ok;          // bit k: row k is an output pixel
 };
 
-// ---- 128-bit variant for full blocks (all 32 columns valid, O % 4 == 0) ----
+// ---- 128-bit variant for full blocks (all 32 columns valid, O % 16 == 0) ----
 // The LSU handles one cache line per cycle, so a float2 store of the fragment layout (8 rows x 32 B per warp
-// instruction) costs 8 line-cycles for 256 B and the epilogue of a tile is bound by ~4000 of them.  One exchange
-// with the neighbouring lane (xor 1) gives every lane FOUR consecutive columns of its rows: even lanes keep
-// their pair of column group i and receive the neighbour's, odd lanes keep group i+1 -- then stores (and the
-// residual / time-embedding loads) are 128-bit, 8 rows x 64 B per instruction: half the line-cycles.
-// One residual element group: the four channels this lane stores for row k of column half h of the block at c0.
-// The epilogue keeps a rolling window of FOUR of them (one per row k): as soon as rs[k] has been added for (c0, h) it is
-// re-loaded for the next use of that slot -- (c0, h + 1), or (next block, 0) -- so each load is in flight for half a
-// block of arithmetic, with 16 registers instead of the 32 a whole block would pin.
-__device__ __forceinline__ float4 epi_res_load(const float* res, const EpiRows& r, int k, int c0, int h, int tq) {
-  const int col4 = (tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq;        // first of this lane's four columns inside a group pair
-  return ((r.ok >> k) & 1) ? __ldg(reinterpret_cast<const float4*>(res + (r.off[k] - 2 * tq) + c0 + 16 * h + col4))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+// instruction) costs 8 line-cycles for 256 B and the epilogue of a tile is bound by ~4000 of them.  128-bit stores (8
+// rows x 64 B per instruction) halve that, but need FOUR consecutive channels per lane where the 16x256b fragment
+// gives two pairs eight columns apart.  Rounds 1-2 exchanged pairs with the neighbouring lane (16 SHFL + 48 FSEL of the
+// 276 instructions of a block).  Now the WEIGHTS are permuted instead: TMEM column 8i + 2tq + j of a 16-column unit
+// holds output channel 4tq + 2i + j, so a lane's two pairs ARE channels 4tq .. 4tq+3.  The permutation costs nothing:
+// the weight matrix is loaded through a 5-D tensor map whose box walks the 16 rows of a unit in that order
+// (make_map_b_perm); memory layout, packing and the dp4a twin are unchanged.
+// The residual elements of one 32-column block: for each column half h and row k the four channels this lane stores.
+// All eight loads of a block are issued together, ahead of the block's TMEM load (the first block's ahead of the wait for
+// the accumulator), and consumed after it.  (A rolling window of four -- re-load rs[k] as soon as it has been added --
+// pins 16 registers instead of 32 but waits for memory four times per half block: 102 us against 71 us on the 128 -> 128
+// 3x3 layer at 32x32.)
+__device__ __forceinline__ void epi_load_residual_v4(float4 (&rs)[2][4], const float* res, const EpiRows& r, int c0, int tq) {
+  const int col4 = 4 * tq;                                      // first of this lane's four channels inside a unit of 16
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      rs[h][k] = ((r.ok >> k) & 1) ? __ldg(reinterpret_cast<const float4*>(res + (r.off[k] - 2 * tq) + c0 + 16 * h + col4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// STATS: also accumulate the GroupNorm statistics of the values stored, in tile-tree order (conv_common.cuh).  st_m1: bit k
-// = row k belongs to the SECOND sample of this quarter (st_two, warp-uniform: the quarter straddles two samples);
-// st_dst: &gn_out[(first sample * 32) * 2].
+// STATS: also accumulate the GroupNorm statistics of the values stored, in tile-tree order (conv_common.cuh).
+// two (warp-uniform): the quarter straddles two samples; dst: &gn_out[(first sample * 32) * 2].
 struct EpiStats {
   double* dst;
-  uint32_t m1;
+  float w0[4], w1[4];   // 1.0 where row k is an output row of the first / second sample, else 0.0: the accumulations are
+                        // fma(x, w, acc) -- exactly acc + x or acc, without predicates
   bool two;
 };
+// Per-thread partials of one 32-column block, {sum, sumsq} of column half 0 then of column half 1: a = rows of the
+// quarter's first sample, b = rows of its second sample (only when EpiStats::two).
+struct EpiPend {
+  float a[4], b[4];
+};
+
+// The butterfly over tr (lane xor 4, 8, 16) of a block's four partials as a reduce-scatter: at xor 4 a lane keeps one
+// column half and hands the other to its partner, at xor 8 it keeps the sum or the sum of squares, so four shuffles
+// instead of twelve produce the same sums from the same pairs (an fp32 add commutes) and sixteen lanes each hold ONE
+// finished value: lane bit 2 = column half, bit 3 = sum / sum of squares, bits 0..1 = tq.
+__device__ __forceinline__ void epi_stats_flush(const float (&a)[4], double* dst, int col_base, int lane, const FastDiv& d_cpg) {
+  const int tq = lane & 3;
+  const bool b4 = lane & 4, b8 = lane & 8;
+  const int col4 = 4 * tq;
+  float kx = b4 ? a[2] : a[0], ky = b4 ? a[3] : a[1];
+  const float sx = b4 ? a[0] : a[2], sy = b4 ? a[1] : a[3];
+  kx = __fadd_rn(kx, __shfl_xor_sync(0xffffffffu, sx, 4));
+  ky = __fadd_rn(ky, __shfl_xor_sync(0xffffffffu, sy, 4));
+  float k = b8 ? ky : kx;
+  const float s = b8 ? kx : ky;
+  k = __fadd_rn(k, __shfl_xor_sync(0xffffffffu, s, 8));
+  k = __fadd_rn(k, __shfl_xor_sync(0xffffffffu, k, 16));
+  if (lane < 16)
+    atomicAdd(dst + 2 * fdiv((unsigned)(col_base + (b4 ? 16 : 0) + col4), d_cpg) + (b8 ? 1 : 0), (double)k);
+}
 
 template <bool ADD, bool STATS>
 __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
-                                             int c0, int tq, const EpiRows& r, float* out, float4 (&rs)[4], const float* res,
-                                             int c0_next, const float* temb, const EpiStats& st, int n0, const FastDiv& d_cpg) {
-  // res: residual tensor or nullptr; rs[k] holds its elements for (c0, h = 0) on entry and for (c0_next, 0) on exit
-  // (c0_next < 0: no further 128-bit block in this tile)
-  const bool odd = tq & 1;
-  const int col4 = odd ? 8 + 2 * (tq - 1) : 2 * tq;
+                                             int c0, int tq, const EpiRows& r, float* out, const float4 (&rs)[2][4], bool has_res,
+                                             const float* temb, const EpiStats& st, EpiPend& pend) {
+  // STATS: the block's partials are left in `pend`; the caller reduces them across the warp (epi_stats_flush) while the
+  // next block's accumulator load is in flight
+  const int col4 = 4 * tq;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {                       // column-group pairs (0,1) and (2,3)
+  for (int h = 0; h < 2; ++h) {                       // the two units of 16 channels: column groups (0,1) and (2,3)
     const int i0 = 2 * h, i1 = 2 * h + 1;
-    const int cl0 = c0 + 8 * i0 + 2 * tq, cl1 = c0 + 8 * i1 + 2 * tq;
-    const ColConst a0c = colc[cl0 & 255], a1c = colc[(cl0 + 1) & 255], b0c = colc[cl1 & 255], b1c = colc[(cl1 + 1) & 255];
+    const int ch = (c0 + 16 * h + col4) & 255;        // this lane's four channels: group i0 holds ch, ch+1; group i1 ch+2, ch+3
+    const ColConst a0c = colc[ch], a1c = colc[ch + 1], b0c = colc[ch + 2], b1c = colc[ch + 3];
     float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j0 = (i0 << 2) | ((k & 1) << 1), j1 = (i1 << 2) | ((k & 1) << 1);
-      const float lo0 = conv_i8_value((int)(k < 2 ? v0[j0] : v1[j0]), a0c.A, a0c.B, r.cs[k], a0c.m, a0c.bias);
-      const float lo1 = conv_i8_value((int)(k < 2 ? v0[j0 | 1] : v1[j0 | 1]), a1c.A, a1c.B, r.cs[k], a1c.m, a1c.bias);
-      const float hi0 = conv_i8_value((int)(k < 2 ? v0[j1] : v1[j1]), b0c.A, b0c.B, r.cs[k], b0c.m, b0c.bias);
-      const float hi1 = conv_i8_value((int)(k < 2 ? v0[j1 | 1] : v1[j1 | 1]), b1c.A, b1c.B, r.cs[k], b1c.m, b1c.bias);
-      // even lanes send their group-i1 pair, odd lanes their group-i0 pair
-      const float sa = odd ? lo0 : hi0, sb = odd ? lo1 : hi1;
-      const float g0 = __shfl_xor_sync(0xffffffffu, sa, 1), g1 = __shfl_xor_sync(0xffffffffu, sb, 1);
-      float4 o = odd ? make_float4(g0, g1, hi0, hi1) : make_float4(lo0, lo1, g0, g1);
+      float4 o;
+      o.x = conv_i8_value((int)(k < 2 ? v0[j0] : v1[j0]), a0c.A, a0c.B, r.cs[k], a0c.m, a0c.bias);
+      o.y = conv_i8_value((int)(k < 2 ? v0[j0 | 1] : v1[j0 | 1]), a1c.A, a1c.B, r.cs[k], a1c.m, a1c.bias);
+      o.z = conv_i8_value((int)(k < 2 ? v0[j1] : v1[j1]), b0c.A, b0c.B, r.cs[k], b0c.m, b0c.bias);
+      o.w = conv_i8_value((int)(k < 2 ? v0[j1 | 1] : v1[j1 | 1]), b1c.A, b1c.B, r.cs[k], b1c.m, b1c.bias);
       const bool ok = (r.ok >> k) & 1;
       if (ADD) {
-        if (res != nullptr) {
-          o.x = __fadd_rn(o.x, rs[k].x); o.y = __fadd_rn(o.y, rs[k].y);
-          o.z = __fadd_rn(o.z, rs[k].z); o.w = __fadd_rn(o.w, rs[k].w);
-          if (h == 0) rs[k] = epi_res_load(res, r, k, c0, 1, tq);
-          else if (c0_next >= 0) rs[k] = epi_res_load(res, r, k, c0_next, 0, tq);
+        if (has_res) {
+          o.x = __fadd_rn(o.x, rs[h][k].x); o.y = __fadd_rn(o.y, rs[h][k].y);
+          o.z = __fadd_rn(o.z, rs[h][k].z); o.w = __fadd_rn(o.w, rs[h][k].w);
         }
         if (temb != nullptr) {
           const float4 te = ok ? __ldg(reinterpret_cast<const float4*>(temb + (r.te_off[k] - 2 * tq) + c0 + 16 * h + col4))
@@ -798,33 +843,15 @@ __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uin
       if (STATS) {
         const float rsum = __fadd_rn(__fadd_rn(o.x, o.y), __fadd_rn(o.z, o.w));
         const float rsq = fmaf(o.w, o.w, fmaf(o.z, o.z, fmaf(o.y, o.y, __fmul_rn(o.x, o.x))));
-        const bool in1 = (st.m1 >> k) & 1;
-        if (ok && !in1) { s0 = __fadd_rn(s0, rsum); q0 = __fadd_rn(q0, rsq); }
-        if (st.two && ok && in1) { s1 = __fadd_rn(s1, rsum); q1 = __fadd_rn(q1, rsq); }
+        s0 = fmaf(rsum, st.w0[k], s0);
+        q0 = fmaf(rsq, st.w0[k], q0);
+        if (st.two) { s1 = fmaf(rsum, st.w1[k], s1); q1 = fmaf(rsq, st.w1[k], q1); }
       }
     }
     if (STATS) {
-#pragma unroll
-      for (int m = 4; m <= 16; m <<= 1) {
-        s0 = __fadd_rn(s0, __shfl_xor_sync(0xffffffffu, s0, m));
-        q0 = __fadd_rn(q0, __shfl_xor_sync(0xffffffffu, q0, m));
-      }
-      if (st.two) {
-#pragma unroll
-        for (int m = 4; m <= 16; m <<= 1) {
-          s1 = __fadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, m));
-          q1 = __fadd_rn(q1, __shfl_xor_sync(0xffffffffu, q1, m));
-        }
-      }
-      if (tq == (int)(threadIdx.x & 31)) {                 // lanes 0..3 (tr == 0) hold the warp's partials of their four channels
-        double* d = st.dst + 2 * fdiv((unsigned)(n0 + c0 + 16 * h + col4), d_cpg);
-        atomicAdd(d, (double)s0);
-        atomicAdd(d + 1, (double)q0);
-        if (st.two) {
-          atomicAdd(d + 2 * kGnGroups, (double)s1);
-          atomicAdd(d + 2 * kGnGroups + 1, (double)q1);
-        }
-      }
+      pend.a[2 * h] = s0;
+      pend.a[2 * h + 1] = q0;
+      if (st.two) { pend.b[2 * h] = s1; pend.b[2 * h + 1] = q1; }
     }
   }
 }
@@ -832,23 +859,26 @@ __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uin
 // odd channel counts (the 3-channel eps output): scalar loads/stores, same static indexing
 __device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
                                                  int c0, int tq, int BN, int n0, int O, const EpiRows& r, float* out,
-                                                 const float* res, const float* temb) {
+                                                 const float* res, const float* temb, bool perm) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
 #pragma unroll
     for (int par = 0; par < 2; ++par) {
-      const int cl = c0 + 8 * i + 2 * tq + par;
+      // the output channel (relative to n0) held by accumulator column c0 + 8i + 2tq + par: with permuted weight rows
+      // (TcGeomH::perm) a unit of 16 columns holds channel 4tq + 2(i & 1) + par at column 8(i & 1) + 2tq + par
+      const int cl = perm ? c0 + 16 * (i >> 1) + 4 * tq + 2 * (i & 1) + par : c0 + 8 * i + 2 * tq + par;
       const bool col_ok = (cl < BN) && (n0 + cl < O);
       if (!col_ok) continue;                 // the 3-channel output: 125 of 128 accumulator columns are padding
       const ColConst cc = colc[cl & 255];
+      const int d = cl - 2 * tq;             // r.off / r.te_off already hold n0 + 2tq
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int j = (i << 2) | ((k & 1) << 1) | par;
         float f = conv_i8_value((int)(k < 2 ? v0[j] : v1[j]), cc.A, cc.B, r.cs[k], cc.m, cc.bias);
         if ((r.ok >> k) & 1) {
-          if (res) f = __fadd_rn(f, res[r.off[k] + c0 + 8 * i + par]);
-          if (temb) f = __fadd_rn(f, temb[r.te_off[k] + c0 + 8 * i + par]);
-          out[r.off[k] + c0 + 8 * i + par] = f;
+          if (res) f = __fadd_rn(f, res[r.off[k] + d]);
+          if (temb) f = __fadd_rn(f, temb[r.te_off[k] + d]);
+          out[r.off[k] + d] = f;
         }
       }
     }
@@ -1082,215 +1112,227 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   };
 
-  if (warp == TC_H_R0 + 2) {
-    {
-      // ===== weight producer (weights are static: no need to wait for the previous kernel) =====
-      if (g.b_resident) {
-        const int ntn_tiles_here = 1;   // resident mode is only chosen when ntn == 1
-        (void)ntn_tiles_here;
-        if (PAIR) {
-          // each CTA loads ITS half of the output channels (rows rank*BN/2 ...); both halves count on the leader's barrier
-          if (rank == 0) mbar_expect_tx_elect(smem_u32(&b_res_bar), (uint32_t)(2 * nkb * b_tile_bytes));
-          for (int kb = 0; kb < nkb; ++kb) {
-            const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
-            tma_load_2d_pair_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK,
-                                   (int)rank * (g.BN >> 1));
+  // Register file: 512 threads x 128 is all of it.  The four role warps (one warpgroup, the highest warp ids) need few
+  // registers; the epilogue's residual block (32), accumulator fragments (32), row state and statistics spilled at 128.
+  // The role warpgroup hands back 72 registers per thread, the three epilogue warpgroups take 24 each.
+  // (setmaxnreg has to sit INSIDE the branch it governs: ptxas allocates the code after a join for the smaller count.)
+  if (warp >= TC_H_R0) {
+    if (TC_H_EPI_WARPS == 12) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
+    if (warp == TC_H_R0 + 2) {
+      {
+        // ===== weight producer (weights are static: no need to wait for the previous kernel) =====
+        if (g.b_resident) {
+          const int ntn_tiles_here = 1;   // resident mode is only chosen when ntn == 1
+          (void)ntn_tiles_here;
+          if (PAIR) {
+            // each CTA loads ITS half of the output channels (rows rank*BN/2 ...); both halves count on the leader's barrier
+            if (rank == 0) mbar_expect_tx_elect(smem_u32(&b_res_bar), (uint32_t)(2 * nkb * b_tile_bytes));
+            for (int kb = 0; kb < nkb; ++kb) {
+              const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
+              if (g.perm) tma_load_5d_pair_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar),
+                                                 tap * p.Cp + cb * TC_BK, (int)rank * (g.BN >> 5));
+              else tma_load_2d_pair_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK,
+                                          (int)rank * (g.BN >> 1));
+            }
+          } else {
+            mbar_expect_tx_elect(smem_u32(&b_res_bar), (uint32_t)(nkb * b_tile_bytes));
+            for (int kb = 0; kb < nkb; ++kb) {
+              const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
+              if (g.perm) tma_load_5d_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK, 0);
+              else tma_load_2d_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK, 0);
+            }
           }
+          geometry_role(1, 2);
         } else {
-          mbar_expect_tx_elect(smem_u32(&b_res_bar), (uint32_t)(nkb * b_tile_bytes));
-          for (int kb = 0; kb < nkb; ++kb) {
-            const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
-            tma_load_2d_elect(base + g.b_off + (uint32_t)kb * b_tile_bytes, &tmB, smem_u32(&b_res_bar), tap * p.Cp + cb * TC_BK, 0);
+          int s = 0;
+          uint32_t ph = 0;
+          for (unsigned tile = tile0; tile - rank < ntiles; tile += gridDim.x) {
+            const int n0 = (int)tile_nt(g, tile) * g.BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+              const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
+              mbar_wait_relaxed(smem_u32(&b_empty[s]), ph ^ 1);
+              mbar_expect_tx_elect(smem_u32(&b_full[s]), (uint32_t)b_tile_bytes);
+              if (g.perm) tma_load_5d_elect(base + g.b_off + (uint32_t)s * b_tile_bytes, &tmB, smem_u32(&b_full[s]), tap * p.Cp + cb * TC_BK, n0 >> 4);
+              else tma_load_2d_elect(base + g.b_off + (uint32_t)s * b_tile_bytes, &tmB, smem_u32(&b_full[s]), tap * p.Cp + cb * TC_BK, n0);
+              if (++s == g.nb) { s = 0; ph ^= 1; }
+            }
           }
         }
-        geometry_role(1, 2);
-      } else {
+      }
+    } else if (warp == TC_H_R0) {
+      pdl_wait();                                        // the codes come from the previous kernel
+      {
+        // ===== activation (halo) producer: one halo per (tile, channel block) =====
+        const int nfull = g.hr >= 256 ? g.hr / 256 : 1;    // a TMA box holds at most 256 rows: nfull boxes of tmA ...
+        const int hr2 = g.hr >= 256 ? g.hr - 256 * nfull : 0;   // ... and the remainder through tmA2
+        int it = 0;
+        for (unsigned tile = tile0; tile - rank < ntiles; tile += gridDim.x, ++it) {
+          const unsigned m0 = tile_mt(g, tile) * TC_BM;
+          const int buf = it & (g.na - 1);
+          if (lane == 0) TC_TRACE(0, it, 0);
+          mbar_wait_relaxed(smem_u32(&a_empty[buf]), (uint32_t)(((it >> g.na_shift) & 1) ^ 1));
+          if (lane == 0) TC_TRACE(0, it, 1);
+          const uint32_t bar = smem_u32(&a_full[buf]);
+          if ((g.dbg & 16) && !PAIR) { mbar_expect_tx_elect(bar, 0u); continue; }       // experiment: no halo loads at all
+          if (PAIR) {
+            // both CTAs' halos count on the LEADER's barrier (its MMA warp issues for the pair)
+            if (rank == 0) mbar_expect_tx_elect(bar, (uint32_t)(2 * g.ncb * g.hr * TC_BK));
+            for (int cb = 0; cb < g.ncb; ++cb) {
+              const uint32_t dst = base + g.a_off + (uint32_t)(buf * g.ncb + cb) * g.hr_stride;
+              for (int bx = 0; bx < nfull; ++bx) tma_load_2d_pair_elect(dst + bx * 256 * TC_BK, &tmA, bar, cb * TC_BK, (int)m0 + 256 * bx);
+              if (hr2 > 0) tma_load_2d_pair_elect(dst + nfull * 256 * TC_BK, &tmA2, bar, cb * TC_BK, (int)m0 + 256 * nfull);
+            }
+          } else {
+            mbar_expect_tx_elect(bar, (uint32_t)(g.ncb * g.hr * TC_BK));
+            for (int cb = 0; cb < g.ncb; ++cb) {
+              const uint32_t dst = base + g.a_off + (uint32_t)(buf * g.ncb + cb) * g.hr_stride;
+              for (int bx = 0; bx < nfull; ++bx) tma_load_2d_elect(dst + bx * 256 * TC_BK, &tmA, bar, cb * TC_BK, (int)m0 + 256 * bx);
+              if (hr2 > 0) tma_load_2d_elect(dst + nfull * 256 * TC_BK, &tmA2, bar, cb * TC_BK, (int)m0 + 256 * nfull);
+            }
+          }
+          if (ADDS && g.res_prefetch) {
+            // this tile's residual rows -> L2, now (the epilogue reaches the tile a few iterations from here): its
+            // 128-bit loads then pay L2 latency, and DRAM streams the block instead of answering scattered requests
+            const unsigned px0 = first_pixel_from_row(p, g, m0), px1 = first_pixel_from_row(p, g, m0 + TC_BM);
+            const uint32_t bytes = (px1 - px0) * (uint32_t)p.O * 4u;
+            if (bytes != 0) {
+              asm volatile(
+                  "{\n\t.reg .pred q;\n\t"
+                  "elect.sync _|q, 0xffffffff;\n\t"
+                  "@q cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}"
+                  ::"l"(p.residual + (size_t)px0 * p.O), "r"(bytes)
+                  : "memory");
+            }
+          }
+          // pull the halos of the tiles 2 and 3 iterations ahead into L2
+          for (int ahead = (it == 0 ? 1 : 3); ahead <= 3; ++ahead) {
+            const unsigned tf = tile + (unsigned)ahead * gridDim.x;
+            if (tf - rank < ntiles) {
+              const unsigned mf = tile_mt(g, tf) * TC_BM;
+              for (int cb = 0; cb < g.ncb; ++cb) {
+                for (int bx = 0; bx < nfull; ++bx) tma_prefetch_2d_elect(&tmA, cb * TC_BK, (int)mf + 256 * bx);
+                if (hr2 > 0) tma_prefetch_2d_elect(&tmA2, cb * TC_BK, (int)mf + 256 * nfull);
+              }
+            }
+          }
+        }
+      }
+    } else if (warp == TC_H_R0 + 1) {
+      pdl_wait();
+      if (rank == 0) {                                   // pair mode: the leader CTA issues for both
+        // ===== MMA issuer =====
+        // The issue loop is scalar code on one warp: anything slow between two tcgen05.mma shows up as idle
+        // tensor-pipe time (an integer division per k-block cost ~200 cycles per MMA).  So: nested loops with
+        // additive address updates only, and descriptors assembled from a constant high word plus a 14-bit
+        // (address >> 4) low field that is simply incremented (+2 per 32-byte K step).
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
+                               ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
+        const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+                                 ((uint64_t)2 << 61);
+        const int kdim = p.taps == 9 ? 3 : 1;
+        const int ksteps_last = ((p.Cp - (g.ncb - 1) * TC_BK) + TC_UMMA_K - 1) / TC_UMMA_K;   // 1..4
+        const uint32_t leader = elect_one();
+  #ifdef ATTNDM_TC_TRACE
+        unsigned long long* const tr_all = g.trace;        // debug: per-tile issue-complete timestamps of every CTA
+  #else
+        unsigned long long* const tr_all = nullptr;
+  #endif
         int s = 0;
         uint32_t ph = 0;
-        for (unsigned tile = tile0; tile - rank < ntiles; tile += gridDim.x) {
-          const int n0 = (int)tile_nt(g, tile) * g.BN;
-          for (int kb = 0; kb < nkb; ++kb) {
-            const int tap = kb / g.ncb, cb = kb - tap * g.ncb;
-            mbar_wait_relaxed(smem_u32(&b_empty[s]), ph ^ 1);
-            mbar_expect_tx_elect(smem_u32(&b_full[s]), (uint32_t)b_tile_bytes);
-            tma_load_2d_elect(base + g.b_off + (uint32_t)s * b_tile_bytes, &tmB, smem_u32(&b_full[s]), tap * p.Cp + cb * TC_BK, n0);
-            if (++s == g.nb) { s = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == TC_H_R0) {
-    pdl_wait();                                        // the codes come from the previous kernel
-    {
-      // ===== activation (halo) producer: one halo per (tile, channel block) =====
-      const int nfull = g.hr >= 256 ? g.hr / 256 : 1;    // a TMA box holds at most 256 rows: nfull boxes of tmA ...
-      const int hr2 = g.hr >= 256 ? g.hr - 256 * nfull : 0;   // ... and the remainder through tmA2
-      int it = 0;
-      for (unsigned tile = tile0; tile - rank < ntiles; tile += gridDim.x, ++it) {
-        const unsigned m0 = tile_mt(g, tile) * TC_BM;
-        const int buf = it & (g.na - 1);
-        if (lane == 0) TC_TRACE(0, it, 0);
-        mbar_wait_relaxed(smem_u32(&a_empty[buf]), (uint32_t)(((it >> g.na_shift) & 1) ^ 1));
-        if (lane == 0) TC_TRACE(0, it, 1);
-        const uint32_t bar = smem_u32(&a_full[buf]);
-        if ((g.dbg & 16) && !PAIR) { mbar_expect_tx_elect(bar, 0u); continue; }       // experiment: no halo loads at all
-        if (PAIR) {
-          // both CTAs' halos count on the LEADER's barrier (its MMA warp issues for the pair)
-          if (rank == 0) mbar_expect_tx_elect(bar, (uint32_t)(2 * g.ncb * g.hr * TC_BK));
-          for (int cb = 0; cb < g.ncb; ++cb) {
-            const uint32_t dst = base + g.a_off + (uint32_t)(buf * g.ncb + cb) * g.hr_stride;
-            for (int bx = 0; bx < nfull; ++bx) tma_load_2d_pair_elect(dst + bx * 256 * TC_BK, &tmA, bar, cb * TC_BK, (int)m0 + 256 * bx);
-            if (hr2 > 0) tma_load_2d_pair_elect(dst + nfull * 256 * TC_BK, &tmA2, bar, cb * TC_BK, (int)m0 + 256 * nfull);
-          }
-        } else {
-          mbar_expect_tx_elect(bar, (uint32_t)(g.ncb * g.hr * TC_BK));
-          for (int cb = 0; cb < g.ncb; ++cb) {
-            const uint32_t dst = base + g.a_off + (uint32_t)(buf * g.ncb + cb) * g.hr_stride;
-            for (int bx = 0; bx < nfull; ++bx) tma_load_2d_elect(dst + bx * 256 * TC_BK, &tmA, bar, cb * TC_BK, (int)m0 + 256 * bx);
-            if (hr2 > 0) tma_load_2d_elect(dst + nfull * 256 * TC_BK, &tmA2, bar, cb * TC_BK, (int)m0 + 256 * nfull);
-          }
-        }
-        if (ADDS && g.res_prefetch) {
-          // this tile's residual rows -> L2, now (the epilogue reaches the tile a few iterations from here): its
-          // 128-bit loads then pay L2 latency, and DRAM streams the block instead of answering scattered requests
-          const unsigned px0 = first_pixel_from_row(p, g, m0), px1 = first_pixel_from_row(p, g, m0 + TC_BM);
-          const uint32_t bytes = (px1 - px0) * (uint32_t)p.O * 4u;
-          if (bytes != 0) {
-            asm volatile(
-                "{\n\t.reg .pred q;\n\t"
-                "elect.sync _|q, 0xffffffff;\n\t"
-                "@q cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}"
-                ::"l"(p.residual + (size_t)px0 * p.O), "r"(bytes)
-                : "memory");
-          }
-        }
-        // pull the halos of the tiles 2 and 3 iterations ahead into L2
-        for (int ahead = (it == 0 ? 1 : 3); ahead <= 3; ++ahead) {
-          const unsigned tf = tile + (unsigned)ahead * gridDim.x;
-          if (tf - rank < ntiles) {
-            const unsigned mf = tile_mt(g, tf) * TC_BM;
-            for (int cb = 0; cb < g.ncb; ++cb) {
-              for (int bx = 0; bx < nfull; ++bx) tma_prefetch_2d_elect(&tmA, cb * TC_BK, (int)mf + 256 * bx);
-              if (hr2 > 0) tma_prefetch_2d_elect(&tmA2, cb * TC_BK, (int)mf + 256 * nfull);
+        int it = 0;
+        for (unsigned tile = tile0; tile - rank < ntiles; tile += gridDim.x, ++it) {
+          const int acc = it & (g.nacc - 1), buf = it & (g.na - 1);
+          if (lane == 0) TC_TRACE(1, it, 0);
+          if (!(g.dbg & 256)) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((it >> g.nacc_shift) & 1) ^ 1));
+          if (lane == 0) TC_TRACE(1, it, 1);
+          if (!(g.dbg & 128)) mbar_wait(smem_u32(&a_full[buf]), (uint32_t)((it >> g.na_shift) & 1));
+          if (g.b_resident && it == 0) { mbar_wait(smem_u32(&b_res_bar), 0); if (lane == 0) TC_SPAN(1); }
+          tcgen05_fence_after();
+          if (lane == 0) TC_TRACE(1, it, 2);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
+          const uint32_t a_buf0 = base + g.a_off + (uint32_t)(buf * g.ncb) * g.hr_stride;
+          uint32_t b_res = base + g.b_off;               // resident mode: walks through the whole weight block
+          uint32_t accumulate = 0;
+          if (g.dbg & 64) {
+            // experiment: no MMAs at all (the commits below arrive at once): the epilogue's own tile rate
+          } else if (g.b_resident) {
+            // no waits inside a tile: the elected lane issues the whole tile from a branch (see umma_i8_lo)
+            const uint32_t a_lo0 = ((a_buf0 >> 4) & 0x3FFF) | 0x10000u;
+            const uint32_t b_lo0 = ((b_res >> 4) & 0x3FFF) | 0x10000u;
+            const uint32_t a_step = (uint32_t)g.hr_stride >> 4, b_step = (uint32_t)b_tile_bytes >> 4;
+  #ifdef ATTNDM_TC_OLD_ISSUE
+            uint32_t b_lo = b_lo0;
+            for (int kh = 0; kh < kdim; ++kh) {
+              for (int kw = 0; kw < kdim; ++kw) {
+                uint32_t a_lo = a_lo0 + (uint32_t)(kh * p.Wp + kw) * (TC_BK >> 4);
+                for (int cb = 0; cb < g.ncb; ++cb) {
+                  umma_i8_x4_if(leader, d_tmem, a_lo, b_lo, idesc, accumulate,
+                                (cb == g.ncb - 1) ? ksteps_last : TC_BK / TC_UMMA_K);
+                  accumulate = 1;
+                  a_lo += a_step;
+                  b_lo += b_step;
+                }
+              }
             }
-          }
-        }
-      }
-    }
-  } else if (warp == TC_H_R0 + 1) {
-    pdl_wait();
-    if (rank == 0) {                                   // pair mode: the leader CTA issues for both
-      // ===== MMA issuer =====
-      // The issue loop is scalar code on one warp: anything slow between two tcgen05.mma shows up as idle
-      // tensor-pipe time (an integer division per k-block cost ~200 cycles per MMA).  So: nested loops with
-      // additive address updates only, and descriptors assembled from a constant high word plus a 14-bit
-      // (address >> 4) low field that is simply incremented (+2 per 32-byte K step).
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
-                             ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
-      const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-                               ((uint64_t)2 << 61);
-      const int kdim = p.taps == 9 ? 3 : 1;
-      const int ksteps_last = ((p.Cp - (g.ncb - 1) * TC_BK) + TC_UMMA_K - 1) / TC_UMMA_K;   // 1..4
-      const uint32_t leader = elect_one();
-#ifdef ATTNDM_TC_TRACE
-      unsigned long long* const tr_all = g.trace;        // debug: per-tile issue-complete timestamps of every CTA
-#else
-      unsigned long long* const tr_all = nullptr;
-#endif
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (unsigned tile = tile0; tile - rank < ntiles; tile += gridDim.x, ++it) {
-        const int acc = it & (g.nacc - 1), buf = it & (g.na - 1);
-        if (lane == 0) TC_TRACE(1, it, 0);
-        if (!(g.dbg & 256)) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (uint32_t)(((it >> g.nacc_shift) & 1) ^ 1));
-        if (lane == 0) TC_TRACE(1, it, 1);
-        if (!(g.dbg & 128)) mbar_wait(smem_u32(&a_full[buf]), (uint32_t)((it >> g.na_shift) & 1));
-        if (g.b_resident && it == 0) { mbar_wait(smem_u32(&b_res_bar), 0); if (lane == 0) TC_SPAN(1); }
-        tcgen05_fence_after();
-        if (lane == 0) TC_TRACE(1, it, 2);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.acc_stride);
-        const uint32_t a_buf0 = base + g.a_off + (uint32_t)(buf * g.ncb) * g.hr_stride;
-        uint32_t b_res = base + g.b_off;               // resident mode: walks through the whole weight block
-        uint32_t accumulate = 0;
-        if (g.dbg & 64) {
-          // experiment: no MMAs at all (the commits below arrive at once): the epilogue's own tile rate
-        } else if (g.b_resident) {
-          // no waits inside a tile: the elected lane issues the whole tile from a branch (see umma_i8_lo)
-          const uint32_t a_lo0 = ((a_buf0 >> 4) & 0x3FFF) | 0x10000u;
-          const uint32_t b_lo0 = ((b_res >> 4) & 0x3FFF) | 0x10000u;
-          const uint32_t a_step = (uint32_t)g.hr_stride >> 4, b_step = (uint32_t)b_tile_bytes >> 4;
-#ifdef ATTNDM_TC_OLD_ISSUE
-          uint32_t b_lo = b_lo0;
+  #else
+            if (leader) {
+              if (PAIR) umma_tile_resident<true>(d_tmem, a_lo0, b_lo0, idesc, kdim, p.Wp * (TC_BK >> 4), g.ncb, a_step, b_step, ksteps_last);
+              else        umma_tile_resident<false>(d_tmem, a_lo0, b_lo0, idesc, kdim, p.Wp * (TC_BK >> 4), g.ncb, a_step, b_step, ksteps_last);
+            }
+            __syncwarp();
+            accumulate = 1;
+  #endif
+          } else
           for (int kh = 0; kh < kdim; ++kh) {
             for (int kw = 0; kw < kdim; ++kw) {
-              uint32_t a_lo = a_lo0 + (uint32_t)(kh * p.Wp + kw) * (TC_BK >> 4);
+              uint32_t a_addr = a_buf0 + (uint32_t)(kh * p.Wp + kw) * TC_BK;
               for (int cb = 0; cb < g.ncb; ++cb) {
-                umma_i8_x4_if(leader, d_tmem, a_lo, b_lo, idesc, accumulate,
-                              (cb == g.ncb - 1) ? ksteps_last : TC_BK / TC_UMMA_K);
-                accumulate = 1;
-                a_lo += a_step;
-                b_lo += b_step;
+                uint32_t b_addr;
+                if (g.b_resident) {
+                  b_addr = b_res;
+                  b_res += (uint32_t)b_tile_bytes;
+                } else {
+                  mbar_wait(smem_u32(&b_full[s]), ph);
+                  tcgen05_fence_after();
+                  b_addr = base + g.b_off + (uint32_t)s * b_tile_bytes;
+                }
+                const int ksteps = (cb == g.ncb - 1) ? ksteps_last : TC_BK / TC_UMMA_K;
+                uint64_t ad = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+                uint64_t bd = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFF);
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_i8_if(leader, d_tmem, ad, bd, idesc, accumulate);
+                  accumulate = 1;
+                  ad += TC_UMMA_K >> 4;
+                  bd += TC_UMMA_K >> 4;
+                }
+                if (!g.b_resident) {
+                  tcgen05_commit_if(leader, smem_u32(&b_empty[s]));
+                  if (++s == g.nb) { s = 0; ph ^= 1; }
+                }
+                a_addr += (uint32_t)g.hr_stride;
               }
             }
           }
-#else
-          if (leader) {
-            if (PAIR) umma_tile_resident<true>(d_tmem, a_lo0, b_lo0, idesc, kdim, p.Wp * (TC_BK >> 4), g.ncb, a_step, b_step, ksteps_last);
-            else        umma_tile_resident<false>(d_tmem, a_lo0, b_lo0, idesc, kdim, p.Wp * (TC_BK >> 4), g.ncb, a_step, b_step, ksteps_last);
+          if (PAIR) {
+            tcgen05_commit_pair_if(leader, smem_u32(&a_empty[buf]));
+            tcgen05_commit_pair_if(leader, smem_u32(&tmem_full_bar[acc]));
+          } else {
+            tcgen05_commit_if(leader, smem_u32(&a_empty[buf]));
+            tcgen05_commit_if(leader, smem_u32(&tmem_full_bar[acc]));
           }
-          __syncwarp();
-          accumulate = 1;
-#endif
-        } else
-        for (int kh = 0; kh < kdim; ++kh) {
-          for (int kw = 0; kw < kdim; ++kw) {
-            uint32_t a_addr = a_buf0 + (uint32_t)(kh * p.Wp + kw) * TC_BK;
-            for (int cb = 0; cb < g.ncb; ++cb) {
-              uint32_t b_addr;
-              if (g.b_resident) {
-                b_addr = b_res;
-                b_res += (uint32_t)b_tile_bytes;
-              } else {
-                mbar_wait(smem_u32(&b_full[s]), ph);
-                tcgen05_fence_after();
-                b_addr = base + g.b_off + (uint32_t)s * b_tile_bytes;
-              }
-              const int ksteps = (cb == g.ncb - 1) ? ksteps_last : TC_BK / TC_UMMA_K;
-              uint64_t ad = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
-              uint64_t bd = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFF);
-              for (int k = 0; k < ksteps; ++k) {
-                umma_i8_if(leader, d_tmem, ad, bd, idesc, accumulate);
-                accumulate = 1;
-                ad += TC_UMMA_K >> 4;
-                bd += TC_UMMA_K >> 4;
-              }
-              if (!g.b_resident) {
-                tcgen05_commit_if(leader, smem_u32(&b_empty[s]));
-                if (++s == g.nb) { s = 0; ph ^= 1; }
-              }
-              a_addr += (uint32_t)g.hr_stride;
-            }
+          if (lane == 0) TC_TRACE(1, it, 3);
+          if (tr_all != nullptr && lane == 0 && it < 32) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory");
+            tr_all[4096 + blockIdx.x * 32 + it] = now;
           }
-        }
-        if (PAIR) {
-          tcgen05_commit_pair_if(leader, smem_u32(&a_empty[buf]));
-          tcgen05_commit_pair_if(leader, smem_u32(&tmem_full_bar[acc]));
-        } else {
-          tcgen05_commit_if(leader, smem_u32(&a_empty[buf]));
-          tcgen05_commit_if(leader, smem_u32(&tmem_full_bar[acc]));
-        }
-        if (lane == 0) TC_TRACE(1, it, 3);
-        if (tr_all != nullptr && lane == 0 && it < 32) {
-          unsigned long long now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory");
-          tr_all[4096 + blockIdx.x * 32 + it] = now;
         }
       }
+    } else if (warp == TC_H_R0 + 3) {
+      geometry_role(0, g.b_resident ? 2 : 1);
     }
-  } else if (warp == TC_H_R0 + 3) {
-    geometry_role(0, g.b_resident ? 2 : 1);
-  } else if (warp >= TC_H_EPI0 && warp < TC_H_R0) {
+  } else {
+    if (TC_H_EPI_WARPS == 12) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;" ::: "memory");
     // ===== epilogue warps (8): quarter = warp % 4, the two warps of a quarter take 32-column chunks round robin.
     // No shared-memory staging: the 16x256b TMEM load shape already hands four consecutive threads 32
     // contiguous bytes of one output row, so results go TMEM -> registers -> global (128-bit per lane after
@@ -1347,7 +1389,9 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         rows.cs[k] = geo_cs[gb][r];
       }
       if (g.dbg & 32) rows.ok = 0;                           // experiment: the epilogue math without loads/stores
-      EpiStats est = {nullptr, 0u, false};
+      EpiStats est;
+      est.dst = nullptr;
+      est.two = false;
       if (STATS) {
         // samples of this quarter's output rows: all rows of the first one go to partial 0, the rest (the next sample:
         // a sample has >= 32 GEMM rows) to partial 1
@@ -1362,21 +1406,21 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mx = __reduce_max_sync(0xffffffffu, mx);
         est.two = mx > mn;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) est.m1 |= (bk[k] > mn ? 1u : 0u) << k;
+        for (int k = 0; k < 4; ++k) {                        // (no output row in this quarter: bk = -1 everywhere, all weights 0)
+          est.w0[k] = bk[k] >= 0 && bk[k] == mn ? 1.f : 0.f;
+          est.w1[k] = bk[k] > mn ? 1.f : 0.f;
+        }
         est.dst = p.gn_out + (long long)(mx >= 0 ? mn : 0) * (2 * kGnGroups);
-        if (mx < 0) est.m1 = 0;                              // no output row in this quarter: every `ok` bit is clear too
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&geo_empty[gb]));
       const int nchunks = (g.BN + 31) >> 5;
-      const bool vec4 = (p.O & 3) == 0;                      // 128-bit path for full 32-column blocks
+      const bool vec4 = g.perm != 0;                         // 128-bit path for full 32-column blocks (permuted weight rows)
       constexpr bool adds = ADDS;
       auto use4_at = [&](int ci) { return vec4 && ci < nchunks && (ci << 5) + 32 <= g.BN && n0 + (ci << 5) + 32 <= p.O; };
-      float4 rs4[4];                                         // rolling residual window (epi_res_load)
-      if (ADDS && p.residual != nullptr && use4_at(ci0)) {   // first block's residual: issued before the wait below
-#pragma unroll
-        for (int k = 0; k < 4; ++k) rs4[k] = epi_res_load(p.residual, rows, k, ci0 << 5, 0, tq);
-      }
+      float4 rs4[2][4];
+      if (ADDS && p.residual != nullptr && use4_at(ci0))     // first block's residual: issued before the wait below
+        epi_load_residual_v4(rs4, p.residual, rows, ci0 << 5, tq);
       mbar_wait_relaxed(smem_u32(&tmem_full_bar[acc]), (uint32_t)((it >> g.nacc_shift) & 1));
       tcgen05_fence_after();
       if (lane == 0) TC_TRACE(4 + ew, it, 0);
@@ -1385,13 +1429,22 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(smem_u32(&tmem_empty_bar[acc])); else mbar_arrive(smem_u32(&tmem_empty_bar[acc])); }
       }
+      EpiPend pend;
+      int pend_c0 = -1;                                      // STATS: the block whose partials wait in `pend`
+      auto stats_flush = [&]() {
+        epi_stats_flush(pend.a, est.dst, n0 + pend_c0, lane, g.d_cpg);
+        if (est.two) epi_stats_flush(pend.b, est.dst + 2 * kGnGroups, n0 + pend_c0, lane, g.d_cpg);
+      };
       for (int ci = ci0; ci < nchunks; ci += ci_step) {
         const int c0 = ci << 5;
         uint32_t v0[16], v1[16];
+        const bool use4 = use4_at(ci);
+        if (ADDS && use4 && p.residual != nullptr && ci != ci0) epi_load_residual_v4(rs4, p.residual, rows, c0, tq);
         __syncwarp();
         if ((g.dbg & 3) < 2) {
           tmem_ld_16x256b_x4(t_acc + (uint32_t)c0, v0);                      // tile rows 32q + 0..15
           tmem_ld_16x256b_x4(t_acc + (16u << 16) + (uint32_t)c0, v1);        // tile rows 32q + 16..31
+          if (STATS && pend_c0 >= 0) stats_flush();          // the previous block's statistics, under the load's latency
           tmem_ld_wait();
           if (lane == 0 && ci == ci0) TC_TRACE(4 + ew, it, 1);
         } else {
@@ -1404,19 +1457,19 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (lane == 0) { if (PAIR) mbar_arrive_leader(smem_u32(&tmem_empty_bar[acc])); else mbar_arrive(smem_u32(&tmem_empty_bar[acc])); }
         }
         if ((g.dbg & 3) >= 1) continue;
-        const bool use4 = use4_at(ci);
         if (use4) {
           // two instantiations only (the kernel's code size is felt in the instruction cache): the plain
           // conv, and one variant that checks the residual / time-embedding pointers at run time
-          const int c0_next = use4_at(ci + ci_step) ? (ci + ci_step) << 5 : -1;
-          if (adds) epi_block_v4<true, STATS>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.residual, c0_next, p.temb, est, n0, g.d_cpg);
-          else      epi_block_v4<false, STATS>(v0, v1, colc, c0, tq, rows, p.out, rs4, nullptr, -1, nullptr, est, n0, g.d_cpg);
+          if (adds) epi_block_v4<true, STATS>(v0, v1, colc, c0, tq, rows, p.out, rs4, p.residual != nullptr, p.temb, est, pend);
+          else      epi_block_v4<false, STATS>(v0, v1, colc, c0, tq, rows, p.out, rs4, false, nullptr, est, pend);
+          if (STATS) pend_c0 = c0;
         } else {
           // ragged last block or O % 4 != 0 (the 3-channel output): scalar, per-column checks
-          epi_block_scalar(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, p.residual, p.temb);
+          epi_block_scalar(v0, v1, colc, c0, tq, g.BN, n0, p.O, rows, p.out, p.residual, p.temb, g.perm != 0);
         }
         if (lane == 0) TC_TRACE(4 + ew, it, ci == ci0 ? 2 : 3);
       }
+      if (STATS && pend_c0 >= 0) stats_flush();
     }
   }
   tcgen05_fence_before();
@@ -1462,6 +1515,24 @@ static int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("qconv_i8_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return ATTNDM_ERR_CUDA; }
+  return ATTNDM_OK;
+}
+
+// The weight matrix [O][K] (O % 16 == 0) as a 5-D tensor {K, j: 2, tq: 4, i: 2, unit: O / 16} over the same memory, row =
+// 16 unit + 4 tq + 2 i + j.  A box {128, 2, 4, 2, n / 16} lands in shared memory as rows 16 u + 8 i + 2 tq + j, i.e. the row
+// (= TMEM column) that the 16x256b fragment hands to thread tq as the j-th element of column group i holds output channel
+// 4 tq + 2 i + j: every lane of the epilogue owns four consecutive channels (epi_block_v4).
+static int make_map_b_perm(CUtensorMap* m, const void* base, uint64_t K, int O, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("qconv_i8_tc: cuTensorMapEncodeTiled not available"); return ATTNDM_ERR_CUDA; }
+  cuuint64_t dims[5] = {K, 2, 4, 2, (cuuint64_t)(O / 16)};
+  cuuint64_t strides[4] = {K, 4 * K, 2 * K, 16 * K};        // bytes: j, tq, i, unit
+  cuuint32_t box[5] = {TC_BK, 2, 4, 2, box_rows / 16};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("qconv_i8_tc: cuTensorMapEncodeTiled (permuted weights) failed (%d)", (int)r); return ATTNDM_ERR_CUDA; }
   return ATTNDM_OK;
 }
 
@@ -1623,7 +1694,9 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st, bool* st
     rc = make_map_2d(&tmA2, p.codes, (uint64_t)p.Cp, (uint64_t)p.rows, TC_BK, (uint32_t)(g.hr % 256));
     if (rc) return rc;
   }
-  rc = make_map_2d(&tmB, p.qw, (uint64_t)p.taps * p.Cp, (uint64_t)p.O, TC_BK, (uint32_t)(g.pair ? g.BN / 2 : g.BN));
+  g.perm = (p.O % 16 == 0) ? 1 : 0;
+  if (g.perm) rc = make_map_b_perm(&tmB, p.qw, (uint64_t)p.taps * p.Cp, p.O, (uint32_t)(g.pair ? g.BN / 2 : g.BN));
+  else rc = make_map_2d(&tmB, p.qw, (uint64_t)p.taps * p.Cp, (uint64_t)p.O, TC_BK, (uint32_t)(g.pair ? g.BN / 2 : g.BN));
   if (rc) return rc;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
