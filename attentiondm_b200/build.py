@@ -34,7 +34,7 @@ def _digest():
 # A/B variants of the library (same sources, extra defines), built next to the default one as
 # libattndm_b200_<name>.so and selected at run time with ATTNDM_LIB=<path> (see _ffi.py):
 VARIANTS = {"silu_guard": ["-DATTNDM_SILU_GUARD"], "silu_accurate": ["-DATTNDM_SILU_ACCURATE"],
-            "tc_trace": ["-DATTNDM_TC_TRACE"],
+            "tc_trace": ["-DATTNDM_TC_TRACE"], "rp_trace": ["-DATTNDM_RP_TRACE"],
             "epi8": ["-DATTNDM_TC_EPI_WARPS=8"], "epi16": ["-DATTNDM_TC_EPI_WARPS=16"]}
 
 

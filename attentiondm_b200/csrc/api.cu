@@ -62,7 +62,7 @@ int attndm_qconv_i8(const int8_t* codes, const int32_t* rowsum, int B, int H, in
   p.qw = qw; p.wsum = wsum; p.w_zp = w_zp; p.O = O; p.taps = taps; p.mult = mult; p.act_zp = act_zp;
   p.bias = bias; p.residual = residual; p.temb = temb; p.out = out;
   if (gn_stats_out && O % 32 != 0) { set_error("qconv_i8: gn_stats_out needs O %% 32 == 0"); return ATTNDM_ERR_ARG; }
-  // The statistics of one shape always follow ONE summation order, whichever kernel computes the conv: tile-tree order
+  // The statistics of one shape always follow ONE summation order, whichever kernel computes the conv: quad order
   // (conv_common.cuh) where the tcgen05 epilogue can produce it, else the order of attndm_gn_stats.
   const bool tiletree = gn_stats_out != nullptr && conv_gn_tiletree_ok(p);
   p.gn_out = tiletree ? gn_stats_out : nullptr;

@@ -21,7 +21,7 @@ struct ConvI8Params {
   const float* residual;   // [B*H*W][O] or NULL
   const float* temb;       // [B][O] or NULL
   float* out;              // [B*H*W][O]
-  double* gn_out;          // [B][32][2] or NULL: GroupNorm {sum, sumsq} of `out`, accumulated (tile-tree order, below)
+  double* gn_out;          // [B][32][2] or NULL: GroupNorm {sum, sumsq} of `out`, accumulated (quad order, below)
 };
 
 // code-row index -> output pixel.  For 3x3 the GEMM row r is the halo-layout row of
@@ -72,15 +72,18 @@ __device__ __forceinline__ float conv_epilogue_add(const float* residual, const 
   return v;
 }
 
-// ---- GroupNorm statistics of a conv output in "tile-tree" order -------------------------------------------------
-// The tcgen05 epilogue holds the output as 128-row tiles of GEMM rows (code-layout rows), a 32-row quarter per warp,
-// thread (tr = lane / 4, tq = lane % 4) owning rows tr + 8k (k = 0..3) x four consecutive channels of every
-// 16-channel unit.  The statistics are DEFINED by that shape so that any kernel can reproduce them bit for bit:
-//   per thread, fp32:   s = sum_k (x0 + x1) + (x2 + x3),  q = sum_k fma(x3,x3, fma(x2,x2, fma(x1,x1, x0*x0)))   (k ascending)
-//   per warp, fp32:     butterfly over tr (lane xor 4, 8, 16)
-//   per (sample, group): the warp partials meet in double-precision atomics (their order can move the last bit of a
-//                        double, far below the fp32 mean / rstd formed from them -- as in attndm_gn_stats).
-// A quarter that straddles two samples keeps two partials (rows of the first sample / rows of the second).
+// ---- GroupNorm statistics of a conv output in "quad" order -------------------------------------------------------
+// The statistics a conv hands to the GroupNorm behind it are DEFINED as follows, so that any kernel can reproduce them:
+//   per output pixel and aligned group of four channels (x0..x3), fp32:
+//       s = (x0 + x1) + (x2 + x3),   q = fma(x3,x3, fma(x2,x2, fma(x1,x1, x0*x0)))
+//   per (sample, GroupNorm group): the sum of these s and q in DOUBLE precision, in whatever order the kernel meets
+//   them (thread partials, shuffles, atomics): reordering moves the last bits of a double, far below the fp32 mean /
+//   rstd formed from the totals -- as in attndm_gn_stats.
+// Nothing in the fp32 part depends on how rows fall into tiles, so a sample's statistics do not depend on its position
+// in the batch (sharding a batch over GPUs gives the same images, tests/test_gpu_parity.py).
+// The tcgen05 epilogue holds the output as 128-row tiles of GEMM rows, a 32-row quarter per warp, thread (tr = lane / 4,
+// tq = lane % 4) owning rows tr + 8k (k = 0..3) x channels 4tq .. 4tq+3 of every 16-channel unit; a quarter that
+// straddles two samples keeps two partials.
 // Supported when O % 128 == 0 (a thread's four channels share a group) and a sample has >= 32 GEMM rows.
 inline bool conv_gn_tiletree_ok(const ConvI8Params& p) {
   return p.O % 128 == 0 && (long long)p.Hp * p.Wp >= 32 && p.rows + 128 < (1LL << 31);

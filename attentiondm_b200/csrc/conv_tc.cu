@@ -772,38 +772,38 @@ __device__ __forceinline__ void epi_load_residual_v4(float4 (&rs)[2][4], const f
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// STATS: also accumulate the GroupNorm statistics of the values stored, in tile-tree order (conv_common.cuh).
-// two (warp-uniform): the quarter straddles two samples; dst: &gn_out[(first sample * 32) * 2].
+// STATS: also accumulate the GroupNorm statistics of the values stored, in quad order (conv_common.cuh): fp32 over the
+// four channels of one pixel, double from there on.  two (warp-uniform): the quarter straddles two samples;
+// dst: &gn_out[(first sample * 32) * 2]; m0 / m1: bit k = row k is an output row of the first / second sample.
 struct EpiStats {
   double* dst;
-  float w0[4], w1[4];   // 1.0 where row k is an output row of the first / second sample, else 0.0: the accumulations are
-                        // fma(x, w, acc) -- exactly acc + x or acc, without predicates
+  uint32_t m0, m1;
   bool two;
 };
 // Per-thread partials of one 32-column block, {sum, sumsq} of column half 0 then of column half 1: a = rows of the
 // quarter's first sample, b = rows of its second sample (only when EpiStats::two).
 struct EpiPend {
-  float a[4], b[4];
+  double a[4], b[4];
 };
 
-// The butterfly over tr (lane xor 4, 8, 16) of a block's four partials as a reduce-scatter: at xor 4 a lane keeps one
-// column half and hands the other to its partner, at xor 8 it keeps the sum or the sum of squares, so four shuffles
-// instead of twelve produce the same sums from the same pairs (an fp32 add commutes) and sixteen lanes each hold ONE
-// finished value: lane bit 2 = column half, bit 3 = sum / sum of squares, bits 0..1 = tq.
-__device__ __forceinline__ void epi_stats_flush(const float (&a)[4], double* dst, int col_base, int lane, const FastDiv& d_cpg) {
+// The reduction over tr (lane xor 4, 8, 16) of a block's four partials as a reduce-scatter: at xor 4 a lane keeps one
+// column half and hands the other to its partner, at xor 8 it keeps the sum or the sum of squares, so sixteen lanes each
+// end up with ONE finished value (lane bit 2 = column half, bit 3 = sum / sum of squares, bits 0..1 = tq) and add it
+// to the (sample, group) accumulator: four shuffled values per block instead of twelve.
+__device__ __forceinline__ void epi_stats_flush(const double (&a)[4], double* dst, int col_base, int lane, const FastDiv& d_cpg) {
   const int tq = lane & 3;
   const bool b4 = lane & 4, b8 = lane & 8;
   const int col4 = 4 * tq;
-  float kx = b4 ? a[2] : a[0], ky = b4 ? a[3] : a[1];
-  const float sx = b4 ? a[0] : a[2], sy = b4 ? a[1] : a[3];
-  kx = __fadd_rn(kx, __shfl_xor_sync(0xffffffffu, sx, 4));
-  ky = __fadd_rn(ky, __shfl_xor_sync(0xffffffffu, sy, 4));
-  float k = b8 ? ky : kx;
-  const float s = b8 ? kx : ky;
-  k = __fadd_rn(k, __shfl_xor_sync(0xffffffffu, s, 8));
-  k = __fadd_rn(k, __shfl_xor_sync(0xffffffffu, k, 16));
+  double kx = b4 ? a[2] : a[0], ky = b4 ? a[3] : a[1];
+  const double sx = b4 ? a[0] : a[2], sy = b4 ? a[1] : a[3];
+  kx += __shfl_xor_sync(0xffffffffu, sx, 4);
+  ky += __shfl_xor_sync(0xffffffffu, sy, 4);
+  double k = b8 ? ky : kx;
+  const double s = b8 ? kx : ky;
+  k += __shfl_xor_sync(0xffffffffu, s, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 16);
   if (lane < 16)
-    atomicAdd(dst + 2 * fdiv((unsigned)(col_base + (b4 ? 16 : 0) + col4), d_cpg) + (b8 ? 1 : 0), (double)k);
+    atomicAdd(dst + 2 * fdiv((unsigned)(col_base + (b4 ? 16 : 0) + col4), d_cpg) + (b8 ? 1 : 0), k);
 }
 
 template <bool ADD, bool STATS>
@@ -818,7 +818,7 @@ __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uin
     const int i0 = 2 * h, i1 = 2 * h + 1;
     const int ch = (c0 + 16 * h + col4) & 255;        // this lane's four channels: group i0 holds ch, ch+1; group i1 ch+2, ch+3
     const ColConst a0c = colc[ch], a1c = colc[ch + 1], b0c = colc[ch + 2], b1c = colc[ch + 3];
-    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+    double ds[4], dq[4];                              // STATS: this half's {sum, sumsq} of each row's four channels
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int j0 = (i0 << 2) | ((k & 1) << 1), j1 = (i1 << 2) | ((k & 1) << 1);
@@ -843,15 +843,18 @@ __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uin
       if (STATS) {
         const float rsum = __fadd_rn(__fadd_rn(o.x, o.y), __fadd_rn(o.z, o.w));
         const float rsq = fmaf(o.w, o.w, fmaf(o.z, o.z, fmaf(o.y, o.y, __fmul_rn(o.x, o.x))));
-        s0 = fmaf(rsum, st.w0[k], s0);
-        q0 = fmaf(rsq, st.w0[k], q0);
-        if (st.two) { s1 = fmaf(rsum, st.w1[k], s1); q1 = fmaf(rsq, st.w1[k], q1); }
+        ds[k] = (double)rsum;
+        dq[k] = (double)rsq;
       }
     }
     if (STATS) {
-      pend.a[2 * h] = s0;
-      pend.a[2 * h + 1] = q0;
-      if (st.two) { pend.b[2 * h] = s1; pend.b[2 * h + 1] = q1; }
+      // rows of the first sample (m0) / of the second (m1); pairwise, so the double adds are two deep instead of four
+      auto pick = [](const double (&d)[4], uint32_t m) {
+        return (((m & 1) ? d[0] : 0.0) + ((m & 2) ? d[1] : 0.0)) + (((m & 4) ? d[2] : 0.0) + ((m & 8) ? d[3] : 0.0));
+      };
+      pend.a[2 * h] = pick(ds, st.m0);
+      pend.a[2 * h + 1] = pick(dq, st.m0);
+      if (st.two) { pend.b[2 * h] = pick(ds, st.m1); pend.b[2 * h + 1] = pick(dq, st.m1); }
     }
   }
 }
@@ -1389,9 +1392,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         rows.cs[k] = geo_cs[gb][r];
       }
       if (g.dbg & 32) rows.ok = 0;                           // experiment: the epilogue math without loads/stores
-      EpiStats est;
-      est.dst = nullptr;
-      est.two = false;
+      EpiStats est = {nullptr, 0u, 0u, false};
       if (STATS) {
         // samples of this quarter's output rows: all rows of the first one go to partial 0, the rest (the next sample:
         // a sample has >= 32 GEMM rows) to partial 1
@@ -1406,9 +1407,9 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mx = __reduce_max_sync(0xffffffffu, mx);
         est.two = mx > mn;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                        // (no output row in this quarter: bk = -1 everywhere, all weights 0)
-          est.w0[k] = bk[k] >= 0 && bk[k] == mn ? 1.f : 0.f;
-          est.w1[k] = bk[k] > mn ? 1.f : 0.f;
+        for (int k = 0; k < 4; ++k) {                        // (no output row in this quarter: bk = -1 everywhere, no bit set)
+          est.m0 |= (bk[k] >= 0 && bk[k] == mn ? 1u : 0u) << k;
+          est.m1 |= (bk[k] > mn ? 1u : 0u) << k;
         }
         est.dst = p.gn_out + (long long)(mx >= 0 ? mn : 0) * (2 * kGnGroups);
       }
@@ -1715,7 +1716,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st, bool* st
   });
   if (attr_err != cudaSuccess) { set_error("qconv_i8_halo: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
   const bool adds = p.residual != nullptr || p.temb != nullptr;
-  // GroupNorm statistics of the output from the epilogue (tile-tree order): every chunk must take the 128-bit path
+  // GroupNorm statistics of the output from the epilogue (quad order): every chunk must take the 128-bit path
   static const bool stats_on = [] { const char* e = getenv("ATTNDM_TC_STATS"); return !(e && e[0] == '0'); }();
   const bool stats = stats_on && p.gn_out != nullptr && conv_gn_tiletree_ok(p) && g.BN % 32 == 0;
 #define ATTNDM_HALO_ARGS dim3(grid), dim3(TC_THREADS_H), smem, st
@@ -1754,18 +1755,18 @@ int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st, bool* stats_fused
 }
 
 
-// ---- GroupNorm statistics of a conv output in tile-tree order, from the output tensor -------------------------
-// The twin of the STATS epilogue above (conv_common.cuh states the order): one warp per 32-row quarter of a 128-row
-// tile of GEMM rows, thread (tr, tq) sums rows tr + 8k of its four channels of every 16-channel unit with the same
-// fp32 operations in the same order, the same butterfly, the same double atomics.  Runs after the dp4a conv kernel and
-// after the ring-fed tcgen05 kernel, so that the statistics of a layer do not depend on which kernel computed it.
+// ---- GroupNorm statistics of a conv output in quad order, from the output tensor ------------------------------
+// The twin of the STATS epilogue above (conv_common.cuh states the order): per pixel and aligned group of four channels
+// the same fp32 sum and sum of squares, everything above that in double.  Runs after the dp4a conv kernel and after the
+// ring-fed tcgen05 kernel, so that the statistics of a layer do not depend on which kernel computed it.  One warp per 32
+// GEMM rows, thread (tr = lane / 4, tq = lane % 4): rows tr + 8k, channels 4tq .. 4tq+3 of every unit of 16.
 __global__ void __launch_bounds__(256) gn_stats_tiletree_kernel(const ConvI8Params p, long long nquarters) {
   pdl_enter();
   const int lane = threadIdx.x & 31, tq = lane & 3, tr = lane >> 2;
   const long long wq = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wq >= nquarters) return;
   const long long row0 = wq * 32;
-  const int col4 = (tq & 1) ? 8 + 2 * (tq - 1) : 2 * tq;
+  const int col4 = 4 * tq;
   const int cpg = p.O / kGnGroups;
   long long pix[4];
   int bk[4], mn = 0x7fffffff, mx = -1;
@@ -1788,30 +1789,30 @@ __global__ void __launch_bounds__(256) gn_stats_tiletree_kernel(const ConvI8Para
   const bool two = mx > mn;
   double* dst = p.gn_out + (long long)mn * (2 * kGnGroups);
   for (int u = 0; u < p.O; u += 16) {
-    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+    double ds[4], dq[4];                              // STATS: this half's {sum, sumsq} of each row's four channels
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (pix[k] < 0) continue;
       const float4 o = __ldg(reinterpret_cast<const float4*>(p.out + pix[k] * p.O + u + col4));
       const float rsum = __fadd_rn(__fadd_rn(o.x, o.y), __fadd_rn(o.z, o.w));
       const float rsq = fmaf(o.w, o.w, fmaf(o.z, o.z, fmaf(o.y, o.y, __fmul_rn(o.x, o.x))));
-      if (bk[k] == mn) { s0 = __fadd_rn(s0, rsum); q0 = __fadd_rn(q0, rsq); }
-      else { s1 = __fadd_rn(s1, rsum); q1 = __fadd_rn(q1, rsq); }
+      if (bk[k] == mn) { s0 += (double)rsum; q0 += (double)rsq; }
+      else { s1 += (double)rsum; q1 += (double)rsq; }
     }
 #pragma unroll
     for (int m = 4; m <= 16; m <<= 1) {
-      s0 = __fadd_rn(s0, __shfl_xor_sync(0xffffffffu, s0, m));
-      q0 = __fadd_rn(q0, __shfl_xor_sync(0xffffffffu, q0, m));
-      s1 = __fadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, m));
-      q1 = __fadd_rn(q1, __shfl_xor_sync(0xffffffffu, q1, m));
+      s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+      q0 += __shfl_xor_sync(0xffffffffu, q0, m);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, m);
     }
     if (lane < 4) {
       double* d = dst + 2 * ((u + col4) / cpg);
-      atomicAdd(d, (double)s0);
-      atomicAdd(d + 1, (double)q0);
+      atomicAdd(d, s0);
+      atomicAdd(d + 1, q0);
       if (two) {
-        atomicAdd(d + 2 * kGnGroups, (double)s1);
-        atomicAdd(d + 2 * kGnGroups + 1, (double)q1);
+        atomicAdd(d + 2 * kGnGroups, s1);
+        atomicAdd(d + 2 * kGnGroups + 1, q1);
       }
     }
   }

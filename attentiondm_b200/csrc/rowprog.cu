@@ -116,8 +116,11 @@ struct RpExt {
   const void* p[4];
 };
 
-// optional timeline (debug): thread 0 of CTA (0,0) stamps globaltimer at phase boundaries of every op
+// optional timeline (debug builds, -DATTNDM_RP_TRACE: `python -m attentiondm_b200.build --variant=rp_trace`, tools/rowprog_trace.py):
+// thread 0 of CTA (0,0) stamps globaltimer at phase boundaries of every op.  Compiled out otherwise -- a hook is a
+// dependent global load of the buffer pointer by every thread, seven of them per conv.
 __device__ unsigned long long* g_rp_trace = nullptr;    // [op][8]
+#ifdef ATTNDM_RP_TRACE
 __device__ __forceinline__ void rp_trace(int opi, int ev) {
   unsigned long long* t = g_rp_trace;
   if (t != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && opi < 256) {
@@ -126,6 +129,9 @@ __device__ __forceinline__ void rp_trace(int opi, int ev) {
     t[opi * 8 + ev] = now;
   }
 }
+#else
+__device__ __forceinline__ void rp_trace(int, int) {}
+#endif
 
 template <int NS>
 __global__ void __launch_bounds__(RP_THREADS, 1)
@@ -431,10 +437,19 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
         //      of the first 256 input channels of tile `warp` are already in registers (prefetched by the
         //      previous conv); anything beyond is loaded here ----
         int acc[RP_MAXT][4], acc2[RP_MAXT][4];
+        float tev[RP_MAXT][4];             // the time-embedding terms of phase C, fetched from global memory ahead of the MMAs
 #pragma unroll
         for (int t = 0; t < RP_MAXT; ++t)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { acc[t][j] = 0; acc2[t][j] = 0; }
+          for (int j = 0; j < 4; ++j) {
+            acc[t][j] = 0;
+            acc2[t][j] = 0;
+            tev[t][j] = 0.f;
+            if (op.g1 != nullptr) {
+              const int o = (warp + t * RP_WARPS) * 16 + grp + 8 * (j >> 1), n = 2 * tig + (j & 1);
+              if (n < NS && o < O && s0 + n < B) tev[t][j] = __ldg(reinterpret_cast<const float*>(op.g1) + (long long)(s0 + n) * O + o);
+            }
+          }
         {
           const int nk32 = (C + 31) >> 5, ntile = (O + 15) >> 4;
           const uint8_t* crow = reinterpret_cast<const uint8_t*>(codes) + grp * crow_bytes + tig * 4;
@@ -453,20 +468,28 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
                 } else {
                   rp_mbar_wait(rp_smem_u32(&s_wbar[warp]), wuse & 1);       // prefetched by the previous conv
                   ++wuse;
+                  rp_trace(opi, 7);
 #pragma unroll
                   for (int j = 0; j < RP_KCH; ++j)
                     if (j < nk32) wf[j] = *reinterpret_cast<const uint4*>(wmine + j * 512);
                 }
+                // all B fragments of the chunk first, then the MMAs back to back (one load-to-use latency per chunk
+                // instead of one per MMA)
+                uint32_t bf0[RP_KCH], bf1[RP_KCH];
+#pragma unroll
+                for (int j = 0; j < RP_KCH; ++j) {
+                  bf0[j] = 0;
+                  bf1[j] = 0;
+                  if (has_n && k0 + j < nk32) {
+                    bf0[j] = *reinterpret_cast<const uint32_t*>(crow + (k0 + j) * 32);
+                    bf1[j] = *reinterpret_cast<const uint32_t*>(crow + (k0 + j) * 32 + 16);
+                  }
+                }
 #pragma unroll
                 for (int j = 0; j < RP_KCH; ++j) {
                   if (k0 + j < nk32) {
-                    uint32_t b0 = 0, b1 = 0;
-                    if (has_n) {
-                      b0 = *reinterpret_cast<const uint32_t*>(crow + (k0 + j) * 32);
-                      b1 = *reinterpret_cast<const uint32_t*>(crow + (k0 + j) * 32 + 16);
-                    }
-                    if (j & 1) rp_mma_s8(acc2[t], wf[j], b0, b1);     // two independent accumulation chains
-                    else rp_mma_s8(acc[t], wf[j], b0, b1);
+                    if (j & 1) rp_mma_s8(acc2[t], wf[j], bf0[j], bf1[j]);     // two independent accumulation chains
+                    else rp_mma_s8(acc[t], wf[j], bf0[j], bf1[j]);
                   }
                 }
               }
@@ -491,7 +514,7 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
                 if (n < NS && o < O) {
                   float v = conv_i8_value(acc[t][j] + acc2[t][j], zp * wsum[o], wzp[o], s_rowsum[n] + zp * C, mult[o], bias[o]);
                   if (aoff >= 0) v = __fadd_rn(v, arena[aoff + n * ald + o]);
-                  if (temb && s0 + n < B) v = __fadd_rn(v, temb[(long long)(s0 + n) * O + o]);
+                  if (temb && s0 + n < B) v = __fadd_rn(v, tev[t][j]);
                   arena[doff + n * dld + o] = v;
                 }
               }

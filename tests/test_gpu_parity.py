@@ -281,8 +281,9 @@ def test_qconv_i8_simt_and_tcgen05_vs_oracle(shape):
 def test_qconv_epilogue_groupnorm_statistics(shape, adds):
     """GroupNorm {sum, sumsq} of the conv output from the tcgen05 epilogue (models/diffusion.py:119-127: every conv of a
     ResidualBlock feeds a GroupNorm): equal to the statistics pass over the stored output up to fp32 summation order
-    (the fp32 mean / rstd the consumers form agree to ~1 ulp), and IDENTICAL -- up to the order of the final double
-    atomics -- to the dp4a path's twin kernel, which walks the output in the same tile-tree order."""
+    (the fp32 mean / rstd the consumers form agree to ~1 ulp), and IDENTICAL -- up to the order of the double-precision
+    additions -- to the dp4a path's twin kernel (quad order, csrc/conv_common.cuh).  The fp32 part of the order is per
+    pixel, so a sample's statistics do not depend on where it sits in the batch (what batch sharding relies on)."""
     from attentiondm_b200 import ops
     B, H, W, C, O, k = shape
     x, w, bias, s, z = _conv_case(B, H, W, C, O, k, seed=3)
@@ -315,6 +316,12 @@ def test_qconv_epilogue_groupnorm_statistics(shape, adds):
     assert (mean_a - mean_w).abs().max() < 2e-7 * ref.abs().max()
     assert ((var_a - var_w).abs() / var_w).max() < 1e-6
     assert torch.allclose(ops.gn_stats(plain), want, rtol=1e-12, atol=1e-9)
+    # the last sample alone (another alignment of its rows to the 128-row tiles): same statistics
+    if B > 1 and not adds:
+        cl, rl, _ = ops.act_quant(xn[B - 1:].contiguous(), sv, zv, 8, want_codes=True, halo=(k == 3))
+        sl = torch.zeros(1, 32, 2, dtype=torch.float64, device=DEV)
+        ops.qconv_i8(cl, rl, 1, H, W, C, pack, taps, mult, azp, bias.to(DEV), None, None, gn_stats_out=sl)
+        assert torch.allclose(sl, a[B - 1:], rtol=1e-13, atol=1e-10), (sl - a[B - 1:]).abs().max()
 
 
 @pytest.mark.parametrize("bits", [(4, 4), (6, 8), (8, 4)])

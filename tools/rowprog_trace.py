@@ -1,4 +1,7 @@
-"""Debug: per-op phase timeline of the trunk program (CTA 0), via attndm_debug_set_rp_trace."""
+"""Debug: per-op phase timeline of the trunk program (CTA 0), via attndm_debug_set_rp_trace.
+The hooks are compiled in only with -DATTNDM_RP_TRACE:
+    python -m attentiondm_b200.build --variant=rp_trace
+    ATTNDM_LIB=attentiondm_b200/libattndm_b200_rp_trace.so python tools/rowprog_trace.py      # on the GPU box"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -39,7 +42,7 @@ for i, o in enumerate(ops_):
     tot.setdefault(key, [0, 0.0]); tot[key][0] += 1; tot[key][1] += dur
     if i < 40:
         if o["type"] == 5:
-            print(f"{i:3d} {key:22s} start={(r[0]-t0)/1e3:8.2f} wait_prm={(r[1]-r[0])/1e3:5.2f} A1={(r[2]-r[1])/1e3:5.2f} A2={(r[3]-r[2])/1e3:5.2f} B={(r[4]-r[3])/1e3:5.2f} C={(r[5]-r[4])/1e3:5.2f} sync={(r[6]-r[5])/1e3:5.2f} total={dur:5.2f}")
+            print(f"{i:3d} {key:22s} start={(r[0]-t0)/1e3:8.2f} wait_prm={(r[1]-r[0])/1e3:5.2f} A1={(r[2]-r[1])/1e3:5.2f} A2={(r[3]-r[2])/1e3:5.2f} Bwait={(r[7]-r[3])/1e3:5.2f} B={(r[4]-r[3])/1e3:5.2f} C={(r[5]-r[4])/1e3:5.2f} sync={(r[6]-r[5])/1e3:5.2f} total={dur:5.2f}")
         else:
             print(f"{i:3d} {key:22s} start={(r[0]-t0)/1e3:8.2f} total={dur:5.2f}")
 print("--- totals")
