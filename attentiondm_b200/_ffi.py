@@ -35,6 +35,8 @@ SIGNATURES = {
     "attndm_gn_stats_cat": [vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp],
     "attndm_act_quant_cat_fits": [i32, i32, i32, i32],
     "attndm_act_quant_cat": [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp, f32, vp, vp, i32, vp],
+    "attndm_act_quant_cat2": [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, f32, vp, vp, i32,
+                              vp, vp, vp, vp, i32, vp],
     "attndm_gn_act_quant_fits": [i32, i32, i32],
     "attndm_gn_act_quant": [vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp, vp, i32, vp, vp],
     "attndm_gn_silu": [vp, i32, i32, i32, i32, vp, vp, vp, f32, vp, vp],

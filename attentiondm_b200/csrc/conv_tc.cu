@@ -1789,7 +1789,7 @@ __global__ void __launch_bounds__(256) gn_stats_tiletree_kernel(const ConvI8Para
   const bool two = mx > mn;
   double* dst = p.gn_out + (long long)mn * (2 * kGnGroups);
   for (int u = 0; u < p.O; u += 16) {
-    double ds[4], dq[4];                              // STATS: this half's {sum, sumsq} of each row's four channels
+    double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (pix[k] < 0) continue;

@@ -39,6 +39,13 @@ struct ActQuantParams {
   long long rows_per_warp;
   const float* x2;         // CAT kernels: x = [B][H/2][W/2][C1] (read through a nearest x2 upsample), x2 = [B][H][W][C - C1]
   int C1;
+  // DUAL kernels: a second, producer-less quantizer of the same input (the shortcut conv of a ResidualBlock reads what
+  // conv1 reads behind GroupNorm+SiLU): same bit width, its own tables, outputs and layout
+  const float* scale2;
+  const float* zp2;
+  int8_t* codes2;
+  int32_t* rowsum2;
+  int halo2;
 };
 
 template <int PRE>
@@ -343,8 +350,10 @@ __device__ __forceinline__ int quant_code_i(float t, float lo, float hi) {
 // CAT: the input is the never-materialised concat of an UpBlock (models/diffusion.py:225-229 + torch.cat): channels
 // [0, C1) are p.x [B][H/2][W/2][C1] seen through a nearest-neighbour x2 upsample, channels [C1, C) are p.x2
 // [B][H][W][C - C1].  C1 % 128 == 0, so each of a lane's NQ float4 slots lies entirely in one part.
-template <int PRE, int NQ, bool A8, bool CAT>
-__global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_rows_kernel(ActQuantParams p) {
+// DUAL: every element is read ONCE and quantized twice -- by the main quantizer (PRE) and by a second one without a
+// producer (ActQuantParams::scale2 ...).
+template <int PRE, int NQ, bool A8, bool CAT, bool DUAL = false>
+__global__ void __launch_bounds__(256, DUAL ? 2 : (NQ == 1 ? 4 : NQ == 2 ? 3 : 2)) act_quant_rows_kernel(ActQuantParams p) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
   const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -376,6 +385,26 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_
     for (int i = 0; i < NQ; ++i) *reinterpret_cast<int*>(p.codes + row * Cp + ((i * 32 + lane) << 2)) = padw[i];
     if (lane == 0) p.rowsum[row] = padsum;
   };
+  float4 s4b[DUAL ? NQ : 1], z4b[DUAL ? NQ : 1];
+  int padwb[DUAL ? NQ : 1], padsumb = 0;
+  if (DUAL) {
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const int c = (i * 32 + lane) << 2;
+      s4b[i] = *reinterpret_cast<const float4*>(p.scale2 + c);
+      z4b[i] = *reinterpret_cast<const float4*>(p.zp2 + c);
+      const int a = (int)fminf(fmaxf(-z4b[i].x, p.qlo), p.qhi), b2 = (int)fminf(fmaxf(-z4b[i].y, p.qlo), p.qhi);
+      const int c2 = (int)fminf(fmaxf(-z4b[i].z, p.qlo), p.qhi), d = (int)fminf(fmaxf(-z4b[i].w, p.qlo), p.qhi);
+      padwb[i] = (a & 0xff) | ((b2 & 0xff) << 8) | ((c2 & 0xff) << 16) | ((d & 0xff) << 24);
+      padsumb += a + b2 + c2 + d;
+    }
+    padsumb = __reduce_add_sync(0xffffffffu, padsumb);
+  }
+  auto ring_row2 = [&](long long row) {
+#pragma unroll
+    for (int i = 0; i < (DUAL ? NQ : 1); ++i) *reinterpret_cast<int*>(p.codes2 + row * Cp + ((i * 32 + lane) << 2)) = padwb[i];
+    if (lane == 0) p.rowsum2[row] = padsumb;
+  };
   int cur_b = -1;
   constexpr int R = NQ <= 2 ? 4 : 2;                    // pixels per step (register budget)
   for (int ir = ir0; ir < ir1; ++ir) {
@@ -403,6 +432,8 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_
     const float* brow = CAT ? p.x2 + (long long)ir * W * C2 + (lane << 2) - p.C1 : nullptr;
     const long long rbase = p.halo ? ((long long)b * Hp + h + 1) * Wp + 1 : (long long)ir * W;   // code row of pixel w = 0
     int8_t* crow = p.codes + rbase * Cp + (lane << 2);
+    const long long rbase2 = !DUAL ? 0 : (p.halo2 ? ((long long)b * (p.H + 2) + h + 1) * (W + 2) + 1 : (long long)ir * W);
+    int8_t* crow2 = DUAL ? p.codes2 + rbase2 * Cp + (lane << 2) : nullptr;
     for (int w0 = 0; w0 < W; w0 += R) {
       float4 v[R][NQ];
 #pragma unroll
@@ -417,12 +448,33 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_
           } else {
             v[k][i] = ldg_stream(reinterpret_cast<const float4*>(brow + (long long)(w0 + k) * C2 + i * 128));
           }
-      int sums[R];
+      int sums[R], sums2[R];
 #pragma unroll
       for (int k = 0; k < R; ++k) {
-        int acc = 0;
+        int acc = 0, acc2 = 0;
 #pragma unroll
         for (int i = 0; i < NQ; ++i) {
+          if (DUAL) {                                          // the second quantizer: s2 * x - zp2, no producer
+            const float4 x4 = v[k][i];
+            const float ux = quant_t<ATTNDM_PRE_NONE>(x4.x, 0.f, 0.f, s4b[i].x, z4b[i].x);
+            const float uy = quant_t<ATTNDM_PRE_NONE>(x4.y, 0.f, 0.f, s4b[i].y, z4b[i].y);
+            const float uz = quant_t<ATTNDM_PRE_NONE>(x4.z, 0.f, 0.f, s4b[i].z, z4b[i].z);
+            const float uw = quant_t<ATTNDM_PRE_NONE>(x4.w, 0.f, 0.f, s4b[i].w, z4b[i].w);
+            int word2;
+            if (A8) {
+              const int ix = __float2int_rn(ux), iy = __float2int_rn(uy), iz = __float2int_rn(uz), iw = __float2int_rn(uw);
+              int hi2;
+              asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi2) : "r"(iw), "r"(iz));
+              asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(word2) : "r"(iy), "r"(ix), "r"(hi2));
+              acc2 = __dp4a(word2, 0x01010101, acc2);
+            } else {
+              const int ix = quant_code_i(ux, p.qlo, p.qhi), iy = quant_code_i(uy, p.qlo, p.qhi);
+              const int iz = quant_code_i(uz, p.qlo, p.qhi), iw = quant_code_i(uw, p.qlo, p.qhi);
+              acc2 += ix + iy + iz + iw;
+              word2 = (ix & 0xff) | ((iy & 0xff) << 8) | ((iz & 0xff) << 16) | (iw << 24);
+            }
+            *reinterpret_cast<int*>(crow2 + (long long)(w0 + k) * Cp + i * 128) = word2;
+          }
           float4 t = v[k][i];                                  // -> the quantizer's pre-round values s * pre(x) - zp
           t.x = quant_t<PRE>(t.x, ga[i].x, gb[i].x, s4[i].x, z4[i].x);
           t.y = quant_t<PRE>(t.y, ga[i].y, gb[i].y, s4[i].y, z4[i].y);
@@ -447,14 +499,20 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_
           *reinterpret_cast<int*>(crow + (long long)(w0 + k) * Cp + i * 128) = word;
         }
         sums[k] = acc;
+        sums2[k] = acc2;
       }
-      int mine = 0;
+      int mine = 0, mine2 = 0;
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         const int t = __reduce_add_sync(0xffffffffu, sums[k]);
         if (lane == k) mine = t;
+        if (DUAL) {
+          const int t2 = __reduce_add_sync(0xffffffffu, sums2[k]);
+          if (lane == k) mine2 = t2;
+        }
       }
       if (lane < R) p.rowsum[rbase + w0 + lane] = mine;
+      if (DUAL && lane < R) p.rowsum2[rbase2 + w0 + lane] = mine2;
     }
     if (p.halo) {                                        // the ring next to this image row
       ring_row(rbase - 1);
@@ -463,6 +521,15 @@ __global__ void __launch_bounds__(256, NQ == 1 ? 4 : NQ == 2 ? 3 : 2) act_quant_
         for (int w = 0; w < Wp; ++w) ring_row(rbase - 1 - Wp + w);
       if (h == p.H - 1)
         for (int w = 0; w < Wp; ++w) ring_row(rbase - 1 + Wp + w);
+    }
+    if (DUAL && p.halo2) {
+      const int Wp2 = W + 2;
+      ring_row2(rbase2 - 1);
+      ring_row2(rbase2 + W);
+      if (h == 0)
+        for (int w = 0; w < Wp2; ++w) ring_row2(rbase2 - 1 - Wp2 + w);
+      if (h == p.H - 1)
+        for (int w = 0; w < Wp2; ++w) ring_row2(rbase2 - 1 + Wp2 + w);
     }
   }
 }
@@ -1217,18 +1284,24 @@ int attndm_act_quant_cat_fits(int H, int W, int C1, int C2) {
           (C / kGnGroups) % 4 == 0 && C1 % (C / kGnGroups) == 0) ? 1 : 0;
 }
 
-int attndm_act_quant_cat(const float* xa, int C1, const float* xb, int C2, int B, int H, int W, const float* scale,
-                         const float* zp, int a_bit, int pre_op, const double* gn_stats, const float* gn_gamma,
-                         const float* gn_beta, float gn_eps, int8_t* codes, int32_t* rowsum, int rows_layout,
-                         void* stream) {
+static int act_quant_cat_impl(const float* xa, int C1, const float* xb, int C2, int B, int H, int W, const float* scale,
+                              const float* zp, int a_bit, int pre_op, const double* gn_stats, const float* gn_gamma,
+                              const float* gn_beta, float gn_eps, int8_t* codes, int32_t* rowsum, int rows_layout,
+                              const float* scale2, const float* zp2, int8_t* codes2, int32_t* rowsum2, int rows_layout2,
+                              void* stream) {
+  const bool dual = scale2 != nullptr;
   ATTNDM_CHECK_ARG(xa && xb && B > 0 && H > 0 && W > 0 && scale && zp && codes && rowsum && a_bit >= 2 && a_bit <= 8,
                    "act_quant_cat: bad args");
   ATTNDM_CHECK_ARG(rows_layout == ATTNDM_ROWS_PLAIN || rows_layout == ATTNDM_ROWS_HALO, "act_quant_cat: bad layout");
   ATTNDM_CHECK_ARG(pre_op == ATTNDM_PRE_NONE || pre_op == ATTNDM_PRE_SILU || (pre_op == ATTNDM_PRE_GN_SILU && gn_stats && gn_gamma && gn_beta),
                    "act_quant_cat: bad pre-op");
+  ATTNDM_CHECK_ARG(!dual || (zp2 && codes2 && rowsum2 && codes2 != codes && rowsum2 != rowsum &&
+                             (rows_layout2 == ATTNDM_ROWS_PLAIN || rows_layout2 == ATTNDM_ROWS_HALO)),
+                   "act_quant_cat2: bad second quantizer");
   const int C = C1 + C2;
   if (!attndm_act_quant_cat_fits(H, W, C1, C2) || (long long)B * H * W * C >= (1LL << 31) ||
-      ((((uintptr_t)xa | (uintptr_t)xb | (uintptr_t)codes | (uintptr_t)scale | (uintptr_t)zp) & 15) != 0)) {
+      ((((uintptr_t)xa | (uintptr_t)xb | (uintptr_t)codes | (uintptr_t)scale | (uintptr_t)zp | (uintptr_t)scale2 |
+         (uintptr_t)zp2 | (uintptr_t)codes2) & 15) != 0)) {
     set_error("act_quant_cat: shape %dx%dx(%d+%d) not supported (see attndm_act_quant_cat_fits)", H, W, C1, C2);
     return ATTNDM_ERR_UNSUPPORTED;
   }
@@ -1242,31 +1315,55 @@ int attndm_act_quant_cat(const float* xa, int C1, const float* xb, int C2, int B
   p.codes = codes; p.rowsum = rowsum; p.halo = rows_layout == ATTNDM_ROWS_HALO ? 1 : 0;
   p.y = nullptr;
   p.rows = p.halo ? (long long)B * (H + 2) * (W + 2) : (long long)B * H * W;
+  p.scale2 = scale2; p.zp2 = zp2; p.codes2 = codes2; p.rowsum2 = rowsum2;
+  p.halo2 = rows_layout2 == ATTNDM_ROWS_HALO ? 1 : 0;
   const int nimg = B * H;
-  int w2 = kNumSMs * 8 * (C == 256 ? 3 : 2);
+  int w2 = kNumSMs * 8 * (dual ? 2 : (C == 256 ? 3 : 2));
   if (w2 > nimg) w2 = nimg;
   p.rows_per_warp = (nimg + w2 - 1) / w2;
   w2 = (nimg + (int)p.rows_per_warp - 1) / (int)p.rows_per_warp;
   const int nb = cdiv(w2, 8);
   cudaStream_t st = (cudaStream_t)stream;
-#define ATTNDM_AQ_CAT_N(PREV, NQV)                                                                                  \
+#define ATTNDM_AQ_CAT_N(PREV, NQV, DUALV)                                                                           \
   do {                                                                                                              \
-    if (a_bit == 8) launch_pdl(act_quant_rows_kernel<PREV, NQV, true, true>, dim3(nb), dim3(256), 0, st, p);        \
-    else launch_pdl(act_quant_rows_kernel<PREV, NQV, false, true>, dim3(nb), dim3(256), 0, st, p);                  \
+    if (a_bit == 8) launch_pdl(act_quant_rows_kernel<PREV, NQV, true, true, DUALV>, dim3(nb), dim3(256), 0, st, p); \
+    else launch_pdl(act_quant_rows_kernel<PREV, NQV, false, true, DUALV>, dim3(nb), dim3(256), 0, st, p);           \
   } while (0)
-#define ATTNDM_AQ_CAT(PREV)                                                                                         \
+#define ATTNDM_AQ_CAT(PREV, DUALV)                                                                                  \
   do {                                                                                                              \
-    if (C == 256) ATTNDM_AQ_CAT_N(PREV, 2);                                                                         \
-    else if (C == 384) ATTNDM_AQ_CAT_N(PREV, 3);                                                                    \
-    else ATTNDM_AQ_CAT_N(PREV, 4);                                                                                  \
+    if (C == 256) ATTNDM_AQ_CAT_N(PREV, 2, DUALV);                                                                  \
+    else if (C == 384) ATTNDM_AQ_CAT_N(PREV, 3, DUALV);                                                             \
+    else ATTNDM_AQ_CAT_N(PREV, 4, DUALV);                                                                           \
   } while (0)
-  if (pre_op == ATTNDM_PRE_GN_SILU) ATTNDM_AQ_CAT(ATTNDM_PRE_GN_SILU);
-  else if (pre_op == ATTNDM_PRE_SILU) ATTNDM_AQ_CAT(ATTNDM_PRE_SILU);
-  else ATTNDM_AQ_CAT(ATTNDM_PRE_NONE);
+  if (dual) {
+    // the pair a ResidualBlock asks for: conv1 behind GroupNorm+SiLU and the shortcut conv on the raw input
+    ATTNDM_CHECK_ARG(pre_op == ATTNDM_PRE_GN_SILU, "act_quant_cat2: the main quantizer must be the GroupNorm+SiLU one");
+    ATTNDM_AQ_CAT(ATTNDM_PRE_GN_SILU, true);
+  } else if (pre_op == ATTNDM_PRE_GN_SILU) ATTNDM_AQ_CAT(ATTNDM_PRE_GN_SILU, false);
+  else if (pre_op == ATTNDM_PRE_SILU) ATTNDM_AQ_CAT(ATTNDM_PRE_SILU, false);
+  else ATTNDM_AQ_CAT(ATTNDM_PRE_NONE, false);
 #undef ATTNDM_AQ_CAT_N
 #undef ATTNDM_AQ_CAT
   ATTNDM_CUDA_LAUNCH_CHECK("act_quant_cat");
   return ATTNDM_OK;
+}
+
+int attndm_act_quant_cat(const float* xa, int C1, const float* xb, int C2, int B, int H, int W, const float* scale,
+                         const float* zp, int a_bit, int pre_op, const double* gn_stats, const float* gn_gamma,
+                         const float* gn_beta, float gn_eps, int8_t* codes, int32_t* rowsum, int rows_layout,
+                         void* stream) {
+  return act_quant_cat_impl(xa, C1, xb, C2, B, H, W, scale, zp, a_bit, pre_op, gn_stats, gn_gamma, gn_beta, gn_eps, codes,
+                            rowsum, rows_layout, nullptr, nullptr, nullptr, nullptr, ATTNDM_ROWS_PLAIN, stream);
+}
+
+int attndm_act_quant_cat2(const float* xa, int C1, const float* xb, int C2, int B, int H, int W, const float* scale,
+                          const float* zp, int a_bit, const double* gn_stats, const float* gn_gamma,
+                          const float* gn_beta, float gn_eps, int8_t* codes, int32_t* rowsum, int rows_layout,
+                          const float* scale2, const float* zp2, int8_t* codes2, int32_t* rowsum2, int rows_layout2,
+                          void* stream) {
+  ATTNDM_CHECK_ARG(scale2 != nullptr, "act_quant_cat2: null second scale");
+  return act_quant_cat_impl(xa, C1, xb, C2, B, H, W, scale, zp, a_bit, ATTNDM_PRE_GN_SILU, gn_stats, gn_gamma, gn_beta,
+                            gn_eps, codes, rowsum, rows_layout, scale2, zp2, codes2, rowsum2, rows_layout2, stream);
 }
 
 int attndm_gn_act_quant_fits(int H, int W, int C) {

@@ -72,7 +72,15 @@ class ResidualBlock(nn.Module):
         out_stats: the block's output goes straight into a GroupNorm (conv2 then also emits its statistics)."""
         if self.training and self.dropout.p > 0:
             raise NotImplementedError("attentiondm_b200 runs the eval-mode path (model.eval()); dropout is identity")
-        h = self.conv1.forward_fused(x, ops.PRE_GN_SILU, _gn_args(self.norm1, x), want_stats=True)
+        gn1 = _gn_args(self.norm1, x)
+        if isinstance(x, ops.CatView) and self.in_channels != self.out_channels:
+            # UpBlock.res1: conv1 and the shortcut conv quantize the same concat -- one pass over it for both
+            sc_conv = self.conv_shortcut if self.use_conv_shortcut else self.nin_shortcut
+            if isinstance(self.conv1, QConv2d) and isinstance(sc_conv, QConv2d):
+                ra, rb = self.conv1.quant_request(x.shape[1], x.shape[2]), sc_conv.quant_request(x.shape[1], x.shape[2])
+                if ra is not None and rb is not None:
+                    x.prepare_pair(ra, rb, gn1)
+        h = self.conv1.forward_fused(x, ops.PRE_GN_SILU, gn1, want_stats=True)
         gn2 = _gn_args(self.norm2, h)
         if self.in_channels != self.out_channels:
             sc = (self.conv_shortcut if self.use_conv_shortcut else self.nin_shortcut).forward_fused(x)

@@ -91,6 +91,34 @@ class CatView:
             self._full = upsample_concat(self.lo, self.skip)
         return self._full
 
+    # -- the two quantizers of UpBlock.res1 (conv1 behind GroupNorm+SiLU, the shortcut conv on the raw concat) in one
+    #    pass over the input (attndm_act_quant_cat2); act_quant() picks the prepared codes up by their table pointers
+    def prepare_pair(self, main, second, gn: "GnArgs"):
+        """main / second: (scale, zp, a_bit, halo) of the GroupNorm+SiLU quantizer and of the producer-less one."""
+        (s1, z1, a1, h1), (s2, z2, a2, h2) = main, second
+        if a1 != a2 or gn is None or gn.stats is None or os.environ.get("ATTNDM_CAT_DUAL", "1") == "0":
+            return False
+        B, H, W, Cc = self.shape
+        Cp = cp_of(Cc)
+        out = []
+        for halo in (h1, h2):
+            rows = B * (H + 2) * (W + 2) if halo else B * H * W
+            out.append((torch.empty(rows, Cp, dtype=torch.int8, device=self.device),
+                        torch.empty(rows, dtype=torch.int32, device=self.device)))
+        call("attndm_act_quant_cat2", ptr(self.lo), self.lo.shape[-1], ptr(self.skip), self.skip.shape[-1], B, H, W,
+             ptr(s1), ptr(z1), int(a1), ptr(gn.stats), ptr(gn.gamma), ptr(gn.beta), float(gn.eps),
+             ptr(out[0][0]), ptr(out[0][1]), ROWS_HALO if h1 else ROWS_PLAIN,
+             ptr(s2), ptr(z2), ptr(out[1][0]), ptr(out[1][1]), ROWS_HALO if h2 else ROWS_PLAIN, stream())
+        self._prepared = {(s1.data_ptr(), z1.data_ptr(), int(a1), PRE_GN_SILU, bool(h1)): out[0],
+                          (s2.data_ptr(), z2.data_ptr(), int(a2), PRE_NONE, bool(h2)): out[1]}
+        return True
+
+    def take_prepared(self, scale, zp, a_bit, pre, halo):
+        prep = getattr(self, "_prepared", None)
+        if not prep:
+            return None
+        return prep.pop((scale.data_ptr(), zp.data_ptr(), int(a_bit), int(pre), bool(halo)), None)
+
     def cpu(self):
         return self.materialize().cpu()
 
@@ -169,6 +197,9 @@ def act_quant(x: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, a_bit: int
               gn: Optional[GnArgs] = None, want_codes: bool = True, halo: bool = False, want_f32: bool = False):
     """Returns (codes int8 [rows, Cp] | None, rowsum int32 [rows] | None, y fp32 NHWC | None)."""
     if isinstance(x, CatView):
+        hit = x.take_prepared(scale, zp, a_bit, pre, halo) if want_codes and not want_f32 else None
+        if hit is not None:                                  # both quantizers of this concat came out of one pass
+            return hit[0], hit[1], None
         if want_codes and not want_f32 and (pre != PRE_GN_SILU or gn.stats is not None):
             B, H, W, Cc = x.shape
             rows = B * (H + 2) * (W + 2) if halo else B * H * W

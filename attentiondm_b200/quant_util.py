@@ -403,6 +403,23 @@ class QConv2d(QModule):
         """Engine hook: `row` is this layer's slice of the staged current-step table."""
         self._staged = row
 
+    def quant_request(self, H: int, W: int):
+        """(scale, zp, a_bit, halo) this layer's next forward_fused will quantize its input with, or None when that
+        call does not take the integer path (calibration, fp32 fallback).  Does not advance index_seq."""
+        if self._calibrate:
+            return None
+        t = 0 if self.index_seq >= self.args.timesteps else self.index_seq
+        tb = self._tables()
+        lay = tb["lay"]
+        if self._staged is not None:
+            row, use_i8 = self._staged, (not self.force_f32) and all(tb["i8_ok"])
+        else:
+            row, use_i8 = tb["tab"][t], (not self.force_f32) and tb["i8_ok"][t]
+        if not use_i8:
+            return None
+        taps = 1 if (self.taps == 9 and H == 1 and W == 1) else self.taps
+        return row[lay["scale"]:], row[lay["zp"]:], self._a_bit, taps == 9
+
     def forward_fused(self, x, pre=ops.PRE_NONE, gn: Optional[ops.GnArgs] = None, residual=None, temb=None,
                       want_stats=False):
         """x: NHWC fp32 CUDA.  residual: NHWC like the output.  temb: [B, O].  want_stats: the output feeds a

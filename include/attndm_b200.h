@@ -95,6 +95,15 @@ int attndm_act_quant_cat(const float* xa, int C1, const float* xb, int C2, int B
                          const float* scale, const float* zp, int a_bit, int pre_op, const double* gn_stats,
                          const float* gn_gamma, const float* gn_beta, float gn_eps, int8_t* codes,
                          int32_t* rowsum, int rows_layout, void* stream);
+/* Both quantizers of UpBlock.res1 in ONE pass over the concat: (codes, rowsum) = the GroupNorm+SiLU quantizer of
+ * res1.conv1 (models/diffusion.py:119-122), (codes2, rowsum2) = the producer-less quantizer of res1.nin_shortcut /
+ * conv_shortcut (:131-134) with its own tables and layout; same bit width.  Bit-identical to two attndm_act_quant_cat
+ * calls (pre_op = ATTNDM_PRE_GN_SILU, then ATTNDM_PRE_NONE); the 200 MB input is read once instead of twice. */
+int attndm_act_quant_cat2(const float* xa, int C1, const float* xb, int C2, int B, int H, int W,
+                          const float* scale, const float* zp, int a_bit, const double* gn_stats,
+                          const float* gn_gamma, const float* gn_beta, float gn_eps, int8_t* codes,
+                          int32_t* rowsum, int rows_layout, const float* scale2, const float* zp2,
+                          int8_t* codes2, int32_t* rowsum2, int rows_layout2, void* stream);
 
 /* GroupNorm(32)+SiLU+quantize in ONE kernel (statistics computed in-kernel, one CTA per sample with
  * the sample's [H*W][C] tile resident in shared memory): same outputs as attndm_gn_stats followed by

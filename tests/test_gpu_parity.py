@@ -476,6 +476,22 @@ def test_upblock_concat_read_in_place(B, H, W, C1, C2, a_bit):
     c_v, _, _ = ops.act_quant(view, sv, zv, a_bit, ops.PRE_GN_SILU, gn_v, want_codes=True, halo=True)
     c_f, _, _ = ops.act_quant(full, sv, zv, a_bit, ops.PRE_GN_SILU, ops.GnArgs(st_f, gamma, beta, 1e-6), want_codes=True, halo=True)
     assert ((c_v.int() - c_f.int()).abs() > 0).float().mean() < 1e-6
+    # both quantizers of UpBlock.res1 in one pass (attndm_act_quant_cat2): conv1 behind GroupNorm+SiLU and the shortcut
+    # conv on the raw concat, each with its own tables and layout -- bit-identical to the two separate passes
+    s2, z2 = R.asym_params(a_bit, torch.tensor(-2.5), torch.tensor(3.5))
+    sv2 = torch.full((C,), float(s2), device=DEV) * (1 + 0.01 * torch.arange(C, device=DEV) / C)
+    zv2 = torch.full((C,), float(z2), device=DEV)
+    gn = ops.GnArgs(st_f, gamma, beta, 1e-6)
+    for h1, h2 in ((True, False), (True, True), (False, False)):
+        v2 = ops.CatView(lo, skip)
+        assert v2.prepare_pair((sv, zv, a_bit, h1), (sv2, zv2, a_bit, h2), gn)
+        ca, ra, _ = ops.act_quant(v2, sv, zv, a_bit, ops.PRE_GN_SILU, gn, want_codes=True, halo=h1)
+        cb, rb, _ = ops.act_quant(v2, sv2, zv2, a_bit, ops.PRE_NONE, None, want_codes=True, halo=h2)
+        assert not v2._prepared                                  # both came from the prepared pair
+        wa = ops.act_quant(full, sv, zv, a_bit, ops.PRE_GN_SILU, gn, want_codes=True, halo=h1)
+        wb = ops.act_quant(full, sv2, zv2, a_bit, ops.PRE_NONE, None, want_codes=True, halo=h2)
+        assert torch.equal(ca, wa[0]) and torch.equal(ra, wa[1]), (h1, h2)
+        assert torch.equal(cb, wb[0]) and torch.equal(rb, wb[1]), (h1, h2)
 
 
 @pytest.mark.gpu
