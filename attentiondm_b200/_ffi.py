@@ -61,7 +61,8 @@ SIGNATURES = {
     "attndm_noise_mix": [vp, vp, vp, vp, i64, vp],
     "attndm_sq_err": [vp, vp, i32, i64, vp, vp],
     "attndm_alpha_entropy_grad": [vp, i32, i32, f32, vp, vp, vp],
-    "attndm_rowprog": [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp],
+    "attndm_rowprog": [vp, vp, i32, i32, i32, i32, i32, i32, vp, i64, vp, i32, vp],
+    "attndm_bcast_rows": [vp, vp, i32, i32, i32, vp, vp],
     "attndm_rowprog_smem_bytes": [i32, i32, i32, i32],
     "attndm_rowprog_packed_weight_bytes": [i32, i32],
     "attndm_rowprog_pack_weights": [vp, i32, i32, vp, vp],

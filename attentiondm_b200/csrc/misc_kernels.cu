@@ -220,6 +220,16 @@ __global__ void stage_copy_kernel(const float* __restrict__ table, long long n, 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[i];
 }
+// the current step's rows of the staged table fanned out to [B][width] tensors (attndm_bcast_rows)
+__global__ void bcast_rows_kernel(const float* __restrict__ cur, const int32_t* __restrict__ desc, int B, float* __restrict__ dst) {
+  pdl_enter();
+  const int off_dst = desc[3 * blockIdx.y], off_src = desc[3 * blockIdx.y + 1], width = desc[3 * blockIdx.y + 2];
+  const int n = B * width;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = i % width;
+    dst[off_dst + i] = cur[off_src + c];
+  }
+}
 __global__ void stage_advance_kernel(int* step, int T) {
   pdl_enter();
   int s = *step + 1;
@@ -434,6 +444,14 @@ int attndm_alpha_entropy_grad(const float* alpha_t, int G, int C, float weight, 
   ATTNDM_CHECK_ARG(alpha_t && grad && G > 0 && G <= 32 && C > 0, "alpha_entropy_grad: bad args (1 <= G <= 32)");
   launch_pdl(alpha_entropy_grad_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, alpha_t, G, C, weight, grad, value);
   ATTNDM_CUDA_LAUNCH_CHECK("alpha_entropy_grad");
+  return ATTNDM_OK;
+}
+
+int attndm_bcast_rows(const float* cur, const int32_t* desc, int n, int B, int max_width, float* dst, void* stream) {
+  ATTNDM_CHECK_ARG(cur && desc && dst && n > 0 && B > 0 && max_width > 0 && (long long)B * max_width < (1LL << 31), "bcast_rows: bad args");
+  launch_pdl(bcast_rows_kernel, dim3((unsigned)cdiv((long long)B * max_width, 256), (unsigned)n), dim3(256), 0, (cudaStream_t)stream,
+             cur, desc, B, dst);
+  ATTNDM_CUDA_LAUNCH_CHECK("bcast_rows");
   return ATTNDM_OK;
 }
 

@@ -99,8 +99,8 @@ __device__ __forceinline__ void rp_gn_pair(const float* x, double inv_n, float e
 #pragma unroll
   for (int i = 0; i < CPG; ++i) {
     const double v = (double)x[i];
-    a[i] = 0.0 + v;
-    q[i] = 0.0 + v * v;
+    a[i] = v;              // (the reduction's "0.0 + v" is v: nine double adds less per pair on a slow FP64 pipe)
+    q[i] = v * v;
   }
 #pragma unroll
   for (int o = CPG >> 1; o > 0; o >>= 1)
@@ -136,7 +136,7 @@ __device__ __forceinline__ void rp_trace(int, int) {}
 template <int NS>
 __global__ void __launch_bounds__(RP_THREADS, 1)
 rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__ prog_start, int B, int arena_floats,
-               int cp_max, int pbuf_floats, const float* __restrict__ cur, const RpExt ext) {
+               int cp_max, int pbuf_floats, const float* __restrict__ cur_base, long long cur_cta_stride, const RpExt ext) {
   extern __shared__ __align__(16) uint8_t rp_smem[];
   __shared__ __align__(16) attndm_rowop s_op[2];       // the current and the next op, staged from global memory
   __shared__ float s_mean[NS * kGnGroups], s_rstd[NS * kGnGroups];
@@ -153,6 +153,9 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s0 = blockIdx.x * NS;
+  // the table row this CTA's samples are quantized with: the staged current-step row, or (cur_cta_stride != 0) row
+  // blockIdx.x of a whole [T][width] table -- the time path of ALL sampler steps in one launch (engine.py)
+  const float* const cur = cur_base + (long long)blockIdx.x * cur_cta_stride;
   const attndm_rowop* prog = ops + prog_start[blockIdx.y];
   constexpr int OPW = (int)(sizeof(attndm_rowop) / 4);
   if (tid < OPW) reinterpret_cast<int*>(&s_op[0])[tid] = reinterpret_cast<const int*>(prog)[tid];
@@ -581,13 +584,14 @@ long long attndm_rowprog_packed_weight_bytes(int O, int Cp) {
 }
 
 int attndm_rowprog(const attndm_rowop* ops, const int32_t* prog_start, int nprog, int B, int ns, int arena_floats,
-                   int cp_max, int pbuf_floats, const float* cur, const void* const* ext_ptrs, int n_ext,
-                   void* stream) {
+                   int cp_max, int pbuf_floats, const float* cur, long long cur_cta_stride, const void* const* ext_ptrs,
+                   int n_ext, void* stream) {
   ATTNDM_CHECK_ARG(ops && prog_start && nprog > 0 && B > 0, "rowprog: bad args");
   ATTNDM_CHECK_ARG(ns == 2 || ns == 4 || ns == 8, "rowprog: ns must be 2, 4 or 8");
   ATTNDM_CHECK_ARG(arena_floats > 0 && (arena_floats & 3) == 0 && cp_max > 0 && (cp_max & 15) == 0, "rowprog: bad arena / cp_max");
   ATTNDM_CHECK_ARG(pbuf_floats >= 4 && (pbuf_floats & 3) == 0, "rowprog: bad pbuf_floats");
   ATTNDM_CHECK_ARG(n_ext >= 0 && n_ext <= 4 && (n_ext == 0 || ext_ptrs), "rowprog: at most 4 external pointers");
+  ATTNDM_CHECK_ARG(cur && cur_cta_stride >= 0 && (cur_cta_stride & 3) == 0, "rowprog: bad table / per-CTA table stride");
   RpExt ext = {{nullptr, nullptr, nullptr, nullptr}};
   for (int i = 0; i < n_ext; ++i) ext.p[i] = ext_ptrs[i];
   const int smem = rp_smem_bytes(ns, arena_floats, cp_max, pbuf_floats);
@@ -595,7 +599,7 @@ int attndm_rowprog(const attndm_rowop* ops, const int32_t* prog_start, int nprog
   dim3 grid(cdiv(B, ns), nprog);
   static std::once_flag once2, once4, once8;
   static cudaError_t attr_err = cudaSuccess;
-  auto raise = [](void (*k)(const attndm_rowop*, const int32_t*, int, int, int, int, const float*, const RpExt)) {
+  auto raise = [](void (*k)(const attndm_rowop*, const int32_t*, int, int, int, int, const float*, long long, const RpExt)) {
     cudaError_t r = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (r != cudaSuccess) attr_err = r;
   };
@@ -603,9 +607,9 @@ int attndm_rowprog(const attndm_rowop* ops, const int32_t* prog_start, int nprog
   else if (ns == 4) { std::call_once(once4, raise, rowprog_kernel<4>); }
   else { std::call_once(once8, raise, rowprog_kernel<8>); }
   if (attr_err != cudaSuccess) { set_error("rowprog: cannot raise dynamic smem: %s", cudaGetErrorString(attr_err)); return ATTNDM_ERR_CUDA; }
-  if (ns == 2) launch_pdl(rowprog_kernel<2>, grid, dim3(RP_THREADS), smem, (cudaStream_t)stream, ops, prog_start, B, arena_floats, cp_max, pbuf_floats, cur, ext);
-  else if (ns == 4) launch_pdl(rowprog_kernel<4>, grid, dim3(RP_THREADS), smem, (cudaStream_t)stream, ops, prog_start, B, arena_floats, cp_max, pbuf_floats, cur, ext);
-  else launch_pdl(rowprog_kernel<8>, grid, dim3(RP_THREADS), smem, (cudaStream_t)stream, ops, prog_start, B, arena_floats, cp_max, pbuf_floats, cur, ext);
+  if (ns == 2) launch_pdl(rowprog_kernel<2>, grid, dim3(RP_THREADS), smem, (cudaStream_t)stream, ops, prog_start, B, arena_floats, cp_max, pbuf_floats, cur, cur_cta_stride, ext);
+  else if (ns == 4) launch_pdl(rowprog_kernel<4>, grid, dim3(RP_THREADS), smem, (cudaStream_t)stream, ops, prog_start, B, arena_floats, cp_max, pbuf_floats, cur, cur_cta_stride, ext);
+  else launch_pdl(rowprog_kernel<8>, grid, dim3(RP_THREADS), smem, (cudaStream_t)stream, ops, prog_start, B, arena_floats, cp_max, pbuf_floats, cur, cur_cta_stride, ext);
   ATTNDM_CUDA_LAUNCH_CHECK("rowprog");
   return ATTNDM_OK;
 }

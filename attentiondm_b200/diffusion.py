@@ -99,11 +99,11 @@ def _time_mlp(time_emb_dim, out_channels, quantization, sequence, args):
 class _TimeBlock(nn.Module):
     def _temb(self, time_emb):
         """SiLU -> QConv2d 1x1 on [B,1,1,temb] -> [B, out] (models/diffusion.py:157-161)."""
-        if self.time_mlp is None or time_emb is None:
-            return None
         pre = getattr(self, "_temb_fused", None)        # written by the fused time_mlp launch (rowprog.py)
         if pre is not None:
             return pre
+        if self.time_mlp is None or time_emb is None:
+            return None
         y = self.time_mlp[1].forward_fused(time_emb, ops.PRE_SILU)
         return y.view(y.shape[0], -1)
 
@@ -292,17 +292,26 @@ class Model(nn.Module):
             return ops.conv1x1_f32_tc(x, cache[id(lin)][1], lin.bias.detach())
         return ops.conv_f32(x, lin.weight.detach().unsqueeze(1).contiguous(), lin.bias.detach())
 
-    def _forward_nhwc(self, x, t):
-        B = x.shape[0]
+    def time_embedding(self, t):
+        """t [B] -> [B, 1, 1, 4 * time_embed_dim] (models/diffusion.py:347-351, 273-277)."""
+        B = t.shape[0]
         t_emb = ops.timestep_embedding(t, self.config.model.time_embed_dim).view(B, 1, 1, -1)
-        # the two un-quantized Linears (models/diffusion.py:273-277) as batch-invariant fp32 1x1 convs
+        # the two un-quantized Linears as batch-invariant fp32 1x1 convs
         l0, l2 = self.time_embed[0], self.time_embed[2]
         t_emb = self._linear_f32(t_emb, l0)
         t_emb = ops.silu(t_emb)
-        t_emb = self._linear_f32(t_emb, l2)
+        return self._linear_f32(t_emb, l2)
+
+    def _forward_nhwc(self, x, t):
         fp = getattr(self, "_fused", None)                 # rowprog.FusedPlans, set by the CUDA-graph engine
-        if fp is not None:
-            fp.run_time_mlps(t_emb, self._fused_cur)
+        if fp is not None and fp.hoisted:
+            # the time path of this step was evaluated at the start of the pass (engine.py): fan its rows out
+            t_emb = None
+            fp.bcast_temb(self._fused_cur)
+        else:
+            t_emb = self.time_embedding(t)
+            if fp is not None:
+                fp.run_time_mlps(t_emb, self._fused_cur)
         h = self.init_conv.forward_fused(x)
         skips = [h]
         if fp is not None and fp.trunk_plan is not None:

@@ -9,6 +9,8 @@ counter -- so a single graph serves all steps with no host work in the loop.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -93,8 +95,26 @@ class SamplerEngine:
             if hasattr(model, "materialize_lazy_layers"):
                 model.materialize_lazy_layers()
             sl = {id(m): s_ for m, s_ in zip(self.layers, self.slices)}
-            self.fused_parts = [rowprog.build(model, self.B, sl, dev)]
+            self.fused_parts = [rowprog.build(model, self.B, sl, dev, T=self.T)]
             self.fused = self.fused_parts[0]
+        # The time path (timestep embedding -> time_embed Linears -> every block's time_mlp; models/diffusion.py:
+        # 157-161,273-277,347-351) depends on the step alone -- generalized_steps gives every sample of the batch the
+        # same t (functions/denoising.py:26) -- so the captured step does not evaluate it B times: at the start of each
+        # pass (load_input) it is evaluated ONCE per step for all T steps (two launches of the same kernels, each
+        # step's time_mlp convs reading that step's table row), the results become extra table columns, and the step
+        # fans the staged row out to the [B, O] tensors its consumers read.  Same kernels, same per-row arithmetic:
+        # bit-identical to the per-step evaluation (ATTNDM_HOIST_TIME=0 restores it).
+        self.hoist = False
+        fp = self.fused
+        if (fp is not None and fp.time_all is not None and os.environ.get("ATTNDM_HOIST_TIME", "1") != "0"
+                and hasattr(model, "time_embedding")):
+            w0 = self.table.shape[1]
+            pad = (-w0) % 4
+            self.temb_off = w0 + pad
+            self.table = torch.cat([self.table, torch.zeros(self.T, pad + fp.temb_cols, device=dev)], dim=1).contiguous()
+            self.cur = torch.zeros(self.table.shape[1], dtype=torch.float32, device=dev)
+            fp.set_hoisted(self.temb_off)
+            self.hoist = True
 
     def _versions(self):
         return tuple((m._tab_key, m._pack_key) for m in self.layers)
@@ -176,6 +196,18 @@ class SamplerEngine:
         if self.start_index != self._table_roll:
             raise RuntimeError("SamplerEngine: index_seq moved since the engine was built; rebuild it "
                                "(SamplerEngine.for_model) or call model.reset_index_seq()")
+        if self.hoist:
+            self._time_path_all_steps()
+
+    def _time_path_all_steps(self):
+        """The time path of every sampler step of this pass (see __init__), on the current stream."""
+        fp = self.fused
+        t_all = self.table[:, self.t_off].contiguous()                      # t of step k = table[k, t_off]
+        te = self.model.time_embedding(t_all)                               # [T, 1, 1, ted4]
+        ted4 = te.shape[-1]
+        te2 = te.view(self.T, 1, ted4).expand(self.T, 2, ted4).reshape(2 * self.T, ted4).contiguous()
+        cols = fp.run_time_all(te2, self.table)
+        self.table[:, self.temb_off:self.temb_off + fp.temb_cols].copy_(cols)
 
     def run_loaded(self, steps=None):
         """Replay `steps` (default T) denoising steps on the already loaded input; async."""

@@ -259,7 +259,7 @@ class Plan:
         self.programs.append(p)
         return p
 
-    def finalize(self, B: int):
+    def finalize(self, B: int, force_ns: Optional[int] = None):
         peak = max(p.arena.peak for p in self.programs)
         self.cp_max = max(p.cp_max for p in self.programs)
         self.pbuf = max(p.pbuf for p in self.programs)
@@ -274,6 +274,10 @@ class Plan:
         target = int(os.environ.get("ATTNDM_ROWPROG_CTAS", "128"))
         while ns > 2 and (B + ns - 1) // ns * len(self.programs) < target:
             ns //= 2
+        if force_ns is not None:
+            if force_ns > ns:
+                raise Unfusable("program does not fit in shared memory at the requested samples per CTA")
+            ns = force_ns
         self.ns = ns
         self.arena_floats = peak * ns
         recs, starts = [], []
@@ -287,10 +291,12 @@ class Plan:
         self.n_ops = len(recs)
         return self
 
-    def run(self, B: int, cur: torch.Tensor, ext: List[torch.Tensor]):
+    def run(self, B: int, cur: torch.Tensor, ext: List[torch.Tensor], cur_cta_stride: int = 0):
+        """cur_cta_stride (floats): 0 = every sample reads the staged row `cur`; else CTA x reads row x of the table."""
         arr = (C.c_void_p * 4)(*([t.data_ptr() for t in ext] + [None] * (4 - len(ext))))
         _ffi.call("attndm_rowprog", _ffi.ptr(self.dev_ops), _ffi.ptr(self.dev_start), len(self.programs), B, self.ns,
-                  self.arena_floats, self.cp_max, self.pbuf, _ffi.ptr(cur), arr, len(ext), _ffi.stream())
+                  self.arena_floats, self.cp_max, self.pbuf, _ffi.ptr(cur), int(cur_cta_stride), arr, len(ext),
+                  _ffi.stream())
 
 
 # ---------------------------------------------------------------------------------------------
@@ -352,9 +358,49 @@ class FusedPlans:
     n_up: int                       # up_blocks[:n_up] are inside the trunk
     trunk_out_ch: int
     B: int
+    # The time path hoisted out of the step (engine.py): every time_mlp for ALL T sampler steps in one launch
+    # (time_all: two identical samples per step, CTA x = step x, reading row x of the whole table), its results kept
+    # as table columns and fanned out per step to the [B, O] tensors of `temb` (views of temb_flat).
+    time_all: Optional[Plan] = None
+    temb_all: Optional[list] = None      # [2T, O] output of each time_mlp, in the order of temb
+    temb_flat: Optional[torch.Tensor] = None
+    temb_cols: int = 0                   # sum of the O (each rounded up to 4)
+    bcast_desc: Optional[torch.Tensor] = None
+    bcast_n: int = 0
+    bcast_wmax: int = 0
+    hoisted: bool = False
 
     def run_time_mlps(self, t_emb: torch.Tensor, cur: torch.Tensor):
         self.time_plan.run(self.B, cur, [t_emb])
+
+    def set_hoisted(self, col0: int):
+        """The engine keeps the hoisted results in table columns [col0, col0 + temb_cols)."""
+        desc, off_dst, off_src = [], 0, col0
+        for o in self.temb_all:
+            w = o.shape[1]
+            desc.append((off_dst, off_src, w))
+            off_dst += self.B * w
+            off_src += (w + 3) // 4 * 4
+        self.bcast_desc = torch.tensor(desc, dtype=torch.int32, device=self.temb_flat.device)
+        self.bcast_n, self.bcast_wmax = len(desc), max(d[2] for d in desc)
+        self.hoisted = True
+
+    def run_time_all(self, t_emb2: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+        """t_emb2: [2T, ted4] (row 2k and 2k+1 = step k).  Returns the [T, temb_cols] block of table columns."""
+        T2 = t_emb2.shape[0]
+        self.time_all.run(T2, table, [t_emb2], cur_cta_stride=table.stride(0))
+        cols = []
+        for o in self.temb_all:
+            w = o.shape[1]
+            c = o[::2]
+            if w % 4:
+                c = torch.cat([c, c.new_zeros(c.shape[0], 4 - w % 4)], dim=1)
+            cols.append(c)
+        return torch.cat(cols, dim=1)
+
+    def bcast_temb(self, cur: torch.Tensor):
+        _ffi.call("attndm_bcast_rows", _ffi.ptr(cur), _ffi.ptr(self.bcast_desc), self.bcast_n, self.B, self.bcast_wmax,
+                  _ffi.ptr(self.temb_flat), _ffi.stream())
 
     def run_trunk(self, h: torch.Tensor, cur: torch.Tensor) -> torch.Tensor:
         out = torch.empty(self.B, 1, 1, self.trunk_out_ch, dtype=torch.float32, device=h.device)
@@ -362,17 +408,46 @@ class FusedPlans:
         return out
 
 
-def build(model, B: int, layer_slice: dict, device) -> Optional[FusedPlans]:
-    """Plans for `model` at batch B, or None when the model/state is outside what the kernel fuses."""
+def build(model, B: int, layer_slice: dict, device, T: int = 0) -> Optional[FusedPlans]:
+    """Plans for `model` at batch B, or None when the model/state is outside what the kernel fuses.
+    T > 0: also the all-steps time plan (FusedPlans.time_all)."""
     if os.environ.get("ATTNDM_FUSED", "1") == "0":
         return None
     global last_unfusable
     last_unfusable = None
     try:
-        return _build(model, B, layer_slice, device)
+        fp = _build(model, B, layer_slice, device)
+        if T > 0:
+            try:
+                _add_time_all(fp, model, layer_slice, device, T)
+            except Unfusable:
+                fp.time_all = None
+        return fp
     except Unfusable as e:
         last_unfusable = str(e)          # why the model / state is outside what the kernel fuses
         return None
+
+
+def _add_time_all(fp: FusedPlans, model, layer_slice, device, T: int):
+    """The time_mlp programs once more, for 2T samples with two samples per CTA: CTA x is sampler step x."""
+    ted4 = model.config.model.time_embed_dim * 4
+    tp = Plan(layer_slice, device)
+    outs = []
+    for blk in list(model.down_blocks) + list(model.up_blocks):
+        if blk.time_mlp is None:
+            continue
+        q = blk.time_mlp[1]
+        out = torch.empty(2 * T, q.out_channels, dtype=torch.float32, device=device)
+        p = tp.new_program()
+        x = p.arena.alloc(ted4)
+        y = p.arena.alloc(q.out_channels)
+        p.load(x, ext=0, g_ld=ted4)
+        p.conv(q, x, y, PRE_SILU)
+        p.store(y, tensor=out)
+        outs.append(out)
+    tp.finalize(2 * T, force_ns=2)
+    fp.time_all, fp.temb_all = tp, outs
+    fp.temb_cols = sum((o.shape[1] + 3) // 4 * 4 for o in outs)
 
 
 def _build(model, B, layer_slice, device) -> FusedPlans:
@@ -381,11 +456,15 @@ def _build(model, B, layer_slice, device) -> FusedPlans:
     # ---- every time_mlp as its own program of one launch ----
     tp = Plan(layer_slice, device)
     temb = {}
+    n_flat = sum(B * blk.time_mlp[1].out_channels for blk in blocks if blk.time_mlp is not None)
+    flat = torch.empty(max(1, n_flat), dtype=torch.float32, device=device)     # every [B, O] output, back to back
+    off_flat = 0
     for blk in blocks:
         if blk.time_mlp is None:
             continue
         q = blk.time_mlp[1]
-        out = torch.empty(B, q.out_channels, dtype=torch.float32, device=device)
+        out = flat[off_flat:off_flat + B * q.out_channels].view(B, q.out_channels)
+        off_flat += B * q.out_channels
         p = tp.new_program()
         x = p.arena.alloc(ted4)
         y = p.arena.alloc(q.out_channels)
@@ -409,7 +488,7 @@ def _build(model, B, layer_slice, device) -> FusedPlans:
         first -= 1
     n_down = len(model.down_blocks)
     if first == n_down or s != 1:
-        return FusedPlans(tp, temb, None, n_down, 0, 0, B)
+        return FusedPlans(tp, temb, None, n_down, 0, 0, B, temb_flat=flat)
     n_up = min(n_down - first, len(model.up_blocks))
     plan = Plan(layer_slice, device)
     p = plan.new_program()
@@ -448,4 +527,4 @@ def _build(model, B, layer_slice, device) -> FusedPlans:
         h = _tail(p, blk, cat, temb.get(id(blk)), release_x=True)
     p.store(h, ext=1)
     plan.finalize(B)
-    return FusedPlans(tp, temb, plan, first, n_up, h.ch, B)
+    return FusedPlans(tp, temb, plan, first, n_up, h.ch, B, temb_flat=flat)

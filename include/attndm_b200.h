@@ -354,12 +354,20 @@ typedef struct {
  * (a program ends at ATTNDM_ROWOP_END).  Grid = ceil(B/ns) x nprog CTAs; ns in {2,4,8}.
  * arena_floats: per-CTA arena size; cp_max: largest input channel count of any CONV (multiple of 16);
  * pbuf_floats: largest parameter block over the CONV ops: (2*Cq + Oq + 4) + (2*C + 3*O) floats.
- * cur: the staged per-step table (attndm_stage_tables).
+ * cur: the staged per-step table (attndm_stage_tables); CTA x reads its rows at cur + x * cur_cta_stride floats
+ * (0: every sample uses the staged row; the row stride of the whole [T][width] table with ns samples per step: the
+ * time path of all T sampler steps in one launch, attentiondm_b200/engine.py).
  * ext: host array of n_ext (<= 4) device pointers bound at launch time, for tensors whose address is
  * only known per call (the program's input and output activations). */
 int attndm_rowprog(const attndm_rowop* ops, const int32_t* prog_start, int nprog, int B, int ns,
-                   int arena_floats, int cp_max, int pbuf_floats, const float* cur,
+                   int arena_floats, int cp_max, int pbuf_floats, const float* cur, long long cur_cta_stride,
                    const void* const* ext, int n_ext, void* stream);
+/* dst[off_dst[j] + b * width[j] + c] = cur[off_src[j] + c] for b < B, c < width[j], j < n: the per-step rows of a staged
+ * table fanned out to [B][width] tensors.  The sampler's time path (timestep embedding -> time_embed Linears ->
+ * every block's time_mlp, models/diffusion.py:157-161,273-277,347-351) depends on the step alone, not on the sample:
+ * the engine evaluates it once per pass for all T steps, keeps the results as table columns, and this kernel hands the
+ * current step's rows to the consumers that expect [B][O].  desc: device int32[n][3] = {off_dst, off_src, width}. */
+int attndm_bcast_rows(const float* cur, const int32_t* desc, int n, int B, int max_width, float* dst, void* stream);
 /* shared memory the kernel would need (bytes), for the host-side planner */
 int attndm_rowprog_smem_bytes(int ns, int arena_floats, int cp_max, int pbuf_floats);
 /* int8 weights [O][Cp] -> MMA-fragment order [ceil(O/16)][ceil(Cp/32)][32 lanes][16 B] (zero padded);

@@ -854,6 +854,9 @@ def test_fused_rowprog_equals_layerwise(ch, ch_mult, size, bw, alpha, B):
     if alpha == "uniform":
         assert eng.fused is not None and eng.fused.trunk_plan is not None, "the fused plan was not built"
         assert eng.fused.n_up >= 1
+        # the time path (timestep embedding -> time_embed -> every time_mlp) is evaluated once per pass for all steps
+        # instead of B times per step (engine.py); the eager run above evaluates it per step, per sample
+        assert eng.hoist and eng.fused.hoisted
     assert torch.isfinite(xs_g[-1]).all()
     assert torch.equal(torch.stack(xs_g[1:]), torch.stack(xs_e[1:]))
     assert torch.equal(torch.stack(x0_g), torch.stack(x0_e))
