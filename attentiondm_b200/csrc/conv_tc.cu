@@ -806,6 +806,9 @@ __device__ __forceinline__ void epi_stats_flush(const double (&a)[4], double* ds
     atomicAdd(dst + 2 * fdiv((unsigned)(col_base + (b4 ? 16 : 0) + col4), d_cpg) + (b8 ? 1 : 0), k);
 }
 
+// where the epilogue constants of column c live in `colc` (see epi_block_v4): 16u + 4a + b  ->  16u + 4b + a
+__device__ __forceinline__ int colc_slot(int c) { return (c & ~15) | ((c & 3) << 2) | ((c >> 2) & 3); }
+
 template <bool ADD, bool STATS>
 __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uint32_t (&v1)[16], const ColConst* colc,
                                              int c0, int tq, const EpiRows& r, float* out, const float4 (&rs)[2][4], bool has_res,
@@ -816,8 +819,12 @@ __device__ __forceinline__ void epi_block_v4(const uint32_t (&v0)[16], const uin
 #pragma unroll
   for (int h = 0; h < 2; ++h) {                       // the two units of 16 channels: column groups (0,1) and (2,3)
     const int i0 = 2 * h, i1 = 2 * h + 1;
-    const int ch = (c0 + 16 * h + col4) & 255;        // this lane's four channels: group i0 holds ch, ch+1; group i1 ch+2, ch+3
-    const ColConst a0c = colc[ch], a1c = colc[ch + 1], b0c = colc[ch + 2], b1c = colc[ch + 3];
+    // this lane's four channels c0 + 16h + 4tq + {0,1,2,3} (group i0 holds the first two, group i1 the others); the
+    // constants of channel 16u + 4tq + j sit in slot 16u + 4j + tq (colc_slot), so each of the four 128-bit loads
+    // reads 64 contiguous bytes across tq -- at the natural index the four lanes were 64 B apart: 2-way bank conflicts
+    // on the shared-memory port the MMAs saturate
+    const int sl = ((c0 + 16 * h) & 255) + tq;
+    const ColConst a0c = colc[sl], a1c = colc[sl + 4], b0c = colc[sl + 8], b1c = colc[sl + 12];
     double ds[4], dq[4];                              // STATS: this half's {sum, sumsq} of each row's four channels
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -872,7 +879,7 @@ __device__ __forceinline__ void epi_block_scalar(const uint32_t (&v0)[16], const
       const int cl = perm ? c0 + 16 * (i >> 1) + 4 * tq + 2 * (i & 1) + par : c0 + 8 * i + 2 * tq + par;
       const bool col_ok = (cl < BN) && (n0 + cl < O);
       if (!col_ok) continue;                 // the 3-channel output: 125 of 128 accumulator columns are padding
-      const ColConst cc = colc[cl & 255];
+      const ColConst cc = colc[colc_slot(cl & 255)];
       const int d = cl - 2 * tq;             // r.off / r.te_off already hold n0 + 2tq
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -1370,7 +1377,7 @@ qconv_i8_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             cc.m = p.mult[o];
             cc.bias = p.bias ? p.bias[o] : 0.f;
           }
-          colc[c] = cc;
+          colc[colc_slot(c)] = cc;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_H_EPI_WARPS) : "memory");
         last_nt = nt;
