@@ -24,52 +24,93 @@ __device__ __forceinline__ float attn_fake_quant(float x, float s, float zp, flo
   return __fmul_rn(__fsub_rn(q, zp), s);
 }
 
+// R query rows per warp (consecutive rows of one sample and head): every K row and every V element the warp loads
+// serves R dot products, and the probabilities are read from shared memory four keys at a time.  With one row per warp
+// the kernel streamed all of V (N x dv floats, 1 MB at N = 1024, dv = 256) from L1/L2 for EVERY query.  The arithmetic of
+// a row -- the order of every sum -- is the one-row kernel's, so results do not depend on R.
+template <int R>
 __global__ void __launch_bounds__(128) attention_kernel(AttnParams p) {
   pdl_enter();
-  extern __shared__ float sm[];                       // [4 warps][N]
+  extern __shared__ __align__(16) float sm[];         // [4 warps][R][N]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* sc = sm + (long long)w * p.N;
-  const long long gw = (long long)blockIdx.x * 4 + w;
-  const long long total = (long long)p.B * p.heads * p.N;
+  float* sc = sm + (long long)w * R * p.N;
+  const long long gw = (long long)blockIdx.x * 4 + w;            // group of R rows
+  const int ngrp = p.N / R;                                      // (the launcher guarantees N % R == 0)
+  const long long total = (long long)p.B * p.heads * ngrp;
   if (gw >= total) return;
-  const int i = (int)(gw % p.N);
-  const int head = (int)((gw / p.N) % p.heads);
-  const int b = (int)(gw / ((long long)p.N * p.heads));
+  const int i0 = (int)(gw % ngrp) * R;
+  const int head = (int)((gw / ngrp) % p.heads);
+  const int b = (int)(gw / ((long long)ngrp * p.heads));
   const int dq = p.d / p.heads, dvh = p.dv / p.heads;
-  const float* qrow = p.q + ((long long)b * p.N + i) * p.d + head * dq;      // q: head-major channels
+  const float* qrow = p.q + ((long long)b * p.N + i0) * p.d + head * dq;     // q: head-major channels; row r at + r * d
   const float* kb = p.k + (long long)b * p.N * p.d;                          // k: channel = e*heads + head
-  float mx = -INFINITY;
+  float mx[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) mx[r] = -INFINITY;
   for (int j = lane; j < p.N; j += 32) {
     const float* krow = kb + (long long)j * p.d;
-    float acc = 0.f;
-    for (int e = 0; e < dq; ++e) acc = fmaf(qrow[e], krow[e * p.heads + head], acc);
-    float s = __fmul_rn(acc, p.scale);
-    if (p.qk_q.bits > 0) s = attn_fake_quant(s, p.qk_q.scale, p.qk_q.zero_point, (float)((1 << p.qk_q.bits) - 1));
-    s = __fmul_rn(s, p.softmax_scale);
-    sc[j] = s;
-    mx = fmaxf(mx, s);
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    for (int e = 0; e < dq; ++e) {
+      const float kv = krow[e * p.heads + head];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(qrow[r * p.d + e], kv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float s = __fmul_rn(acc[r], p.scale);
+      if (p.qk_q.bits > 0) s = attn_fake_quant(s, p.qk_q.scale, p.qk_q.zero_point, (float)((1 << p.qk_q.bits) - 1));
+      s = __fmul_rn(s, p.softmax_scale);
+      sc[r * p.N + j] = s;
+      mx[r] = fmaxf(mx[r], s);
+    }
   }
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int j = lane; j < p.N; j += 32) {
-    float e = expf(sc[j] - mx);
-    sc[j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  __syncwarp();
-  for (int j = lane; j < p.N; j += 32) {
-    float pr = __fdiv_rn(sc[j], sum);
-    if (p.p_q.bits > 0) pr = attn_fake_quant(pr, p.p_q.scale, p.p_q.zero_point, (float)((1 << p.p_q.bits) - 1));
-    sc[j] = pr;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float m = warp_max(mx[r]);
+    float sum = 0.f;
+    for (int j = lane; j < p.N; j += 32) {
+      float e = expf(sc[r * p.N + j] - m);
+      sc[r * p.N + j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    for (int j = lane; j < p.N; j += 32) {
+      float pr = __fdiv_rn(sc[r * p.N + j], sum);
+      if (p.p_q.bits > 0) pr = attn_fake_quant(pr, p.p_q.scale, p.p_q.zero_point, (float)((1 << p.p_q.bits) - 1));
+      sc[r * p.N + j] = pr;
+    }
   }
   __syncwarp();
   const float* vb = p.v + (long long)b * p.N * p.dv + head * dvh;
-  float* orow = p.out + ((long long)b * p.N + i) * p.dv + head * dvh;
+  float* orow = p.out + ((long long)b * p.N + i0) * p.dv + head * dvh;
+  const int n4 = (R > 1 && (p.N & 3) == 0) ? p.N : 0;            // keys taken four at a time (128-bit reads of the probabilities)
   for (int c = lane; c < dvh; c += 32) {
-    float acc = 0.f;
-    for (int j = 0; j < p.N; ++j) acc = fmaf(sc[j], vb[(long long)j * p.dv + c], acc);
-    orow[c] = acc;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    int j = 0;
+    for (; j < n4; j += 4) {
+      const float v0 = vb[(long long)j * p.dv + c], v1 = vb[(long long)(j + 1) * p.dv + c];
+      const float v2 = vb[(long long)(j + 2) * p.dv + c], v3 = vb[(long long)(j + 3) * p.dv + c];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 pr = *reinterpret_cast<const float4*>(sc + r * p.N + j);
+        acc[r] = fmaf(pr.x, v0, acc[r]);
+        acc[r] = fmaf(pr.y, v1, acc[r]);
+        acc[r] = fmaf(pr.z, v2, acc[r]);
+        acc[r] = fmaf(pr.w, v3, acc[r]);
+      }
+    }
+    for (; j < p.N; ++j) {
+      const float vv = vb[(long long)j * p.dv + c];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(sc[r * p.N + j], vv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) orow[(long long)r * p.dv + c] = acc[r];
   }
 }
 
@@ -354,13 +395,19 @@ int attndm_attention(const float* q, const float* k, const float* v, float* out,
   AttnParams p;
   p.q = q; p.k = k; p.v = v; p.out = out; p.B = B; p.N = N; p.d = d; p.dv = dv; p.heads = heads;
   p.scale = scale; p.softmax_scale = softmax_scale; p.qk_q = qk_q; p.p_q = p_q;
-  long long total = (long long)B * heads * N;
-  size_t smem = 4 * (size_t)N * sizeof(float);
+  // rows per warp: four where the score rows of a CTA (4 warps x R x N floats) fit in 96 KB and there are enough row
+  // groups to fill the chip, else two, else one
+  int R = 1;
+  for (int r = 4; r >= 2; r >>= 1)
+    if (N % r == 0 && 4 * (size_t)r * N * sizeof(float) <= 96 * 1024 && (long long)B * heads * (N / r) >= 4LL * 2 * kNumSMs) { R = r; break; }
+  const long long total = (long long)B * heads * (N / R);
+  const size_t smem = 4 * (size_t)R * N * sizeof(float);
+  auto kern = R == 4 ? attention_kernel<4> : (R == 2 ? attention_kernel<2> : attention_kernel<1>);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("attention: smem attr: %s", cudaGetErrorString(e)); return ATTNDM_ERR_CUDA; }
   }
-  launch_pdl(attention_kernel, dim3(cdiv(total, 4)), dim3(128), smem, (cudaStream_t)stream, p);
+  launch_pdl(kern, dim3((unsigned)cdiv(total, 4)), dim3(128), smem, (cudaStream_t)stream, p);
   ATTNDM_CUDA_LAUNCH_CHECK("attention");
   return ATTNDM_OK;
 }
