@@ -584,6 +584,10 @@ def test_attention_core():
 
 
 def test_mixed_precision_attention_vs_restatement():
+    """PARITY PINNED AT `quantize_tensor` ONLY: MixedPrecisionAttention.forward is shape-broken in the
+    reference (K permuted to [B, h, HW, d], utils/attention_quant_utils.py:70), so no reference output exists for it.
+    This test compares the kernel with the oracle's restatement of the evident intent (K as [B, h, d, HW]); the
+    quantizer inside it is pinned bit-exactly to reference fixtures by test_attention_quantize_tensor."""
     import attentiondm_b200 as A
     g = torch.Generator().manual_seed(7)
     for bits in (4, 6, 8):
