@@ -73,7 +73,7 @@ int attndm_qconv_i8(const int8_t* codes, const int32_t* rowsum, int B, int H, in
   else { set_error("qconv_i8: unknown impl %d", impl); return ATTNDM_ERR_ARG; }
   if (rc) return rc;
   if (gn_stats_out && !fused)
-    return tiletree ? launch_gn_stats_tiletree(p, (cudaStream_t)stream) : attndm_gn_stats(out, B, H, W, O, gn_stats_out, stream);
+    return tiletree ? launch_gn_stats_quad(out, B, H * W, O, gn_stats_out, (cudaStream_t)stream) : attndm_gn_stats(out, B, H, W, O, gn_stats_out, stream);
   return ATTNDM_OK;
 }
 

@@ -88,7 +88,7 @@ __device__ __forceinline__ float conv_epilogue_add(const float* residual, const 
 inline bool conv_gn_tiletree_ok(const ConvI8Params& p) {
   return p.O % 128 == 0 && (long long)p.Hp * p.Wp >= 32 && p.rows + 128 < (1LL << 31);
 }
-int launch_gn_stats_tiletree(const ConvI8Params& p, cudaStream_t st);     // from p.out (the twin of the fused epilogue)
+int launch_gn_stats_quad(const float* out, int B, int HW, int C, double* stats, cudaStream_t st);   // from the stored output (quant_kernels.cu)
 
 int launch_qconv_i8_simt(const ConvI8Params& p, cudaStream_t st);
 // *stats_fused = true when the kernel that ran also accumulated p.gn_out in its epilogue

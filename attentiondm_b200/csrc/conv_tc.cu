@@ -1762,77 +1762,6 @@ int launch_qconv_i8_tc(const ConvI8Params& p, cudaStream_t st, bool* stats_fused
 }
 
 
-// ---- GroupNorm statistics of a conv output in quad order, from the output tensor ------------------------------
-// The twin of the STATS epilogue above (conv_common.cuh states the order): per pixel and aligned group of four channels
-// the same fp32 sum and sum of squares, everything above that in double.  Runs after the dp4a conv kernel and after the
-// ring-fed tcgen05 kernel, so that the statistics of a layer do not depend on which kernel computed it.  One warp per 32
-// GEMM rows, thread (tr = lane / 4, tq = lane % 4): rows tr + 8k, channels 4tq .. 4tq+3 of every unit of 16.
-__global__ void __launch_bounds__(256) gn_stats_tiletree_kernel(const ConvI8Params p, long long nquarters) {
-  pdl_enter();
-  const int lane = threadIdx.x & 31, tq = lane & 3, tr = lane >> 2;
-  const long long wq = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wq >= nquarters) return;
-  const long long row0 = wq * 32;
-  const int col4 = 4 * tq;
-  const int cpg = p.O / kGnGroups;
-  long long pix[4];
-  int bk[4], mn = 0x7fffffff, mx = -1;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    pix[k] = -1;
-    bk[k] = -1;
-    long long px = 0;
-    int b = 0;
-    if (conv_row_to_pixel(p, row0 + tr + 8 * k, px, b)) {
-      pix[k] = px;
-      bk[k] = (int)(px / ((long long)p.H * p.W));
-      mn = min(mn, bk[k]);
-      mx = max(mx, bk[k]);
-    }
-  }
-  mn = __reduce_min_sync(0xffffffffu, mn);
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if (mx < 0) return;
-  const bool two = mx > mn;
-  double* dst = p.gn_out + (long long)mn * (2 * kGnGroups);
-  for (int u = 0; u < p.O; u += 16) {
-    double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (pix[k] < 0) continue;
-      const float4 o = __ldg(reinterpret_cast<const float4*>(p.out + pix[k] * p.O + u + col4));
-      const float rsum = __fadd_rn(__fadd_rn(o.x, o.y), __fadd_rn(o.z, o.w));
-      const float rsq = fmaf(o.w, o.w, fmaf(o.z, o.z, fmaf(o.y, o.y, __fmul_rn(o.x, o.x))));
-      if (bk[k] == mn) { s0 += (double)rsum; q0 += (double)rsq; }
-      else { s1 += (double)rsum; q1 += (double)rsq; }
-    }
-#pragma unroll
-    for (int m = 4; m <= 16; m <<= 1) {
-      s0 += __shfl_xor_sync(0xffffffffu, s0, m);
-      q0 += __shfl_xor_sync(0xffffffffu, q0, m);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-      q1 += __shfl_xor_sync(0xffffffffu, q1, m);
-    }
-    if (lane < 4) {
-      double* d = dst + 2 * ((u + col4) / cpg);
-      atomicAdd(d, s0);
-      atomicAdd(d + 1, q0);
-      if (two) {
-        atomicAdd(d + 2 * kGnGroups, s1);
-        atomicAdd(d + 2 * kGnGroups + 1, q1);
-      }
-    }
-  }
-}
-
-int launch_gn_stats_tiletree(const ConvI8Params& p, cudaStream_t st) {
-  ATTNDM_CHECK_ARG(p.gn_out && p.out && conv_gn_tiletree_ok(p), "gn_stats_tiletree: shape not supported");
-  const long long nquarters = (p.rows + 31) / 32;
-  launch_pdl(gn_stats_tiletree_kernel, dim3((unsigned)cdiv(nquarters, 8)), dim3(256), 0, st, p, nquarters);
-  ATTNDM_CUDA_LAUNCH_CHECK("gn_stats_tiletree");
-  return ATTNDM_OK;
-}
-
 // =====================================================================================================
 // fp32 GEMM on the tensor cores with fp32-level accuracy ("3xTF32"): out[M][N] = x[M][K] . w[N][K]^T + bias
 // Reference op: the lazily created fp32 `channel_proj` 1x1 conv of UpBlock (models/diffusion.py:235-242), the one

@@ -793,7 +793,10 @@ __global__ void __launch_bounds__(256) gn_act_quant_sample_kernel(GnActParams p)
 // cpg / g0 / mult: the tensor may be one PART of a GroupNorm input (the upsampled half or the skip half of an
 // UpBlock's concat, which is never materialised): its channels fall into groups of cpg channels starting at group g0
 // of the stats row, and every sum is scaled by mult (4 for the half that nearest-neighbour upsampling repeats 2x2).
-template <int UNROLL>
+// QUAD: the "quad order" of csrc/conv_common.cuh -- per pixel and aligned group of four channels the fp32 sum
+// (x0 + x1) + (x2 + x3) and the fp32 fma chain of the squares, double from there on: the same statistics the tcgen05
+// conv epilogue accumulates, for convs computed by another kernel (cpg % 4 == 0 there).
+template <int UNROLL, bool QUAD = false>
 __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int P, int rows_per_block,
                                 double* __restrict__ stats, int reverse, int cpg, int g0, double mult) {
   pdl_enter();
@@ -815,18 +818,28 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int 
       for (int u = 0; u < UNROLL; ++u) v[u] = ldg_stream(reinterpret_cast<const float4*>(base + (long long)(r + u * P) * C));
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        a0 += v[u].x; q0 += (double)v[u].x * v[u].x;
-        a1 += v[u].y; q1 += (double)v[u].y * v[u].y;
-        a2 += v[u].z; q2 += (double)v[u].z * v[u].z;
-        a3 += v[u].w; q3 += (double)v[u].w * v[u].w;
+        if (QUAD) {
+          a0 += (double)__fadd_rn(__fadd_rn(v[u].x, v[u].y), __fadd_rn(v[u].z, v[u].w));
+          q0 += (double)fmaf(v[u].w, v[u].w, fmaf(v[u].z, v[u].z, fmaf(v[u].y, v[u].y, __fmul_rn(v[u].x, v[u].x))));
+        } else {
+          a0 += v[u].x; q0 += (double)v[u].x * v[u].x;
+          a1 += v[u].y; q1 += (double)v[u].y * v[u].y;
+          a2 += v[u].z; q2 += (double)v[u].z * v[u].z;
+          a3 += v[u].w; q3 += (double)v[u].w * v[u].w;
+        }
       }
     }
     for (; r < r1; r += P) {
       float4 v = ldg_stream(reinterpret_cast<const float4*>(base + (long long)r * C));
-      a0 += v.x; q0 += (double)v.x * v.x;
-      a1 += v.y; q1 += (double)v.y * v.y;
-      a2 += v.z; q2 += (double)v.z * v.z;
-      a3 += v.w; q3 += (double)v.w * v.w;
+      if (QUAD) {
+        a0 += (double)__fadd_rn(__fadd_rn(v.x, v.y), __fadd_rn(v.z, v.w));
+        q0 += (double)fmaf(v.w, v.w, fmaf(v.z, v.z, fmaf(v.y, v.y, __fmul_rn(v.x, v.x))));
+      } else {
+        a0 += v.x; q0 += (double)v.x * v.x;
+        a1 += v.y; q1 += (double)v.y * v.y;
+        a2 += v.z; q2 += (double)v.z * v.z;
+        a3 += v.w; q3 += (double)v.w * v.w;
+      }
     }
     const int c = q << 2;
     if ((cpg & 3) == 0) {   // all four channels of the quad are in one group
@@ -1414,7 +1427,8 @@ int attndm_gn_silu(const float* x, int B, int H, int W, int C, const double* gn_
                         nullptr, nullptr, ATTNDM_ROWS_PLAIN, y, false, (cudaStream_t)stream);
 }
 
-static int gn_stats_impl(const float* x, int B, int HW, int C, int cpg, int g0, double mult, double* stats, cudaStream_t st) {
+static int gn_stats_impl(const float* x, int B, int HW, int C, int cpg, int g0, double mult, double* stats, cudaStream_t st,
+                         bool quad = false) {
   const int Q = C / 4;
   int P = Q >= 256 ? 1 : 256 / Q;
   if (P > HW) P = HW;
@@ -1431,7 +1445,9 @@ static int gn_stats_impl(const float* x, int B, int HW, int C, int cpg, int g0, 
   dim3 grid(splits, B);
   // (the partial sums of a sample's `splits` blocks meet in double-precision atomics: their order can change the last
   // bit of a double, far below the fp32 mean / rstd the consumers form from them)
-  if (tune_unroll >= 8)
+  if (quad)
+    launch_pdl(gn_stats_kernel<4, true>, dim3(grid), dim3(threads), 0, st, x, HW, C, P, rows_per_block, stats, reverse, cpg, g0, mult);
+  else if (tune_unroll >= 8)
     launch_pdl(gn_stats_kernel<8>, dim3(grid), dim3(threads), 0, st, x, HW, C, P, rows_per_block, stats, reverse, cpg, g0, mult);
   else
     launch_pdl(gn_stats_kernel<4>, dim3(grid), dim3(threads), 0, st, x, HW, C, P, rows_per_block, stats, reverse, cpg, g0, mult);
@@ -1444,6 +1460,17 @@ int attndm_gn_stats(const float* x, int B, int H, int W, int C, double* stats, v
   ATTNDM_CHECK_ARG(C % kGnGroups == 0 && C % 4 == 0 && C <= 4096, "gn_stats: C must be a multiple of 32, <= 4096");
   return gn_stats_impl(x, B, H * W, C, C / kGnGroups, 0, 1.0, stats, (cudaStream_t)stream);
 }
+
+extern "C++" {
+namespace attndm {
+// GroupNorm statistics of a conv output in quad order, from the stored output (the twin of the tcgen05 epilogue's
+// accumulation: same fp32 quad sums, double above; conv_common.cuh)
+int launch_gn_stats_quad(const float* out, int B, int HW, int C, double* stats, cudaStream_t st) {
+  ATTNDM_CHECK_ARG(out && stats && C % 128 == 0, "gn_stats_quad: C must be a multiple of 128");
+  return gn_stats_impl(out, B, HW, C, C / kGnGroups, 0, 1.0, stats, st, true);
+}
+}  // namespace attndm
+}  // extern "C++"
 
 int attndm_gn_stats_cat(const float* xa, int Ha, int Wa, int C1, const float* xb, int H, int W, int C2, int B,
                         double* stats, void* stream) {
