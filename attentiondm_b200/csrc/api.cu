@@ -64,8 +64,8 @@ int attndm_qconv_i8(const int8_t* codes, const int32_t* rowsum, int B, int H, in
   if (gn_stats_out && O % 32 != 0) { set_error("qconv_i8: gn_stats_out needs O %% 32 == 0"); return ATTNDM_ERR_ARG; }
   // The statistics of one shape always follow ONE summation order, whichever kernel computes the conv: quad order
   // (conv_common.cuh) where the tcgen05 epilogue can produce it, else the order of attndm_gn_stats.
-  const bool tiletree = gn_stats_out != nullptr && conv_gn_tiletree_ok(p);
-  p.gn_out = tiletree ? gn_stats_out : nullptr;
+  const bool quad_order = gn_stats_out != nullptr && conv_gn_quad_ok(p);
+  p.gn_out = quad_order ? gn_stats_out : nullptr;
   bool fused = false;
   int rc;
   if (impl == ATTNDM_CONV_TCGEN05) rc = launch_qconv_i8_tc(p, (cudaStream_t)stream, &fused);
@@ -73,7 +73,7 @@ int attndm_qconv_i8(const int8_t* codes, const int32_t* rowsum, int B, int H, in
   else { set_error("qconv_i8: unknown impl %d", impl); return ATTNDM_ERR_ARG; }
   if (rc) return rc;
   if (gn_stats_out && !fused)
-    return tiletree ? launch_gn_stats_quad(out, B, H * W, O, gn_stats_out, (cudaStream_t)stream) : attndm_gn_stats(out, B, H, W, O, gn_stats_out, stream);
+    return quad_order ? launch_gn_stats_quad(out, B, H * W, O, gn_stats_out, (cudaStream_t)stream) : attndm_gn_stats(out, B, H, W, O, gn_stats_out, stream);
   return ATTNDM_OK;
 }
 

@@ -85,7 +85,7 @@ __device__ __forceinline__ float conv_epilogue_add(const float* residual, const 
 // tq = lane % 4) owning rows tr + 8k (k = 0..3) x channels 4tq .. 4tq+3 of every 16-channel unit; a quarter that
 // straddles two samples keeps two partials.
 // Supported when O % 128 == 0 (a thread's four channels share a group) and a sample has >= 32 GEMM rows.
-inline bool conv_gn_tiletree_ok(const ConvI8Params& p) {
+inline bool conv_gn_quad_ok(const ConvI8Params& p) {
   return p.O % 128 == 0 && (long long)p.Hp * p.Wp >= 32 && p.rows + 128 < (1LL << 31);
 }
 int launch_gn_stats_quad(const float* out, int B, int HW, int C, double* stats, cudaStream_t st);   // from the stored output (quant_kernels.cu)

@@ -1725,7 +1725,7 @@ static int launch_qconv_i8_halo(const ConvI8Params& p, cudaStream_t st, bool* st
   const bool adds = p.residual != nullptr || p.temb != nullptr;
   // GroupNorm statistics of the output from the epilogue (quad order): every chunk must take the 128-bit path
   static const bool stats_on = [] { const char* e = getenv("ATTNDM_TC_STATS"); return !(e && e[0] == '0'); }();
-  const bool stats = stats_on && p.gn_out != nullptr && conv_gn_tiletree_ok(p) && g.BN % 32 == 0;
+  const bool stats = stats_on && p.gn_out != nullptr && conv_gn_quad_ok(p) && g.BN % 32 == 0;
 #define ATTNDM_HALO_ARGS dim3(grid), dim3(TC_THREADS_H), smem, st
 #define ATTNDM_HALO_PARAMS tmA, tmA2, tmB, p, g
 #define ATTNDM_HALO_LAUNCH(STATSV)                                                                                  \
