@@ -117,6 +117,15 @@ __device__ __forceinline__ float quant_code_t(float t, float lo, float hi) {
 }
 
 
+// MixedPrecisionAttention.quantize_tensor (utils/attention_quant_utils.py:30-38), shared by attention_kernel and the
+// fused one-position attention of rowprog.cu
+__device__ __forceinline__ float attn_fake_quant(float x, float s, float zp, float qmax) {
+  // clamp(round(x / scale) + zero_point, 0, qmax); (x_q - zero_point) * scale
+  float q = __fadd_rn(rintf(__fdiv_rn(x, s)), zp);
+  q = fminf(fmaxf(q, 0.f), qmax);
+  return __fmul_rn(__fsub_rn(q, zp), s);
+}
+
 // GroupNorm(32) finalisation and application, shared by every kernel that normalises (so that the fused
 // and the stand-alone paths agree bit for bit): mean / rstd from double sums, each step separately rounded.
 __device__ __forceinline__ void gn_mean_rstd(double s, double ss, double inv_n, float eps, float& mean, float& rstd) {

@@ -17,13 +17,6 @@ struct AttnParams {
   attndm_attn_quant qk_q, p_q;
 };
 
-__device__ __forceinline__ float attn_fake_quant(float x, float s, float zp, float qmax) {
-  // clamp(round(x / scale) + zero_point, 0, qmax); (x_q - zero_point) * scale
-  float q = __fadd_rn(rintf(__fdiv_rn(x, s)), zp);
-  q = fminf(fmaxf(q, 0.f), qmax);
-  return __fmul_rn(__fsub_rn(q, zp), s);
-}
-
 // R query rows per warp (consecutive rows of one sample and head): every K row and every V element the warp loads
 // serves R dot products, and the probabilities are read from shared memory four keys at a time.  With one row per warp
 // the kernel streamed all of V (N x dv floats, 1 MB at N = 1024, dv = 256) from L1/L2 for EVERY query.  The arithmetic of

@@ -141,7 +141,7 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
   __shared__ __align__(16) attndm_rowop s_op[2];       // the current and the next op, staged from global memory
   __shared__ float s_mean[NS * kGnGroups], s_rstd[NS * kGnGroups];
   __shared__ int s_rowsum[8];
-  __shared__ float s_prob[8];
+  __shared__ float s_prob[8 * 8];                      // [NS][heads <= 8]
   __shared__ __align__(8) uint64_t s_wbar[RP_WARPS];   // per warp: its staged A fragments have landed
   __shared__ __align__(8) uint64_t s_pbar[2];          // per parameter buffer
   pdl_launch_dependents();
@@ -269,26 +269,34 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
             arena[doff + n * dld + c] = __fadd_rn(__fmul_rn(g, arena[soff + n * sld + c]), arena[aoff + n * ald + c]);
         break;
       }
-      case ATTNDM_ROWOP_ATTN1: {           // attention_kernel with N = 1, heads = 1: C = d (q/k channels), O = dv
-        if (tid < NS) {
-          const float* qr = arena + op.src_off + tid * op.src_ld;
-          const float* kr = arena + op.add0_off + tid * op.add0_ld;
+      case ATTNDM_ROWOP_ATTN1: {           // attention_kernel with N = 1: C = d (q/k channels), O = dv
+        // op.g0 (optional): 8 floats {heads, softmax_scale, qk scale, qk zero point, qk bits, p scale, p zero point,
+        // p bits} -- MixedPrecisionAttention (utils/attention_quant_utils.py:51-107); NULL: one head, no quantizers
+        const float* ap = reinterpret_cast<const float*>(op.g0);
+        const int heads = ap ? (int)ap[0] : 1;
+        if (tid < NS * heads) {
+          const int n = tid / heads, head = tid - n * heads, dq = C / heads;
+          const float* qr = arena + op.src_off + n * op.src_ld + head * dq;       // q: head-major channels
+          const float* kr = arena + op.add0_off + n * op.add0_ld;                 // k: channel = e * heads + head
           float acc = 0.f;
-          for (int e = 0; e < C; ++e) acc = fmaf(qr[e], kr[e], acc);
+          for (int e = 0; e < dq; ++e) acc = fmaf(qr[e], kr[e * heads + head], acc);
           float s = __fmul_rn(acc, op.fparam);
-          s = __fmul_rn(s, 1.0f);
+          if (ap && (int)ap[4] > 0) s = attn_fake_quant(s, ap[2], ap[3], (float)((1 << (int)ap[4]) - 1));
+          s = __fmul_rn(s, ap ? ap[1] : 1.0f);
           const float mx = fmaxf(-INFINITY, s);
           const float e1 = expf(s - mx);
           float sum = e1;
 #pragma unroll
           for (int k = 0; k < 5; ++k) sum += 0.f;      // the warp reduction over 31 empty lanes
-          s_prob[tid] = __fdiv_rn(e1, sum);
+          float pr = __fdiv_rn(e1, sum);
+          if (ap && (int)ap[7] > 0) pr = attn_fake_quant(pr, ap[5], ap[6], (float)((1 << (int)ap[7]) - 1));
+          s_prob[tid] = pr;
         }
         rp_sync();
-        const int doff = op.dst_off, dld = op.dst_ld, aoff = op.aux_off, ald = op.aux_ld;
+        const int doff = op.dst_off, dld = op.dst_ld, aoff = op.aux_off, ald = op.aux_ld, dvh = O / heads;
         for (int n = 0; n < NS; ++n)
           for (int c = tid; c < O; c += RP_THREADS)
-            arena[doff + n * dld + c] = fmaf(s_prob[n], arena[aoff + n * ald + c], 0.f);
+            arena[doff + n * dld + c] = fmaf(s_prob[n * heads + c / dvh], arena[aoff + n * ald + c], 0.f);
         break;
       }
       case ATTNDM_ROWOP_FCONV: {           // conv_f32_simt_kernel: sequential fmaf over c, then + bias

@@ -125,6 +125,16 @@ class SamplerEngine:
                 m._tables()
         except Exception:
             return False
+        # the fused trunk bakes the scalar parameters of every MixedPrecisionAttention into its ops: stale once
+        # update_quantization_params ran (it drops the module's host cache) or the bit width changed
+        for fp in self.fused_parts:
+            plan = fp.trunk_plan if fp is not None else None
+            for mpa, vals in (plan.attn_params if plan is not None else []):
+                if mpa._host is None or float(mpa.num_heads) != vals[0]:
+                    return False
+                eff = mpa.get_effective_bits(None)
+                if float(max(4, int(eff)) if eff <= 6 else 0) != vals[4] or float(max(3, int(eff - 1)) if eff <= 4 else 0) != vals[7]:
+                    return False
         return self._versions() == self.versions
 
     # ---- one denoising step on the current stream ----

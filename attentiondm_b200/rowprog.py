@@ -171,8 +171,10 @@ class Program:
         self._emit(type=OP_FCONV, C=Cc, O=O, src=src, dst=dst, g0=self.plan.keep(wt),
                    g1=self.plan.keep(conv.bias.detach() if conv.bias is not None else None))
 
-    def attn1(self, q: Buf, k: Buf, v: Buf, dst: Buf, scale: float):
-        self._emit(type=OP_ATTN1, C=q.ch, O=v.ch, src=q, add0=k, aux=v, dst=dst, fparam=float(scale))
+    def attn1(self, q: Buf, k: Buf, v: Buf, dst: Buf, scale: float, params: Optional[torch.Tensor] = None):
+        """params: the 8 floats of a MixedPrecisionAttention (rowprog.cu, ATTN1), or None for the plain softmax branch."""
+        self._emit(type=OP_ATTN1, C=q.ch, O=v.ch, src=q, add0=k, aux=v, dst=dst, fparam=float(scale),
+                   g0=self.plan.keep(params))
 
     def scale_add(self, a: Buf, x: Buf, dst: Buf, gamma: torch.Tensor):
         self._emit(type=OP_SCALE_ADD, C=a.ch, src=a, add0=x, dst=dst, g0=self.plan.keep(gamma))
@@ -226,6 +228,7 @@ class Plan:
         self.device = device
         self.programs: List[Program] = []
         self._keep = []                      # tensors whose storage the op list points into
+        self.attn_params = []                # (MixedPrecisionAttention, the 8 values baked into its ATTN1 op)
         self._packed = {}
         self.ns = 0
         self.dev_ops = None
@@ -318,15 +321,29 @@ def _res_block(p: Program, rb, x: Buf, temb: Optional[torch.Tensor]) -> Buf:
 
 def _attention(p: Program, at, x: Buf) -> Buf:
     """EnhancedQSelfAttention.forward_fused at one position (plain softmax branch)."""
-    if at.mixed_precision:
-        raise Unfusable("mixed-precision attention is not part of the fused program")
+    params = None
+    scale = at.key_channels ** -0.5
+    if at.mixed_precision and at.quantization:
+        # MixedPrecisionAttention.forward_nhwc as Model.forward reaches it (timestep=None: the base bit width)
+        mpa = at.attention_processor
+        if mpa.num_heads > 8 or at.key_channels % mpa.num_heads or at.value_channels % mpa.num_heads:
+            raise Unfusable("attention heads outside what the fused program takes")
+        h = mpa.refresh_host_params()
+        eff = mpa.get_effective_bits(None)
+        qk_bits = max(4, int(eff)) if eff <= 6 else 0
+        p_bits = max(3, int(eff - 1)) if eff <= 4 else 0
+        vals = [float(mpa.num_heads), h["softmax_scale"], h["scale_qk"], h["zero_qk"], float(qk_bits),
+                h["scale_attn"], h["zero_attn"], float(p_bits)]
+        params = torch.tensor(vals, dtype=torch.float32, device=p.plan.device)
+        p.plan.attn_params.append((mpa, tuple(vals)))
+        scale = mpa.scaling_factor
     q = p.arena.alloc(at.key_channels)
     k = p.arena.alloc(at.key_channels)
     v = p.arena.alloc(at.value_channels)
     p.conv(at.query_conv, x, q)
     p.conv(at.key_conv, x, k)
     p.conv(at.value_conv, x, v)
-    p.attn1(q, k, v, v, at.key_channels ** -0.5)
+    p.attn1(q, k, v, v, scale, params)
     o = p.arena.alloc(at.in_channels)
     p.conv(at.output_conv, v, o)
     p.scale_add(o, x, o, at.gamma.detach())

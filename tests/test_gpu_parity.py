@@ -833,18 +833,33 @@ def test_per_layer_trace_vs_reference_fixture(golden):
 # that works on a 1x1 map inside one kernel each; the result must equal the layer-by-layer kernels
 # (which the in-situ tests above pin to the oracle) bit for bit.
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("ch,ch_mult,size,bw,alpha,B", [
-    (32, (1, 2), 4, 8, "uniform", 3),          # 4 -> 2 -> 1 -> 1: pooled trunk input, 32/64 channels (1-2 per group)
-    (64, (1, 2, 2), 8, 8, "uniform", 9),       # 8 -> 4 -> 2 -> 1 ..., 128 channels, ragged sample tile
-    (32, (1, 2), 4, 6, "uniform", 2),          # 6-bit activations (4-bit key projection)
-    (32, (1, 2), 4, 4, "attn_random", 2),      # trained attention alphas -> those layers leave the integer path
+@pytest.mark.parametrize("ch,ch_mult,size,bw,alpha,B,mixed", [
+    (32, (1, 2), 4, 8, "uniform", 3, False),   # 4 -> 2 -> 1 -> 1: pooled trunk input, 32/64 channels (1-2 per group)
+    (64, (1, 2, 2), 8, 8, "uniform", 9, False),    # 8 -> 4 -> 2 -> 1 ..., 128 channels, ragged sample tile
+    (32, (1, 2), 4, 6, "uniform", 2, False),   # 6-bit activations (4-bit key projection)
+    (32, (1, 2), 4, 4, "attn_random", 2, False),   # trained attention alphas -> those layers leave the integer path
+    # MixedPrecisionAttention (8 heads, softmax scale, fake-quantized scores at <= 6 bits and probabilities at <= 4) at one
+    # position inside the fused trunk (utils/attention_quant_utils.py:51-107)
+    (64, (1, 2), 4, 8, "uniform", 3, True),
+    (64, (1, 2), 4, 6, "uniform", 2, True),
+    (64, (1, 2), 4, 4, "uniform", 5, True),
 ])
-def test_fused_rowprog_equals_layerwise(ch, ch_mult, size, bw, alpha, B):
+def test_fused_rowprog_equals_layerwise(ch, ch_mult, size, bw, alpha, B, mixed):
     import attentiondm_b200 as A
     from attentiondm_b200.engine import SamplerEngine
     spec = S.tiny_spec(T=4, bitwidth=bw, ch=ch, ch_mult=ch_mult, image_size=size)
     sd = S.synth_state_dict(spec, seed=11, alpha_mode=alpha)
     m = build_cuda_model(spec, sd)
+    if mixed:
+        n_mixed = 0
+        for mod in m.modules():
+            if isinstance(mod, A.EnhancedQSelfAttention):
+                mod.gamma.data.fill_(0.5)
+                mod.enable_mixed_precision()
+                mod.attention_processor.update_quantization_params(-6.0, 7.0, 0.0, 1.0)
+                mod.attention_processor.softmax_scale.data.fill_(1.25)
+                n_mixed += 1
+        assert n_mixed > 0
     betas = R.beta_schedule_linear().to(DEV)
     x = torch.randn(B, 3, size, size, generator=torch.Generator().manual_seed(4)).to(DEV)
     m.set_calibrate(True)
