@@ -6,7 +6,7 @@ from attentiondm_b200 import rowprog
 from attentiondm_b200.engine import SamplerEngine
 dev = torch.device("cuda")
 bench.T_STEPS = 100
-for name in ("church_w8a8", "celeba_w8a8"):
+for name in sys.argv[1:] or ("church_w8a8", "celeba_w8a8", "cifar10_w4_attn"):
     CFG = bench.CONFIGS[name]
     m, seq = bench.build_model(dev, CFG)
     for n, q in m.qconvs():
