@@ -176,6 +176,52 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
   uint8_t* const wmine = wstage + (size_t)warp * (RP_KCH * 512) + lane * 16;    // this lane's slots of the staged fragments
   uint32_t wuse = 0;                   // how many times this warp's fragment barrier has completed (parity)
 
+  // out[n][o] = (sum over c, sequential fmaf, of x[n][c] * wt[c][o]) + bias[o]: the arithmetic of conv_f32_simt_kernel on a
+  // 1x1 map.  Used by the FCONV op (the un-quantized channel_proj) and by CONV ops whose layer takes the fp32 path.
+  // Weight-bandwidth bound per CTA (every CTA streams the whole [C][O] matrix for its few samples): each thread owns four
+  // consecutive output channels and keeps 16 independent 128-bit loads in flight.  bias: global or shared, or NULL.
+  auto fconv_rows = [&](const float* wt, const float* bias, const float* x0, int ld, int doff, int dld, int C, int O) {
+    const float* xs = x0 + hh * NST * ld;
+    for (int o = 4 * ot; o < O; o += 4 * RP_OCH) {
+      float acc[NST][4];
+#pragma unroll
+      for (int n = 0; n < NST; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+      const float* wp = wt + o;
+      int c = 0;
+      for (; c + 16 <= C; c += 16) {
+        float4 w[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wp + (long long)(c + u) * O));
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+#pragma unroll
+          for (int n = 0; n < NST; ++n) {
+            const float xv = xs[n * ld + c + u];
+            fma2(acc[n][0], acc[n][1], xv, w[u].x, w[u].y);      // packed fp32 FMAs: same results as fmaf
+            fma2(acc[n][2], acc[n][3], xv, w[u].z, w[u].w);
+          }
+      }
+      for (; c < C; ++c) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (long long)c * O));
+#pragma unroll
+        for (int n = 0; n < NST; ++n) {
+          const float xv = xs[n * ld + c];
+          fma2(acc[n][0], acc[n][1], xv, w.x, w.y);
+          fma2(acc[n][2], acc[n][3], xv, w.z, w.w);
+        }
+      }
+      float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) bz = *reinterpret_cast<const float4*>(bias + o);
+#pragma unroll
+      for (int n = 0; n < NST; ++n) {
+        float* d = arena + doff + (hh * NST + n) * dld + o;
+        d[0] = acc[n][0] + bz.x; d[1] = acc[n][1] + bz.y; d[2] = acc[n][2] + bz.z; d[3] = acc[n][3] + bz.w;
+      }
+    }
+  };
+
   for (int opi = 0;; ++opi) {
     const attndm_rowop& op = s_op[opi & 1];
     const int type = op.type;
@@ -300,50 +346,8 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
         break;
       }
       case ATTNDM_ROWOP_FCONV: {           // conv_f32_simt_kernel: sequential fmaf over c, then + bias
-        // Weight-bandwidth bound per CTA (every CTA streams the whole [C][O] matrix for its few samples): each
-        // thread owns four consecutive output channels and keeps 16 independent 128-bit loads in flight.
-        const float* wt = reinterpret_cast<const float*>(op.g0);     // [C][O], O % 4 == 0
-        const float* bias = reinterpret_cast<const float*>(op.g1);
-        const int doff = op.dst_off, dld = op.dst_ld, ld = op.src_ld;
-        const float* xs = arena + op.src_off + hh * NST * ld;
-        for (int o = 4 * ot; o < O; o += 4 * RP_OCH) {
-          float acc[NST][4];
-#pragma unroll
-          for (int n = 0; n < NST; ++n)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
-          const float* wp = wt + o;
-          int c = 0;
-          for (; c + 16 <= C; c += 16) {
-            float4 w[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wp + (long long)(c + u) * O));
-#pragma unroll
-            for (int u = 0; u < 16; ++u)
-#pragma unroll
-              for (int n = 0; n < NST; ++n) {
-                const float xv = xs[n * ld + c + u];
-                fma2(acc[n][0], acc[n][1], xv, w[u].x, w[u].y);      // packed fp32 FMAs: same results as fmaf
-                fma2(acc[n][2], acc[n][3], xv, w[u].z, w[u].w);
-              }
-          }
-          for (; c < C; ++c) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (long long)c * O));
-#pragma unroll
-            for (int n = 0; n < NST; ++n) {
-              const float xv = xs[n * ld + c];
-              fma2(acc[n][0], acc[n][1], xv, w.x, w.y);
-              fma2(acc[n][2], acc[n][3], xv, w.z, w.w);
-            }
-          }
-          float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bias) bz = *reinterpret_cast<const float4*>(bias + o);
-#pragma unroll
-          for (int n = 0; n < NST; ++n) {
-            float* d = arena + doff + (hh * NST + n) * dld + o;
-            d[0] = acc[n][0] + bz.x; d[1] = acc[n][1] + bz.y; d[2] = acc[n][2] + bz.z; d[3] = acc[n][3] + bz.w;
-          }
-        }
+        fconv_rows(reinterpret_cast<const float*>(op.g0), reinterpret_cast<const float*>(op.g1), arena + op.src_off, op.src_ld,
+                   op.dst_off, op.dst_ld, C, O);
         break;
       }
       case ATTNDM_ROWOP_CONV: {
@@ -359,6 +363,9 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
         const int32_t* wsum = reinterpret_cast<const int32_t*>(stat + 2 * C + O);
         const int32_t* wzp = reinterpret_cast<const int32_t*>(stat + 2 * C + 2 * O);
         const int pre = op.pre;
+        // rsv0 != NULL: the layer takes the fp32 path on every step (non-uniform alpha, off-grid weights; QConv2d.forward_fused):
+        // same quantizer, then the fp32 conv of its fake-quantized input (op.qw = fp32 weights [C][O], op.aux = scratch row)
+        const bool f32 = op.rsv0 != nullptr;
         const float qlo = -(float)(1 << (op.a_bit - 1)), qhi = (float)((1 << (op.a_bit - 1)) - 1);
         const float* src = arena + op.src_off;
         const int sld = op.src_ld;
@@ -432,6 +439,9 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
             const float tx = pre == ATTNDM_PRE_NONE ? __fsub_rn(__fmul_rn(s2.x, v.x), z2.x) : silu_quant_t(v.x, s2.x, z2.x);
             const float ty = pre == ATTNDM_PRE_NONE ? __fsub_rn(__fmul_rn(s2.y, v.y), z2.y) : silu_quant_t(v.y, s2.y, z2.y);
             const int ix = (int)quant_code_t(tx, qlo, qhi), iy = (int)quant_code_t(ty, qlo, qhi);
+            if (f32)          // fp32 path: the fake-quantized activation itself (dequant of the same code, common.cuh)
+              *reinterpret_cast<float2*>(arena + op.aux_off + n * op.aux_ld + c) =
+                  make_float2(dequant((float)ix, s2.x, z2.x), dequant((float)iy, s2.y, z2.y));
             *reinterpret_cast<char2*>(codes + n * crow_bytes + c) = make_char2((signed char)ix, (signed char)iy);
             int part = ix + iy;
             if (warp_rows) {
@@ -447,6 +457,16 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
         // ---- phase B: the GEMM on the tensor cores.  warp = one 16-channel tile (two for O > 256); the A fragments
         //      of the first 256 input channels of tile `warp` are already in registers (prefetched by the
         //      previous conv); anything beyond is loaded here ----
+        if (f32) {
+          // the fragment prefetch an earlier op issued for this conv (it cannot know the path) is consumed unread
+          if (warp < ((O + 15) >> 4)) { rp_mbar_wait(rp_smem_u32(&s_wbar[warp]), wuse & 1); ++wuse; }
+          fconv_rows(reinterpret_cast<const float*>(op.qw), bias, arena + op.aux_off, op.aux_ld, op.dst_off, op.dst_ld, C, O);
+          rp_trace(opi, 4);
+          RP_PREFETCH_ISSUE(nconv + 1);
+          ++nconv;
+          rp_trace(opi, 5);
+          break;
+        }
         int acc[RP_MAXT][4], acc2[RP_MAXT][4];
         float tev[RP_MAXT][4];             // the time-embedding terms of phase C, fetched from global memory ahead of the MMAs
 #pragma unroll

@@ -134,8 +134,11 @@ class Program:
     def conv(self, q, src: Buf, dst: Buf, pre=PRE_NONE, norm: Optional[nn.GroupNorm] = None, add0: Optional[Buf] = None,
              temb: Optional[torch.Tensor] = None):
         """One QConv2d on a 1x1 map (QConv2d.forward_fused's integer branch)."""
-        if q._calibrate or not q.int8_ok_all_steps():
-            raise Unfusable("layer is calibrating or not on the integer path for every step")
+        if q._calibrate:
+            raise Unfusable("layer is calibrating")
+        f32 = not q.int8_ok_all_steps()              # the engine's rule: the fp32 path unless EVERY step may use int8
+        if f32 and (add0 is not None or temb is not None or q.in_channels % 4):
+            raise Unfusable("fp32-path layer with a fused residual / time embedding")
         if q.in_channels % 16 or q.out_channels % 4 or q.out_channels > MAX_CONV_O or q.in_channels != src.ch or q.out_channels != dst.ch:
             raise Unfusable("channel counts outside the fused kernel's range")
         if norm is not None and (norm.num_groups != 32 or q.in_channels % 32):
@@ -152,12 +155,27 @@ class Program:
         self.cp_max = max(self.cp_max, Cc)
         self.pbuf = max(self.pbuf, (2 * ((Cc + 3) // 4 * 4) + (O + 3) // 4 * 4 + 4 + 2 * Cc + 3 * O + 3) // 4 * 4)
         # static block: gamma[C] beta[C] bias[O] | wsum[O] w_zp[O] (int32 bit patterns)
-        dev = i8.wsum.device
+        dev = w_eff.device
         z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
         stat = torch.cat([norm.weight.detach().float() if norm is not None else z(Cc),
                           norm.bias.detach().float() if norm is not None else z(Cc),
                           q.bias.detach().float() if q.bias is not None else z(O),
-                          i8.wsum.view(torch.float32), i8.w_zp.view(torch.float32)]).contiguous()
+                          i8.wsum.view(torch.float32) if i8 is not None else z(O),
+                          i8.w_zp.view(torch.float32) if i8 is not None else z(O)]).contiguous()
+        if f32:
+            # QConv2d.forward_fused's fp32 branch on a 1x1 map: quantize -> de-quantize, then conv_f32 with the clamped fp32
+            # weights (centre tap); the kernel runs the same quantizer phases and the FCONV loop (rowprog.cu)
+            if O % 4 or O > MAX_O:
+                raise Unfusable("fp32-path layer width outside the fused kernel's range")
+            wt = w_eff.detach().reshape(O, Cc).t().contiguous()              # [C][O]
+            if wt.numel() * 4 < ((O + 15) // 16) * ((Cc + 31) // 32) * 512:
+                raise Unfusable("fp32 weights smaller than the fragment prefetch")
+            y = self.arena.alloc(Cc)                                         # the fake-quantized row
+            self._emit(type=OP_CONV, C=Cc, O=O, src=src, dst=dst, aux=y, pre=pre,
+                       a_bit=q._a_bit, tab_off=off, fparam=float(norm.eps) if norm is not None else 0.0,
+                       qw=self.plan.keep(wt), stat=self.plan.keep(stat), rsv0=1)
+            self.arena.release(y)
+            return
         self._emit(type=OP_CONV, C=Cc, O=O, src=src, dst=dst, add0=add0, pre=pre,
                    a_bit=q._a_bit, tab_off=off, fparam=float(norm.eps) if norm is not None else 0.0,
                    g1=self.plan.keep(temb), qw=self.plan.packed_weights(i8), stat=self.plan.keep(stat))
@@ -210,7 +228,7 @@ class Program:
                 setattr(r, name, int(o.get(name, 0)))
             r.fparam = o.get("fparam", 0.0)
             r.g0_ext = int(o.get("g0_ext", -1))
-            for name in ("g0", "g1", "qw", "stat"):
+            for name in ("g0", "g1", "qw", "stat", "rsv0"):
                 setattr(r, name, o.get(name))
             nx = o.get("nx")
             if nx is not None:

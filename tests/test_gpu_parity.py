@@ -838,6 +838,7 @@ def test_per_layer_trace_vs_reference_fixture(golden):
     (64, (1, 2, 2), 8, 8, "uniform", 9, False),    # 8 -> 4 -> 2 -> 1 ..., 128 channels, ragged sample tile
     (32, (1, 2), 4, 6, "uniform", 2, False),   # 6-bit activations (4-bit key projection)
     (32, (1, 2), 4, 4, "attn_random", 2, False),   # trained attention alphas -> those layers leave the integer path
+    (64, (1, 2, 2), 8, 4, "attn_random", 5, True),     # the same with mixed-precision attention (BASELINE.json config 3)
     # MixedPrecisionAttention (8 heads, softmax scale, fake-quantized scores at <= 6 bits and probabilities at <= 4) at one
     # position inside the fused trunk (utils/attention_quant_utils.py:51-107)
     (64, (1, 2), 4, 8, "uniform", 3, True),
@@ -870,8 +871,9 @@ def test_fused_rowprog_equals_layerwise(ch, ch_mult, size, bw, alpha, B, mixed):
     m.reset_index_seq()
     xs_g, x0_g = A.generalized_steps(x, spec.seq, m, betas, eta=0.0, use_graph=True)
     eng = SamplerEngine.for_model(m, spec.seq, betas, 0.0, tuple(x.shape))
+    # (attn_random: the attention convs take the fp32 path -- quantize, de-quantize, fp32 conv -- inside the fused trunk)
+    assert eng.fused is not None and eng.fused.trunk_plan is not None, "the fused plan was not built"
     if alpha == "uniform":
-        assert eng.fused is not None and eng.fused.trunk_plan is not None, "the fused plan was not built"
         assert eng.fused.n_up >= 1
         # the time path (timestep embedding -> time_embed -> every time_mlp) is evaluated once per pass for all steps
         # instead of B times per step (engine.py); the eager run above evaluates it per step, per sample
