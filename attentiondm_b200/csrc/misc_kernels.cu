@@ -85,6 +85,25 @@ __global__ void __launch_bounds__(128) attention_kernel(AttnParams p) {
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
     int j = 0;
+    // sixteen keys per step, all sixteen V loads issued before the first FMA, where the score rows leave room for enough
+    // warps per SM (N <= 512: 236 -> 130 us at N = 256, heads 8, batch 32; at N = 1024 the same loop measured 3.25 ms
+    // against 3.0 ms for four loads per step)
+    const int n16 = p.N <= 512 ? n4 : 0;
+    for (; j + 16 <= n16; j += 16) {
+      float vv[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) vv[u] = __ldg(vb + (long long)(j + u) * p.dv + c);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 pr = *reinterpret_cast<const float4*>(sc + r * p.N + j + 4 * q4);
+          acc[r] = fmaf(pr.x, vv[4 * q4], acc[r]);
+          acc[r] = fmaf(pr.y, vv[4 * q4 + 1], acc[r]);
+          acc[r] = fmaf(pr.z, vv[4 * q4 + 2], acc[r]);
+          acc[r] = fmaf(pr.w, vv[4 * q4 + 3], acc[r]);
+        }
+    }
     for (; j < n4; j += 4) {
       const float v0 = vb[(long long)j * p.dv + c], v1 = vb[(long long)(j + 1) * p.dv + c];
       const float v2 = vb[(long long)(j + 2) * p.dv + c], v3 = vb[(long long)(j + 3) * p.dv + c];
