@@ -182,6 +182,37 @@ rowprog_kernel(const attndm_rowop* __restrict__ ops, const int32_t* __restrict__
   // consecutive output channels and keeps 16 independent 128-bit loads in flight.  bias: global or shared, or NULL.
   auto fconv_rows = [&](const float* wt, const float* bias, const float* x0, int ld, int doff, int dld, int C, int O) {
     const float* xs = x0 + hh * NST * ld;
+    if (O <= RP_OCH) {
+      // narrow outputs (the q/k/v/out convs of an attention block on the fp32 path: O <= 256): ONE output channel per
+      // thread, 32 loads in flight each -- with four channels per thread only O/4 threads per sample half had work
+      // and the bytes in flight per CTA bounded the stream (12 us per 256 -> 256 conv)
+      const int o = ot;
+      if (o < O) {
+        float acc[NST];
+#pragma unroll
+        for (int n = 0; n < NST; ++n) acc[n] = 0.f;
+        const float* wp = wt + o;
+        int c = 0;
+        for (; c + 32 <= C; c += 32) {
+          float w[32];
+#pragma unroll
+          for (int u = 0; u < 32; ++u) w[u] = __ldg(wp + (long long)(c + u) * O);
+#pragma unroll
+          for (int u = 0; u < 32; ++u)
+#pragma unroll
+            for (int n = 0; n < NST; ++n) acc[n] = fmaf(xs[n * ld + c + u], w[u], acc[n]);
+        }
+        for (; c < C; ++c) {
+          const float w = __ldg(wp + (long long)c * O);
+#pragma unroll
+          for (int n = 0; n < NST; ++n) acc[n] = fmaf(xs[n * ld + c], w, acc[n]);
+        }
+        const float bz = bias ? bias[o] : 0.f;
+#pragma unroll
+        for (int n = 0; n < NST; ++n) arena[doff + (hh * NST + n) * dld + o] = acc[n] + bz;
+      }
+      return;
+    }
     for (int o = 4 * ot; o < O; o += 4 * RP_OCH) {
       float acc[NST][4];
 #pragma unroll
