@@ -20,6 +20,7 @@ bash tools/gpu_round2_s.sh > gpurun_out/r02_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:qconv_i8_halo -s 3 -c 1 \
     -f -o gpurun_out/prof_conv_r02b python tools/conv_bench.py --graph 0 --shapes c128_32 --iters 3 > gpurun_out/r02_ncu_conv.log 2>&1
 echo "ncu conv rc=$?"
+python -c "import __graft_entry__ as g; g.smoke(); print(\"smoke ok\")" 2>&1 | tail -2
 tail -3 gpurun_out/r02_tests.log; cat gpurun_out/r02_conv_bench.log
 python - <<'PY'
 import json
