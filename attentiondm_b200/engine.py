@@ -88,6 +88,7 @@ class SamplerEngine:
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = 0
+        self.launches_per_pass = 0
         # fused per-sample programs (time_mlp of every block; all blocks on 1x1 maps): graph mode only
         self.fused = None
         self.fused_parts = [None]
@@ -207,7 +208,10 @@ class SamplerEngine:
             raise RuntimeError("SamplerEngine: index_seq moved since the engine was built; rebuild it "
                                "(SamplerEngine.for_model) or call model.reset_index_seq()")
         if self.hoist:
+            from . import _ffi
+            before = _ffi.launches
             self._time_path_all_steps()
+            self.launches_per_pass = _ffi.launches - before       # our kernels that run once per pass, outside the graph
 
     def _time_path_all_steps(self):
         """The time path of every sampler step of this pass (see __init__), on the current stream."""

@@ -568,7 +568,8 @@ def run_ours(args):
         "e2e_keep_last": {"value": rate(e2e_ms["last"]), "unit": "images/s",
                           "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": d2h["last"],
                           "api": "same call with keep='last' (only the final images and x0 come back)"},
-        "gpu_launches": int((eng.launches_per_step or 0) * T_STEPS * args.steps),
+        "gpu_launches": int(((eng.launches_per_step or 0) * T_STEPS + (eng.launches_per_pass or 0)) * args.steps),
+        "launches_per_pass_outside_graph": int(eng.launches_per_pass or 0),
         "launches_per_denoising_step": int(eng.launches_per_step or 0),
         "whole_step_conv_tops": step_tops,
         "roofline": roof, "roofline_hbm": roof_hbm, "int8_peak": i8pk,
