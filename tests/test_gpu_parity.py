@@ -888,6 +888,51 @@ def test_fused_rowprog_equals_layerwise(ch, ch_mult, size, bw, alpha, B, mixed):
         assert torch.equal(xs_r[-1], xs_e[-1])
 
 
+
+def test_bcast_rows_and_time_path_all_steps():
+    """The time path of the sampler is evaluated once per pass for all steps and fanned out per step (engine.py):
+    attndm_bcast_rows copies the staged row's column ranges to [B, width] tensors, and the all-steps evaluation
+    (time_embedding on [T] rows + the time_mlp programs with one table row per CTA) gives, for every step, exactly what
+    the per-step per-sample evaluation gives."""
+    import attentiondm_b200 as A
+    from attentiondm_b200 import _ffi, ops
+    from attentiondm_b200.engine import SamplerEngine
+    cur = torch.arange(200, dtype=torch.float32, device=DEV) * 0.5
+    desc = torch.tensor([[0, 17, 5], [35, 100, 12], [119, 4, 3]], dtype=torch.int32, device=DEV)
+    B = 7
+    dst = torch.full((B * (5 + 12 + 3),), -1.0, device=DEV)
+    _ffi.call("attndm_bcast_rows", _ffi.ptr(cur), _ffi.ptr(desc), 3, B, 12, _ffi.ptr(dst), _ffi.stream())
+    assert torch.equal(dst[:35].view(B, 5), cur[17:22].expand(B, 5))
+    assert torch.equal(dst[35:119].view(B, 12), cur[100:112].expand(B, 12))
+    assert torch.equal(dst[119:].view(B, 3), cur[4:7].expand(B, 3))
+    # the hoisted time path against the per-step one, on the tiny model
+    spec = S.tiny_spec(T=4, bitwidth=8)
+    m = build_cuda_model(spec, S.synth_state_dict(spec, seed=5))
+    betas = R.beta_schedule_linear().to(DEV)
+    x = torch.randn(3, 3, 16, 16, generator=torch.Generator().manual_seed(2)).to(DEV)
+    m.set_calibrate(True)
+    A.generalized_steps(x, spec.seq, m, betas, eta=0.0, keep="last")
+    m.set_calibrate(False)
+    m.reset_index_seq()
+    eng = SamplerEngine(m, spec.seq, betas, 0.0, tuple(x.shape))
+    assert eng.hoist
+    eng.load_input(x)                                        # runs the all-steps time path into the table columns
+    fp = eng.fused
+    blocks = [b for b in list(m.down_blocks) + list(m.up_blocks) if b.time_mlp is not None]
+    for k in range(eng.T):
+        t = eng.table[k, eng.t_off:eng.t_off + 3].contiguous()
+        te = m.time_embedding(t)
+        col = eng.temb_off
+        for blk in blocks:
+            q = blk.time_mlp[1]
+            q.index_seq = k
+            want = q.forward_fused(te, ops.PRE_SILU).view(3, -1)          # per step, per sample (the eager path)
+            w = q.out_channels
+            got = eng.table[k, col:col + w]
+            assert torch.equal(want, got.expand(3, w)), (k, w)
+            col += (w + 3) // 4 * 4
+    m.reset_index_seq()
+
 # ---------------------------------------------------------------------------
 # full-size properties (oracle too slow): CIFAR config, batch 8
 # ---------------------------------------------------------------------------
