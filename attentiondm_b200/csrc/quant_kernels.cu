@@ -597,7 +597,7 @@ static int act_quant_impl(const float* x, int B, int H, int W, int C, const floa
   ATTNDM_CHECK_ARG(pre != ATTNDM_PRE_GN_SILU || (gn_stats && gamma && beta && C % kGnGroups == 0 && C % 4 == 0),
                    "act_quant: GroupNorm pre-op needs stats/gamma/beta and C %% 32 == 0");
   ATTNDM_CHECK_ARG(rows_layout == ATTNDM_ROWS_PLAIN || rows_layout == ATTNDM_ROWS_HALO, "act_quant: bad layout");
-  ActQuantParams p;
+  ActQuantParams p = {};
   p.x = x; p.B = B; p.H = H; p.W = W; p.C = C; p.Cp = round_up(C, 16);
   p.scale = scale; p.zp = zp;
   p.qlo = quant ? -(float)(1 << (a_bit - 1)) : 0.f;
@@ -1318,7 +1318,7 @@ static int act_quant_cat_impl(const float* xa, int C1, const float* xb, int C2, 
     set_error("act_quant_cat: shape %dx%dx(%d+%d) not supported (see attndm_act_quant_cat_fits)", H, W, C1, C2);
     return ATTNDM_ERR_UNSUPPORTED;
   }
-  ActQuantParams p;
+  ActQuantParams p = {};
   p.x = xa; p.x2 = xb; p.C1 = C1;
   p.B = B; p.H = H; p.W = W; p.C = C; p.Cp = round_up(C, 16);
   p.scale = scale; p.zp = zp;
